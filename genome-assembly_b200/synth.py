@@ -1,0 +1,100 @@
+"""Synthetic read sets for the binning hot path.
+
+Restates the *distribution* of the reference's generate_reads.py (generate_reads.py:93-112):
+an i.i.d. uniform genome over ACGT, fixed-length forward-strand substrings, one read per
+``\\n``-terminated line.  Two things the script lacks are added, as SURVEY.md §8(d) prescribes:
+the seed is applied *before* the genome is drawn (the script seeds after, generate_reads.py:96-97,
+so its genome is not reproducible), and i.i.d. per-base substitution to one of the other three
+bases at rate ``error_rate`` (the script has no error model).
+
+``starts="triangular"`` replays the script's chained ``random.triangular(0, G-1-L, mode)`` walk
+(generate_reads.py:98-105) with Python's ``random`` module; it is inherently sequential, so it is
+used for the 1 M-read configuration only.  ``starts="uniform"`` draws i.i.d. uniform starts from a
+counter-based numpy generator (Philox) and is used for the larger configurations.
+"""
+from __future__ import annotations
+
+import random
+from dataclasses import dataclass
+
+import numpy as np
+
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+@dataclass
+class ReadSet:
+    """Fixed-stride ASCII reads: row i is ``buf[i*stride : i*stride+read_len]`` followed by ``\\n``."""
+
+    buf: np.ndarray  # uint8 [n_reads * stride]
+    n_reads: int
+    read_len: int
+    stride: int
+    genome_len: int
+    seed: int
+    error_rate: float
+    starts_kind: str
+
+    def as_bytes(self) -> bytes:
+        return self.buf.tobytes()
+
+    def rows(self) -> np.ndarray:
+        return self.buf.reshape(self.n_reads, self.stride)[:, : self.read_len]
+
+
+def default_genome_len(n_reads: int, read_len: int, coverage: float = 30.0) -> int:
+    """genome length = n_reads * L / 30 (about 30x coverage)."""
+    return max(read_len + 2, int(n_reads * read_len / coverage))
+
+
+def generate(n_reads: int, read_len: int, *, genome_len: int | None = None, error_rate: float = 0.01,
+             seed: int = 20, starts: str = "uniform", chunk: int = 1 << 18) -> ReadSet:
+    if genome_len is None:
+        genome_len = default_genome_len(n_reads, read_len)
+    if genome_len < read_len + 2:
+        raise ValueError("genome shorter than a read")
+    rng = np.random.Generator(np.random.Philox(seed))
+    genome = _ACGT[rng.integers(0, 4, size=genome_len, dtype=np.uint8)]
+    hi = genome_len - 1 - read_len  # generate_reads.py:98
+    if starts == "triangular":
+        r = random.Random(seed)
+        mode = r.randint(0, hi)
+        pos = np.empty(n_reads, dtype=np.int64)
+        for i in range(n_reads):
+            mode = int(r.triangular(0, hi, mode))
+            pos[i] = mode
+    elif starts == "uniform":
+        pos = rng.integers(0, hi + 1, size=n_reads, dtype=np.int64)
+    else:
+        raise ValueError(starts)
+    stride = read_len + 1
+    buf = np.empty(n_reads * stride, dtype=np.uint8)
+    view = buf.reshape(n_reads, stride)
+    view[:, read_len] = ord("\n")
+    ar = np.arange(read_len, dtype=np.int64)
+    for lo in range(0, n_reads, chunk):
+        hi_i = min(n_reads, lo + chunk)
+        idx = pos[lo:hi_i, None] + ar[None, :]
+        bases = genome[idx]
+        if error_rate > 0:
+            hit = rng.random(bases.shape, dtype=np.float32) < error_rate
+            nhit = int(hit.sum())
+            if nhit:
+                # substitute with one of the three *other* bases: rotate the ACGT index by 1..3
+                lut = np.zeros(256, dtype=np.uint8)
+                lut[_ACGT] = np.arange(4, dtype=np.uint8)
+                cur = lut[bases[hit]]
+                rot = rng.integers(1, 4, size=nhit, dtype=np.uint8)
+                bases[hit] = _ACGT[(cur + rot) & 3]
+        view[lo:hi_i, :read_len] = bases
+    return ReadSet(buf=buf, n_reads=n_reads, read_len=read_len, stride=stride, genome_len=genome_len,
+                   seed=seed, error_rate=error_rate, starts_kind=starts)
+
+
+# BASELINE.json configs 2-5 (config 1 is the bundled reads.txt)
+WORKLOADS = {
+    "cfg2": dict(n_reads=1_000_000, read_len=100, k=31, m=11, cutoff=1, error_rate=0.01, starts="triangular"),
+    "cfg3": dict(n_reads=100_000_000, read_len=150, k=31, m=11, cutoff=1, error_rate=0.01, starts="uniform"),
+    "cfg4": dict(n_reads=10_000_000, read_len=250, k=63, m=15, cutoff=1, error_rate=0.01, starts="uniform"),
+    "cfg5": dict(n_reads=50_000_000, read_len=150, k=25, m=9, cutoff=1, error_rate=0.05, starts="uniform"),
+}

@@ -1,0 +1,307 @@
+"""ctypes mirror of include/gbin.h (libgbin.so).  No computation happens in Python and there is no
+fallback: if the shared library is missing, or the machine has no CUDA device, calls raise."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgbin.so")
+
+GBIN_OK = 0
+GBIN_E_INVALID_CONFIG = -1
+GBIN_E_CUDA = -2
+GBIN_E_NOMEM = -3
+GBIN_E_NON_ACGT = -4
+GBIN_E_STATE = -5
+GBIN_E_TOO_LARGE = -6
+GBIN_E_INVALID_ARG = -7
+GBIN_E_IO = -8
+
+
+class GbinError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"gbin error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("kmer_size", C.c_int32), ("mmer_size", C.c_int32), ("abundance_cutoff", C.c_int32), ("device", C.c_int32)]
+
+
+class CTable(C.Structure):
+    _fields_ = [("kmer_size", C.c_int32), ("mmer_size", C.c_int32), ("abundance_cutoff", C.c_int32), ("kmer_words", C.c_int32),
+                ("on_device", C.c_int32), ("ctx_owned", C.c_int32),
+                ("n_instances", C.c_uint64), ("n_distinct", C.c_uint64), ("n_buckets", C.c_uint64), ("n_kmers", C.c_uint64),
+                ("n_ids", C.c_uint64),
+                ("mmer_codes", C.c_void_p), ("mmer_kmer_off", C.c_void_p), ("kmer_codes", C.c_void_p),
+                ("kmer_id_off", C.c_void_p), ("read_ids", C.c_void_p)]
+
+
+class CReads(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("data_bytes", C.c_uint64), ("n_reads", C.c_uint64), ("stride", C.c_uint64),
+                ("read_len", C.c_uint32), ("id_base", C.c_int32), ("starts", C.c_void_p), ("lens", C.c_void_p),
+                ("read_ids", C.c_void_p), ("max_read_len", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class Timings(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("scan_ms", C.c_float), ("sort_ms", C.c_float), ("group_ms", C.c_float),
+                ("d2h_ms", C.c_float), ("total_ms", C.c_float), ("kernel_launches", C.c_uint32), ("sort_passes", C.c_uint32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+# every symbol include/gbin.h declares (tests check that the library exports all of them)
+EXPORTS = [
+    "gbin_strerror", "gbin_last_error", "gbin_version", "gbin_create", "gbin_destroy", "gbin_get_config",
+    "gbin_bin_reads_host", "gbin_table_clone", "gbin_table_free", "gbin_pinned_alloc", "gbin_pinned_free",
+    "gbin_bin_reads_device", "gbin_table_to_host", "gbin_get_timings", "gbin_record_bytes",
+    "gbin_count_instances_device", "gbin_scan_reads_device", "gbin_partition_records_device",
+    "gbin_group_records_device", "gbin_read_file_fgets", "gbin_table_dump", "gbin_table_dump_reference_format",
+    "getval", "getbp", "getscore", "process_read", "prune_data", "gbin_ref_configure", "gbin_ref_last_status",
+    "gbin_ref_reset", "gbin_table_to_zhash", "gbin_zhash_release",
+]
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Loads libgbin.so (built in-tree by `make -C genome-assembly_b200` / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `make -C genome-assembly_b200` "
+                          "(there is no CPU or PyTorch fallback for the binning path)")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32
+    L.gbin_strerror.restype = C.c_char_p
+    L.gbin_strerror.argtypes = [C.c_int]
+    L.gbin_last_error.restype = C.c_char_p
+    L.gbin_last_error.argtypes = [vp]
+    L.gbin_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.gbin_destroy.argtypes = [vp]
+    L.gbin_destroy.restype = None
+    L.gbin_get_config.argtypes = [vp, C.POINTER(Config)]
+    L.gbin_bin_reads_host.argtypes = [vp, C.POINTER(CReads), C.POINTER(CTable)]
+    L.gbin_bin_reads_device.argtypes = [vp, C.POINTER(CReads), vp, C.POINTER(CTable)]
+    L.gbin_table_to_host.argtypes = [vp, C.POINTER(CTable), C.POINTER(CTable)]
+    L.gbin_table_clone.argtypes = [C.POINTER(CTable), C.POINTER(CTable)]
+    L.gbin_table_free.argtypes = [C.POINTER(CTable)]
+    L.gbin_table_free.restype = None
+    L.gbin_pinned_alloc.argtypes = [C.c_size_t]
+    L.gbin_pinned_alloc.restype = vp
+    L.gbin_pinned_free.argtypes = [vp]
+    L.gbin_pinned_free.restype = None
+    L.gbin_get_timings.argtypes = [vp, C.POINTER(Timings)]
+    L.gbin_record_bytes.argtypes = [vp]
+    L.gbin_record_bytes.restype = u32
+    L.gbin_count_instances_device.argtypes = [vp, C.POINTER(CReads), vp, C.POINTER(u64)]
+    L.gbin_scan_reads_device.argtypes = [vp, C.POINTER(CReads), u32, vp, u64, vp, C.POINTER(u64)]
+    L.gbin_partition_records_device.argtypes = [vp, vp, u64, u32, vp, vp, C.POINTER(u64)]
+    L.gbin_group_records_device.argtypes = [vp, vp, u64, vp, i32, vp, C.POINTER(CTable)]
+    L.gbin_read_file_fgets.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(vp),
+                                       C.POINTER(u64)]
+    L.gbin_table_dump.argtypes = [C.POINTER(CTable), C.c_char_p]
+    L.gbin_table_dump_reference_format.argtypes = [C.POINTER(CTable), C.c_char_p]
+    L.getval.argtypes = [C.c_char]
+    L.getval.restype = C.c_int
+    L.getbp.argtypes = [C.c_int]
+    L.getbp.restype = C.c_char
+    L.getscore.argtypes = [C.c_char_p]
+    L.getscore.restype = C.c_int
+    L.process_read.argtypes = [vp, C.c_char_p, C.c_int]
+    L.process_read.restype = vp
+    L.prune_data.argtypes = [vp]
+    L.prune_data.restype = vp
+    L.gbin_ref_configure.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    L.gbin_ref_last_status.restype = C.c_int
+    L.gbin_ref_reset.argtypes = [vp]
+    L.gbin_ref_reset.restype = None
+    L.gbin_table_to_zhash.argtypes = [C.POINTER(CTable), vp]
+    L.gbin_zhash_release.argtypes = [vp]
+    L.gbin_zhash_release.restype = None
+    _lib = L
+    return L
+
+
+@dataclass
+class HostTable:
+    """The pruned mmer -> kmer -> read-id table as numpy arrays (copies; canonical order)."""
+    K: int
+    M: int
+    cutoff: int
+    kw: int
+    n_instances: int
+    n_distinct: int
+    mmer_codes: np.ndarray
+    mmer_kmer_off: np.ndarray
+    kmer_codes: np.ndarray
+    kmer_id_off: np.ndarray
+    read_ids: np.ndarray
+
+    @property
+    def n_buckets(self):
+        return len(self.mmer_codes)
+
+    @property
+    def n_kmers(self):
+        return len(self.kmer_id_off) - 1
+
+    @property
+    def n_ids(self):
+        return len(self.read_ids)
+
+
+def _np_from(ptr, n, dtype):
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=n).copy()
+
+
+def host_table_from_c(t: CTable) -> HostTable:
+    assert not t.on_device
+    return HostTable(K=t.kmer_size, M=t.mmer_size, cutoff=t.abundance_cutoff, kw=t.kmer_words,
+                     n_instances=int(t.n_instances), n_distinct=int(t.n_distinct),
+                     mmer_codes=_np_from(t.mmer_codes, t.n_buckets, np.uint32),
+                     mmer_kmer_off=_np_from(t.mmer_kmer_off, t.n_buckets + 1, np.uint64),
+                     kmer_codes=_np_from(t.kmer_codes, t.n_kmers * t.kmer_words, np.uint64),
+                     kmer_id_off=_np_from(t.kmer_id_off, t.n_kmers + 1, np.uint64),
+                     read_ids=_np_from(t.read_ids, t.n_ids, np.int32))
+
+
+def _ptr(x):
+    """Raw address of a numpy array / torch tensor / int / None."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    raise TypeError(type(x))
+
+
+class Binner:
+    """One context per GPU (gbin_ctx): K, M and the cutoff are the runtime form of binning.c:10-12."""
+
+    def __init__(self, k: int = 31, m: int = 4, cutoff: int = 1, device: int = 0):
+        self.lib = load_library()
+        self.cfg = Config(k, m, cutoff, device)
+        h = C.c_void_p()
+        rc = self.lib.gbin_create(C.byref(self.cfg), C.byref(h))
+        if rc != GBIN_OK:
+            raise GbinError(rc, self.lib.gbin_strerror(rc).decode())
+        self.h = h
+        self.k, self.m, self.cutoff, self.device = k, m, cutoff, device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gbin_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != GBIN_OK:
+            raise GbinError(rc, f"{self.lib.gbin_strerror(rc).decode()}: {self.lib.gbin_last_error(self.h).decode()}")
+
+    @property
+    def record_bytes(self) -> int:
+        return int(self.lib.gbin_record_bytes(self.h))
+
+    def timings(self) -> dict:
+        t = Timings()
+        self.lib.gbin_get_timings(self.h, C.byref(t))
+        return t.as_dict()
+
+    @staticmethod
+    def _reads(data, data_bytes, n_reads, stride=0, read_len=0, starts=None, lens=None, read_ids=None, id_base=0, max_read_len=0):
+        return CReads(_ptr(data), data_bytes, n_reads, stride, read_len, id_base, _ptr(starts), _ptr(lens), _ptr(read_ids),
+                      max_read_len, 0)
+
+    # ---- host buffers in, host table out (H2D + pipeline + D2H)
+    def bin_host_raw(self, reads: CReads) -> CTable:
+        """Returns the ctx-owned pinned table (valid until the next call) without copying it."""
+        t = CTable()
+        self._check(self.lib.gbin_bin_reads_host(self.h, C.byref(reads), C.byref(t)))
+        return t
+
+    def bin_host(self, data, n_reads, *, stride=0, read_len=0, starts=None, lens=None, read_ids=None, id_base=0) -> HostTable:
+        if isinstance(data, (bytes, bytearray)):
+            data = np.frombuffer(data, dtype=np.uint8)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        keep = [data]
+        if starts is not None:
+            starts = np.ascontiguousarray(starts, dtype=np.uint64)
+            lens = np.ascontiguousarray(lens, dtype=np.uint32)
+            keep += [starts, lens]
+        if read_ids is not None:
+            read_ids = np.ascontiguousarray(read_ids, dtype=np.int32)
+            keep.append(read_ids)
+        rd = self._reads(data, data.size, n_reads, stride, read_len, starts, lens, read_ids, id_base)
+        return host_table_from_c(self.bin_host_raw(rd))
+
+    # ---- device buffers in, device table out
+    def bin_device_raw(self, reads: CReads, stream: int | None = None) -> CTable:
+        t = CTable()
+        self._check(self.lib.gbin_bin_reads_device(self.h, C.byref(reads), stream, C.byref(t)))
+        return t
+
+    def table_to_host(self, dev: CTable) -> HostTable:
+        h = CTable()
+        self._check(self.lib.gbin_table_to_host(self.h, C.byref(dev), C.byref(h)))
+        try:
+            return host_table_from_c(h)
+        finally:
+            self.lib.gbin_table_free(C.byref(h))
+
+    # ---- staged device entry points
+    def count_instances_device(self, reads: CReads, stream=None) -> int:
+        n = C.c_uint64()
+        self._check(self.lib.gbin_count_instances_device(self.h, C.byref(reads), stream, C.byref(n)))
+        return int(n.value)
+
+    def scan_device(self, reads: CReads, arrival_base: int, d_records, capacity: int, stream=None) -> int:
+        n = C.c_uint64()
+        self._check(self.lib.gbin_scan_reads_device(self.h, C.byref(reads), arrival_base, _ptr(d_records), capacity, stream, C.byref(n)))
+        return int(n.value)
+
+    def partition_device(self, d_records, n: int, n_parts: int, d_out, stream=None) -> list[int]:
+        counts = (C.c_uint64 * n_parts)()
+        self._check(self.lib.gbin_partition_records_device(self.h, _ptr(d_records), n, n_parts, _ptr(d_out), stream, counts))
+        return [int(c) for c in counts]
+
+    def group_device(self, d_records, n: int, d_ids_by_arrival=None, id_base: int = 0, stream=None) -> CTable:
+        t = CTable()
+        self._check(self.lib.gbin_group_records_device(self.h, _ptr(d_records), n, _ptr(d_ids_by_arrival), id_base, stream, C.byref(t)))
+        return t
+
+
+def read_file_fgets(path: str, read_length_define: int):
+    """main's read loop (binning.c:1154-1166) -> (data bytes, starts u64[n], lens u32[n])."""
+    L = load_library()
+    data, starts, lens = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    nbytes, n = C.c_uint64(), C.c_uint64()
+    rc = L.gbin_read_file_fgets(path.encode(), read_length_define, C.byref(data), C.byref(nbytes), C.byref(starts), C.byref(lens),
+                                C.byref(n))
+    if rc != GBIN_OK:
+        raise GbinError(rc, L.gbin_strerror(rc).decode())
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    try:
+        return (_np_from(data.value, nbytes.value, np.uint8), _np_from(starts.value, n.value, np.uint64),
+                _np_from(lens.value, n.value, np.uint32))
+    finally:
+        for p in (data, starts, lens):
+            libc.free(p)

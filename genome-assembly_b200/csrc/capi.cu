@@ -1,0 +1,595 @@
+// capi.cu — the extern "C" layer of libgbin.so: context, HBM workspace and the pipeline
+//   scan (process_read, binning.c:918-1040) -> sort (zhash grouping, :1044-1069) -> run-length + prune (:1085-1144).
+// There is no CPU fallback anywhere in this file: every entry point either runs the CUDA kernels or
+// returns an error code.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "../../include/gbin.h"
+#include "gbin_internal.h"
+#include "prefix_scan.cuh"
+
+using namespace gbin;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 16 + 256;  // a little slack so near-equal batches do not reallocate
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const { return static_cast<T *>(p); }
+};
+
+struct HostBuf {  // page-locked
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Misc {  // small device-resident scalars
+    GroupCounts counts;
+    unsigned long long bad_bases;
+    unsigned long long total_windows;
+    unsigned int max_len;
+    unsigned int pad;
+    uint64_t part_counts[256];
+};
+
+}  // namespace
+
+struct gbin_ctx {
+    gbin_config cfg;
+    int KW;
+    int sm_count;
+    cudaStream_t stream;
+    char err[512];
+    gbin_timings tm;
+    cudaEvent_t ev[6];
+    // inputs staged by the host path
+    DevBuf d_reads, d_starts, d_lens, d_ids;
+    // pipeline workspace
+    DevBuf rec_a, rec_b, radix_scratch, win_counts, rec_off, scan_scratch;
+    DevBuf group_of, run_start, surv_index, id_offset, surv_group, bucket_of;
+    DevBuf misc;
+    // device-resident result
+    DevBuf o_mmer_codes, o_mmer_kmer_off, o_kmer_codes, o_kmer_id_off, o_read_ids;
+    // pinned host arena for results of the host path + small readbacks
+    HostBuf h_misc, h_result;
+};
+
+namespace {
+
+int fail(gbin_ctx *ctx, int code, const char *fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof ctx->err, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess) {                                                                             \
+            (void)cudaGetLastError();                                                                         \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? GBIN_E_NOMEM : GBIN_E_CUDA, "%s: %s (%s:%d)", \
+                        #call, cudaGetErrorString(e__), __FILE__, __LINE__);                                  \
+        }                                                                                                     \
+    } while (0)
+
+int check_config(const gbin_config *c) {
+    if (!c) return GBIN_E_INVALID_ARG;
+    const int K = c->kmer_size, M = c->mmer_size;
+    if (M < 2 || M > 15) return GBIN_E_INVALID_CONFIG;       // int scores (binning.c:911) hold 4^15-1 at most
+    if (K < 2 * M || K > 64) return GBIN_E_INVALID_CONFIG;   // binning.c:997 is dead code only for K >= 2M
+    return GBIN_OK;
+}
+
+__global__ void max_len_kernel(const uint32_t *__restrict__ lens, uint64_t n, unsigned int *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int v = i < n ? lens[i] : 0u;
+    v = __reduce_max_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && v) atomicMax(out, v);
+}
+
+struct WinCountIn {
+    const uint32_t *c;
+    __device__ __forceinline__ uint64_t operator()(uint64_t j) const { return c[j]; }
+};
+
+// Validates the reads descriptor (device pointers), finds max length and instance count.
+// On return: *n_inst, *max_len, and for the ragged form ctx->rec_off holds per-read record offsets.
+int plan_reads(gbin_ctx *ctx, const gbin_reads *rd, cudaStream_t st, uint64_t *n_inst, uint32_t *max_len, int *launches) {
+    const int K = ctx->cfg.kmer_size;
+    Misc *dm = ctx->misc.as<Misc>();
+    Misc *hm = static_cast<Misc *>(ctx->h_misc.p);
+    if (rd->n_reads == 0) {
+        *n_inst = 0;
+        *max_len = 0;
+        return GBIN_OK;
+    }
+    if (!rd->data) return fail(ctx, GBIN_E_INVALID_ARG, "reads->data is NULL");
+    if (rd->n_reads >= (1ull << 32)) return fail(ctx, GBIN_E_TOO_LARGE, "more than 2^32-1 reads in one batch");
+    if (!rd->starts) {
+        if (rd->stride < rd->read_len) return fail(ctx, GBIN_E_INVALID_ARG, "stride < read_len");
+        if (rd->data_bytes && (rd->n_reads - 1) * rd->stride + rd->read_len > rd->data_bytes)
+            return fail(ctx, GBIN_E_INVALID_ARG, "fixed-stride reads exceed data_bytes");
+        *max_len = rd->read_len;
+        *n_inst = rd->read_len >= (uint32_t)K ? rd->n_reads * (uint64_t)(rd->read_len - K + 1) : 0;
+        return GBIN_OK;
+    }
+    if (!rd->lens) return fail(ctx, GBIN_E_INVALID_ARG, "ragged reads need lens");
+    ReadsView rv{reinterpret_cast<const uint8_t *>(rd->data), rd->data_bytes, rd->n_reads, rd->stride, rd->read_len, rd->starts, rd->lens};
+    CU(ctx->win_counts.ensure(rd->n_reads * sizeof(uint32_t)));
+    CU(ctx->rec_off.ensure((rd->n_reads + 1) * sizeof(uint64_t)));
+    CU(ctx->scan_scratch.ensure(group_scan_scratch_bytes(rd->n_reads)));
+    CU(cudaMemsetAsync(&dm->max_len, 0, sizeof(unsigned int), st));
+    if (rd->max_read_len == 0) {
+        max_len_kernel<<<(unsigned)((rd->n_reads + 255) / 256), 256, 0, st>>>(rd->lens, rd->n_reads, &dm->max_len);
+        (*launches)++;
+    }
+    *launches += launch_count_windows(rv, K, ctx->win_counts.as<uint32_t>(), st);
+    *launches += exclusive_scan<uint64_t, WinCountIn>(WinCountIn{ctx->win_counts.as<uint32_t>()}, ctx->rec_off.as<uint64_t>(), rd->n_reads,
+                                                      ctx->scan_scratch.as<uint64_t>(),
+                                                      reinterpret_cast<uint64_t *>(&dm->total_windows), st);
+    CU(cudaMemcpyAsync(&hm->total_windows, &dm->total_windows, sizeof(unsigned long long) + sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_inst = hm->total_windows;
+    *max_len = rd->max_read_len ? rd->max_read_len : hm->max_len;
+    return GBIN_OK;
+}
+
+int run_scan(gbin_ctx *ctx, const gbin_reads *rd, uint32_t arrival_base, void *d_records, uint32_t max_len, cudaStream_t st, int *launches) {
+    Misc *dm = ctx->misc.as<Misc>();
+    ReadsView rv{reinterpret_cast<const uint8_t *>(rd->data), rd->data_bytes, rd->n_reads, rd->stride, rd->read_len, rd->starts, rd->lens};
+    CU(cudaMemsetAsync(&dm->bad_bases, 0, sizeof(unsigned long long), st));
+    *launches += launch_scan_reads(rv, rd->starts ? ctx->rec_off.as<uint64_t>() : nullptr, ctx->cfg.kmer_size, ctx->cfg.mmer_size, ctx->KW,
+                                   arrival_base, max_len ? max_len : 1, d_records, &dm->bad_bases, ctx->sm_count, st);
+    CU(cudaGetLastError());
+    return GBIN_OK;
+}
+
+// Sort + run-length + prune + emit of n records living in `recs` (scratch twin `twin`).
+int run_group(gbin_ctx *ctx, void *recs, void *twin, uint64_t n, const int32_t *d_ids, int32_t id_base, cudaStream_t st,
+              gbin_table *out, int *launches, cudaEvent_t ev_sorted) {
+    const int KW = ctx->KW, K = ctx->cfg.kmer_size, M = ctx->cfg.mmer_size, cutoff = ctx->cfg.abundance_cutoff;
+    Misc *dm = ctx->misc.as<Misc>();
+    Misc *hm = static_cast<Misc *>(ctx->h_misc.p);
+    memset(out, 0, sizeof *out);
+    out->kmer_size = K;
+    out->mmer_size = M;
+    out->abundance_cutoff = cutoff;
+    out->kmer_words = KW;
+    out->on_device = 1;
+    out->ctx_owned = 1;
+    out->n_instances = n;
+
+    CU(ctx->radix_scratch.ensure(radix_scratch_bytes(n)));
+    bool in_b = false;
+    int passes = 0;
+    *launches += radix_sort_records(recs, twin, n, KW, K, M, ctx->radix_scratch.p, &in_b, &passes, st);
+    CU(cudaGetLastError());
+    ctx->tm.sort_passes = (uint32_t)passes;
+    const void *sorted = in_b ? twin : recs;
+    if (ev_sorted) CU(cudaEventRecord(ev_sorted, st));
+
+    GroupWorkspace ws{};
+    CU(ctx->group_of.ensure((n + 1) * sizeof(uint32_t)));
+    CU(ctx->run_start.ensure((n + 2) * sizeof(uint32_t)));
+    CU(ctx->scan_scratch.ensure(group_scan_scratch_bytes(n)));
+    ws.group_of = ctx->group_of.as<uint32_t>();
+    ws.run_start = ctx->run_start.as<uint32_t>();
+    ws.scan_scratch = ctx->scan_scratch.p;
+    ws.counts = &dm->counts;
+    ws.cutoff = cutoff;
+
+    *launches += group_find_runs(sorted, n, KW, ws, st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(hm, dm, sizeof(GroupCounts) + sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (hm->bad_bases) return fail(ctx, GBIN_E_NON_ACGT, "%llu bases other than A/C/G/T in the batch", hm->bad_bases);
+    const uint64_t G = hm->counts.n_distinct;
+    out->n_distinct = G;
+
+    uint64_t S = 0, NS = 0, B = 0;
+    if (G) {
+        CU(ctx->surv_index.ensure((G + 1) * sizeof(uint32_t)));
+        CU(ctx->id_offset.ensure((G + 1) * sizeof(uint64_t)));
+        ws.surv_index = ctx->surv_index.as<uint32_t>();
+        ws.id_offset = ctx->id_offset.as<uint64_t>();
+        *launches += group_prune_offsets(n, G, cutoff, ws, st);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&hm->counts, &dm->counts, sizeof(GroupCounts), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        S = hm->counts.n_kmers;
+        NS = hm->counts.n_ids;
+    }
+    if (S) {
+        CU(ctx->surv_group.ensure(S * sizeof(uint32_t)));
+        CU(ctx->bucket_of.ensure(S * sizeof(uint32_t)));
+        ws.surv_group = ctx->surv_group.as<uint32_t>();
+        ws.bucket_of = ctx->bucket_of.as<uint32_t>();
+        *launches += group_mark_buckets(sorted, KW, G, S, ws, st);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&hm->counts, &dm->counts, sizeof(GroupCounts), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        B = hm->counts.n_buckets;
+    }
+    CU(ctx->o_mmer_codes.ensure((B + 1) * sizeof(uint32_t)));
+    CU(ctx->o_mmer_kmer_off.ensure((B + 1) * sizeof(uint64_t)));
+    CU(ctx->o_kmer_codes.ensure((S * KW + 1) * sizeof(uint64_t)));
+    CU(ctx->o_kmer_id_off.ensure((S + 1) * sizeof(uint64_t)));
+    CU(ctx->o_read_ids.ensure((NS + 1) * sizeof(int32_t)));
+    TableOut to{ctx->o_mmer_codes.as<uint32_t>(), ctx->o_mmer_kmer_off.as<uint64_t>(), ctx->o_kmer_codes.as<uint64_t>(),
+                ctx->o_kmer_id_off.as<uint64_t>(), ctx->o_read_ids.as<int32_t>()};
+    *launches += group_emit(sorted, n, KW, G, S, NS, B, d_ids, id_base, ws, to, st);
+    CU(cudaGetLastError());
+    out->n_kmers = S;
+    out->n_ids = NS;
+    out->n_buckets = B;
+    out->mmer_codes = to.mmer_codes;
+    out->mmer_kmer_off = to.mmer_kmer_off;
+    out->kmer_codes = to.kmer_codes;
+    out->kmer_id_off = to.kmer_id_off;
+    out->read_ids = to.read_ids;
+    return GBIN_OK;
+}
+
+int bin_device_impl(gbin_ctx *ctx, const gbin_reads *rd, cudaStream_t st, gbin_table *out, int *launches) {
+    uint64_t n = 0;
+    uint32_t max_len = 0;
+    int rc = plan_reads(ctx, rd, st, &n, &max_len, launches);
+    if (rc) return rc;
+    if (max_len > GBIN_MAX_READ_LEN) return fail(ctx, GBIN_E_TOO_LARGE, "read length %u exceeds GBIN_MAX_READ_LEN", max_len);
+    if (n >= (1ull << 32) - 8192) return fail(ctx, GBIN_E_TOO_LARGE, "%llu k-mer instances in one batch (limit 2^32)", (unsigned long long)n);
+    const size_t rb = sizeof(uint64_t) * ctx->KW + 8;
+    CU(ctx->rec_a.ensure((n + 1) * rb));
+    CU(ctx->rec_b.ensure((n + 1) * rb));
+    rc = run_scan(ctx, rd, 0, ctx->rec_a.p, max_len, st, launches);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[2], st));
+    rc = run_group(ctx, ctx->rec_a.p, ctx->rec_b.p, n, rd->read_ids, rd->id_base, st, out, launches, ctx->ev[3]);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[4], st));
+    return GBIN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *gbin_strerror(int code) {
+    switch (code) {
+        case GBIN_OK: return "ok";
+        case GBIN_E_INVALID_CONFIG: return "unsupported K/M (need 2 <= M <= 15 and 2M <= K <= 64)";
+        case GBIN_E_CUDA: return "CUDA error";
+        case GBIN_E_NOMEM: return "out of memory";
+        case GBIN_E_NON_ACGT: return "read contains a byte other than A/C/G/T";
+        case GBIN_E_STATE: return "call sequence error";
+        case GBIN_E_TOO_LARGE: return "batch exceeds an implementation limit";
+        case GBIN_E_INVALID_ARG: return "invalid argument";
+        case GBIN_E_IO: return "I/O error";
+        default: return "unknown error";
+    }
+}
+
+const char *gbin_last_error(const gbin_ctx *ctx) { return ctx ? ctx->err : ""; }
+int gbin_version(void) { return 100; }
+
+int gbin_create(const gbin_config *cfg, gbin_ctx **out) {
+    if (!out) return GBIN_E_INVALID_ARG;
+    *out = nullptr;
+    int rc = check_config(cfg);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        return GBIN_E_CUDA;  // no CPU fallback: without a CUDA device the library refuses to work
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return GBIN_E_INVALID_ARG;
+    gbin_ctx *ctx = new (std::nothrow) gbin_ctx();
+    if (!ctx) return GBIN_E_NOMEM;
+    ctx->cfg = *cfg;
+    ctx->KW = cfg->kmer_size <= 32 ? 1 : 2;
+    ctx->err[0] = 0;
+    memset(&ctx->tm, 0, sizeof ctx->tm);
+    cudaError_t e = cudaSetDevice(cfg->device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev[i]);
+    if (e == cudaSuccess) e = ctx->misc.ensure(sizeof(Misc));
+    if (e == cudaSuccess) e = ctx->h_misc.ensure(sizeof(Misc));
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        delete ctx;
+        return GBIN_E_CUDA;
+    }
+    *out = ctx;
+    return GBIN_OK;
+}
+
+void gbin_destroy(gbin_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->d_reads, &ctx->d_starts, &ctx->d_lens, &ctx->d_ids, &ctx->rec_a, &ctx->rec_b, &ctx->radix_scratch,
+                      &ctx->win_counts, &ctx->rec_off, &ctx->scan_scratch, &ctx->group_of, &ctx->run_start, &ctx->surv_index,
+                      &ctx->id_offset, &ctx->surv_group, &ctx->bucket_of, &ctx->misc, &ctx->o_mmer_codes, &ctx->o_mmer_kmer_off,
+                      &ctx->o_kmer_codes, &ctx->o_kmer_id_off, &ctx->o_read_ids};
+    for (DevBuf *b : bufs) b->release();
+    ctx->h_misc.release();
+    ctx->h_result.release();
+    for (int i = 0; i < 6; i++) cudaEventDestroy(ctx->ev[i]);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int gbin_get_config(const gbin_ctx *ctx, gbin_config *out) {
+    if (!ctx || !out) return GBIN_E_INVALID_ARG;
+    *out = ctx->cfg;
+    return GBIN_OK;
+}
+
+int gbin_get_timings(const gbin_ctx *ctx, gbin_timings *out) {
+    if (!ctx || !out) return GBIN_E_INVALID_ARG;
+    *out = ctx->tm;
+    return GBIN_OK;
+}
+
+uint32_t gbin_record_bytes(const gbin_ctx *ctx) { return ctx ? (uint32_t)(8 * ctx->KW + 8) : 0; }
+
+void *gbin_pinned_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void gbin_pinned_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+static void finish_timings(gbin_ctx *ctx, int launches, bool host_path) {
+    auto ms = [&](int a, int b) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, ctx->ev[a], ctx->ev[b]) != cudaSuccess) {
+            (void)cudaGetLastError();
+            t = 0.f;
+        }
+        return t;
+    };
+    ctx->tm.h2d_ms = host_path ? ms(0, 1) : 0.f;
+    ctx->tm.scan_ms = ms(1, 2);
+    ctx->tm.sort_ms = ms(2, 3);
+    ctx->tm.group_ms = ms(3, 4);
+    ctx->tm.d2h_ms = host_path ? ms(4, 5) : 0.f;
+    ctx->tm.total_ms = ms(0, host_path ? 5 : 4);
+    ctx->tm.kernel_launches = (uint32_t)launches;
+}
+
+int gbin_bin_reads_device(gbin_ctx *ctx, const gbin_reads *reads, void *stream, gbin_table *out) {
+    if (!ctx || !reads || !out) return GBIN_E_INVALID_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    int launches = 0;
+    CU(cudaEventRecord(ctx->ev[0], st));
+    CU(cudaEventRecord(ctx->ev[1], st));
+    int rc = bin_device_impl(ctx, reads, st, out, &launches);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(st));
+    finish_timings(ctx, launches, false);
+    return GBIN_OK;
+}
+
+int gbin_bin_reads_host(gbin_ctx *ctx, const gbin_reads *reads, gbin_table *out) {
+    if (!ctx || !reads || !out) return GBIN_E_INVALID_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = ctx->stream;
+    int launches = 0;
+    gbin_reads d = *reads;
+    CU(cudaEventRecord(ctx->ev[0], st));
+    if (reads->n_reads) {
+        if (!reads->data || reads->data_bytes == 0) return fail(ctx, GBIN_E_INVALID_ARG, "host reads need data and data_bytes");
+        CU(ctx->d_reads.ensure(reads->data_bytes + 64));
+        CU(cudaMemcpyAsync(ctx->d_reads.p, reads->data, reads->data_bytes, cudaMemcpyHostToDevice, st));
+        d.data = ctx->d_reads.as<char>();
+        if (reads->starts) {
+            if (!reads->lens) return fail(ctx, GBIN_E_INVALID_ARG, "ragged reads need lens");
+            CU(ctx->d_starts.ensure(reads->n_reads * sizeof(uint64_t)));
+            CU(ctx->d_lens.ensure(reads->n_reads * sizeof(uint32_t)));
+            CU(cudaMemcpyAsync(ctx->d_starts.p, reads->starts, reads->n_reads * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(ctx->d_lens.p, reads->lens, reads->n_reads * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            d.starts = ctx->d_starts.as<uint64_t>();
+            d.lens = ctx->d_lens.as<uint32_t>();
+            if (d.max_read_len == 0) {  // known on the host: spare the device reduction
+                uint32_t mx = 0;
+                for (uint64_t i = 0; i < reads->n_reads; i++) {
+                    if (reads->lens[i] > mx) mx = reads->lens[i];
+                    if (reads->data_bytes && reads->starts[i] + reads->lens[i] > reads->data_bytes)
+                        return fail(ctx, GBIN_E_INVALID_ARG, "read %llu exceeds data_bytes", (unsigned long long)i);
+                }
+                d.max_read_len = mx ? mx : 1;
+            }
+        }
+        if (reads->read_ids) {
+            CU(ctx->d_ids.ensure(reads->n_reads * sizeof(int32_t)));
+            CU(cudaMemcpyAsync(ctx->d_ids.p, reads->read_ids, reads->n_reads * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            d.read_ids = ctx->d_ids.as<int32_t>();
+        }
+    }
+    CU(cudaEventRecord(ctx->ev[1], st));
+    gbin_table dev;
+    int rc = bin_device_impl(ctx, &d, st, &dev, &launches);
+    if (rc) return rc;
+    // D2H into the pinned arena
+    const uint64_t B = dev.n_buckets, S = dev.n_kmers, NS = dev.n_ids;
+    const int KW = dev.kmer_words;
+    const size_t sz_kc = (S * KW + 1) * sizeof(uint64_t), sz_ko = (S + 1) * sizeof(uint64_t), sz_mo = (B + 1) * sizeof(uint64_t);
+    const size_t sz_id = ((NS + 2) & ~1ull) * sizeof(int32_t), sz_mc = ((B + 2) & ~1ull) * sizeof(uint32_t);
+    CU(ctx->h_result.ensure(sz_kc + sz_ko + sz_mo + sz_id + sz_mc + 64));
+    char *h = static_cast<char *>(ctx->h_result.p);
+    *out = dev;
+    out->on_device = 0;
+    out->kmer_codes = reinterpret_cast<uint64_t *>(h);
+    h += sz_kc;
+    out->kmer_id_off = reinterpret_cast<uint64_t *>(h);
+    h += sz_ko;
+    out->mmer_kmer_off = reinterpret_cast<uint64_t *>(h);
+    h += sz_mo;
+    out->read_ids = reinterpret_cast<int32_t *>(h);
+    h += sz_id;
+    out->mmer_codes = reinterpret_cast<uint32_t *>(h);
+    CU(cudaMemcpyAsync(out->kmer_codes, dev.kmer_codes, S * KW * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out->kmer_id_off, dev.kmer_id_off, (S + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out->mmer_kmer_off, dev.mmer_kmer_off, (B + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out->read_ids, dev.read_ids, NS * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out->mmer_codes, dev.mmer_codes, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(ctx->ev[5], st));
+    CU(cudaStreamSynchronize(st));
+    finish_timings(ctx, launches, true);
+    return GBIN_OK;
+}
+
+int gbin_table_to_host(gbin_ctx *ctx, const gbin_table *dev, gbin_table *host) {
+    if (!ctx || !dev || !host || !dev->on_device) return GBIN_E_INVALID_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    const uint64_t B = dev->n_buckets, S = dev->n_kmers, NS = dev->n_ids;
+    const int KW = dev->kmer_words;
+    *host = *dev;
+    host->on_device = 0;
+    host->ctx_owned = 0;
+    host->mmer_codes = static_cast<uint32_t *>(malloc((B + 1) * sizeof(uint32_t)));
+    host->mmer_kmer_off = static_cast<uint64_t *>(malloc((B + 1) * sizeof(uint64_t)));
+    host->kmer_codes = static_cast<uint64_t *>(malloc((S * KW + 1) * sizeof(uint64_t)));
+    host->kmer_id_off = static_cast<uint64_t *>(malloc((S + 1) * sizeof(uint64_t)));
+    host->read_ids = static_cast<int32_t *>(malloc((NS + 1) * sizeof(int32_t)));
+    if (!host->mmer_codes || !host->mmer_kmer_off || !host->kmer_codes || !host->kmer_id_off || !host->read_ids) {
+        gbin_table_free(host);
+        return fail(ctx, GBIN_E_NOMEM, "host table allocation failed");
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(host->mmer_codes, dev->mmer_codes, B * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(host->mmer_kmer_off, dev->mmer_kmer_off, (B + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(host->kmer_codes, dev->kmer_codes, S * KW * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(host->kmer_id_off, dev->kmer_id_off, (S + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(host->read_ids, dev->read_ids, NS * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return GBIN_OK;
+}
+
+// ---------------------------------------------------------------- staged entry points (multi-GPU path)
+
+int gbin_count_instances_device(gbin_ctx *ctx, const gbin_reads *reads, void *stream, uint64_t *n_out) {
+    if (!ctx || !reads || !n_out) return GBIN_E_INVALID_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    uint32_t max_len = 0;
+    int launches = 0;
+    return plan_reads(ctx, reads, st, n_out, &max_len, &launches);
+}
+
+int gbin_scan_reads_device(gbin_ctx *ctx, const gbin_reads *reads, uint32_t arrival_base, void *d_records, uint64_t capacity,
+                           void *stream, uint64_t *n_out) {
+    if (!ctx || !reads || !n_out) return GBIN_E_INVALID_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    uint64_t n = 0;
+    uint32_t max_len = 0;
+    int launches = 0;
+    int rc = plan_reads(ctx, reads, st, &n, &max_len, &launches);
+    if (rc) return rc;
+    if (max_len > GBIN_MAX_READ_LEN) return fail(ctx, GBIN_E_TOO_LARGE, "read length %u exceeds GBIN_MAX_READ_LEN", max_len);
+    if (n > capacity) return fail(ctx, GBIN_E_INVALID_ARG, "record buffer too small: need %llu", (unsigned long long)n);
+    if (n && !d_records) return GBIN_E_INVALID_ARG;
+    rc = run_scan(ctx, reads, arrival_base, d_records, max_len, st, &launches);
+    if (rc) return rc;
+    Misc *dm = ctx->misc.as<Misc>();
+    Misc *hm = static_cast<Misc *>(ctx->h_misc.p);
+    CU(cudaMemcpyAsync(&hm->bad_bases, &dm->bad_bases, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (hm->bad_bases) return fail(ctx, GBIN_E_NON_ACGT, "%llu bases other than A/C/G/T in the batch", hm->bad_bases);
+    *n_out = n;
+    ctx->tm.kernel_launches = (uint32_t)launches;
+    return GBIN_OK;
+}
+
+int gbin_partition_records_device(gbin_ctx *ctx, const void *d_records, uint64_t n, uint32_t n_parts, void *d_out, void *stream,
+                                  uint64_t *counts_host) {
+    if (!ctx || !counts_host || n_parts == 0 || n_parts > 256) return GBIN_E_INVALID_ARG;
+    if (n >= (1ull << 32) - 8192) return fail(ctx, GBIN_E_TOO_LARGE, "too many records in one partition call");
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    Misc *dm = ctx->misc.as<Misc>();
+    Misc *hm = static_cast<Misc *>(ctx->h_misc.p);
+    CU(ctx->radix_scratch.ensure(radix_scratch_bytes(n)));
+    int launches = radix_partition_by_owner(d_records, d_out, n, ctx->KW, n_parts, ctx->radix_scratch.p, dm->part_counts, st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(hm->part_counts, dm->part_counts, sizeof(uint64_t) * n_parts, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(counts_host, hm->part_counts, sizeof(uint64_t) * n_parts);
+    ctx->tm.kernel_launches = (uint32_t)launches;
+    return GBIN_OK;
+}
+
+int gbin_group_records_device(gbin_ctx *ctx, void *d_records, uint64_t n, const int32_t *d_ids_by_arrival, int32_t id_base,
+                              void *stream, gbin_table *out) {
+    if (!ctx || !out || (n && !d_records)) return GBIN_E_INVALID_ARG;
+    if (n >= (1ull << 32) - 8192) return fail(ctx, GBIN_E_TOO_LARGE, "%llu records in one group call (limit 2^32)", (unsigned long long)n);
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    const size_t rb = sizeof(uint64_t) * ctx->KW + 8;
+    CU(ctx->rec_b.ensure((n + 1) * rb));
+    int launches = 0;
+    Misc *dm = ctx->misc.as<Misc>();
+    CU(cudaMemsetAsync(&dm->bad_bases, 0, sizeof(unsigned long long), st));
+    CU(cudaEventRecord(ctx->ev[0], st));
+    CU(cudaEventRecord(ctx->ev[1], st));
+    CU(cudaEventRecord(ctx->ev[2], st));
+    int rc = run_group(ctx, d_records, ctx->rec_b.p, n, d_ids_by_arrival, id_base, st, out, &launches, ctx->ev[3]);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[4], st));
+    CU(cudaStreamSynchronize(st));
+    finish_timings(ctx, launches, false);
+    return GBIN_OK;
+}
+
+}  // extern "C"

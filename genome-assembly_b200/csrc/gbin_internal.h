@@ -1,0 +1,61 @@
+// gbin_internal.h — host-side declarations of the kernel launchers (one .cu per stage).
+// Every launcher returns the number of kernels it launched (for gbin_timings.kernel_launches).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "gbin_device.cuh"
+
+namespace gbin {
+
+// ---- scan_reads.cu
+int launch_count_windows(const ReadsView &rv, int K, uint32_t *counts, cudaStream_t st);
+int launch_scan_reads(const ReadsView &rv, const uint64_t *rec_off, int K, int M, int KW, uint32_t arrival_base, uint32_t max_len,
+                      void *out, unsigned long long *bad_bases, int sm_count, cudaStream_t st);
+int launch_pack_reads(const ReadsView &rv, uint32_t words_per_read, uint32_t *packed, unsigned long long *bad_bases, cudaStream_t st);
+
+// ---- radix_sort.cu
+// Stable LSD radix sort of n records by (mmer, kmer) ascending.  The result lands in `a` or `b`;
+// the function returns which through *result_in_b.  tile_hist: scratch of radix_scratch_bytes(n).
+size_t radix_scratch_bytes(uint64_t n);
+int radix_sort_records(void *a, void *b, uint64_t n, int KW, int K, int M, void *scratch, bool *result_in_b, int *passes_out,
+                       cudaStream_t st);
+// Stable partition by owner = mmer % n_parts: in -> out, part sizes to d_counts[n_parts] (device, u64).
+int radix_partition_by_owner(const void *in, void *out, uint64_t n, int KW, uint32_t n_parts, void *scratch, uint64_t *d_counts,
+                             cudaStream_t st);
+
+// ---- group_prune.cu
+struct GroupCounts {  // device-resident scalars, copied to the host between phases
+    uint32_t n_distinct, n_kmers, n_buckets, pad;
+    uint64_t n_ids;
+};
+struct GroupWorkspace {  // all device pointers, sized by the caller (capi.cu)
+    uint32_t *group_of;     // [n]    group index of every sorted record
+    uint32_t *run_start;    // [n+1]  first record of every group (+ sentinel n)
+    uint32_t *surv_index;   // [n_distinct+1] exclusive count of surviving groups
+    uint64_t *id_offset;    // [n_distinct+1] exclusive sum of surviving run lengths
+    uint32_t *surv_group;   // [n_kmers] group index of surviving k-mer s
+    uint32_t *bucket_of;    // [n_kmers] bucket index of surviving k-mer s
+    void *scan_scratch;     // prefix-scan scratch (u64 elements)
+    GroupCounts *counts;    // device
+    int cutoff;             // ABUNDANCE_CUTOFF (binning.c:12); < 0 keeps everything
+};
+size_t group_scan_scratch_bytes(uint64_t n);
+// Phase 1: run-length over sorted records -> group_of, run_start, counts->n_distinct.
+int group_find_runs(const void *sorted, uint64_t n, int KW, GroupWorkspace &ws, cudaStream_t st);
+// Phase 2 (needs n_distinct on the host): prune decision + offsets -> counts->n_kmers, n_ids.
+int group_prune_offsets(uint64_t n, uint64_t n_distinct, int cutoff, GroupWorkspace &ws, cudaStream_t st);
+// Phase 3 (needs n_kmers on the host): bucket boundaries over surviving k-mers -> counts->n_buckets.
+int group_mark_buckets(const void *sorted, int KW, uint64_t n_distinct, uint64_t n_kmers, GroupWorkspace &ws, cudaStream_t st);
+// Phase 4: emit the flat table.
+struct TableOut {
+    uint32_t *mmer_codes;
+    uint64_t *mmer_kmer_off;
+    uint64_t *kmer_codes;
+    uint64_t *kmer_id_off;
+    int32_t *read_ids;
+};
+int group_emit(const void *sorted, uint64_t n, int KW, uint64_t n_distinct, uint64_t n_kmers, uint64_t n_ids, uint64_t n_buckets,
+               const int32_t *ids_by_arrival, int32_t id_base, GroupWorkspace &ws, const TableOut &out, cudaStream_t st);
+
+}  // namespace gbin

@@ -1,0 +1,211 @@
+// scan_reads.cu — process_read's per-read work (binning.c:918-1040) as one warp per read:
+//   1. ASCII -> 2-bit codes (getval map A=3 C=2 G=1 T=0, binning.c:91-111), packed MSB-first in smem;
+//   2. the signature chain: at a restart window i the signature is the LEFTMOST m-mer position
+//      p in [i, i+K-M] maximising w(p) = max(s(p), 4^M-1-s(p)) (binning.c:931-988, strict '>' at :972),
+//      and it is kept for every following window until the window start passes it (binning.c:922;
+//      the else-branch loop at :997 never runs for K >= 2M).  So the chain hops i -> sig+1: one
+//      warp-wide arg-max (REDUX max + REDUX min) per hop instead of the reference's per-window scan;
+//   3. per window: oriented k-mer code (bitwise complement when the signature's complement won,
+//      binning.c:1029-1040 — the reference complements without reversing), m-mer code = w(sig).
+// Output: one Rec<KW> per window, in arrival order (read-major, window-minor).
+#include "gbin_device.cuh"
+#include "gbin_internal.h"
+
+namespace gbin {
+
+constexpr int SCAN_WARPS = 8;
+
+__host__ __device__ inline uint32_t scan_raw_bytes(uint32_t max_len) { return (max_len + 15u) & ~15u; }
+__host__ __device__ inline uint32_t scan_pk_words(uint32_t max_len) { return scan_raw_bytes(max_len) / 16 + 6; }
+__host__ __device__ inline uint32_t scan_warp_smem(uint32_t max_len) {
+    return scan_raw_bytes(max_len) + 4 * scan_pk_words(max_len) + 4 * max_len + 16;
+}
+
+// windows per read (ragged form) -> u32, consumed by exclusive_scan
+__global__ void count_windows_kernel(ReadsView rv, int K, uint32_t *__restrict__ counts) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rv.n_reads) return;
+    const uint32_t L = rv.len(r);
+    counts[r] = L >= (uint32_t)K ? L - K + 1 : 0;
+}
+
+// 2M-bit code of the m-mer starting at base p, from the MSB-first packed words.
+__device__ __forceinline__ uint32_t mmer_at(const uint32_t *pk, uint32_t p, int M) {
+    const uint32_t bit = 2 * p, wi = bit >> 5, sh = bit & 31;
+    const uint64_t x = ((uint64_t)pk[wi] << 32) | pk[wi + 1];
+    return (uint32_t)((x << sh) >> (64 - 2 * M));
+}
+
+template <int KW>
+__device__ __forceinline__ void kmer_at(const uint32_t *pk, uint32_t q, int K, bool rev, uint64_t (&out)[KW]) {
+    const uint32_t bit = 2 * q, wi = bit >> 5, sh = bit & 31;
+    if (KW == 1) {
+        const uint32_t a = __funnelshift_l(pk[wi + 1], pk[wi], sh);
+        const uint32_t b = __funnelshift_l(pk[wi + 2], pk[wi + 1], sh);
+        uint64_t x = (((uint64_t)a << 32) | b) >> (64 - 2 * K);
+        if (rev) x = ~x & (K == 32 ? ~0ull : ((1ull << (2 * K)) - 1));
+        out[0] = x;
+    } else {
+        const uint32_t a = __funnelshift_l(pk[wi + 1], pk[wi], sh);
+        const uint32_t b = __funnelshift_l(pk[wi + 2], pk[wi + 1], sh);
+        const uint32_t c = __funnelshift_l(pk[wi + 3], pk[wi + 2], sh);
+        const uint32_t d = __funnelshift_l(pk[wi + 4], pk[wi + 3], sh);
+        uint64_t hi = ((uint64_t)a << 32) | b, lo = ((uint64_t)c << 32) | d;
+        const int r = 128 - 2 * K;  // 0..62 for 33 <= K <= 64
+        if (r) {
+            lo = (lo >> r) | (hi << (64 - r));
+            hi >>= r;
+        }
+        if (rev) {
+            hi = ~hi & (K == 64 ? ~0ull : ((1ull << (2 * K - 64)) - 1));
+            lo = ~lo;
+        }
+        out[0] = hi;
+        out[KW - 1] = lo;
+    }
+}
+
+template <int KW>
+__global__ void __launch_bounds__(SCAN_WARPS * 32)
+    scan_reads_kernel(ReadsView rv, const uint64_t *__restrict__ rec_off, int K, int M, uint32_t arrival_base, uint32_t max_len,
+                      Rec<KW> *__restrict__ out, unsigned long long *__restrict__ bad_bases) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *wbase = smem + (size_t)warp * scan_warp_smem(max_len);
+    uint8_t *raw = wbase;
+    uint32_t *pk = reinterpret_cast<uint32_t *>(wbase + scan_raw_bytes(max_len));
+    uint32_t *winfo = pk + scan_pk_words(max_len);
+    const uint32_t FULL = (1u << (2 * M)) - 1;
+    const uint32_t C = K - M + 1;  // m-mer positions per window
+    const uint64_t warps_total = (uint64_t)gridDim.x * SCAN_WARPS;
+    uint32_t nbad = 0;
+
+    for (uint64_t r = (uint64_t)blockIdx.x * SCAN_WARPS + warp; r < rv.n_reads; r += warps_total) {
+        const uint32_t L = rv.len(r);
+        if (L < (uint32_t)K) continue;
+        const uint32_t W = L - K + 1;
+        const uint8_t *src = rv.data + rv.start(r);
+        // ---- stage the read (coalesced byte loads), then pack 16 bases per word
+        for (uint32_t p = lane; p < L; p += 32) raw[p] = src[p];
+        __syncwarp();
+        const uint32_t nwords = (L + 15) / 16;
+        for (uint32_t j = lane; j < nwords + 5; j += 32) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int t = 0; t < 16; t++) {
+                const uint32_t p = 16 * j + t;
+                uint32_t v = 0;
+                if (p < L) {
+                    bool ok;
+                    v = base_code(raw[p], ok);
+                    nbad += ok ? 0 : 1;
+                }
+                word = (word << 2) | v;
+            }
+            pk[j] = word;
+        }
+        __syncwarp();
+        // ---- signature chain: hop from restart window to restart window
+        uint32_t i = 0;
+        while (i < W) {
+            uint32_t best_w = 0, best_p = 0xffffffffu;
+            for (uint32_t b = 0; b < C; b += 32) {
+                const uint32_t off = b + lane;
+                if (off < C) {
+                    const uint32_t p = i + off;
+                    const uint32_t s = mmer_at(pk, p, M);
+                    const uint32_t w = max(s, FULL - s);
+                    if (w > best_w) {  // strict: the earlier (smaller p) candidate survives ties
+                        best_w = w;
+                        best_p = p;
+                    }
+                }
+            }
+            const uint32_t mx = __reduce_max_sync(0xffffffffu, best_w);
+            const uint32_t sig = __reduce_min_sync(0xffffffffu, best_w == mx ? best_p : 0xffffffffu);
+            const uint32_t s_sig = mmer_at(pk, sig, M);
+            const uint32_t info = (mx << 1) | (s_sig != mx ? 1u : 0u);  // bit0 = is_rev (binning.c:943,948)
+            const uint32_t next = min(sig + 1, W);
+            for (uint32_t q = i + lane; q < next; q += 32) winfo[q] = info;
+            i = next;
+        }
+        __syncwarp();
+        // ---- one record per window
+        const uint64_t o = rec_off ? rec_off[r] : r * (uint64_t)W;
+        const uint32_t arrival = arrival_base + (uint32_t)r;
+        for (uint32_t q = lane; q < W; q += 32) {
+            const uint32_t info = winfo[q];
+            Rec<KW> rec;
+            kmer_at<KW>(pk, q, K, info & 1u, rec.k);
+            rec.mmer = info >> 1;
+            rec.arrival = arrival;
+            store_rec<KW>(out + o + q, rec);
+        }
+        __syncwarp();
+    }
+    if (nbad) atomicAdd(bad_bases, (unsigned long long)nbad);
+}
+
+// ---- standalone pack kernel: ASCII -> 2-bit packed reads in HBM (16 bases per u32, MSB first),
+// row r at packed[r * words_per_read].  Not on the fused path above (which packs in shared
+// memory); exported for consumers that want the packed form and for packing parity tests.
+__global__ void pack_reads_kernel(ReadsView rv, uint32_t words_per_read, uint32_t *__restrict__ packed,
+                                  unsigned long long *__restrict__ bad_bases) {
+    const uint64_t gw = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t r = gw / words_per_read;
+    const uint32_t j = (uint32_t)(gw % words_per_read);
+    if (r >= rv.n_reads) return;
+    const uint32_t L = rv.len(r);
+    const uint8_t *src = rv.data + rv.start(r);
+    uint32_t word = 0, nbad = 0;
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        const uint32_t p = 16 * j + t;
+        uint32_t v = 0;
+        if (p < L) {
+            bool ok;
+            v = base_code(src[p], ok);
+            nbad += ok ? 0 : 1;
+        }
+        word = (word << 2) | v;
+    }
+    packed[gw] = word;
+    if (nbad) atomicAdd(bad_bases, (unsigned long long)nbad);
+}
+
+// ------------------------------------------------------------------ host launchers
+
+int launch_count_windows(const ReadsView &rv, int K, uint32_t *counts, cudaStream_t st) {
+    if (rv.n_reads == 0) return 0;
+    const unsigned blocks = (unsigned)((rv.n_reads + 255) / 256);
+    count_windows_kernel<<<blocks, 256, 0, st>>>(rv, K, counts);
+    return 1;
+}
+
+int launch_scan_reads(const ReadsView &rv, const uint64_t *rec_off, int K, int M, int KW, uint32_t arrival_base, uint32_t max_len,
+                      void *out, unsigned long long *bad_bases, int sm_count, cudaStream_t st) {
+    if (rv.n_reads == 0) return 0;
+    const size_t smem = (size_t)SCAN_WARPS * scan_warp_smem(max_len);
+    uint64_t blocks = (rv.n_reads + SCAN_WARPS - 1) / SCAN_WARPS;
+    const uint64_t cap = (uint64_t)sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (KW == 1) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(scan_reads_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        scan_reads_kernel<1><<<(unsigned)blocks, SCAN_WARPS * 32, smem, st>>>(rv, rec_off, K, M, arrival_base, max_len,
+                                                                            static_cast<Rec<1> *>(out), bad_bases);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(scan_reads_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        scan_reads_kernel<2><<<(unsigned)blocks, SCAN_WARPS * 32, smem, st>>>(rv, rec_off, K, M, arrival_base, max_len,
+                                                                            static_cast<Rec<2> *>(out), bad_bases);
+    }
+    return 1;
+}
+
+int launch_pack_reads(const ReadsView &rv, uint32_t words_per_read, uint32_t *packed, unsigned long long *bad_bases, cudaStream_t st) {
+    const uint64_t total = rv.n_reads * words_per_read;
+    if (total == 0) return 0;
+    pack_reads_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(rv, words_per_read, packed, bad_bases);
+    return 1;
+}
+
+}  // namespace gbin

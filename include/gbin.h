@@ -1,0 +1,200 @@
+/*
+ * gbin.h — C ABI of libgbin.so: the B200-native k-mer binning hot path of twitu/genome-assembly.
+ *
+ * The reference has no plugin/FFI layer; its boundary is the plain C function surface of binning.c
+ * (SURVEY.md §8b).  libgbin.so therefore exports
+ *   (1) the reference's own entry points for this path, same names and argument meaning:
+ *         process_read  (binning.c:902)   prune_data (binning.c:1130)
+ *         getval        (binning.c:91)    getbp      (binning.c:69)     getscore (binning.c:114)
+ *       operating on the reference's own struct ZHashTable / ZHashEntry / ll_node layouts
+ *       (zhash.h:14-26, llist.h:7-13; restated in gbin_ref_types.h), and
+ *   (2) the batch / device entry points below (gbin_*), which are the fast path the shims call.
+ *
+ * Everything is extern "C", plain pointers and sizes; no CUDA or torch types appear in signatures
+ * (streams are passed as void*, i.e. a cudaStream_t).  Errors are returned as negative ints — the
+ * library never calls exit() (the reference's zmalloc does, zhash.c:230-250).
+ *
+ * Contract differences from the reference, all deliberate and documented in DESIGN.md:
+ *   - K, M and the cutoff are runtime values (reference: #defines at binning.c:10-13).
+ *     Supported: 2 <= M <= 15, 2M <= K <= 64 (for K < 2M the reference's else-branch loop at
+ *     binning.c:997 is live and scores overflow; every BASELINE config has K >= 2M).
+ *   - Reads must consist of A/C/G/T only; any other byte makes the call fail with
+ *     GBIN_E_NON_ACGT (the reference would keep the raw byte inside un-flipped keys,
+ *     binning.c:1023-1026, which a 2-bit code cannot represent).
+ *   - The result is a flat table in canonical order (m-mer code ascending, k-mer code ascending,
+ *     read ids newest-first) instead of a pointer graph whose iteration order depends on hash
+ *     layout; gbin_table_to_zhash() materialises the reference's pointer graph when a consumer
+ *     needs it.
+ */
+#ifndef GBIN_H
+#define GBIN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GBIN_OK 0
+#define GBIN_E_INVALID_CONFIG (-1) /* K/M/cutoff outside the supported range */
+#define GBIN_E_CUDA (-2)           /* a CUDA call failed; see gbin_last_error() */
+#define GBIN_E_NOMEM (-3)
+#define GBIN_E_NON_ACGT (-4)       /* a read holds a byte other than A, C, G, T */
+#define GBIN_E_STATE (-5)          /* call sequence error (e.g. process_read after prune_data) */
+#define GBIN_E_TOO_LARGE (-6)      /* batch exceeds an implementation limit */
+#define GBIN_E_INVALID_ARG (-7)
+#define GBIN_E_IO (-8)
+
+#define GBIN_MAX_READ_LEN 4096
+
+/* Runtime form of binning.c:10-12. */
+typedef struct gbin_config {
+    int32_t kmer_size;        /* KMER_SIZE        (binning.c:11) */
+    int32_t mmer_size;        /* MMER_SIZE        (binning.c:10) */
+    int32_t abundance_cutoff; /* ABUNDANCE_CUTOFF (binning.c:12): keep a k-mer iff its list length > cutoff; < 0 disables the prune */
+    int32_t device;           /* CUDA device ordinal */
+} gbin_config;
+
+/* The pruned two-level store mmer_hash -> kmer_hash -> read-id list (binning.c:1044-1069 after
+ * prune_data), flattened.  All codes are base-4 with T,G,C,A = 0..3 (getval, binning.c:91-111) and
+ * the first character most significant, i.e. getscore() of the key string (binning.c:114-124).
+ *   bucket b  : m-mer mmer_codes[b], owns k-mers [mmer_kmer_off[b], mmer_kmer_off[b+1])
+ *   k-mer  s  : code kmer_codes[s*kmer_words .. ] (most significant word first),
+ *               owns read ids [kmer_id_off[s], kmer_id_off[s+1]) — newest first, exactly the order
+ *               in which the reference's linked list is walked from its head (binning.c:1059-1069).
+ * Buckets ascend by m-mer code; k-mers ascend by code within a bucket. */
+typedef struct gbin_table {
+    int32_t kmer_size, mmer_size, abundance_cutoff;
+    int32_t kmer_words;      /* 1 when K <= 32, else 2 */
+    int32_t on_device;       /* 1: the pointers below are device pointers owned by the context */
+    int32_t ctx_owned;       /* 1: arrays belong to the context (valid until its next call); gbin_table_free is then a no-op */
+    uint64_t n_instances;    /* k-mer instances (windows) processed */
+    uint64_t n_distinct;     /* distinct (m-mer, k-mer) pairs before the prune */
+    uint64_t n_buckets;      /* surviving m-mer buckets */
+    uint64_t n_kmers;        /* surviving k-mers */
+    uint64_t n_ids;          /* read-id nodes in surviving lists */
+    uint32_t *mmer_codes;    /* [n_buckets] */
+    uint64_t *mmer_kmer_off; /* [n_buckets + 1] */
+    uint64_t *kmer_codes;    /* [n_kmers * kmer_words] */
+    uint64_t *kmer_id_off;   /* [n_kmers + 1] */
+    int32_t *read_ids;       /* [n_ids] */
+} gbin_table;
+
+/* Reads are given either fixed-stride (starts == NULL: read i is reads[i*stride .. i*stride+read_len))
+ * or ragged (read i is reads[starts[i] .. starts[i]+lens[i])).  Reads shorter than K yield nothing
+ * but still own their arrival index / id, as in main (binning.c:1165).  read_ids == NULL means
+ * id = id_base + i. Arrival order == index order. */
+typedef struct gbin_reads {
+    const char *data;       /* ASCII bases; host or device memory depending on the entry point */
+    uint64_t data_bytes;    /* bytes addressable from data */
+    uint64_t n_reads;
+    uint64_t stride;        /* fixed-stride form */
+    uint32_t read_len;      /* fixed-stride form */
+    int32_t id_base;
+    const uint64_t *starts; /* ragged form (NULL for fixed stride) */
+    const uint32_t *lens;
+    const int32_t *read_ids; /* optional explicit ids (what process_read's read_id argument carries) */
+    uint32_t max_read_len;  /* ragged form: upper bound on lens[] (0 = let the library find it) */
+    uint32_t reserved;
+} gbin_reads;
+
+typedef struct gbin_ctx gbin_ctx;
+
+/* Per-stage device times of the last gbin_bin_* call, in milliseconds (CUDA events on the call's stream). */
+typedef struct gbin_timings {
+    float h2d_ms, scan_ms, sort_ms, group_ms, d2h_ms, total_ms;
+    uint32_t kernel_launches; /* kernels launched by the last call */
+    uint32_t sort_passes;
+} gbin_timings;
+
+const char *gbin_strerror(int code);
+const char *gbin_last_error(const gbin_ctx *ctx);
+int gbin_version(void);
+
+int gbin_create(const gbin_config *cfg, gbin_ctx **out);
+void gbin_destroy(gbin_ctx *ctx);
+int gbin_get_config(const gbin_ctx *ctx, gbin_config *out);
+
+/* Whole hot path, HOST buffers: H2D copy of the reads, pack + window/signature scan (process_read,
+ * binning.c:918-1040), grouping (the two-level zhash insert, binning.c:1044-1069), prune
+ * (binning.c:1085-1144), D2H of the table into the context's pinned result arena (ctx_owned = 1:
+ * valid until the next call on the context; gbin_table_clone makes an independent malloc'ed copy). */
+int gbin_bin_reads_host(gbin_ctx *ctx, const gbin_reads *reads, gbin_table *out);
+int gbin_table_clone(const gbin_table *host, gbin_table *out);
+void gbin_table_free(gbin_table *t);
+/* Page-locked host memory for read buffers handed to gbin_bin_reads_host (pageable memory works, slower). */
+void *gbin_pinned_alloc(size_t bytes);
+void gbin_pinned_free(void *p);
+
+/* Same, DEVICE-resident: reads->data/starts/lens/read_ids are device pointers, the table's arrays
+ * stay in HBM, owned by the context and valid until the next call on it. `stream` is a cudaStream_t
+ * (NULL = the context's own stream); the call returns after the work is complete on that stream. */
+int gbin_bin_reads_device(gbin_ctx *ctx, const gbin_reads *reads, void *stream, gbin_table *out);
+
+/* Copies a device-resident table to freshly malloc'ed host arrays. */
+int gbin_table_to_host(gbin_ctx *ctx, const gbin_table *dev, gbin_table *host);
+
+int gbin_get_timings(const gbin_ctx *ctx, gbin_timings *out);
+
+/* ---- staged device entry points (multi-GPU path: scan -> partition by owner -> exchange -> group) ---- */
+
+/* Bytes per k-mer instance record produced by the scan stage (16 when K <= 32, 24 otherwise).
+ * Layout: { u64 kmer words (most significant first) ; u32 mmer_code ; u32 arrival }. */
+uint32_t gbin_record_bytes(const gbin_ctx *ctx);
+/* Number of k-mer instances the reads will produce (reads in device memory). */
+int gbin_count_instances_device(gbin_ctx *ctx, const gbin_reads *reads, void *stream, uint64_t *n_out);
+/* process_read's window/signature stage for every read: writes n records in arrival order to
+ * d_records (capacity in records).  arrival = arrival_base + read index. */
+int gbin_scan_reads_device(gbin_ctx *ctx, const gbin_reads *reads, uint32_t arrival_base, void *d_records,
+                           uint64_t capacity, void *stream, uint64_t *n_out);
+/* Stable partition of records by owner = mmer_code % n_parts into d_out;
+ * counts_host[p] receives the number of records of part p (parts are laid out in order). */
+int gbin_partition_records_device(gbin_ctx *ctx, const void *d_records, uint64_t n, uint32_t n_parts, void *d_out,
+                                  void *stream, uint64_t *counts_host);
+/* Grouping + prune of n records that are already in arrival order (d_records is used as sort
+ * scratch and is clobbered).  ids: device array mapping arrival -> read id, or NULL for id_base+arrival. */
+int gbin_group_records_device(gbin_ctx *ctx, void *d_records, uint64_t n, const int32_t *d_ids_by_arrival,
+                              int32_t id_base, void *stream, gbin_table *out);
+
+/* ---- host helpers ---- */
+
+/* main's read loop (binning.c:1154-1166) over a file: fgets(buf, read_length_define), drop the last
+ * char, one read id per fgets return.  Outputs are malloc'ed (free with free()). */
+int gbin_read_file_fgets(const char *path, int read_length_define, char **data_out, uint64_t *data_bytes_out,
+                         uint64_t **starts_out, uint32_t **lens_out, uint64_t *n_reads_out);
+/* Writes "<mmer> <kmer> <id> <id> ...\n" per surviving k-mer of a HOST table to `path` ("-" = stdout). */
+int gbin_table_dump(const gbin_table *host, const char *path);
+/* Writes the table in print_kmer_read_ids's layout *before* expand_read_id_list (binning.c:792-823):
+ * m-mer line, then per k-mer a key line and one line of ids, blank line after each bucket. */
+int gbin_table_dump_reference_format(const gbin_table *host, const char *path);
+
+/* ---- the reference's own entry points (binning.c) ---- */
+struct ZHashTable;
+int getval(char c);            /* binning.c:91 */
+char getbp(int bp);            /* binning.c:69 */
+int getscore(char *string);    /* binning.c:114 */
+/* Enqueues the read (copied; the caller's buffer is not retained) for the table; work happens at
+ * prune_data.  Returns hash_table, as the reference does (binning.c:1075). */
+struct ZHashTable *process_read(struct ZHashTable *hash_table, char *read, int read_id);
+/* Flush point: runs the GPU pipeline over everything enqueued for hash_table and materialises the
+ * pruned two-level table into *hash_table using the reference's struct layouts, so unmodified
+ * downstream reference code (iterate_level_one_hash, zhash_get, print_kmers ...) can consume it.
+ * Returns hash_table (the reference falls off the end without returning, binning.c:1130-1144). */
+struct ZHashTable *prune_data(struct ZHashTable *hash_table);
+/* K / M / cutoff / device used by process_read + prune_data (defaults 31 / 4 / 1 / 0 = binning.c:10-12). */
+int gbin_ref_configure(int kmer_size, int mmer_size, int abundance_cutoff, int device);
+/* Status of the last process_read / prune_data call (they cannot return one). */
+int gbin_ref_last_status(void);
+/* Forgets the staging session bound to a table pointer (so the address can be reused for a new table). */
+void gbin_ref_reset(struct ZHashTable *hash_table);
+/* Builds the reference pointer graph for a HOST table into *into (an empty table from
+ * zcreate_hash_table, or zeroed memory). Keys are strcpy-owned by the table (zhash.c:148-161). */
+int gbin_table_to_zhash(const gbin_table *host, struct ZHashTable *into);
+/* Frees a graph built by gbin_table_to_zhash / prune_data (entries, keys, lists; not the root struct). */
+void gbin_zhash_release(struct ZHashTable *table);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,173 @@
+"""CPU: the C-ABI library loads, exports every symbol include/gbin.h declares, and its host-only
+pieces (scalar helpers, main's fgets reader, the ZHashTable adapter, dumps) agree with the oracle.
+No compute entry point is exercised here (they need a GPU and have no fallback)."""
+import ctypes as C
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from genome_assembly_b200 import binding as B
+
+ROOT = O.ROOT
+CASES = O.load_pins()
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "gbin.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", src))
+    return sorted(n for n in names if n.startswith("gbin_") or n in ("getval", "getbp", "getscore", "process_read", "prune_data"))
+
+
+def test_library_exports_every_declared_symbol():
+    L = B.load_library()
+    decl = declared_functions()
+    assert len(decl) >= 30
+    for name in decl:
+        assert hasattr(L, name), f"libgbin.so does not export {name}"
+    assert sorted(B.EXPORTS) == decl, "binding.EXPORTS out of sync with include/gbin.h"
+
+
+def test_scalar_helpers_match_reference_kats():
+    """binning.c:69-124 known answers."""
+    L = B.load_library()
+    for s, v in [(b"AAGTCC", 3914), (b"TTCAGG", 181), (b"AAAA", 255), (b"CTTT", 128), (b"AACA", 251), (b"CAGA", 183)]:
+        assert L.getscore(s) == v
+    OL = O.lib()
+    for c in range(1, 256):
+        ch = bytes([c])
+        assert L.getval(ch) == OL.orc_getval(ch)
+    for v in range(-3, 8):
+        assert L.getbp(v) == OL.orc_getbp(v)
+
+
+def test_invalid_configs_are_rejected_without_touching_cuda():
+    L = B.load_library()
+    for k, m in [(6, 4), (31, 16), (65, 4), (31, 1), (20, 11)]:
+        h = C.c_void_p()
+        assert L.gbin_create(C.byref(B.Config(k, m, 1, 0)), C.byref(h)) == B.GBIN_E_INVALID_CONFIG
+        assert L.gbin_ref_configure(k, m, 1, 0) == B.GBIN_E_INVALID_CONFIG
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    """On a machine without a CUDA device the product refuses to run instead of falling back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(B.GbinError) as e:
+        B.Binner(31, 4, 1, 0)
+    assert e.value.code == B.GBIN_E_CUDA
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c["name"] in ("cfg1_reads", "fuzz_ragged_k15", "fuzz_nonacgt", "short_reads")],
+                         ids=lambda c: c["name"])
+def test_fgets_reader_matches_oracle(case, tmp_path):
+    data = O.load_case_bytes(case)
+    p = tmp_path / "reads.txt"
+    p.write_bytes(data)
+    d, starts, lens = B.read_file_fgets(str(p), case["read_length_define"])
+    os_, ol = O.fgets_split(data, case["read_length_define"])
+    assert d.tobytes() == data
+    np.testing.assert_array_equal(starts, os_)
+    np.testing.assert_array_equal(lens, ol)
+    assert len(starts) == case["read_ids"]
+
+
+def c_table_from_oracle(t: O.Table):
+    """A host gbin_table whose arrays are the oracle's (stand-in for a GPU result in CPU-only tests)."""
+    keep = dict(mc=np.ascontiguousarray(t.mmer_codes, np.uint32), mo=np.ascontiguousarray(t.mmer_kmer_off, np.uint64),
+                kc=np.ascontiguousarray(t.kmer_codes, np.uint64), ko=np.ascontiguousarray(t.kmer_id_off, np.uint64),
+                ids=np.ascontiguousarray(t.read_ids, np.int32))
+    ct = B.CTable(t.K, t.M, t.cutoff, t.kw, 0, 1, t.n_instances, t.n_distinct, t.n_buckets, t.n_kmers, len(t.read_ids),
+                  keep["mc"].ctypes.data, keep["mo"].ctypes.data, keep["kc"].ctypes.data, keep["ko"].ctypes.data,
+                  keep["ids"].ctypes.data)
+    return ct, keep
+
+
+class ZEntry(C.Structure):
+    pass
+
+
+ZEntry._fields_ = [("key", C.c_char_p), ("val", C.c_void_p), ("next", C.POINTER(ZEntry))]
+
+
+class ZTable(C.Structure):
+    _fields_ = [("size_index", C.c_size_t), ("entry_count", C.c_size_t), ("entries", C.POINTER(C.POINTER(ZEntry)))]
+
+
+class LNode(C.Structure):
+    pass
+
+
+LNode._fields_ = [("next", C.POINTER(LNode)), ("read_id", C.c_int), ("_pad", C.c_int)]
+
+ZSIZES = [53, 101, 211, 503, 1553, 3407, 6803, 12503, 25013, 50261, 104729, 250007, 500009, 1000003]
+
+
+def walk_zhash(root: ZTable):
+    """Walks the pointer graph the way iterate_level_one/two_hash do (binning.c:298-460)."""
+    assert C.sizeof(ZEntry) == 24 and C.sizeof(ZTable) == 24 and C.sizeof(LNode) == 16  # zhash.h:14-26, llist.h:7-13
+    lines = []
+    for i in range(ZSIZES[root.size_index]):
+        e = root.entries[i]
+        while e:
+            kt = C.cast(e.contents.val, C.POINTER(ZTable)).contents
+            for j in range(ZSIZES[kt.size_index]):
+                ke = kt.entries[j]
+                while ke:
+                    ids = []
+                    n = C.cast(ke.contents.val, C.POINTER(LNode))
+                    while n:
+                        ids.append(n.contents.read_id)
+                        n = n.contents.next
+                    lines.append(e.contents.key + b" " + ke.contents.key + b"".join(b" %d" % x for x in ids))
+                    ke = ke.contents.next
+            e = e.contents.next
+    return lines
+
+
+def ref_hash(key: bytes, size: int) -> int:
+    h = 0
+    for ch in key:
+        h = (17 * h + ch) % size
+    return h
+
+
+@pytest.mark.parametrize("name", ["cfg1_reads", "cfg2_small", "cfg4_small"])
+def test_zhash_adapter_and_dumps(name, tmp_path):
+    case = next(c for c in CASES if c["name"] == name)
+    data = O.load_case_bytes(case)
+    starts, lens = O.fgets_split(data, case["read_length_define"])
+    t = O.run(data, starts, lens, case["k"], case["m"], case["cutoff"])
+    ct, keep = c_table_from_oracle(t)
+    L = B.load_library()
+    # flat dump
+    p = tmp_path / "dump.txt"
+    assert L.gbin_table_dump(C.byref(ct), str(p).encode()) == 0
+    lines = p.read_bytes().split(b"\n")[:-1]
+    assert hashlib.md5(b"".join(x + b"\n" for x in sorted(lines))).hexdigest() == case["md5"]
+    # reference print_kmer_read_ids layout
+    p2 = tmp_path / "dump_ref.txt"
+    assert L.gbin_table_dump_reference_format(C.byref(ct), str(p2).encode()) == 0
+    blocks = p2.read_bytes().split(b"\n\n")
+    assert len([b for b in blocks if b.strip()]) == case["surviving_buckets"]
+    # pointer graph with the reference's struct layouts
+    root = ZTable(0, 0, None)
+    assert L.gbin_table_to_zhash(C.byref(ct), C.byref(root)) == 0
+    assert root.entry_count == case["surviving_buckets"]
+    got = walk_zhash(root)
+    assert hashlib.md5(b"".join(x + b"\n" for x in sorted(got))).hexdigest() == case["md5"]
+    # entries sit in the chain the reference's zgenerate_hash (zhash.c:171-182) would look in
+    size = ZSIZES[root.size_index]
+    assert root.entry_count <= size // 2 or root.size_index == len(ZSIZES) - 1
+    for i in range(size):
+        e = root.entries[i]
+        while e:
+            assert ref_hash(e.contents.key, size) == i
+            e = e.contents.next
+    L.gbin_zhash_release(C.byref(root))
+    assert not root.entries

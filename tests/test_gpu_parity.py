@@ -1,0 +1,306 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (libgbin.so via ctypes), against
+the oracle on the same inputs and against the reference-execution pins in tests/golden/pins.json.
+Bit-exact everywhere (integer / byte / index work)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from genome_assembly_b200 import binding as B
+from genome_assembly_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+CASES = O.load_pins()
+GPU_CASES = [c for c in CASES if c["acgt_only"] and c["k"] >= 2 * c["m"]]
+
+
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    return torch
+
+
+def assert_tables_equal(got: B.HostTable, want: O.Table):
+    assert (got.K, got.M, got.kw) == (want.K, want.M, want.kw)
+    assert got.n_instances == want.n_instances
+    assert got.n_distinct == want.n_distinct
+    np.testing.assert_array_equal(got.mmer_codes, want.mmer_codes)
+    np.testing.assert_array_equal(got.mmer_kmer_off, want.mmer_kmer_off)
+    np.testing.assert_array_equal(got.kmer_codes, want.kmer_codes.reshape(-1))
+    np.testing.assert_array_equal(got.kmer_id_off, want.kmer_id_off)
+    np.testing.assert_array_equal(got.read_ids, want.read_ids)
+
+
+def as_oracle_table(t: B.HostTable) -> O.Table:
+    return O.Table(t.K, t.M, t.cutoff, t.n_instances, t.n_distinct, t.mmer_codes, t.mmer_kmer_off, t.kmer_codes, t.kmer_id_off,
+                   t.read_ids)
+
+
+def records_to_numpy(torch, buf, n, kw):
+    raw = buf[: n * (8 * kw + 8)].cpu().numpy()
+    dt = np.dtype([("k", "<u8", (kw,)), ("mmer", "<u4"), ("arrival", "<u4")])
+    return raw.view(dt)
+
+
+def dev_reads(torch, data, starts, lens, ids=None):
+    d = torch.from_numpy(np.frombuffer(data, dtype=np.uint8).copy()).cuda()
+    s = torch.from_numpy(starts.astype(np.int64)).cuda()
+    l = torch.from_numpy(lens.astype(np.int32)).cuda()
+    i = torch.from_numpy(ids.astype(np.int32)).cuda() if ids is not None else None
+    rd = B.Binner._reads(d, d.numel(), len(starts), starts=s, lens=l, read_ids=i)
+    return rd, (d, s, l, i)
+
+
+@pytest.mark.parametrize("case", GPU_CASES, ids=lambda c: c["name"])
+def test_scan_stage_matches_process_read(case):
+    """Per-window (m-mer, oriented k-mer, arrival) records == the oracle's process_read restatement."""
+    torch = torch_cuda()
+    data = O.load_case_bytes(case)
+    starts, lens = O.fgets_split(data, case["read_length_define"])
+    K, M = case["k"], case["m"]
+    tup, _ = O.scan_all(data, starts, lens, K, M)
+    b = B.Binner(K, M, case["cutoff"])
+    rd, keep = dev_reads(torch, data, starts, lens)
+    assert b.count_instances_device(rd) == len(tup) == case["instances"]
+    kw = 1 if K <= 32 else 2
+    buf = torch.zeros(max(len(tup), 1) * b.record_bytes, dtype=torch.uint8, device="cuda")
+    n = b.scan_device(rd, 0, buf, len(tup))
+    assert n == len(tup)
+    rec = records_to_numpy(torch, buf, n, kw)
+    np.testing.assert_array_equal(rec["mmer"], tup["mmer"])
+    np.testing.assert_array_equal(rec["arrival"], tup["arrival"])
+    np.testing.assert_array_equal(rec["k"][:, -1], tup["klo"])
+    if kw == 2:
+        np.testing.assert_array_equal(rec["k"][:, 0], tup["khi"])
+    b.close()
+
+
+@pytest.mark.parametrize("case", GPU_CASES, ids=lambda c: c["name"])
+def test_table_matches_oracle_and_reference_pin(case, tmp_path):
+    """Whole path through gbin_read_file_fgets + gbin_bin_reads_host: identical arrays to the oracle and
+    the same md5 as the reference binary's sorted dump."""
+    torch_cuda()
+    data = O.load_case_bytes(case)
+    p = tmp_path / "reads.txt"
+    p.write_bytes(data)
+    d, starts, lens = B.read_file_fgets(str(p), case["read_length_define"])
+    b = B.Binner(case["k"], case["m"], case["cutoff"])
+    got = b.bin_host(d, len(starts), starts=starts, lens=lens)
+    want = O.run(data, starts, lens, case["k"], case["m"], case["cutoff"])
+    assert_tables_equal(got, want)
+    assert got.n_kmers == case["surviving_kmers"] and got.n_buckets == case["surviving_buckets"]
+    assert as_oracle_table(got).md5() == case["md5"]
+    tm = b.timings()
+    assert tm["kernel_launches"] > 0
+    b.close()
+
+
+def test_device_path_and_staged_path_agree_with_host_path():
+    torch = torch_cuda()
+    case = next(c for c in CASES if c["name"] == "cfg2_small")
+    data = O.load_case_bytes(case)
+    starts, lens = O.fgets_split(data, case["read_length_define"])
+    K, M, cut = case["k"], case["m"], case["cutoff"]
+    want = O.run(data, starts, lens, K, M, cut)
+    b = B.Binner(K, M, cut)
+    rd, keep = dev_reads(torch, data, starts, lens)
+    dev = b.bin_device_raw(rd, torch.cuda.current_stream().cuda_stream)
+    assert dev.on_device == 1
+    assert_tables_equal(b.table_to_host(dev), want)
+    # staged: scan -> group
+    n = b.count_instances_device(rd)
+    buf = torch.empty(n * b.record_bytes, dtype=torch.uint8, device="cuda")
+    assert b.scan_device(rd, 0, buf, n) == n
+    dev2 = b.group_device(buf, n)
+    assert_tables_equal(b.table_to_host(dev2), want)
+    b.close()
+
+
+def test_fixed_stride_form_and_explicit_ids():
+    torch_cuda()
+    rs = synth.generate(4000, 100, error_rate=0.02, seed=5, starts="uniform")
+    K, M = 31, 11
+    starts = np.arange(rs.n_reads, dtype=np.uint64) * rs.stride
+    lens = np.full(rs.n_reads, rs.read_len, dtype=np.uint32)
+    ids = (np.arange(rs.n_reads, dtype=np.int32) * 7 + 100)[::-1].copy()  # arbitrary caller ids, not sorted
+    b = B.Binner(K, M, 1)
+    got = b.bin_host(rs.buf, rs.n_reads, stride=rs.stride, read_len=rs.read_len)
+    want = O.run(rs.as_bytes(), starts, lens, K, M, 1)
+    assert_tables_equal(got, want)
+    got = b.bin_host(rs.buf, rs.n_reads, stride=rs.stride, read_len=rs.read_len, read_ids=ids)
+    want = O.run(rs.as_bytes(), starts, lens, K, M, 1, ids=ids)
+    assert_tables_equal(got, want)
+    got = b.bin_host(rs.buf, rs.n_reads, stride=rs.stride, read_len=rs.read_len, id_base=1000)
+    np.testing.assert_array_equal(got.read_ids, O.run(rs.as_bytes(), starts, lens, K, M, 1).read_ids + 1000)
+    b.close()
+
+
+@pytest.mark.parametrize("K,M,cutoff,L", [(32, 15, 1, 80), (33, 8, 0, 90), (64, 15, 1, 200), (8, 4, 2, 40), (4, 2, 5, 30),
+                                          (31, 4, -1, 60), (40, 13, 3, 150), (63, 2, 1, 100)])
+def test_key_width_and_parameter_edges(K, M, cutoff, L):
+    """K = 32/33/64 (64-bit and 128-bit code boundaries), smallest/largest M, cutoff 0 / none."""
+    torch_cuda()
+    rs = synth.generate(1500, L, genome_len=2000, error_rate=0.01, seed=K * 100 + M, starts="uniform")
+    starts = np.arange(rs.n_reads, dtype=np.uint64) * rs.stride
+    lens = np.full(rs.n_reads, rs.read_len, dtype=np.uint32)
+    b = B.Binner(K, M, cutoff)
+    got = b.bin_host(rs.buf, rs.n_reads, stride=rs.stride, read_len=rs.read_len)
+    want = O.run(rs.as_bytes(), starts, lens, K, M, cutoff)
+    assert want.n_kmers > 0
+    assert_tables_equal(got, want)
+    b.close()
+
+
+def test_empty_and_degenerate_batches():
+    torch_cuda()
+    b = B.Binner(31, 4, 1)
+    t = b.bin_host(np.zeros(1, np.uint8), 0)
+    assert (t.n_instances, t.n_kmers, t.n_buckets, t.n_ids) == (0, 0, 0, 0)
+    # every read shorter than K
+    data = b"ACGT\nACGTACGT\n\n"
+    starts, lens = O.fgets_split(data, 101)
+    t = b.bin_host(data, len(starts), starts=starts, lens=lens)
+    assert (t.n_instances, t.n_kmers) == (0, 0)
+    np.testing.assert_array_equal(t.kmer_id_off, [0])
+    # one read exactly K long: one instance, pruned away at cutoff 1, kept with the prune disabled
+    one = b"A" * 31 + b"\n"
+    s1, l1 = np.array([0], np.uint64), np.array([31], np.uint32)
+    t = b.bin_host(one, 1, starts=s1, lens=l1)
+    assert (t.n_instances, t.n_distinct, t.n_kmers) == (1, 1, 0)
+    b2 = B.Binner(31, 4, -1)
+    t = b2.bin_host(one, 1, starts=s1, lens=l1)
+    assert_tables_equal(t, O.run(one, s1, l1, 31, 4, -1))
+    # a homopolymer batch: one giant group (every window identical)
+    poly = (b"A" * 100 + b"\n") * 3000
+    sp, lp = np.arange(3000, dtype=np.uint64) * 101, np.full(3000, 100, np.uint32)
+    t = b.bin_host(poly, 3000, stride=101, read_len=100)
+    w = O.run(poly, sp, lp, 31, 4, 1)
+    assert w.n_kmers == 1 and w.n_instances == 210000
+    assert_tables_equal(t, w)
+    b.close()
+    b2.close()
+
+
+def test_non_acgt_input_is_rejected():
+    torch_cuda()
+    case = next(c for c in CASES if c["name"] == "fuzz_nonacgt")
+    data = O.load_case_bytes(case)
+    starts, lens = O.fgets_split(data, case["read_length_define"])
+    b = B.Binner(case["k"], case["m"], case["cutoff"])
+    with pytest.raises(B.GbinError) as e:
+        b.bin_host(data, len(starts), starts=starts, lens=lens)
+    assert e.value.code == B.GBIN_E_NON_ACGT
+    b.close()
+
+
+def test_owner_partition_is_stable_and_complete():
+    torch = torch_cuda()
+    case = next(c for c in CASES if c["name"] == "cfg5_small")
+    data = O.load_case_bytes(case)
+    starts, lens = O.fgets_split(data, case["read_length_define"])
+    K, M = case["k"], case["m"]
+    tup, _ = O.scan_all(data, starts, lens, K, M)
+    b = B.Binner(K, M, 1)
+    rd, keep = dev_reads(torch, data, starts, lens)
+    n = len(tup)
+    buf = torch.empty(n * b.record_bytes, dtype=torch.uint8, device="cuda")
+    out = torch.empty_like(buf)
+    assert b.scan_device(rd, 0, buf, n) == n
+    for parts in (1, 2, 3, 8):
+        counts = b.partition_device(buf, n, parts, out)
+        owner = tup["mmer"] % parts
+        assert counts == [int((owner == p).sum()) for p in range(parts)]
+        rec = records_to_numpy(torch, out, n, 1)
+        order = np.argsort(owner, kind="stable")
+        np.testing.assert_array_equal(rec["mmer"], tup["mmer"][order])
+        np.testing.assert_array_equal(rec["arrival"], tup["arrival"][order])
+        np.testing.assert_array_equal(rec["k"][:, 0], tup["klo"][order])
+    b.close()
+
+
+def test_reference_entry_points_process_read_prune_data():
+    """The reference-named shims: process_read per read, prune_data as the flush, result walked through
+    the reference's own struct layouts (cfg1 replayed exactly as main does, binning.c:1150-1169)."""
+    torch_cuda()
+    from test_capi_cpu import ZTable, walk_zhash
+    import hashlib
+    case = next(c for c in CASES if c["name"] == "cfg1_reads")
+    data = O.load_case_bytes(case)
+    starts, lens = O.fgets_split(data, 101)
+    L = B.load_library()
+    assert L.gbin_ref_configure(31, 4, 1, 0) == 0
+    root = ZTable(0, 0, None)
+    for i in range(len(starts)):  # read_id++ for every fgets return, empty reads included
+        read = data[int(starts[i]):int(starts[i]) + int(lens[i])]
+        r = L.process_read(C.addressof(root), read, i)
+        assert r == C.addressof(root)
+    assert L.gbin_ref_last_status() == 0
+    assert L.prune_data(C.addressof(root)) == C.addressof(root)
+    assert L.gbin_ref_last_status() == 0
+    got = walk_zhash(root)
+    assert len(got) == case["surviving_kmers"]
+    assert hashlib.md5(b"".join(x + b"\n" for x in sorted(got))).hexdigest() == case["md5"]
+    # inserting after the flush is a state error, reported through gbin_ref_last_status
+    L.process_read(C.addressof(root), b"ACGT", 0)
+    assert L.gbin_ref_last_status() == B.GBIN_E_STATE
+    L.gbin_zhash_release(C.addressof(root))
+    L.gbin_ref_reset(C.addressof(root))
+
+
+def test_medium_synthetic_cfg2_shape():
+    """60 000 reads x 100 bp (4.2 M instances, 1026 sort tiles): multi-tile sort, multi-level scans."""
+    torch_cuda()
+    rs = synth.generate(60000, 100, error_rate=0.01, seed=20, starts="triangular")
+    starts = np.arange(rs.n_reads, dtype=np.uint64) * rs.stride
+    lens = np.full(rs.n_reads, rs.read_len, dtype=np.uint32)
+    b = B.Binner(31, 11, 1)
+    got = b.bin_host(rs.buf, rs.n_reads, stride=rs.stride, read_len=rs.read_len)
+    want = O.run(rs.as_bytes(), starts, lens, 31, 11, 1)
+    assert_tables_equal(got, want)
+    b.close()
+
+
+def check_table_invariants(t: B.HostTable, n_reads, W):
+    """Size-independent properties of a pruned table (used at BASELINE's full sizes)."""
+    assert t.n_instances == n_reads * W
+    assert (np.diff(t.mmer_codes.astype(np.int64)) > 0).all(), "buckets ascend strictly by m-mer code"
+    assert (t.mmer_codes >= (1 << (2 * t.M - 1))).all(), "stored m-mer is the larger of m-mer / complement"
+    assert t.mmer_kmer_off[0] == 0 and t.mmer_kmer_off[-1] == t.n_kmers and (np.diff(t.mmer_kmer_off.astype(np.int64)) > 0).all()
+    assert t.kmer_id_off[0] == 0 and t.kmer_id_off[-1] == t.n_ids
+    cnt = np.diff(t.kmer_id_off.astype(np.int64))
+    assert (cnt > t.cutoff).all(), "every surviving k-mer has more than cutoff occurrences"
+    if t.kw == 1:  # k-mers ascend strictly inside a bucket
+        kc = t.kmer_codes
+        asc = kc[1:] > kc[:-1]
+        bucket_start = np.zeros(t.n_kmers, dtype=bool)
+        bucket_start[t.mmer_kmer_off[:-1].astype(np.int64)] = True
+        assert (asc | bucket_start[1:]).all()
+    # ids newest-first inside every list
+    ids = t.read_ids.astype(np.int64)
+    desc = ids[1:] <= ids[:-1]
+    list_start = np.zeros(t.n_ids, dtype=bool)
+    list_start[t.kmer_id_off[:-1].astype(np.int64)] = True
+    assert (desc | list_start[1:]).all()
+    assert ids.min() >= 0 and ids.max() < n_reads
+    assert t.n_ids <= t.n_instances and t.n_kmers <= t.n_distinct <= t.n_instances
+
+
+def test_full_size_cfg2_properties_and_prefix_parity():
+    """BASELINE config 2 at full size (1 M reads x 100 bp, K=31, M=11): invariants on the whole table,
+    checksum agreement between two runs, and exact parity with the oracle on a 30 000-read prefix."""
+    torch_cuda()
+    rs = synth.generate(1_000_000, 100, error_rate=0.01, seed=20, starts="triangular")
+    b = B.Binner(31, 11, 1)
+    t = b.bin_host(rs.buf, rs.n_reads, stride=rs.stride, read_len=rs.read_len)
+    check_table_invariants(t, rs.n_reads, 70)
+    t2 = b.bin_host(rs.buf, rs.n_reads, stride=rs.stride, read_len=rs.read_len)
+    for a in ("mmer_codes", "mmer_kmer_off", "kmer_codes", "kmer_id_off", "read_ids"):
+        np.testing.assert_array_equal(getattr(t, a), getattr(t2, a))  # idempotent / deterministic
+    n = 30000
+    starts = np.arange(n, dtype=np.uint64) * rs.stride
+    lens = np.full(n, rs.read_len, dtype=np.uint32)
+    got = b.bin_host(rs.buf[: n * rs.stride], n, stride=rs.stride, read_len=rs.read_len)
+    assert_tables_equal(got, O.run(rs.buf[: n * rs.stride].tobytes(), starts, lens, 31, 11, 1))
+    b.close()

@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py — canonical k-mers binned+pruned per second on B200 (BASELINE.json metric).
+
+A step = one pass of the hot path (process_read over every read -> two-level grouping -> prune)
+over one batch of synthetic reads.  N=1: BASELINE config 2 (1 M reads x 100 bp, K=31, M=11, 1 %
+substitutions, generate_reads.py's triangular start walk).  N>1: weak scaling — every rank holds a
+config-2-sized shard drawn from one shared genome N times longer; records are exchanged by m-mer
+owner with one NCCL all-to-all.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl reference]
+
+One JSON line on stdout (rank 0).  `value` is device-resident throughput (inputs in HBM when the
+timed region starts), `e2e` goes through the public host-buffer call (pinned H2D + pipeline + D2H of
+the table inside the timed region), `roofline` is the dominant kernel (stable radix scatter) timed
+live with CUDA events on its launching stream, `cpu_baseline` is the UNMODIFIED reference binary
+(oracle/_ref) on one host core over a bounded prefix of the same reads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "canonical k-mers binned+pruned per second"
+UNIT = "k-mers/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gbin", choices=["gbin", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--reads-per-gpu", type=int, default=0, help="override the workload's read count (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_params(name, reads_override=0):
+    from genome_assembly_b200 import synth
+    w = dict(synth.WORKLOADS[name])
+    if reads_override:
+        w["n_reads"] = reads_override
+    return w
+
+
+def make_reads(w, rank, world):
+    """This rank's shard: config-shaped reads from one shared genome (world x the config's genome)."""
+    from genome_assembly_b200 import synth
+    n = w["n_reads"]
+    glen = synth.default_genome_len(n * world, w["read_len"])
+    return synth.generate(n, w["read_len"], genome_len=glen, error_rate=w["error_rate"], seed=20, read_seed=20 + rank,
+                          starts=w["starts"])
+
+
+# ------------------------------------------------------------------------------------------ CPU reference leg
+
+def ref_binary(w):
+    name = f"ref_K{w['k']}_M{w['m']}_C{w['cutoff']}_R{w['read_len'] + 2}"
+    return os.path.join(ROOT, "oracle", "_ref", name)
+
+
+def time_reference(w, rs, n_sample_reads):
+    """Times the reference's own process_read loop + prune_data (binning.c:1158-1169) on the first
+    n_sample_reads reads of the shard; returns (k-mers/s, dict)."""
+    exe = ref_binary(w)
+    n = min(n_sample_reads, rs.n_reads)
+    inst = n * (rs.read_len - w["k"] + 1)
+    with tempfile.NamedTemporaryFile(suffix=".txt", delete=False) as tf:
+        tf.write(rs.buf[: n * rs.stride].tobytes())
+        path = tf.name
+    try:
+        if os.path.exists(exe):
+            p = subprocess.run([exe, path, "--time"], capture_output=True, text=True, check=True)
+            st = json.loads(p.stdout.strip().splitlines()[-1])
+            secs = st["process_s"] + st["prune_s"]
+            assert st["instances"] == inst
+            kind = "reference"
+        else:  # the reference could not be built here: fall back to the oracle port (still CPU, still 1 thread)
+            cli = os.path.join(ROOT, "oracle", "_build", "gbin_oracle_cli")
+            p = subprocess.run([cli, path, str(w["k"]), str(w["m"]), str(w["cutoff"]), str(w["read_len"] + 2), "--time"],
+                               capture_output=True, text=True, check=True)
+            st = json.loads(p.stdout.strip().splitlines()[-1])
+            secs = st["total_s"]
+            kind = "port"
+    finally:
+        os.unlink(path)
+    return inst / secs, dict(kind=kind, cores=1, seconds=secs, instances=inst,
+                             sample=f"first {n} reads of the rank-0 shard ({inst} k-mer instances), process_read loop + prune_data, 1 thread (the reference is single-threaded and non-reentrant, binning.c:300-303)")
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    w = workload_params(a.workload, a.reads_per_gpu)
+    rs = make_reads(w, 0, max(a.gpus, 1))
+    sample_reads = min(w["n_reads"], 40_000)  # ~2.8 M instances, a few seconds per step
+    for _ in range(a.warmup):
+        time_reference(w, rs, sample_reads)
+    vals, info = [], None
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        v, info = time_reference(w, rs, sample_reads)
+        vals.append(v)
+    wall = time.perf_counter() - t0
+    inst = info["instances"]
+    value = inst * a.steps / sum(inst / v for v in vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * wall / max(a.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": config_dict(a, w, max(a.gpus, 1)),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ helpers
+
+def config_dict(a, w, world):
+    return {"workload": f"{a.workload}: {w['n_reads']} reads x {w['read_len']} bp per GPU, K={w['k']}, M={w['m']}, cutoff={w['cutoff']}, "
+                        f"{w['error_rate'] * 100:g}% substitutions, {w['starts']} starts, genome {world}x{w['n_reads'] * w['read_len'] // 30} bp",
+            "k": w["k"], "m": w["m"], "cutoff": w["cutoff"], "reads_per_gpu": w["n_reads"], "read_len": w["read_len"],
+            "parallelism": f"reads split evenly over {world} GPU(s); records exchanged by owner = mmer % {world}" if world > 1 else "single GPU",
+            "l2": "L2 flushed (256 MiB memset) before every timed step; per-step device times summed"}
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.tf = tempfile.NamedTemporaryFile(suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=self.tf, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tf.close()
+        sm, mx, reasons = [], [], set()
+        with open(self.tf.name) as f:
+            for ln in f:
+                p = [x.strip() for x in ln.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        os.unlink(self.tf.name)
+        if sm:
+            top = sorted(sm)[len(sm) // 2:]  # under load = upper half of the samples
+            out.update(sm_mhz=statistics.median(top), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import genome_assembly_b200 as g
+    from genome_assembly_b200.dist import GpuStages, ShardedBinner
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the binning path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    w = workload_params(a.workload, a.reads_per_gpu)
+    K, M, cutoff = w["k"], w["m"], w["cutoff"]
+    rs = make_reads(w, rank, world)
+    W = rs.read_len - K + 1
+    n_inst_rank = rs.n_reads * W
+    n_inst_total = n_inst_rank * world
+
+    binner = g.Binner(K, M, cutoff, device=local)
+    B = g.binding
+    # host copy in pinned memory (e2e leg) and device-resident copy (value leg)
+    h_reads = torch.from_numpy(rs.buf).pin_memory()
+    d_reads = h_reads.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream().cuda_stream
+    rd_dev = B.Binner._reads(d_reads, d_reads.numel(), rs.n_reads, stride=rs.stride, read_len=rs.read_len, id_base=rank * rs.n_reads)
+    rd_host = B.Binner._reads(h_reads, h_reads.numel(), rs.n_reads, stride=rs.stride, read_len=rs.read_len, id_base=rank * rs.n_reads)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    stages = GpuStages(binner)
+    sharded = ShardedBinner(stages, time_stages=False) if world > 1 else None
+
+    def step_device():
+        if world == 1:
+            return binner.bin_device_raw(rd_dev, stream)
+        return sharded.run(rd_dev, arrival_base=rank * rs.n_reads)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also sizes every workspace buffer)
+    table = None
+    for _ in range(max(a.warmup, 0)):
+        table = step_device()
+    barrier()
+
+    # ---- timed region: K steps, L2 flushed before each, device time per step from CUDA events
+    binner.set_kernel_profiling(True)
+    launches = 0
+    launches_before = stages.launches
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    t_wall0 = time.perf_counter()
+    step_ms = []
+    for _ in range(a.steps):
+        flush.zero_()
+        if world > 1:
+            dist.barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        table = step_device()
+        e1.record()
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        launches += binner.timings()["kernel_launches"] if world == 1 else 0
+    barrier()
+    wall_s = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if sampler else None
+    prof = binner.kernel_profile()
+    binner.set_kernel_profiling(False)
+    if world > 1:
+        launches = stages.launches - launches_before
+    total_ms = float(sum(step_ms))
+    tms = torch.tensor([total_ms, float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = tms.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tms.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        total_ms = float(mx[0])
+        launches = int(sm[1])
+    value = n_inst_total * a.steps / (total_ms / 1e3)
+
+    # ---- table stats of the last step (sanity: work was really done)
+    stats = {"instances": int(table.n_instances), "distinct": int(table.n_distinct), "surviving_kmers": int(table.n_kmers),
+             "surviving_ids": int(table.n_ids), "buckets": int(table.n_buckets)}
+
+    # ---- e2e: public host-buffer call, pinned H2D + pipeline + D2H of the table inside the timed region
+    e2e = None
+    if not a.no_e2e and world == 1:
+        for _ in range(2):
+            binner.bin_host_raw(rd_host)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(a.steps):
+            t = binner.bin_host_raw(rd_host)
+            d2h = int(t.n_kmers * (8 * t.kmer_words + 8) + 8 + t.n_ids * 4 + t.n_buckets * 12 + 8)
+        e2e_s = time.perf_counter() - t0
+        e2e = {"value": n_inst_total * a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h_reads.numel()),
+               "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / a.steps, "timing": "host wall clock around gbin_bin_reads_host",
+               "stage_ms_last_step": binner.timings()}
+    elif not a.no_e2e:
+        # multi-GPU e2e: pinned H2D of every rank's shard + sharded pipeline + D2H of every owner table
+        def e2e_step():
+            d = h_reads.to(dev, non_blocking=True)
+            rdx = B.Binner._reads(d, d.numel(), rs.n_reads, stride=rs.stride, read_len=rs.read_len, id_base=rank * rs.n_reads)
+            tb = sharded.run(rdx, arrival_base=rank * rs.n_reads)
+            ht = binner.table_to_host(tb)
+            return int(ht.n_kmers * (8 * ht.kw + 8) + 8 + ht.n_ids * 4 + ht.n_buckets * 12 + 8)
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(a.steps):
+            d2h = e2e_step()
+        barrier()
+        e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_inst_total * a.steps / float(e2e_s[0]), "unit": UNIT, "h2d_bytes_per_step": int(h_reads.numel()) * world,
+               "d2h_bytes_per_step": d2h * world, "ms_per_step": 1e3 * float(e2e_s[0]) / a.steps,
+               "timing": "host wall clock, max over ranks; table D2H into pageable memory"}
+
+    # ---- roofline of the dominant kernel (stable radix scatter): algorithmic bytes = read + write of every record
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    rb = binner.record_bytes
+    roofline = None
+    if "radix_scatter" in prof and prof["radix_scatter"]["launches"]:
+        sc = prof["radix_scatter"]
+        n_rec = stats["instances"] if world > 1 else n_inst_rank  # records one launch moves on this rank
+        alg = 2.0 * rb * n_rec
+        avg_ms = sc["ms"] / sc["launches"]
+        ach = alg / (avg_ms / 1e3) / 1e9
+        pipe_bytes_per_inst = (rs.read_len + 1) / W + 2 * rb + 4
+        pipe_ach = pipe_bytes_per_inst * n_inst_rank * a.steps / (float(sum(step_ms)) / 1e3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "radix_scatter_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg, "launches": sc["launches"], "avg_launch_ms": avg_ms,
+                    "share_of_step": sc["ms"] / float(sum(step_ms)),
+                    "pipeline": {"algorithmic_bytes_per_kmer": pipe_bytes_per_inst, "achieved": pipe_ach, "frac": pipe_ach / peak,
+                                 "note": "whole step against SURVEY §8(d)'s compulsory-traffic model"},
+                    "per_kernel_ms_per_step": {k: v["ms"] / a.steps for k, v in prof.items()}}
+
+    # ---- CPU baseline (rank 0, N=1 only): the unmodified reference binary on one host core
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        try:
+            v, info = time_reference(w, rs, 200_000)
+            cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"],
+                   "seconds": info["seconds"], "host_cores_available": os.cpu_count()}
+        except Exception as e:  # noqa: BLE001
+            cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": f"{type(e).__name__}: {e}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64" if K <= 32 else "u128", "data": "synthetic",
+            "config": config_dict(a, w, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu, "table": stats,
+            "wall_s_timed_region": wall_s, "step_ms": step_ms,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    binner.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -55,11 +55,16 @@ class Timings(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class KernelProfile(C.Structure):
+    _fields_ = [("ms", C.c_float * 8), ("launches", C.c_uint32 * 8)]
+
+
 # every symbol include/gbin.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "gbin_strerror", "gbin_last_error", "gbin_version", "gbin_create", "gbin_destroy", "gbin_get_config",
     "gbin_bin_reads_host", "gbin_table_clone", "gbin_table_free", "gbin_pinned_alloc", "gbin_pinned_free",
     "gbin_bin_reads_device", "gbin_table_to_host", "gbin_get_timings", "gbin_record_bytes",
+    "gbin_set_kernel_profiling", "gbin_get_kernel_profile", "gbin_kernel_kind_name",
     "gbin_count_instances_device", "gbin_scan_reads_device", "gbin_partition_records_device",
     "gbin_group_records_device", "gbin_read_file_fgets", "gbin_table_dump", "gbin_table_dump_reference_format",
     "getval", "getbp", "getscore", "process_read", "prune_data", "gbin_ref_configure", "gbin_ref_last_status",
@@ -98,6 +103,10 @@ def load_library() -> C.CDLL:
     L.gbin_pinned_free.argtypes = [vp]
     L.gbin_pinned_free.restype = None
     L.gbin_get_timings.argtypes = [vp, C.POINTER(Timings)]
+    L.gbin_set_kernel_profiling.argtypes = [vp, C.c_int]
+    L.gbin_get_kernel_profile.argtypes = [vp, C.POINTER(KernelProfile)]
+    L.gbin_kernel_kind_name.argtypes = [C.c_int]
+    L.gbin_kernel_kind_name.restype = C.c_char_p
     L.gbin_record_bytes.argtypes = [vp]
     L.gbin_record_bytes.restype = u32
     L.gbin_count_instances_device.argtypes = [vp, C.POINTER(CReads), vp, C.POINTER(u64)]
@@ -224,6 +233,20 @@ class Binner:
         t = Timings()
         self.lib.gbin_get_timings(self.h, C.byref(t))
         return t.as_dict()
+
+    def set_kernel_profiling(self, enable: bool):
+        self._check(self.lib.gbin_set_kernel_profiling(self.h, int(enable)))
+
+    def kernel_profile(self) -> dict:
+        """{kernel class: {"ms": accumulated device ms, "launches": n}} since profiling was enabled."""
+        p = KernelProfile()
+        self._check(self.lib.gbin_get_kernel_profile(self.h, C.byref(p)))
+        out = {}
+        for i in range(8):
+            name = self.lib.gbin_kernel_kind_name(i).decode()
+            if name:
+                out[name] = {"ms": float(p.ms[i]), "launches": int(p.launches[i])}
+        return out
 
     @staticmethod
     def _reads(data, data_bytes, n_reads, stride=0, read_len=0, starts=None, lens=None, read_ids=None, id_base=0, max_read_len=0):

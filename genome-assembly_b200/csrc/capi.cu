@@ -92,6 +92,7 @@ struct gbin_ctx {
     DevBuf o_mmer_codes, o_mmer_kmer_off, o_kmer_codes, o_kmer_id_off, o_read_ids;
     // pinned host arena for results of the host path + small readbacks
     HostBuf h_misc, h_result;
+    KernelProf prof;
 };
 
 namespace {
@@ -182,8 +183,11 @@ int run_scan(gbin_ctx *ctx, const gbin_reads *rd, uint32_t arrival_base, void *d
     Misc *dm = ctx->misc.as<Misc>();
     ReadsView rv{reinterpret_cast<const uint8_t *>(rd->data), rd->data_bytes, rd->n_reads, rd->stride, rd->read_len, rd->starts, rd->lens};
     CU(cudaMemsetAsync(&dm->bad_bases, 0, sizeof(unsigned long long), st));
-    *launches += launch_scan_reads(rv, rd->starts ? ctx->rec_off.as<uint64_t>() : nullptr, ctx->cfg.kmer_size, ctx->cfg.mmer_size, ctx->KW,
-                                   arrival_base, max_len ? max_len : 1, d_records, &dm->bad_bases, ctx->sm_count, st);
+    const bool on = ctx->prof.begin(KK_SCAN, st);
+    const int ls = launch_scan_reads(rv, rd->starts ? ctx->rec_off.as<uint64_t>() : nullptr, ctx->cfg.kmer_size, ctx->cfg.mmer_size, ctx->KW,
+                                     arrival_base, max_len ? max_len : 1, d_records, &dm->bad_bases, ctx->sm_count, st);
+    ctx->prof.end(on, ls, st);
+    *launches += ls;
     CU(cudaGetLastError());
     return GBIN_OK;
 }
@@ -206,7 +210,7 @@ int run_group(gbin_ctx *ctx, void *recs, void *twin, uint64_t n, const int32_t *
     CU(ctx->radix_scratch.ensure(radix_scratch_bytes(n)));
     bool in_b = false;
     int passes = 0;
-    *launches += radix_sort_records(recs, twin, n, KW, K, M, ctx->radix_scratch.p, &in_b, &passes, st);
+    *launches += radix_sort_records(recs, twin, n, KW, K, M, ctx->radix_scratch.p, &in_b, &passes, &ctx->prof, st);
     CU(cudaGetLastError());
     ctx->tm.sort_passes = (uint32_t)passes;
     const void *sorted = in_b ? twin : recs;
@@ -222,7 +226,10 @@ int run_group(gbin_ctx *ctx, void *recs, void *twin, uint64_t n, const int32_t *
     ws.counts = &dm->counts;
     ws.cutoff = cutoff;
 
-    *launches += group_find_runs(sorted, n, KW, ws, st);
+    bool on = ctx->prof.begin(KK_RUNS, st);
+    int lg = group_find_runs(sorted, n, KW, ws, st);
+    ctx->prof.end(on, lg, st);
+    *launches += lg;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(hm, dm, sizeof(GroupCounts) + sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -236,7 +243,10 @@ int run_group(gbin_ctx *ctx, void *recs, void *twin, uint64_t n, const int32_t *
         CU(ctx->id_offset.ensure((G + 1) * sizeof(uint64_t)));
         ws.surv_index = ctx->surv_index.as<uint32_t>();
         ws.id_offset = ctx->id_offset.as<uint64_t>();
-        *launches += group_prune_offsets(n, G, cutoff, ws, st);
+        on = ctx->prof.begin(KK_PRUNE, st);
+        lg = group_prune_offsets(n, G, cutoff, ws, st);
+        ctx->prof.end(on, lg, st);
+        *launches += lg;
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(&hm->counts, &dm->counts, sizeof(GroupCounts), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -248,7 +258,10 @@ int run_group(gbin_ctx *ctx, void *recs, void *twin, uint64_t n, const int32_t *
         CU(ctx->bucket_of.ensure(S * sizeof(uint32_t)));
         ws.surv_group = ctx->surv_group.as<uint32_t>();
         ws.bucket_of = ctx->bucket_of.as<uint32_t>();
-        *launches += group_mark_buckets(sorted, KW, G, S, ws, st);
+        on = ctx->prof.begin(KK_PRUNE, st);
+        lg = group_mark_buckets(sorted, KW, G, S, ws, st);
+        ctx->prof.end(on, lg, st);
+        *launches += lg;
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(&hm->counts, &dm->counts, sizeof(GroupCounts), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -261,7 +274,10 @@ int run_group(gbin_ctx *ctx, void *recs, void *twin, uint64_t n, const int32_t *
     CU(ctx->o_read_ids.ensure((NS + 1) * sizeof(int32_t)));
     TableOut to{ctx->o_mmer_codes.as<uint32_t>(), ctx->o_mmer_kmer_off.as<uint64_t>(), ctx->o_kmer_codes.as<uint64_t>(),
                 ctx->o_kmer_id_off.as<uint64_t>(), ctx->o_read_ids.as<int32_t>()};
-    *launches += group_emit(sorted, n, KW, G, S, NS, B, d_ids, id_base, ws, to, st);
+    on = ctx->prof.begin(KK_EMIT, st);
+    lg = group_emit(sorted, n, KW, G, S, NS, B, d_ids, id_base, ws, to, st);
+    ctx->prof.end(on, lg, st);
+    *launches += lg;
     CU(cudaGetLastError());
     out->n_kmers = S;
     out->n_ids = NS;
@@ -332,6 +348,7 @@ int gbin_create(const gbin_config *cfg, gbin_ctx **out) {
     ctx->KW = cfg->kmer_size <= 32 ? 1 : 2;
     ctx->err[0] = 0;
     memset(&ctx->tm, 0, sizeof ctx->tm);
+    ctx->prof.reset();
     cudaError_t e = cudaSetDevice(cfg->device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -358,6 +375,7 @@ void gbin_destroy(gbin_ctx *ctx) {
     for (DevBuf *b : bufs) b->release();
     ctx->h_misc.release();
     ctx->h_result.release();
+    ctx->prof.destroy();
     for (int i = 0; i < 6; i++) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -405,6 +423,28 @@ static void finish_timings(gbin_ctx *ctx, int launches, bool host_path) {
     ctx->tm.d2h_ms = host_path ? ms(4, 5) : 0.f;
     ctx->tm.total_ms = ms(0, host_path ? 5 : 4);
     ctx->tm.kernel_launches = (uint32_t)launches;
+    ctx->prof.collect();
+}
+
+int gbin_set_kernel_profiling(gbin_ctx *ctx, int enable) {
+    if (!ctx) return GBIN_E_INVALID_ARG;
+    ctx->prof.enabled = enable != 0;
+    ctx->prof.reset();
+    return GBIN_OK;
+}
+
+int gbin_get_kernel_profile(const gbin_ctx *ctx, gbin_kernel_profile *out) {
+    if (!ctx || !out) return GBIN_E_INVALID_ARG;
+    for (int i = 0; i < GBIN_KERNEL_KINDS; i++) {
+        out->ms[i] = i < KK_COUNT ? ctx->prof.ms[i] : 0.f;
+        out->launches[i] = i < KK_COUNT ? ctx->prof.launches[i] : 0u;
+    }
+    return GBIN_OK;
+}
+
+const char *gbin_kernel_kind_name(int kind) {
+    static const char *names[] = {"scan_reads", "radix_hist", "radix_tile_scan", "radix_scatter", "find_runs", "prune_offsets", "emit_table"};
+    return (kind >= 0 && kind < KK_COUNT) ? names[kind] : "";
 }
 
 int gbin_bin_reads_device(gbin_ctx *ctx, const gbin_reads *reads, void *stream, gbin_table *out) {
@@ -546,6 +586,7 @@ int gbin_scan_reads_device(gbin_ctx *ctx, const gbin_reads *reads, uint32_t arri
     Misc *hm = static_cast<Misc *>(ctx->h_misc.p);
     CU(cudaMemcpyAsync(&hm->bad_bases, &dm->bad_bases, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    ctx->prof.collect();
     if (hm->bad_bases) return fail(ctx, GBIN_E_NON_ACGT, "%llu bases other than A/C/G/T in the batch", hm->bad_bases);
     *n_out = n;
     ctx->tm.kernel_launches = (uint32_t)launches;

@@ -8,6 +8,52 @@
 
 namespace gbin {
 
+// Per-kernel-class device timing (CUDA events on the launching stream), for the roofline numbers
+// bench.py reports.  Disabled by default; when disabled begin/end cost one branch.
+enum KernelKind { KK_SCAN = 0, KK_RADIX_HIST, KK_RADIX_TILESCAN, KK_RADIX_SCATTER, KK_RUNS, KK_PRUNE, KK_EMIT, KK_COUNT };
+struct KernelProf {
+    static constexpr int MAX_REGIONS = 256;
+    bool enabled = false;
+    bool created = false;
+    int n = 0;
+    cudaEvent_t a[MAX_REGIONS], b[MAX_REGIONS];
+    unsigned char kind[MAX_REGIONS];
+    float ms[KK_COUNT];
+    unsigned launches[KK_COUNT];
+    void reset() {
+        n = 0;
+        for (int i = 0; i < KK_COUNT; i++) { ms[i] = 0.f; launches[i] = 0; }
+    }
+    bool begin(int k, cudaStream_t st) {
+        if (!enabled || n >= MAX_REGIONS) return false;
+        if (!created) {
+            for (int i = 0; i < MAX_REGIONS; i++) { cudaEventCreate(&a[i]); cudaEventCreate(&b[i]); }
+            created = true;
+        }
+        kind[n] = (unsigned char)k;
+        cudaEventRecord(a[n], st);
+        return true;
+    }
+    void end(bool on, int nlaunch, cudaStream_t st) {
+        if (!on) return;
+        cudaEventRecord(b[n], st);
+        launches[kind[n]] += (unsigned)nlaunch;
+        n++;
+    }
+    void collect() {  // call after the stream is synchronised
+        for (int i = 0; i < n; i++) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, a[i], b[i]) == cudaSuccess) ms[kind[i]] += t;
+            else (void)cudaGetLastError();
+        }
+        n = 0;
+    }
+    void destroy() {
+        if (created) for (int i = 0; i < MAX_REGIONS; i++) { cudaEventDestroy(a[i]); cudaEventDestroy(b[i]); }
+        created = false;
+    }
+};
+
 // ---- scan_reads.cu
 int launch_count_windows(const ReadsView &rv, int K, uint32_t *counts, cudaStream_t st);
 int launch_scan_reads(const ReadsView &rv, const uint64_t *rec_off, int K, int M, int KW, uint32_t arrival_base, uint32_t max_len,
@@ -19,7 +65,7 @@ int launch_pack_reads(const ReadsView &rv, uint32_t words_per_read, uint32_t *pa
 // the function returns which through *result_in_b.  tile_hist: scratch of radix_scratch_bytes(n).
 size_t radix_scratch_bytes(uint64_t n);
 int radix_sort_records(void *a, void *b, uint64_t n, int KW, int K, int M, void *scratch, bool *result_in_b, int *passes_out,
-                       cudaStream_t st);
+                       KernelProf *prof, cudaStream_t st);
 // Stable partition by owner = mmer % n_parts: in -> out, part sizes to d_counts[n_parts] (device, u64).
 int radix_partition_by_owner(const void *in, void *out, uint64_t n, int KW, uint32_t n_parts, void *scratch, uint64_t *d_counts,
                              cudaStream_t st);

@@ -145,32 +145,40 @@ size_t radix_scratch_bytes(uint64_t n) {
 }
 
 template <int KW>
-static int one_pass(const Rec<KW> *in, Rec<KW> *out, uint64_t n, const DigitSel &sel, uint32_t *scratch, cudaStream_t st) {
+static int one_pass(const Rec<KW> *in, Rec<KW> *out, uint64_t n, const DigitSel &sel, uint32_t *scratch, KernelProf *prof,
+                    cudaStream_t st) {
     const uint32_t nt = ntiles_of(n);
     const uint64_t table = (uint64_t)RS_RADIX * nt;
     uint32_t *tile_hist = scratch;
     uint32_t *scan_tmp = scratch + table;
     int launches = 0;
+    bool on = prof && prof->begin(KK_RADIX_HIST, st);
     radix_hist_kernel<KW><<<nt, RS_THREADS, 0, st>>>(in, n, sel, tile_hist, nt);
+    if (prof) prof->end(on, 1, st);
     launches++;
-    launches += exclusive_scan<uint32_t, PtrIn<uint32_t>>(PtrIn<uint32_t>{tile_hist}, tile_hist, table, scan_tmp, nullptr, st);
+    on = prof && prof->begin(KK_RADIX_TILESCAN, st);
+    const int ls = exclusive_scan<uint32_t, PtrIn<uint32_t>>(PtrIn<uint32_t>{tile_hist}, tile_hist, table, scan_tmp, nullptr, st);
+    if (prof) prof->end(on, ls, st);
+    launches += ls;
     const size_t smem = (size_t)RS_TILE * sizeof(Rec<KW>) + (RS_WARPS * RS_RADIX + 2 * RS_RADIX) * sizeof(uint32_t);
     static bool attr_set[3] = {false, false, false};
     if (!attr_set[KW]) {
         cudaFuncSetAttribute(radix_scatter_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set[KW] = true;
     }
+    on = prof && prof->begin(KK_RADIX_SCATTER, st);
     radix_scatter_kernel<KW><<<nt, RS_THREADS, smem, st>>>(in, out, n, sel, tile_hist, nt);
+    if (prof) prof->end(on, 1, st);
     return launches + 1;
 }
 
 template <int KW>
 static int sort_impl(Rec<KW> *a, Rec<KW> *b, uint64_t n, int K, int M, uint32_t *scratch, bool *result_in_b, int *passes_out,
-                     cudaStream_t st) {
+                     KernelProf *prof, cudaStream_t st) {
     int launches = 0, passes = 0;
     Rec<KW> *src = a, *dst = b;
     auto run = [&](DigitSel sel) {
-        launches += one_pass<KW>(src, dst, n, sel, scratch, st);
+        launches += one_pass<KW>(src, dst, n, sel, scratch, prof, st);
         Rec<KW> *t = src;
         src = dst;
         dst = t;
@@ -190,15 +198,15 @@ static int sort_impl(Rec<KW> *a, Rec<KW> *b, uint64_t n, int K, int M, uint32_t 
 }
 
 int radix_sort_records(void *a, void *b, uint64_t n, int KW, int K, int M, void *scratch, bool *result_in_b, int *passes_out,
-                       cudaStream_t st) {
+                       KernelProf *prof, cudaStream_t st) {
     *result_in_b = false;
     *passes_out = 0;
     if (n == 0) return 0;
     if (KW == 1)
         return sort_impl<1>(static_cast<Rec<1> *>(a), static_cast<Rec<1> *>(b), n, K, M, static_cast<uint32_t *>(scratch), result_in_b,
-                            passes_out, st);
+                            passes_out, prof, st);
     return sort_impl<2>(static_cast<Rec<2> *>(a), static_cast<Rec<2> *>(b), n, K, M, static_cast<uint32_t *>(scratch), result_in_b,
-                        passes_out, st);
+                        passes_out, prof, st);
 }
 
 int radix_partition_by_owner(const void *in, void *out, uint64_t n, int KW, uint32_t n_parts, void *scratch, uint64_t *d_counts,
@@ -210,9 +218,9 @@ int radix_partition_by_owner(const void *in, void *out, uint64_t n, int KW, uint
     const DigitSel sel{2, 0, 0, n_parts};
     int launches;
     if (KW == 1)
-        launches = one_pass<1>(static_cast<const Rec<1> *>(in), static_cast<Rec<1> *>(out), n, sel, static_cast<uint32_t *>(scratch), st);
+        launches = one_pass<1>(static_cast<const Rec<1> *>(in), static_cast<Rec<1> *>(out), n, sel, static_cast<uint32_t *>(scratch), nullptr, st);
     else
-        launches = one_pass<2>(static_cast<const Rec<2> *>(in), static_cast<Rec<2> *>(out), n, sel, static_cast<uint32_t *>(scratch), st);
+        launches = one_pass<2>(static_cast<const Rec<2> *>(in), static_cast<Rec<2> *>(out), n, sel, static_cast<uint32_t *>(scratch), nullptr, st);
     part_counts_kernel<<<1, RS_RADIX, 0, st>>>(static_cast<uint32_t *>(scratch), ntiles_of(n), n_parts, n, d_counts);
     return launches + 1;
 }

@@ -1,0 +1,181 @@
+"""Multi-GPU binning: one process per GPU, torch.distributed for the plumbing.
+
+    reads split evenly by contiguous id range (rank g holds arrival indices [base_g, base_g + n_g))
+      -> scan stage on every rank (process_read's window/signature work, embarrassingly parallel)
+      -> stable partition of the k-mer instance records by owner = mmer_code % world
+      -> ONE personalised all-to-all-v of records (count exchange, then payload)
+      -> sort / run-length / prune on the owner, which now holds whole m-mer buckets.
+
+Receiving in source-rank order keeps arrival order inside every key (rank ranges are ordered and each
+rank's records are in arrival order), so the owner's stable sort yields the reference's list order.
+The result stays sharded: every rank returns the table of the m-mer buckets it owns.
+
+The compute stages are C-ABI calls into libgbin.so on device buffers (`GpuStages`).  The class takes
+the stage object as a parameter only so that the host-side logic (split sizes, exchange, merge) can be
+exercised on CPU with the gloo backend by tests that plug in the oracle; the product path has no
+other implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import binding as B
+
+
+def split_reads_evenly(n_reads: int, world: int):
+    """Contiguous read ranges per rank: rank g gets [bounds[g], bounds[g+1])."""
+    return [(n_reads * g) // world for g in range(world + 1)]
+
+
+class GpuStages:
+    """The product stages: scan / partition / group through the C ABI on torch-allocated HBM buffers."""
+
+    def __init__(self, binner: B.Binner):
+        self.b = binner
+        self.device = torch.device("cuda", binner.device)
+        self.record_bytes = binner.record_bytes
+        self.launches = 0  # kernels launched by the stages since construction
+
+    def _count(self):
+        self.launches += self.b.timings()["kernel_launches"]
+
+    def stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def alloc_records(self, n: int) -> torch.Tensor:
+        return torch.empty(max(n, 1) * self.record_bytes, dtype=torch.uint8, device=self.device)
+
+    def scan(self, reads: B.CReads, arrival_base: int):
+        n = self.b.count_instances_device(reads, self.stream())
+        rec = self.alloc_records(n)
+        got = self.b.scan_device(reads, arrival_base, rec, n, self.stream())
+        assert got == n
+        self._count()
+        return rec, n
+
+    def partition(self, rec: torch.Tensor, n: int, parts: int):
+        out = self.alloc_records(n)
+        counts = self.b.partition_device(rec, n, parts, out, self.stream())
+        self._count()
+        return out, counts
+
+    def group(self, rec: torch.Tensor, n: int, id_base: int):
+        t = self.b.group_device(rec, n, None, id_base, self.stream())
+        self._count()
+        return t
+
+
+@dataclass
+class ExchangeStats:
+    sent_records: int = 0
+    recv_records: int = 0
+    sent_bytes_offrank: int = 0
+    scan_ms: float = 0.0
+    partition_ms: float = 0.0
+    exchange_ms: float = 0.0
+    group_ms: float = 0.0
+    extra: dict = field(default_factory=dict)
+
+
+class ShardedBinner:
+    """Runs the hot path across the ranks of a torch.distributed process group."""
+
+    def __init__(self, stages, group=None, time_stages: bool = False):
+        self.stages = stages
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.time_stages = time_stages
+        self.stats = ExchangeStats()
+
+    def _ev(self):
+        if not self.time_stages:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def exchange(self, part: torch.Tensor, send_counts: list[int]):
+        """All-to-all-v of records laid out part-major in `part`. Returns (received buffer, n received)."""
+        rb = self.stages.record_bytes
+        words = rb // 8
+        dev = part.device
+        send = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        recv_counts = [int(x) for x in recv.tolist()]
+        n_in = sum(recv_counts)
+        n_out = sum(send_counts)
+        inbuf = self.stages.alloc_records(n_in)
+        src = part.view(torch.int64)[: n_out * words]
+        dst = inbuf.view(torch.int64)[: n_in * words]
+        dist.all_to_all_single(dst, src, output_split_sizes=[c * words for c in recv_counts],
+                               input_split_sizes=[c * words for c in send_counts], group=self.group)
+        self.stats.sent_records = n_out
+        self.stats.recv_records = n_in
+        self.stats.sent_bytes_offrank = (n_out - send_counts[self.rank]) * rb
+        return inbuf, n_in
+
+    def run(self, reads, arrival_base: int, id_base: int = 0):
+        """reads: this rank's shard (device CReads); arrival_base: global index of its first read.
+        Returns the device table of the m-mer buckets this rank owns."""
+        e0 = self._ev()
+        rec, n = self.stages.scan(reads, arrival_base)
+        e1 = self._ev()
+        if self.world == 1:
+            inbuf, n_in = rec, n
+            e2 = e3 = e1
+        else:
+            part, counts = self.stages.partition(rec, n, self.world)
+            del rec
+            e2 = self._ev()
+            inbuf, n_in = self.exchange(part, counts)
+            del part
+            e3 = self._ev()
+        table = self.stages.group(inbuf, n_in, id_base)
+        e4 = self._ev()
+        if self.time_stages:
+            torch.cuda.synchronize()
+            self.stats.scan_ms = e0.elapsed_time(e1)
+            self.stats.partition_ms = e1.elapsed_time(e2)
+            self.stats.exchange_ms = e2.elapsed_time(e3)
+            self.stats.group_ms = e3.elapsed_time(e4)
+        self._keep = inbuf  # the group stage's input must outlive the call (it is sort scratch)
+        return table
+
+
+def merge_owner_tables(tables: list[B.HostTable]) -> B.HostTable:
+    """Union of per-owner tables (disjoint m-mer buckets) in canonical order — for parity checks."""
+    t0 = tables[0]
+    kw = t0.kw
+    entries = []
+    for t in tables:
+        kc = t.kmer_codes.reshape(-1, kw)
+        for b in range(t.n_buckets):
+            entries.append((int(t.mmer_codes[b]), t, kc, int(t.mmer_kmer_off[b]), int(t.mmer_kmer_off[b + 1])))
+    entries.sort(key=lambda e: e[0])
+    mmer_codes, mmer_off, kcs, id_lens, ids = [], [0], [], [], []
+    for code, t, kc, s0, s1 in entries:
+        mmer_codes.append(code)
+        kcs.append(kc[s0:s1])
+        lo, hi = int(t.kmer_id_off[s0]), int(t.kmer_id_off[s1])
+        id_lens.append(np.diff(t.kmer_id_off[s0:s1 + 1].astype(np.int64)))
+        ids.append(t.read_ids[lo:hi])
+        mmer_off.append(mmer_off[-1] + (s1 - s0))
+    if entries:
+        kmer_codes = np.concatenate(kcs).reshape(-1)
+        id_off = np.concatenate([[0], np.cumsum(np.concatenate(id_lens))]).astype(np.uint64)
+        read_ids = np.concatenate(ids).astype(np.int32)
+    else:
+        kmer_codes = np.zeros(0, np.uint64)
+        id_off = np.zeros(1, np.uint64)
+        read_ids = np.zeros(0, np.int32)
+    return B.HostTable(K=t0.K, M=t0.M, cutoff=t0.cutoff, kw=kw,
+                       n_instances=sum(t.n_instances for t in tables), n_distinct=sum(t.n_distinct for t in tables),
+                       mmer_codes=np.array(mmer_codes, dtype=np.uint32), mmer_kmer_off=np.array(mmer_off, dtype=np.uint64),
+                       kmer_codes=kmer_codes, kmer_id_off=id_off, read_ids=read_ids)

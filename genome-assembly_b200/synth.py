@@ -48,7 +48,9 @@ def default_genome_len(n_reads: int, read_len: int, coverage: float = 30.0) -> i
 
 
 def generate(n_reads: int, read_len: int, *, genome_len: int | None = None, error_rate: float = 0.01,
-             seed: int = 20, starts: str = "uniform", chunk: int = 1 << 18) -> ReadSet:
+             seed: int = 20, starts: str = "uniform", chunk: int = 1 << 18, read_seed: int | None = None) -> ReadSet:
+    """``seed`` fixes the genome; ``read_seed`` (default: ``seed``) fixes starts and substitutions, so that
+    several ranks can draw disjoint read shards from one shared genome."""
     if genome_len is None:
         genome_len = default_genome_len(n_reads, read_len)
     if genome_len < read_len + 2:
@@ -56,8 +58,12 @@ def generate(n_reads: int, read_len: int, *, genome_len: int | None = None, erro
     rng = np.random.Generator(np.random.Philox(seed))
     genome = _ACGT[rng.integers(0, 4, size=genome_len, dtype=np.uint8)]
     hi = genome_len - 1 - read_len  # generate_reads.py:98
+    if read_seed is not None and read_seed != seed:
+        rng = np.random.Generator(np.random.Philox(key=read_seed + (1 << 40)))
+    else:
+        read_seed = seed
     if starts == "triangular":
-        r = random.Random(seed)
+        r = random.Random(read_seed)
         mode = r.randint(0, hi)
         pos = np.empty(n_reads, dtype=np.int64)
         for i in range(n_reads):

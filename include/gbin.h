@@ -137,6 +137,17 @@ int gbin_table_to_host(gbin_ctx *ctx, const gbin_table *dev, gbin_table *host);
 
 int gbin_get_timings(const gbin_ctx *ctx, gbin_timings *out);
 
+/* Optional per-kernel-class device timing (CUDA events around each launch on the call's stream),
+ * accumulated over calls since it was enabled; what bench.py's roofline line is computed from. */
+#define GBIN_KERNEL_KINDS 8
+typedef struct gbin_kernel_profile {
+    float ms[GBIN_KERNEL_KINDS];          /* accumulated device time per kernel class */
+    uint32_t launches[GBIN_KERNEL_KINDS]; /* kernels launched per class */
+} gbin_kernel_profile;
+int gbin_set_kernel_profiling(gbin_ctx *ctx, int enable); /* also resets the accumulators */
+int gbin_get_kernel_profile(const gbin_ctx *ctx, gbin_kernel_profile *out);
+const char *gbin_kernel_kind_name(int kind); /* "" past the last kind */
+
 /* ---- staged device entry points (multi-GPU path: scan -> partition by owner -> exchange -> group) ---- */
 
 /* Bytes per k-mer instance record produced by the scan stage (16 when K <= 32, 24 otherwise).

@@ -201,24 +201,17 @@ size_t orc_scan_all(const char *data, const uint64_t *starts, const uint32_t *le
     return n;
 }
 
-/* process_read for every read, then the grouping the two-level zhash performs implicitly
- * (binning.c:1044-1069: one ll_node per instance, newest id at the head) and prune_data /
- * prune_kmers (binning.c:1085-1144: keep iff list length > ABUNDANCE_CUTOFF; drop emptied buckets). */
-int orc_run(const char *data, const uint64_t *starts, const uint32_t *lens, size_t n_reads,
-            const int32_t *ids, int K, int M, int cutoff, orc_result *out)
+/* The grouping the two-level zhash performs implicitly (binning.c:1044-1069: one ll_node per
+ * instance, newest id at the head) and prune_data / prune_kmers (binning.c:1085-1144: keep iff list
+ * length > ABUNDANCE_CUTOFF; drop emptied buckets), over tuples given in arrival order.
+ * Sorts `t` in place. ids maps arrival -> read id (NULL: id = id_base + arrival). */
+int orc_group_tuples(orc_tuple *t, size_t n, const int32_t *ids, int32_t id_base, int K, int M, int cutoff, orc_result *out)
 {
     memset(out, 0, sizeof *out);
     out->K = K;
     out->M = M;
     out->cutoff = cutoff;
     out->kw = K <= 32 ? 1 : 2;
-    size_t total = 0;
-    for (size_t r = 0; r < n_reads; r++)
-        if ((int)lens[r] >= K) total += lens[r] - K + 1;
-    orc_tuple *t = malloc((total ? total : 1) * sizeof *t);
-    if (!t) return -1;
-    size_t n = orc_scan_all(data, starts, lens, n_reads, K, M, t, NULL);
-    if (n != total) { free(t); return -2; }
     qsort(t, n, sizeof *t, tuple_cmp);
 
     /* pass 1: count */
@@ -262,7 +255,7 @@ int orc_run(const char *data, const uint64_t *starts, const uint32_t *lens, size
             out->kmer_id_off[s] = idp;
             for (size_t q = j; q-- > i;) { /* newest (latest arrival) first */
                 uint32_t a = t[q].arrival;
-                out->read_ids[idp++] = ids ? ids[a] : (int32_t)a;
+                out->read_ids[idp++] = ids ? ids[a] : id_base + (int32_t)a;
             }
             s++;
         }
@@ -271,8 +264,23 @@ int orc_run(const char *data, const uint64_t *starts, const uint32_t *lens, size
     out->kmer_id_off[s] = idp;
     out->mmer_kmer_off[B] = s;
     out->n_buckets = B;
-    free(t);
     return 0;
+}
+
+/* process_read for every read, then grouping + prune. */
+int orc_run(const char *data, const uint64_t *starts, const uint32_t *lens, size_t n_reads,
+            const int32_t *ids, int K, int M, int cutoff, orc_result *out)
+{
+    size_t total = 0;
+    for (size_t r = 0; r < n_reads; r++)
+        if ((int)lens[r] >= K) total += lens[r] - K + 1;
+    orc_tuple *t = malloc((total ? total : 1) * sizeof *t);
+    if (!t) return -1;
+    size_t n = orc_scan_all(data, starts, lens, n_reads, K, M, t, NULL);
+    if (n != total) { free(t); return -2; }
+    int rc = orc_group_tuples(t, n, ids, 0, K, M, cutoff, out);
+    free(t);
+    return rc;
 }
 
 void orc_result_free(orc_result *r)

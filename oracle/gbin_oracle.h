@@ -79,6 +79,9 @@ typedef struct orc_result {
 int orc_run(const char *data, const uint64_t *starts, const uint32_t *lens, size_t n_reads,
             const int32_t *ids, int K, int M, int cutoff, orc_result *out);
 void orc_result_free(orc_result *r);
+/* Grouping + prune over externally supplied tuples in arrival order (sorted in place); used by the
+ * multi-rank host-logic tests where each rank groups the tuples it received. */
+int orc_group_tuples(orc_tuple *t, size_t n, const int32_t *ids, int32_t id_base, int K, int M, int cutoff, orc_result *out);
 
 /* Emits all tuples of all reads in arrival order (pre-sort), for scan-kernel parity.
  * tuples must hold sum(max(0,len-K+1)) entries. Returns the count. */

@@ -57,6 +57,8 @@ def lib():
                               C.POINTER(OrcResult)]
         L.orc_run.restype = C.c_int
         L.orc_result_free.argtypes = [C.POINTER(OrcResult)]
+        L.orc_group_tuples.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int32, C.c_int, C.c_int, C.c_int, C.POINTER(OrcResult)]
+        L.orc_group_tuples.restype = C.c_int
         L.orc_scan_all.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_scan_all.restype = C.c_size_t
         L.orc_dump_strings.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_int,
@@ -139,17 +141,7 @@ class Table:
         return hashlib.md5(b"".join(x + b"\n" for x in sorted(self.dump_lines()))).hexdigest()
 
 
-def run(data: bytes, starts, lens, K, M, cutoff, ids=None) -> Table:
-    L = lib()
-    starts = np.ascontiguousarray(starts, dtype=np.uint64)
-    lens = np.ascontiguousarray(lens, dtype=np.uint32)
-    idp = None
-    if ids is not None:
-        ids = np.ascontiguousarray(ids, dtype=np.int32)
-        idp = ids.ctypes.data
-    r = OrcResult()
-    rc = L.orc_run(data, starts.ctypes.data, lens.ctypes.data, len(starts), idp, K, M, cutoff, C.byref(r))
-    assert rc == 0, rc
+def _table_from_result(L, r, K, M, cutoff) -> "Table":
     kw = r.kw
 
     def arr(p, n, dt):
@@ -163,6 +155,30 @@ def run(data: bytes, starts, lens, K, M, cutoff, ids=None) -> Table:
               arr(r.read_ids, r.n_ids, np.int32))
     L.orc_result_free(C.byref(r))
     return t
+
+
+def group_tuples(tuples: np.ndarray, K, M, cutoff, id_base=0) -> "Table":
+    """Grouping + prune of tuples given in arrival order (the owner-side work of the multi-rank path)."""
+    L = lib()
+    t = np.ascontiguousarray(tuples, dtype=TUPLE_DT).copy()
+    r = OrcResult()
+    rc = L.orc_group_tuples(t.ctypes.data, len(t), None, id_base, K, M, cutoff, C.byref(r))
+    assert rc == 0
+    return _table_from_result(L, r, K, M, cutoff)
+
+
+def run(data: bytes, starts, lens, K, M, cutoff, ids=None) -> Table:
+    L = lib()
+    starts = np.ascontiguousarray(starts, dtype=np.uint64)
+    lens = np.ascontiguousarray(lens, dtype=np.uint32)
+    idp = None
+    if ids is not None:
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        idp = ids.ctypes.data
+    r = OrcResult()
+    rc = L.orc_run(data, starts.ctypes.data, lens.ctypes.data, len(starts), idp, K, M, cutoff, C.byref(r))
+    assert rc == 0, rc
+    return _table_from_result(L, r, K, M, cutoff)
 
 
 def scan_all(data: bytes, starts, lens, K, M):

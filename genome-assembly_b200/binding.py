@@ -184,6 +184,17 @@ def host_table_from_c(t: CTable) -> HostTable:
                      read_ids=_np_from(t.read_ids, t.n_ids, np.int32))
 
 
+CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy: explicit handle of the legacy default stream
+
+
+def stream_handle(torch_stream) -> int:
+    """cudaStream_t to hand to the C ABI for a torch stream.  torch's default stream has handle 0, which
+    the C ABI reads as "use the context's own stream"; map it to cudaStreamLegacy so that work is
+    ordered with whatever torch enqueued on its default stream."""
+    h = int(torch_stream.cuda_stream)
+    return h if h else CUDA_STREAM_LEGACY
+
+
 def _ptr(x):
     """Raw address of a numpy array / torch tensor / int / None."""
     if x is None:

@@ -45,7 +45,7 @@ class GpuStages:
         self.launches += self.b.timings()["kernel_launches"]
 
     def stream(self):
-        return torch.cuda.current_stream(self.device).cuda_stream
+        return B.stream_handle(torch.cuda.current_stream(self.device))
 
     def alloc_records(self, n: int) -> torch.Tensor:
         return torch.empty(max(n, 1) * self.record_bytes, dtype=torch.uint8, device=self.device)

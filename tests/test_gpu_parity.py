@@ -106,7 +106,7 @@ def test_device_path_and_staged_path_agree_with_host_path():
     want = O.run(data, starts, lens, K, M, cut)
     b = B.Binner(K, M, cut)
     rd, keep = dev_reads(torch, data, starts, lens)
-    dev = b.bin_device_raw(rd, torch.cuda.current_stream().cuda_stream)
+    dev = b.bin_device_raw(rd, B.stream_handle(torch.cuda.current_stream()))
     assert dev.on_device == 1
     assert_tables_equal(b.table_to_host(dev), want)
     # staged: scan -> group

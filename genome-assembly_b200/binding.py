@@ -56,7 +56,7 @@ class Timings(C.Structure):
 
 
 class KernelProfile(C.Structure):
-    _fields_ = [("ms", C.c_float * 8), ("launches", C.c_uint32 * 8)]
+    _fields_ = [("ms", C.c_float * 12), ("launches", C.c_uint32 * 12)]
 
 
 # every symbol include/gbin.h declares (tests check that the library exports all of them)
@@ -64,9 +64,10 @@ EXPORTS = [
     "gbin_strerror", "gbin_last_error", "gbin_version", "gbin_create", "gbin_destroy", "gbin_get_config",
     "gbin_bin_reads_host", "gbin_table_clone", "gbin_table_free", "gbin_pinned_alloc", "gbin_pinned_free",
     "gbin_bin_reads_device", "gbin_table_to_host", "gbin_get_timings", "gbin_record_bytes",
-    "gbin_set_kernel_profiling", "gbin_get_kernel_profile", "gbin_kernel_kind_name",
+    "gbin_set_kernel_profiling", "gbin_get_kernel_profile", "gbin_kernel_kind_name", "gbin_set_pipeline", "gbin_get_pipeline_info",
     "gbin_count_instances_device", "gbin_scan_reads_device", "gbin_partition_records_device",
-    "gbin_group_records_device", "gbin_read_file_fgets", "gbin_table_dump", "gbin_table_dump_reference_format",
+    "gbin_group_records_device", "gbin_skr_record_bytes", "gbin_scan_skr_device", "gbin_partition_skr_device", "gbin_group_skr_device",
+    "gbin_read_file_fgets", "gbin_table_dump", "gbin_table_dump_reference_format",
     "getval", "getbp", "getscore", "process_read", "prune_data", "gbin_ref_configure", "gbin_ref_last_status",
     "gbin_ref_reset", "gbin_table_to_zhash", "gbin_zhash_release",
 ]
@@ -103,6 +104,8 @@ def load_library() -> C.CDLL:
     L.gbin_pinned_free.argtypes = [vp]
     L.gbin_pinned_free.restype = None
     L.gbin_get_timings.argtypes = [vp, C.POINTER(Timings)]
+    L.gbin_set_pipeline.argtypes = [vp, C.c_int]
+    L.gbin_get_pipeline_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint32)]
     L.gbin_set_kernel_profiling.argtypes = [vp, C.c_int]
     L.gbin_get_kernel_profile.argtypes = [vp, C.POINTER(KernelProfile)]
     L.gbin_kernel_kind_name.argtypes = [C.c_int]
@@ -113,6 +116,11 @@ def load_library() -> C.CDLL:
     L.gbin_scan_reads_device.argtypes = [vp, C.POINTER(CReads), u32, vp, u64, vp, C.POINTER(u64)]
     L.gbin_partition_records_device.argtypes = [vp, vp, u64, u32, vp, vp, C.POINTER(u64)]
     L.gbin_group_records_device.argtypes = [vp, vp, u64, vp, i32, vp, C.POINTER(CTable)]
+    L.gbin_skr_record_bytes.argtypes = [vp]
+    L.gbin_skr_record_bytes.restype = u32
+    L.gbin_scan_skr_device.argtypes = [vp, C.POINTER(CReads), u32, vp, u64, vp, C.POINTER(u64), C.POINTER(u64)]
+    L.gbin_partition_skr_device.argtypes = [vp, vp, u64, u32, vp, vp, C.POINTER(u64)]
+    L.gbin_group_skr_device.argtypes = [vp, vp, u64, vp, i32, vp, C.POINTER(CTable), C.POINTER(C.c_int)]
     L.gbin_read_file_fgets.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(vp),
                                        C.POINTER(u64)]
     L.gbin_table_dump.argtypes = [C.POINTER(CTable), C.c_char_p]
@@ -211,7 +219,7 @@ def _ptr(x):
 class Binner:
     """One context per GPU (gbin_ctx): K, M and the cutoff are the runtime form of binning.c:10-12."""
 
-    def __init__(self, k: int = 31, m: int = 4, cutoff: int = 1, device: int = 0):
+    def __init__(self, k: int = 31, m: int = 4, cutoff: int = 1, device: int = 0, pipeline: int | None = None):
         self.lib = load_library()
         self.cfg = Config(k, m, cutoff, device)
         h = C.c_void_p()
@@ -220,6 +228,8 @@ class Binner:
             raise GbinError(rc, self.lib.gbin_strerror(rc).decode())
         self.h = h
         self.k, self.m, self.cutoff, self.device = k, m, cutoff, device
+        if pipeline is not None:
+            self.set_pipeline(pipeline)
 
     def close(self):
         if getattr(self, "h", None):
@@ -245,6 +255,14 @@ class Binner:
         self.lib.gbin_get_timings(self.h, C.byref(t))
         return t.as_dict()
 
+    def set_pipeline(self, pipeline: int):
+        self._check(self.lib.gbin_set_pipeline(self.h, pipeline))
+
+    def pipeline_info(self) -> dict:
+        a, b, c = C.c_int(), C.c_int(), C.c_uint32()
+        self._check(self.lib.gbin_get_pipeline_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"configured": a.value, "last_used": b.value, "fallbacks": c.value}
+
     def set_kernel_profiling(self, enable: bool):
         self._check(self.lib.gbin_set_kernel_profiling(self.h, int(enable)))
 
@@ -253,7 +271,7 @@ class Binner:
         p = KernelProfile()
         self._check(self.lib.gbin_get_kernel_profile(self.h, C.byref(p)))
         out = {}
-        for i in range(8):
+        for i in range(12):
             name = self.lib.gbin_kernel_kind_name(i).decode()
             if name:
                 out[name] = {"ms": float(p.ms[i]), "launches": int(p.launches[i])}
@@ -315,6 +333,28 @@ class Binner:
         counts = (C.c_uint64 * n_parts)()
         self._check(self.lib.gbin_partition_records_device(self.h, _ptr(d_records), n, n_parts, _ptr(d_out), stream, counts))
         return [int(c) for c in counts]
+
+    # ---- staged entry points, super-k-mer form
+    @property
+    def skr_record_bytes(self) -> int:
+        return int(self.lib.gbin_skr_record_bytes(self.h))
+
+    def scan_skr_device(self, reads: CReads, arrival_base: int, d_skr, capacity: int, stream=None):
+        """-> (n_records, n_instances)"""
+        n, ni = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.gbin_scan_skr_device(self.h, C.byref(reads), arrival_base, _ptr(d_skr), capacity, stream, C.byref(n), C.byref(ni)))
+        return int(n.value), int(ni.value)
+
+    def partition_skr_device(self, d_skr, n: int, n_parts: int, d_out, stream=None) -> list[int]:
+        counts = (C.c_uint64 * n_parts)()
+        self._check(self.lib.gbin_partition_skr_device(self.h, _ptr(d_skr), n, n_parts, _ptr(d_out), stream, counts))
+        return [int(c) for c in counts]
+
+    def group_skr_device(self, d_skr, n_skr: int, d_ids_by_arrival=None, id_base: int = 0, stream=None) -> CTable:
+        t = CTable()
+        fb = C.c_int()
+        self._check(self.lib.gbin_group_skr_device(self.h, _ptr(d_skr), n_skr, _ptr(d_ids_by_arrival), id_base, stream, C.byref(t), C.byref(fb)))
+        return t
 
     def group_device(self, d_records, n: int, d_ids_by_arrival=None, id_base: int = 0, stream=None) -> CTable:
         t = CTable()

@@ -70,6 +70,10 @@ struct Misc {  // small device-resident scalars
     unsigned int max_len;
     unsigned int pad;
     uint64_t part_counts[256];
+    // pipeline v2
+    unsigned long long skr_counters[4];  // [0] bad bases, [1] records, [2] instances
+    SkrGroupCounters gc;
+    uint32_t skr_ticket, n_inst_dev, n_runs_dev, n_buckets_dev;
 };
 
 }  // namespace
@@ -88,6 +92,11 @@ struct gbin_ctx {
     DevBuf rec_a, rec_b, radix_scratch, win_counts, rec_off, scan_scratch;
     DevBuf group_of, run_start, surv_index, id_offset, surv_group, bucket_of;
     DevBuf misc;
+    // pipeline v2 workspace
+    DevBuf skr_a, skr_b, tile_state, inst_prefix, run_excl, skr_run_start, small_prefix, unit_base, units, unit_state, o_kmer_mmer, bucket_excl;
+    int pipeline;        // 2: super-k-mer path with v1 as fallback (default); 1: v1 only
+    int last_pipeline;   // which one produced the last table
+    uint32_t fallbacks;  // v2 -> v1 fallbacks since creation
     // device-resident result
     DevBuf o_mmer_codes, o_mmer_kmer_off, o_kmer_codes, o_kmer_id_off, o_read_ids;
     // pinned host arena for results of the host path + small readbacks
@@ -290,6 +299,163 @@ int run_group(gbin_ctx *ctx, void *recs, void *twin, uint64_t n, const int32_t *
     return GBIN_OK;
 }
 
+// ---- pipeline v2: super-k-mer records -> stable sort by m-mer -> grouping in shared memory
+
+// Scan stage: one record per signature segment, in arrival order, into ctx->skr_a (own == true) or into the
+// caller's buffer `ext` of `ext_cap` records.  *n_skr receives the record count.
+int run_v2_scan(gbin_ctx *ctx, const gbin_reads *rd, uint64_t n, uint32_t max_len, uint32_t arrival_base, void *ext, uint64_t ext_cap,
+                cudaStream_t st, uint64_t *n_skr_out, int *launches) {
+    const int K = ctx->cfg.kmer_size, M = ctx->cfg.mmer_size;
+    const int NW = K <= 32 ? 8 : 12;
+    Misc *dm = ctx->misc.as<Misc>();
+    Misc *hm = static_cast<Misc *>(ctx->h_misc.p);
+    ReadsView rv{reinterpret_cast<const uint8_t *>(rd->data), rd->data_bytes, rd->n_reads, rd->stride, rd->read_len, rd->starts, rd->lens};
+    uint64_t cap = ext ? ext_cap : n / 4 + rd->n_reads + 1024;
+    if (!ext && cap > n) cap = n;
+    uint64_t n_skr = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (!ext) CU(ctx->skr_a.ensure((cap + 1) * NW * 4));
+        CU(ctx->tile_state.ensure((size_t)skr_scan_tiles(rd->n_reads, K, max_len) * 8 + 8));
+        CU(cudaMemsetAsync(dm->skr_counters, 0, sizeof dm->skr_counters, st));
+        const bool on = ctx->prof.begin(KK_SKR_SCAN, st);
+        const int ls = launch_skr_scan(rv, K, M, arrival_base, max_len, ext ? ext : ctx->skr_a.p, cap, ctx->tile_state.as<unsigned long long>(),
+                                       &dm->skr_ticket, dm->skr_counters, ctx->sm_count, st);
+        ctx->prof.end(on, ls, st);
+        *launches += ls;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(hm->skr_counters, dm->skr_counters, sizeof dm->skr_counters, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (hm->skr_counters[0]) return fail(ctx, GBIN_E_NON_ACGT, "%llu bases other than A/C/G/T in the batch", hm->skr_counters[0]);
+        n_skr = hm->skr_counters[1];
+        if (hm->skr_counters[2] != n)
+            return fail(ctx, GBIN_E_CUDA, "internal: scan produced %llu instances, expected %llu", hm->skr_counters[2], (unsigned long long)n);
+        if (n_skr <= cap) break;
+        if (ext) return fail(ctx, GBIN_E_INVALID_ARG, "super-k-mer buffer too small: need %llu records", (unsigned long long)n_skr);
+        cap = n_skr;  // more segments than estimated: the kernel only counted; run it again with room for all
+    }
+    *n_skr_out = n_skr;
+    return GBIN_OK;
+}
+
+// Sort + plan + group + emit over n_skr records in `skr` (clobbered; `twin` is the sort's second buffer).
+// *done = false when a unit overflowed and the batch must go through pipeline v1.
+int run_v2_group(gbin_ctx *ctx, void *skr, void *twin, uint64_t n_skr, const int32_t *d_ids, int32_t id_base, cudaStream_t st, gbin_table *out,
+                 int *launches, bool *done, uint64_t *n_inst_out) {
+    *done = false;
+    const int K = ctx->cfg.kmer_size, M = ctx->cfg.mmer_size, cutoff = ctx->cfg.abundance_cutoff, KW = ctx->KW;
+    const int NW = K <= 32 ? 8 : 12;
+    Misc *dm = ctx->misc.as<Misc>();
+    Misc *hm = static_cast<Misc *>(ctx->h_misc.p);
+
+    // ---- level 1: stable sort of the records by m-mer code
+    CU(ctx->radix_scratch.ensure(radix_scratch_bytes(n_skr)));
+    bool in_b = false;
+    int passes = 0;
+    *launches += radix_sort_skr_by_mmer(skr, twin, n_skr, NW, M, ctx->radix_scratch.p, &in_b, &passes, &ctx->prof, st);
+    CU(cudaGetLastError());
+    ctx->tm.sort_passes = (uint32_t)passes;
+    const void *sorted = in_b ? twin : skr;
+    CU(cudaEventRecord(ctx->ev[3], st));
+
+    // ---- plan: instance prefix, m-mer runs, units
+    CU(ctx->inst_prefix.ensure((n_skr + 2) * 4));
+    CU(ctx->run_excl.ensure((n_skr + 2) * 4));
+    CU(ctx->skr_run_start.ensure((n_skr + 2) * 4));
+    CU(ctx->scan_scratch.ensure(group_scan_scratch_bytes(n_skr)));
+    bool on = ctx->prof.begin(KK_SKR_PLAN, st);
+    int lp = skr_plan_runs(sorted, n_skr, NW, ctx->inst_prefix.as<uint32_t>(), ctx->run_excl.as<uint32_t>(), ctx->skr_run_start.as<uint32_t>(),
+                           ctx->scan_scratch.as<uint32_t>(), &dm->n_inst_dev, &dm->n_runs_dev, st);
+    ctx->prof.end(on, lp, st);
+    *launches += lp;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&hm->n_inst_dev, &dm->n_inst_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const uint64_t n_runs = hm->n_runs_dev, n = hm->n_inst_dev;
+    *n_inst_out = n;
+    const uint64_t max_units = skr_max_units(n, n_runs);
+    CU(ctx->small_prefix.ensure((n_runs + 1) * 4));
+    CU(ctx->unit_base.ensure((n_runs + 1) * 4));
+    CU(ctx->units.ensure(max_units * skr_unit_bytes()));
+    CU(ctx->unit_state.ensure(max_units * 8));
+    CU(ctx->scan_scratch.ensure(group_scan_scratch_bytes(n / 2 + n_runs + 1024)));
+    on = ctx->prof.begin(KK_SKR_PLAN, st);
+    lp = skr_plan_units(sorted, K, ctx->inst_prefix.as<uint32_t>(), ctx->skr_run_start.as<uint32_t>(), n_runs, ctx->small_prefix.as<uint32_t>(),
+                        ctx->unit_base.as<uint32_t>(), ctx->scan_scratch.as<uint32_t>(), ctx->units.p, max_units, &dm->gc, ctx->sm_count, st);
+    ctx->prof.end(on, lp, st);
+    *launches += lp;
+    CU(cudaGetLastError());
+
+    // ---- level 2 + prune + emit. Output bounds: a surviving k-mer has more than `cutoff` instances.
+    const uint64_t kmer_cap = cutoff >= 0 ? n / ((uint64_t)cutoff + 1) + 1 : n + 1;
+    CU(ctx->o_kmer_codes.ensure((kmer_cap * KW + 1) * sizeof(uint64_t)));
+    CU(ctx->o_kmer_mmer.ensure((kmer_cap + 1) * sizeof(uint32_t)));
+    CU(ctx->o_kmer_id_off.ensure((kmer_cap + 2) * sizeof(uint64_t)));
+    CU(ctx->o_read_ids.ensure((n + 1) * sizeof(int32_t)));
+    on = ctx->prof.begin(KK_SKR_GROUP, st);
+    lp = skr_group_launch(sorted, K, cutoff, ctx->inst_prefix.as<uint32_t>(), ctx->units.p, ctx->unit_state.as<unsigned long long>(), max_units,
+                          &dm->gc, d_ids, id_base, ctx->o_kmer_codes.as<uint64_t>(), ctx->o_kmer_mmer.as<uint32_t>(),
+                          ctx->o_kmer_id_off.as<uint64_t>(), ctx->o_read_ids.as<int32_t>(), kmer_cap, n, ctx->sm_count, st);
+    ctx->prof.end(on, lp, st);
+    *launches += lp;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&hm->gc, &dm->gc, sizeof(SkrGroupCounters), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (hm->gc.overflow) {  // a unit did not fit shared memory: this batch goes through pipeline v1
+        ctx->fallbacks++;
+        return GBIN_OK;
+    }
+    const uint64_t S = hm->gc.total_kmers, NS = hm->gc.total_ids;
+
+    // ---- bucket directory
+    CU(ctx->bucket_excl.ensure((S + 1) * 4));
+    CU(ctx->o_mmer_codes.ensure((S + 1) * sizeof(uint32_t)));
+    CU(ctx->o_mmer_kmer_off.ensure((S + 2) * sizeof(uint64_t)));
+    on = ctx->prof.begin(KK_EMIT, st);
+    lp = skr_emit_buckets(ctx->o_kmer_mmer.as<uint32_t>(), S, NS, ctx->bucket_excl.as<uint32_t>(), ctx->scan_scratch.as<uint32_t>(),
+                          ctx->o_mmer_codes.as<uint32_t>(), ctx->o_mmer_kmer_off.as<uint64_t>(), ctx->o_kmer_id_off.as<uint64_t>(),
+                          &dm->n_buckets_dev, st);
+    ctx->prof.end(on, lp, st);
+    *launches += lp;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&hm->n_buckets_dev, &dm->n_buckets_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+
+    memset(out, 0, sizeof *out);
+    out->kmer_size = K;
+    out->mmer_size = M;
+    out->abundance_cutoff = cutoff;
+    out->kmer_words = KW;
+    out->on_device = 1;
+    out->ctx_owned = 1;
+    out->n_instances = n;
+    out->n_distinct = hm->gc.distinct;
+    out->n_kmers = S;
+    out->n_ids = NS;
+    out->n_buckets = hm->n_buckets_dev;
+    out->mmer_codes = ctx->o_mmer_codes.as<uint32_t>();
+    out->mmer_kmer_off = ctx->o_mmer_kmer_off.as<uint64_t>();
+    out->kmer_codes = ctx->o_kmer_codes.as<uint64_t>();
+    out->kmer_id_off = ctx->o_kmer_id_off.as<uint64_t>();
+    out->read_ids = ctx->o_read_ids.as<int32_t>();
+    *done = true;
+    return GBIN_OK;
+}
+
+int run_v2(gbin_ctx *ctx, const gbin_reads *rd, uint64_t n, uint32_t max_len, cudaStream_t st, gbin_table *out, int *launches, bool *done) {
+    *done = false;
+    if (n == 0 || n >= (1ull << 31)) return GBIN_OK;
+    const int NW = ctx->cfg.kmer_size <= 32 ? 8 : 12;
+    uint64_t n_skr = 0, n_chk = 0;
+    int rc = run_v2_scan(ctx, rd, n, max_len, 0, nullptr, 0, st, &n_skr, launches);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[2], st));
+    CU(ctx->skr_b.ensure((n_skr + 1) * NW * 4));
+    rc = run_v2_group(ctx, ctx->skr_a.p, ctx->skr_b.p, n_skr, rd->read_ids, rd->id_base, st, out, launches, done, &n_chk);
+    if (rc) return rc;
+    if (n_chk != n) return fail(ctx, GBIN_E_CUDA, "internal: record windows sum to %llu, expected %llu", (unsigned long long)n_chk, (unsigned long long)n);
+    return GBIN_OK;
+}
+
 int bin_device_impl(gbin_ctx *ctx, const gbin_reads *rd, cudaStream_t st, gbin_table *out, int *launches) {
     uint64_t n = 0;
     uint32_t max_len = 0;
@@ -297,6 +463,17 @@ int bin_device_impl(gbin_ctx *ctx, const gbin_reads *rd, cudaStream_t st, gbin_t
     if (rc) return rc;
     if (max_len > GBIN_MAX_READ_LEN) return fail(ctx, GBIN_E_TOO_LARGE, "read length %u exceeds GBIN_MAX_READ_LEN", max_len);
     if (n >= (1ull << 32) - 8192) return fail(ctx, GBIN_E_TOO_LARGE, "%llu k-mer instances in one batch (limit 2^32)", (unsigned long long)n);
+    if (ctx->pipeline == 2) {
+        bool done = false;
+        rc = run_v2(ctx, rd, n, max_len, st, out, launches, &done);
+        if (rc) return rc;
+        if (done) {
+            ctx->last_pipeline = 2;
+            CU(cudaEventRecord(ctx->ev[4], st));
+            return GBIN_OK;
+        }
+    }
+    ctx->last_pipeline = 1;
     const size_t rb = sizeof(uint64_t) * ctx->KW + 8;
     CU(ctx->rec_a.ensure((n + 1) * rb));
     CU(ctx->rec_b.ensure((n + 1) * rb));
@@ -347,6 +524,10 @@ int gbin_create(const gbin_config *cfg, gbin_ctx **out) {
     ctx->cfg = *cfg;
     ctx->KW = cfg->kmer_size <= 32 ? 1 : 2;
     ctx->err[0] = 0;
+    ctx->pipeline = 2;
+    if (const char *e = getenv("GBIN_PIPELINE")) ctx->pipeline = atoi(e) == 1 ? 1 : 2;
+    ctx->last_pipeline = 0;
+    ctx->fallbacks = 0;
     memset(&ctx->tm, 0, sizeof ctx->tm);
     ctx->prof.reset();
     cudaError_t e = cudaSetDevice(cfg->device);
@@ -371,7 +552,9 @@ void gbin_destroy(gbin_ctx *ctx) {
     DevBuf *bufs[] = {&ctx->d_reads, &ctx->d_starts, &ctx->d_lens, &ctx->d_ids, &ctx->rec_a, &ctx->rec_b, &ctx->radix_scratch,
                       &ctx->win_counts, &ctx->rec_off, &ctx->scan_scratch, &ctx->group_of, &ctx->run_start, &ctx->surv_index,
                       &ctx->id_offset, &ctx->surv_group, &ctx->bucket_of, &ctx->misc, &ctx->o_mmer_codes, &ctx->o_mmer_kmer_off,
-                      &ctx->o_kmer_codes, &ctx->o_kmer_id_off, &ctx->o_read_ids};
+                      &ctx->o_kmer_codes, &ctx->o_kmer_id_off, &ctx->o_read_ids, &ctx->skr_a, &ctx->skr_b, &ctx->tile_state,
+                      &ctx->inst_prefix, &ctx->run_excl, &ctx->skr_run_start, &ctx->small_prefix, &ctx->unit_base, &ctx->units,
+                      &ctx->unit_state, &ctx->o_kmer_mmer, &ctx->bucket_excl};
     for (DevBuf *b : bufs) b->release();
     ctx->h_misc.release();
     ctx->h_result.release();
@@ -426,6 +609,20 @@ static void finish_timings(gbin_ctx *ctx, int launches, bool host_path) {
     ctx->prof.collect();
 }
 
+int gbin_set_pipeline(gbin_ctx *ctx, int pipeline) {
+    if (!ctx || (pipeline != 1 && pipeline != 2)) return GBIN_E_INVALID_ARG;
+    ctx->pipeline = pipeline;
+    return GBIN_OK;
+}
+
+int gbin_get_pipeline_info(const gbin_ctx *ctx, int *configured, int *last_used, uint32_t *fallbacks) {
+    if (!ctx) return GBIN_E_INVALID_ARG;
+    if (configured) *configured = ctx->pipeline;
+    if (last_used) *last_used = ctx->last_pipeline;
+    if (fallbacks) *fallbacks = ctx->fallbacks;
+    return GBIN_OK;
+}
+
 int gbin_set_kernel_profiling(gbin_ctx *ctx, int enable) {
     if (!ctx) return GBIN_E_INVALID_ARG;
     ctx->prof.enabled = enable != 0;
@@ -443,7 +640,8 @@ int gbin_get_kernel_profile(const gbin_ctx *ctx, gbin_kernel_profile *out) {
 }
 
 const char *gbin_kernel_kind_name(int kind) {
-    static const char *names[] = {"scan_reads", "radix_hist", "radix_tile_scan", "radix_scatter", "find_runs", "prune_offsets", "emit_table"};
+    static const char *names[] = {"scan_reads", "radix_hist", "radix_tile_scan", "radix_scatter", "find_runs", "prune_offsets", "emit_table",
+                                  "skr_scan", "skr_plan", "skr_group"};
     return (kind >= 0 && kind < KK_COUNT) ? names[kind] : "";
 }
 
@@ -608,6 +806,86 @@ int gbin_partition_records_device(gbin_ctx *ctx, const void *d_records, uint64_t
     CU(cudaStreamSynchronize(st));
     memcpy(counts_host, hm->part_counts, sizeof(uint64_t) * n_parts);
     ctx->tm.kernel_launches = (uint32_t)launches;
+    return GBIN_OK;
+}
+
+uint32_t gbin_skr_record_bytes(const gbin_ctx *ctx) { return ctx ? (ctx->cfg.kmer_size <= 32 ? 32u : 48u) : 0u; }
+
+int gbin_scan_skr_device(gbin_ctx *ctx, const gbin_reads *reads, uint32_t arrival_base, void *d_skr, uint64_t capacity, void *stream,
+                         uint64_t *n_skr_out, uint64_t *n_instances_out) {
+    if (!ctx || !reads || !n_skr_out) return GBIN_E_INVALID_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    uint64_t n = 0, n_skr = 0;
+    uint32_t max_len = 0;
+    int launches = 0;
+    int rc = plan_reads(ctx, reads, st, &n, &max_len, &launches);
+    if (rc) return rc;
+    if (max_len > GBIN_MAX_READ_LEN) return fail(ctx, GBIN_E_TOO_LARGE, "read length %u exceeds GBIN_MAX_READ_LEN", max_len);
+    if (n && !d_skr) return GBIN_E_INVALID_ARG;
+    if (n) {
+        rc = run_v2_scan(ctx, reads, n, max_len, arrival_base, d_skr, capacity, st, &n_skr, &launches);
+        if (rc) return rc;
+    }
+    ctx->prof.collect();
+    *n_skr_out = n_skr;
+    if (n_instances_out) *n_instances_out = n;
+    ctx->tm.kernel_launches = (uint32_t)launches;
+    return GBIN_OK;
+}
+
+int gbin_partition_skr_device(gbin_ctx *ctx, const void *d_skr, uint64_t n, uint32_t n_parts, void *d_out, void *stream, uint64_t *counts_host) {
+    if (!ctx || !counts_host || n_parts == 0 || n_parts > 256) return GBIN_E_INVALID_ARG;
+    if (n >= (1ull << 32) - 8192) return fail(ctx, GBIN_E_TOO_LARGE, "too many records in one partition call");
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    Misc *dm = ctx->misc.as<Misc>();
+    Misc *hm = static_cast<Misc *>(ctx->h_misc.p);
+    CU(ctx->radix_scratch.ensure(radix_scratch_bytes(n)));
+    int launches = radix_partition_skr_by_owner(d_skr, d_out, n, ctx->cfg.kmer_size <= 32 ? 8 : 12, n_parts, ctx->radix_scratch.p, dm->part_counts, st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(hm->part_counts, dm->part_counts, sizeof(uint64_t) * n_parts, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(counts_host, hm->part_counts, sizeof(uint64_t) * n_parts);
+    ctx->tm.kernel_launches = (uint32_t)launches;
+    return GBIN_OK;
+}
+
+int gbin_group_skr_device(gbin_ctx *ctx, void *d_skr, uint64_t n_skr, const int32_t *d_ids_by_arrival, int32_t id_base, void *stream,
+                          gbin_table *out, int *used_fallback) {
+    if (!ctx || !out || (n_skr && !d_skr)) return GBIN_E_INVALID_ARG;
+    if (n_skr >= (1ull << 31)) return fail(ctx, GBIN_E_TOO_LARGE, "too many super-k-mer records in one call");
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    const int NW = ctx->cfg.kmer_size <= 32 ? 8 : 12;
+    int launches = 0;
+    if (used_fallback) *used_fallback = 0;
+    CU(cudaEventRecord(ctx->ev[0], st));
+    CU(cudaEventRecord(ctx->ev[1], st));
+    CU(cudaEventRecord(ctx->ev[2], st));
+    bool done = false;
+    uint64_t n = 0;
+    if (n_skr) {
+        CU(ctx->skr_b.ensure((n_skr + 1) * NW * 4));
+        int rc = run_v2_group(ctx, d_skr, ctx->skr_b.p, n_skr, d_ids_by_arrival, id_base, st, out, &launches, &done, &n);
+        if (rc) return rc;
+        if (!done) {
+            // overflow: expand the (sorted or unsorted, either is fine: expansion keeps per-record order and the v1 sort is
+            // stable on arrival only within equal keys, which requires arrival order) — records must be re-sorted by
+            // arrival first; simplest correct route: report it and let the caller re-run through the instance-record path.
+            if (used_fallback) *used_fallback = 1;
+            return fail(ctx, GBIN_E_STATE, "a shared-memory unit overflowed; re-run this batch through gbin_group_records_device");
+        }
+    } else {
+        Misc *dm = ctx->misc.as<Misc>();
+        CU(cudaMemsetAsync(&dm->bad_bases, 0, sizeof(unsigned long long), st));
+        int rc = run_group(ctx, nullptr, nullptr, 0, d_ids_by_arrival, id_base, st, out, &launches, ctx->ev[3]);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(ctx->ev[4], st));
+    CU(cudaStreamSynchronize(st));
+    finish_timings(ctx, launches, false);
+    ctx->last_pipeline = 2;
     return GBIN_OK;
 }
 

@@ -10,7 +10,7 @@ namespace gbin {
 
 // Per-kernel-class device timing (CUDA events on the launching stream), for the roofline numbers
 // bench.py reports.  Disabled by default; when disabled begin/end cost one branch.
-enum KernelKind { KK_SCAN = 0, KK_RADIX_HIST, KK_RADIX_TILESCAN, KK_RADIX_SCATTER, KK_RUNS, KK_PRUNE, KK_EMIT, KK_COUNT };
+enum KernelKind { KK_SCAN = 0, KK_RADIX_HIST, KK_RADIX_TILESCAN, KK_RADIX_SCATTER, KK_RUNS, KK_PRUNE, KK_EMIT, KK_SKR_SCAN, KK_SKR_PLAN, KK_SKR_GROUP, KK_COUNT };
 struct KernelProf {
     static constexpr int MAX_REGIONS = 256;
     bool enabled = false;
@@ -69,6 +69,38 @@ int radix_sort_records(void *a, void *b, uint64_t n, int KW, int K, int M, void 
 // Stable partition by owner = mmer % n_parts: in -> out, part sizes to d_counts[n_parts] (device, u64).
 int radix_partition_by_owner(const void *in, void *out, uint64_t n, int KW, uint32_t n_parts, void *scratch, uint64_t *d_counts,
                              cudaStream_t st);
+
+// v2: super-k-mer records (skr.cuh), sorted / partitioned on their m-mer code (word 1).
+int radix_sort_skr_by_mmer(void *a, void *b, uint64_t n, int skr_words, int M, void *scratch, bool *result_in_b, int *passes_out,
+                           KernelProf *prof, cudaStream_t st);
+int radix_partition_skr_by_owner(const void *in, void *out, uint64_t n, int skr_words, uint32_t n_parts, void *scratch, uint64_t *d_counts,
+                                 cudaStream_t st);
+
+// ---- skr_scan.cu
+int launch_skr_scan(const ReadsView &rv, int K, int M, uint32_t arrival_base, uint32_t max_len, void *out, uint64_t capacity,
+                    unsigned long long *tile_state, uint32_t *ticket, unsigned long long *counters, int sm_count, cudaStream_t st);
+uint32_t skr_scan_tiles(uint64_t n_reads, int K, uint32_t max_len);
+
+// ---- skr_group.cu (pipeline v2: plan units, group in shared memory, emit)
+struct SkrGroupCounters {  // mirror of GroupCounters in skr_group.cu
+    unsigned long long distinct;
+    unsigned long long total_kmers, total_ids;
+    unsigned int overflow, ticket, n_units, pad;
+};
+size_t skr_group_smem_bytes(int KW);
+uint64_t skr_max_units(uint64_t n_inst, uint64_t n_runs);
+int skr_plan_runs(const void *skr_sorted, uint64_t n_skr, int skr_words, uint32_t *inst_prefix, uint32_t *run_excl, uint32_t *run_start,
+                  uint32_t *scratch, uint32_t *n_inst_dev, uint32_t *n_runs_dev, cudaStream_t st);
+size_t skr_unit_bytes();
+int skr_plan_units(const void *skr_sorted, int K, const uint32_t *inst_prefix, const uint32_t *run_start, uint64_t n_runs,
+                   uint32_t *small_prefix, uint32_t *unit_base, uint32_t *scratch, void *units, uint64_t max_units, void *gc_dev, int sm_count,
+                   cudaStream_t st);
+int skr_group_launch(const void *skr_sorted, int K, int cutoff, const uint32_t *inst_prefix, const void *units, unsigned long long *unit_state,
+                     uint64_t max_units, void *gc_dev, const int32_t *ids_by_arrival, int32_t id_base, uint64_t *kmer_codes,
+                     uint32_t *kmer_mmer, uint64_t *kmer_id_off, int32_t *read_ids, uint64_t kmer_cap, uint64_t id_cap, int sm_count,
+                     cudaStream_t st);
+int skr_emit_buckets(const uint32_t *kmer_mmer, uint64_t n_kmers, uint64_t n_ids, uint32_t *bucket_excl, uint32_t *scratch,
+                     uint32_t *mmer_codes, uint64_t *mmer_kmer_off, uint64_t *kmer_id_off, uint32_t *n_buckets_dev, cudaStream_t st);
 
 // ---- group_prune.cu
 struct GroupCounts {  // device-resident scalars, copied to the host between phases

@@ -1,15 +1,17 @@
-// radix_sort.cu — stable LSD radix sort of k-mer instance records by (mmer, kmer), 8 bits per pass.
+// radix_sort.cu — stable LSD radix passes (8 bits per pass) over fixed-size records in HBM.
 //
-// This replaces the reference's per-k-mer hash chaining (zhash_get/zhash_set + strcmp along the
-// chain, binning.c:1044-1058, zhash.c:53-93): equal (m-mer, k-mer) keys become adjacent, and because
-// every pass is stable and the scan stage emits records in arrival order, the records of one key
-// stay in arrival order — which is what the linked list's head-insert order encodes
-// (binning.c:1059-1069), read backwards.
+// Two users:
+//   * pipeline v1: k-mer instance records Rec<KW> sorted on (mmer, kmer).  This replaces the reference's
+//     per-k-mer hash chaining (zhash_get/zhash_set + strcmp along the chain, binning.c:1044-1058,
+//     zhash.c:53-93): equal (m-mer, k-mer) keys become adjacent, and because every pass is stable and the
+//     scan stage emits records in arrival order, the records of one key stay in arrival order — which is
+//     what the linked list's head-insert order encodes (binning.c:1059-1069), read backwards;
+//   * pipeline v2: super-k-mer records sorted on the m-mer code only (level 1 of the two-level store).
+// With digit = mmer % n_parts the same pass is the stable owner partition of the multi-GPU path.
 //
 // Per pass: (1) per-tile digit histogram, (2) exclusive scan of the [256][tiles] table,
 // (3) stable scatter: warp-level match ranking, tile-local reorder through shared memory so that
 // every digit run leaves the SM as one contiguous, coalesced store.
-// The same machinery with digit = mmer % n_parts is the stable owner partition of the multi-GPU path.
 #include "gbin_device.cuh"
 #include "gbin_internal.h"
 #include "prefix_scan.cuh"
@@ -18,73 +20,116 @@ namespace gbin {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 records per tile
 constexpr int RS_RADIX = 256;
 
-struct DigitSel {
-    int mode;  // 0: k-mer word `word` >> shift ; 1: mmer >> shift ; 2: mmer % nparts
-    int word;
-    int shift;
-    uint32_t nparts;
+// A record seen as NU64 64-bit words (Rec<1>: 2, Rec<2>: 3, 32-byte super-k-mer: 4, 48-byte: 6).
+template <int NU64>
+struct __align__(8) Blob {
+    uint64_t w[NU64];
 };
-
-template <int KW>
-__device__ __forceinline__ uint32_t digit_of(const Rec<KW> &r, const DigitSel &s) {
-    if (s.mode == 0) return (uint32_t)((s.word == 0 ? r.k[0] : r.k[KW - 1]) >> s.shift) & 0xffu;  // no dynamic indexing: keeps records in registers
-    if (s.mode == 1) return (r.mmer >> s.shift) & 0xffu;
-    return r.mmer % s.nparts;
+template <int NU64>
+__device__ __forceinline__ Blob<NU64> load_blob(const Blob<NU64> *p) {
+    Blob<NU64> b;
+    if (NU64 % 2 == 0) {  // 16-byte aligned record sizes: 128-bit accesses
+        const uint4 *q = reinterpret_cast<const uint4 *>(p);
+#pragma unroll
+        for (int i = 0; i < NU64 / 2; i++) {
+            const uint4 v = q[i];
+            b.w[2 * i] = (uint64_t)v.x | ((uint64_t)v.y << 32);
+            b.w[2 * i + 1] = (uint64_t)v.z | ((uint64_t)v.w << 32);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NU64; i++) b.w[i] = p->w[i];
+    }
+    return b;
+}
+template <int NU64>
+__device__ __forceinline__ void store_blob(Blob<NU64> *p, const Blob<NU64> &b) {
+    if (NU64 % 2 == 0) {
+        uint4 *q = reinterpret_cast<uint4 *>(p);
+#pragma unroll
+        for (int i = 0; i < NU64 / 2; i++)
+            q[i] = make_uint4((uint32_t)b.w[2 * i], (uint32_t)(b.w[2 * i] >> 32), (uint32_t)b.w[2 * i + 1], (uint32_t)(b.w[2 * i + 1] >> 32));
+    } else {
+#pragma unroll
+        for (int i = 0; i < NU64; i++) p->w[i] = b.w[i];
+    }
 }
 
-template <int KW>
+template <int NU64>
+struct TileShape {  // records per thread chosen so a thread keeps <= 64 registers of payload
+    static constexpr int ITEMS = NU64 <= 2 ? 16 : (NU64 <= 4 ? 8 : 4);
+    static constexpr int TILE = RS_THREADS * ITEMS;
+};
+
+struct DigitSel {
+    int word64;    // which 64-bit word of the record holds the digit
+    int shift;     // right shift inside that word
+    uint32_t mod;  // 0: digit = (word >> shift) & 0xff ; else digit = (u32)(word >> shift) % mod (owner partition)
+};
+
+template <int NU64>
+__device__ __forceinline__ uint32_t digit_of(const Blob<NU64> &r, const DigitSel &s) {
+    uint64_t x = r.w[0];
+#pragma unroll
+    for (int i = 1; i < NU64; i++)
+        if (s.word64 == i) x = r.w[i];  // no dynamic indexing: keeps records in registers
+    x >>= s.shift;
+    return s.mod ? (uint32_t)x % s.mod : (uint32_t)x & 0xffu;
+}
+
+template <int NU64>
 __global__ void __launch_bounds__(RS_THREADS)
-    radix_hist_kernel(const Rec<KW> *__restrict__ in, uint64_t n, DigitSel sel, uint32_t *__restrict__ tile_hist, uint32_t ntiles) {
+    radix_hist_kernel(const Blob<NU64> *__restrict__ in, uint64_t n, DigitSel sel, uint32_t *__restrict__ tile_hist, uint32_t ntiles) {
+    constexpr int ITEMS = TileShape<NU64>::ITEMS, TILE = TileShape<NU64>::TILE;
     __shared__ uint32_t h[RS_RADIX];
     h[threadIdx.x] = 0;
     __syncthreads();
-    const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
+    const uint64_t base = (uint64_t)blockIdx.x * TILE;
 #pragma unroll 4
-    for (int i = 0; i < RS_ITEMS; i++) {
+    for (int i = 0; i < ITEMS; i++) {
         const uint64_t j = base + (uint64_t)i * RS_THREADS + threadIdx.x;
         if (j < n) {
-            const Rec<KW> r = load_rec<KW>(in + j);
-            atomicAdd(&h[digit_of<KW>(r, sel)], 1u);
+            const Blob<NU64> r = load_blob<NU64>(in + j);
+            atomicAdd(&h[digit_of<NU64>(r, sel)], 1u);
         }
     }
     __syncthreads();
     tile_hist[(uint64_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
 }
 
-template <int KW>
+template <int NU64>
 __global__ void __launch_bounds__(RS_THREADS)
-    radix_scatter_kernel(const Rec<KW> *__restrict__ in, Rec<KW> *__restrict__ out, uint64_t n, DigitSel sel,
+    radix_scatter_kernel(const Blob<NU64> *__restrict__ in, Blob<NU64> *__restrict__ out, uint64_t n, DigitSel sel,
                          const uint32_t *__restrict__ tile_off, uint32_t ntiles) {
+    constexpr int ITEMS = TileShape<NU64>::ITEMS, TILE = TileShape<NU64>::TILE;
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    Rec<KW> *exch = reinterpret_cast<Rec<KW> *>(smem_raw);
-    uint32_t *wc = reinterpret_cast<uint32_t *>(smem_raw + (size_t)RS_TILE * sizeof(Rec<KW>));  // [RS_WARPS][256]
+    Blob<NU64> *exch = reinterpret_cast<Blob<NU64> *>(smem_raw);
+    uint32_t *wc = reinterpret_cast<uint32_t *>(smem_raw + (size_t)TILE * sizeof(Blob<NU64>));  // [RS_WARPS][256]
     uint32_t *dstart = wc + RS_WARPS * RS_RADIX;
     uint32_t *goff = dstart + RS_RADIX;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
-    const uint32_t count = (uint32_t)min((uint64_t)RS_TILE, n - base);
+    const uint64_t base = (uint64_t)blockIdx.x * TILE;
+    const uint32_t count = (uint32_t)min((uint64_t)TILE, n - base);
     for (uint32_t i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) wc[i] = 0;
     __syncthreads();
 
-    // warp `warp` owns the contiguous slice [warp*512, warp*512+512) of the tile, 16 rounds of 32
-    Rec<KW> items[RS_ITEMS];
-    uint32_t rank[RS_ITEMS];
+    // warp `warp` owns the contiguous slice [warp*32*ITEMS, (warp+1)*32*ITEMS) of the tile, ITEMS rounds of 32
+    Blob<NU64> items[ITEMS];
+    uint32_t rank[ITEMS];
     uint32_t *mywc = wc + warp * RS_RADIX;
     const uint32_t lt_mask = (1u << lane) - 1;
 #pragma unroll
-    for (int r = 0; r < RS_ITEMS; r++) {
-        const uint32_t idx = warp * (32 * RS_ITEMS) + r * 32 + lane;
+    for (int r = 0; r < ITEMS; r++) {
+        const uint32_t idx = warp * (32 * ITEMS) + r * 32 + lane;
         const bool valid = idx < count;
         const unsigned act = __ballot_sync(0xffffffffu, valid);
         rank[r] = 0;
         if (valid) {
-            items[r] = load_rec<KW>(in + base + idx);
-            const uint32_t d = digit_of<KW>(items[r], sel);
+            items[r] = load_blob<NU64>(in + base + idx);
+            const uint32_t d = digit_of<NU64>(items[r], sel);
             const unsigned peers = __match_any_sync(act, d);
             const int leader = __ffs(peers) - 1;
             uint32_t c = 0;
@@ -113,18 +158,18 @@ __global__ void __launch_bounds__(RS_THREADS)
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < RS_ITEMS; r++) {
-        const uint32_t idx = warp * (32 * RS_ITEMS) + r * 32 + lane;
+    for (int r = 0; r < ITEMS; r++) {
+        const uint32_t idx = warp * (32 * ITEMS) + r * 32 + lane;
         if (idx < count) {
-            const uint32_t d = digit_of<KW>(items[r], sel);
+            const uint32_t d = digit_of<NU64>(items[r], sel);
             exch[dstart[d] + mywc[d] + rank[r]] = items[r];
         }
     }
     __syncthreads();
     for (uint32_t i = tid; i < count; i += RS_THREADS) {
-        const Rec<KW> r = exch[i];
-        const uint32_t d = digit_of<KW>(r, sel);
-        store_rec<KW>(out + (uint32_t)(goff[d] + i), r);
+        const Blob<NU64> r = exch[i];
+        const uint32_t d = digit_of<NU64>(r, sel);
+        store_blob<NU64>(out + (uint32_t)(goff[d] + i), r);
     }
 }
 
@@ -137,49 +182,70 @@ __global__ void part_counts_kernel(const uint32_t *__restrict__ tile_off, uint32
     counts[p] = hi - lo;
 }
 
-static inline uint32_t ntiles_of(uint64_t n) { return (uint32_t)((n + RS_TILE - 1) / RS_TILE); }
+static inline uint32_t ntiles_of(uint64_t n, int tile) { return (uint32_t)((n + tile - 1) / tile); }
+
+static uint32_t ntiles_any(int nu64, uint64_t n) {
+    switch (nu64) {
+        case 2: return ntiles_of(n, TileShape<2>::TILE);
+        case 3: return ntiles_of(n, TileShape<3>::TILE);
+        case 4: return ntiles_of(n, TileShape<4>::TILE);
+        default: return ntiles_of(n, TileShape<6>::TILE);
+    }
+}
 
 size_t radix_scratch_bytes(uint64_t n) {
-    const uint64_t table = (uint64_t)RS_RADIX * ntiles_of(n ? n : 1);
+    const uint64_t table = (uint64_t)RS_RADIX * ntiles_of(n ? n : 1, TileShape<6>::TILE);  // smallest tile of any record size
     return (table + scan_scratch_elems(table) + 16) * sizeof(uint32_t);
 }
 
-template <int KW>
-static int one_pass(const Rec<KW> *in, Rec<KW> *out, uint64_t n, const DigitSel &sel, uint32_t *scratch, KernelProf *prof,
-                    cudaStream_t st) {
-    const uint32_t nt = ntiles_of(n);
+template <int NU64>
+static int one_pass(const void *in_v, void *out_v, uint64_t n, const DigitSel &sel, uint32_t *scratch, KernelProf *prof, cudaStream_t st) {
+    const Blob<NU64> *in = static_cast<const Blob<NU64> *>(in_v);
+    Blob<NU64> *out = static_cast<Blob<NU64> *>(out_v);
+    constexpr int TILE = TileShape<NU64>::TILE;
+    const uint32_t nt = ntiles_of(n, TILE);
     const uint64_t table = (uint64_t)RS_RADIX * nt;
     uint32_t *tile_hist = scratch;
     uint32_t *scan_tmp = scratch + table;
     int launches = 0;
     bool on = prof && prof->begin(KK_RADIX_HIST, st);
-    radix_hist_kernel<KW><<<nt, RS_THREADS, 0, st>>>(in, n, sel, tile_hist, nt);
+    radix_hist_kernel<NU64><<<nt, RS_THREADS, 0, st>>>(in, n, sel, tile_hist, nt);
     if (prof) prof->end(on, 1, st);
     launches++;
     on = prof && prof->begin(KK_RADIX_TILESCAN, st);
     const int ls = exclusive_scan<uint32_t, PtrIn<uint32_t>>(PtrIn<uint32_t>{tile_hist}, tile_hist, table, scan_tmp, nullptr, st);
     if (prof) prof->end(on, ls, st);
     launches += ls;
-    const size_t smem = (size_t)RS_TILE * sizeof(Rec<KW>) + (RS_WARPS * RS_RADIX + 2 * RS_RADIX) * sizeof(uint32_t);
-    static bool attr_set[3] = {false, false, false};
-    if (!attr_set[KW]) {
-        cudaFuncSetAttribute(radix_scatter_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set[KW] = true;
-    }
+    const size_t smem = (size_t)TILE * sizeof(Blob<NU64>) + (RS_WARPS * RS_RADIX + 2 * RS_RADIX) * sizeof(uint32_t);
+    cudaFuncSetAttribute(radix_scatter_kernel<NU64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     on = prof && prof->begin(KK_RADIX_SCATTER, st);
-    radix_scatter_kernel<KW><<<nt, RS_THREADS, smem, st>>>(in, out, n, sel, tile_hist, nt);
+    radix_scatter_kernel<NU64><<<nt, RS_THREADS, smem, st>>>(in, out, n, sel, tile_hist, nt);
     if (prof) prof->end(on, 1, st);
     return launches + 1;
 }
 
-template <int KW>
-static int sort_impl(Rec<KW> *a, Rec<KW> *b, uint64_t n, int K, int M, uint32_t *scratch, bool *result_in_b, int *passes_out,
-                     KernelProf *prof, cudaStream_t st) {
+static int one_pass_any(int nu64, const void *in, void *out, uint64_t n, const DigitSel &sel, uint32_t *scratch, KernelProf *prof,
+                        cudaStream_t st) {
+    switch (nu64) {
+        case 2: return one_pass<2>(in, out, n, sel, scratch, prof, st);
+        case 3: return one_pass<3>(in, out, n, sel, scratch, prof, st);
+        case 4: return one_pass<4>(in, out, n, sel, scratch, prof, st);
+        default: return one_pass<6>(in, out, n, sel, scratch, prof, st);
+    }
+}
+
+// v1: instance records {u64 k[KW]; u32 mmer; u32 arrival}: k-mer words are w[0..KW-1] (most significant first),
+// the m-mer code is the low half of w[KW].
+int radix_sort_records(void *a, void *b, uint64_t n, int KW, int K, int M, void *scratch, bool *result_in_b, int *passes_out,
+                       KernelProf *prof, cudaStream_t st) {
+    *result_in_b = false;
+    *passes_out = 0;
+    if (n == 0) return 0;
     int launches = 0, passes = 0;
-    Rec<KW> *src = a, *dst = b;
+    void *src = a, *dst = b;
     auto run = [&](DigitSel sel) {
-        launches += one_pass<KW>(src, dst, n, sel, scratch, prof, st);
-        Rec<KW> *t = src;
+        launches += one_pass_any(KW + 1, src, dst, n, sel, static_cast<uint32_t *>(scratch), prof, st);
+        void *t = src;
         src = dst;
         dst = t;
         passes++;
@@ -188,25 +254,13 @@ static int sort_impl(Rec<KW> *a, Rec<KW> *b, uint64_t n, int K, int M, uint32_t 
     int kbits = 2 * K;
     for (int w = KW - 1; w >= 0; w--) {
         const int bits = kbits > 64 ? 64 : kbits;
-        for (int s = 0; s < bits; s += 8) run(DigitSel{0, w, s, 0});
+        for (int s = 0; s < bits; s += 8) run(DigitSel{w, s, 0});
         kbits -= bits;
     }
-    for (int s = 0; s < 2 * M; s += 8) run(DigitSel{1, 0, s, 0});
+    for (int s = 0; s < 2 * M; s += 8) run(DigitSel{KW, s, 0});
     *result_in_b = (src == b);
     *passes_out = passes;
     return launches;
-}
-
-int radix_sort_records(void *a, void *b, uint64_t n, int KW, int K, int M, void *scratch, bool *result_in_b, int *passes_out,
-                       KernelProf *prof, cudaStream_t st) {
-    *result_in_b = false;
-    *passes_out = 0;
-    if (n == 0) return 0;
-    if (KW == 1)
-        return sort_impl<1>(static_cast<Rec<1> *>(a), static_cast<Rec<1> *>(b), n, K, M, static_cast<uint32_t *>(scratch), result_in_b,
-                            passes_out, prof, st);
-    return sort_impl<2>(static_cast<Rec<2> *>(a), static_cast<Rec<2> *>(b), n, K, M, static_cast<uint32_t *>(scratch), result_in_b,
-                        passes_out, prof, st);
 }
 
 int radix_partition_by_owner(const void *in, void *out, uint64_t n, int KW, uint32_t n_parts, void *scratch, uint64_t *d_counts,
@@ -215,13 +269,41 @@ int radix_partition_by_owner(const void *in, void *out, uint64_t n, int KW, uint
         cudaMemsetAsync(d_counts, 0, sizeof(uint64_t) * n_parts, st);
         return 0;
     }
-    const DigitSel sel{2, 0, 0, n_parts};
-    int launches;
-    if (KW == 1)
-        launches = one_pass<1>(static_cast<const Rec<1> *>(in), static_cast<Rec<1> *>(out), n, sel, static_cast<uint32_t *>(scratch), nullptr, st);
-    else
-        launches = one_pass<2>(static_cast<const Rec<2> *>(in), static_cast<Rec<2> *>(out), n, sel, static_cast<uint32_t *>(scratch), nullptr, st);
-    part_counts_kernel<<<1, RS_RADIX, 0, st>>>(static_cast<uint32_t *>(scratch), ntiles_of(n), n_parts, n, d_counts);
+    const DigitSel sel{KW, 0, n_parts};
+    const int launches = one_pass_any(KW + 1, in, out, n, sel, static_cast<uint32_t *>(scratch), nullptr, st);
+    part_counts_kernel<<<1, RS_RADIX, 0, st>>>(static_cast<uint32_t *>(scratch), ntiles_any(KW + 1, n), n_parts, n, d_counts);
+    return launches + 1;
+}
+
+// v2: super-k-mer records (skr.cuh): word 1 (= high half of w[0]) is the m-mer code.
+int radix_sort_skr_by_mmer(void *a, void *b, uint64_t n, int skr_words, int M, void *scratch, bool *result_in_b, int *passes_out,
+                           KernelProf *prof, cudaStream_t st) {
+    *result_in_b = false;
+    *passes_out = 0;
+    if (n == 0) return 0;
+    int launches = 0, passes = 0;
+    void *src = a, *dst = b;
+    for (int s = 0; s < 2 * M; s += 8) {
+        launches += one_pass_any(skr_words / 2, src, dst, n, DigitSel{0, 32 + s, 0}, static_cast<uint32_t *>(scratch), prof, st);
+        void *t = src;
+        src = dst;
+        dst = t;
+        passes++;
+    }
+    *result_in_b = (src == b);
+    *passes_out = passes;
+    return launches;
+}
+
+int radix_partition_skr_by_owner(const void *in, void *out, uint64_t n, int skr_words, uint32_t n_parts, void *scratch, uint64_t *d_counts,
+                                 cudaStream_t st) {
+    if (n == 0) {
+        cudaMemsetAsync(d_counts, 0, sizeof(uint64_t) * n_parts, st);
+        return 0;
+    }
+    const int nu64 = skr_words / 2;
+    const int launches = one_pass_any(nu64, in, out, n, DigitSel{0, 32, n_parts}, static_cast<uint32_t *>(scratch), nullptr, st);
+    part_counts_kernel<<<1, RS_RADIX, 0, st>>>(static_cast<uint32_t *>(scratch), ntiles_any(nu64, n), n_parts, n, d_counts);
     return launches + 1;
 }
 

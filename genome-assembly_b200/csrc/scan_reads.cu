@@ -10,16 +10,14 @@
 // Output: one Rec<KW> per window, in arrival order (read-major, window-minor).
 #include "gbin_device.cuh"
 #include "gbin_internal.h"
+#include "read_pack.cuh"
 
 namespace gbin {
 
 constexpr int SCAN_WARPS = 8;
 
-__host__ __device__ inline uint32_t scan_raw_bytes(uint32_t max_len) { return (max_len + 15u) & ~15u; }
-__host__ __device__ inline uint32_t scan_pk_words(uint32_t max_len) { return scan_raw_bytes(max_len) / 16 + 6; }
-__host__ __device__ inline uint32_t scan_warp_smem(uint32_t max_len) {
-    return scan_raw_bytes(max_len) + 4 * scan_pk_words(max_len) + 4 * max_len + 16;
-}
+// per warp: packed words, m-mer scores w(p), per-window info
+__host__ __device__ inline uint32_t scan_warp_smem(uint32_t max_len) { return 4 * scan_pk_words(max_len) + 4 * max_len + 4 * max_len + 16; }
 
 // windows per read (ragged form) -> u32, consumed by exclusive_scan
 __global__ void count_windows_kernel(ReadsView rv, int K, uint32_t *__restrict__ counts) {
@@ -27,13 +25,6 @@ __global__ void count_windows_kernel(ReadsView rv, int K, uint32_t *__restrict__
     if (r >= rv.n_reads) return;
     const uint32_t L = rv.len(r);
     counts[r] = L >= (uint32_t)K ? L - K + 1 : 0;
-}
-
-// 2M-bit code of the m-mer starting at base p, from the MSB-first packed words.
-__device__ __forceinline__ uint32_t mmer_at(const uint32_t *pk, uint32_t p, int M) {
-    const uint32_t bit = 2 * p, wi = bit >> 5, sh = bit & 31;
-    const uint64_t x = ((uint64_t)pk[wi] << 32) | pk[wi + 1];
-    return (uint32_t)((x << sh) >> (64 - 2 * M));
 }
 
 template <int KW>
@@ -72,9 +63,9 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32)
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *wbase = smem + (size_t)warp * scan_warp_smem(max_len);
-    uint8_t *raw = wbase;
-    uint32_t *pk = reinterpret_cast<uint32_t *>(wbase + scan_raw_bytes(max_len));
-    uint32_t *winfo = pk + scan_pk_words(max_len);
+    uint32_t *pk = reinterpret_cast<uint32_t *>(wbase);
+    uint32_t *wv = pk + scan_pk_words(max_len);
+    uint32_t *winfo = wv + max_len;
     const uint32_t FULL = (1u << (2 * M)) - 1;
     const uint32_t C = K - M + 1;  // m-mer positions per window
     const uint64_t warps_total = (uint64_t)gridDim.x * SCAN_WARPS;
@@ -85,44 +76,14 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32)
         if (L < (uint32_t)K) continue;
         const uint32_t W = L - K + 1;
         const uint8_t *src = rv.data + rv.start(r);
-        // ---- stage the read (coalesced byte loads), then pack 16 bases per word
-        for (uint32_t p = lane; p < L; p += 32) raw[p] = src[p];
-        __syncwarp();
-        const uint32_t nwords = (L + 15) / 16;
-        for (uint32_t j = lane; j < nwords + 5; j += 32) {
-            uint32_t word = 0;
-#pragma unroll
-            for (int t = 0; t < 16; t++) {
-                const uint32_t p = 16 * j + t;
-                uint32_t v = 0;
-                if (p < L) {
-                    bool ok;
-                    v = base_code(raw[p], ok);
-                    nbad += ok ? 0 : 1;
-                }
-                word = (word << 2) | v;
-            }
-            pk[j] = word;
-        }
-        __syncwarp();
+        // ---- pack 16 bases per word (aligned 32-bit loads, byte-parallel conversion), then all m-mer scores
+        nbad += warp_pack_read(pk, src, L, lane);
+        warp_mmer_scores(pk, wv, L, M, FULL, lane);
         // ---- signature chain: hop from restart window to restart window
         uint32_t i = 0;
         while (i < W) {
-            uint32_t best_w = 0, best_p = 0xffffffffu;
-            for (uint32_t b = 0; b < C; b += 32) {
-                const uint32_t off = b + lane;
-                if (off < C) {
-                    const uint32_t p = i + off;
-                    const uint32_t s = mmer_at(pk, p, M);
-                    const uint32_t w = max(s, FULL - s);
-                    if (w > best_w) {  // strict: the earlier (smaller p) candidate survives ties
-                        best_w = w;
-                        best_p = p;
-                    }
-                }
-            }
-            const uint32_t mx = __reduce_max_sync(0xffffffffu, best_w);
-            const uint32_t sig = __reduce_min_sync(0xffffffffu, best_w == mx ? best_p : 0xffffffffu);
+            uint32_t mx;
+            const uint32_t sig = warp_signature_hop(wv, i, C, lane, &mx);
             const uint32_t s_sig = mmer_at(pk, sig, M);
             const uint32_t info = (mx << 1) | (s_sig != mx ? 1u : 0u);  // bit0 = is_rev (binning.c:943,948)
             const uint32_t next = min(sig + 1, W);

@@ -1,0 +1,677 @@
+// skr_group.cu — pipeline v2: level-2 grouping, prune and emit, in shared memory.
+//
+// Input: super-k-mer records (skr.cuh) stably sorted by m-mer code, i.e. level 1 of the reference's
+// two-level store (binning.c:1044-1049) is already formed and, inside a bucket, records are in arrival
+// order.  This file
+//   1. plans *units*: runs of whole m-mer buckets whose k-mer instances fit one CTA's shared memory
+//      (small buckets packed by windows of T instances; a bucket larger than CAP is range-partitioned
+//      on the 64-bit prefix of the oriented k-mer with splitters taken from a sorted sample of the
+//      bucket, which keeps ascending k-mer order across the slices);
+//   2. runs a persistent kernel, one unit at a time per CTA, that expands the windows of every
+//      record (rolling 2-bit shift, complement when is_rev — binning.c:1029-1040), groups equal
+//      (m-mer, k-mer) keys with a shared-memory hash (level-2 zhash insert + ll_node push,
+//      binning.c:1052-1069), applies the prune (count > ABUNDANCE_CUTOFF, binning.c:1094-1102),
+//      sorts the survivors by key, orders every id list newest-first and writes the flat table at
+//      offsets obtained from a chained scan over units (so the output is in canonical order);
+//   3. derives the bucket directory (mmer_codes / mmer_kmer_off) from the emitted k-mers
+//      (prune_data drops buckets that lost all their k-mers, binning.c:1136-1142).
+// Anything that does not fit (a single key with more instances than a unit can hold, skewed
+// sub-units) raises an overflow flag; the caller then runs the batch through pipeline v1.
+#include "gbin_device.cuh"
+#include "gbin_internal.h"
+#include "prefix_scan.cuh"
+#include "skr.cuh"
+
+namespace gbin {
+
+// A unit holds at most CAP k-mer instances (template parameter of the kernel: 2048 or 4096).
+//   window  T    = CAP/2 : small buckets (<= T instances) are packed into windows of T
+//   sub-unit TSUB = CAP/2 : expected instances per sub-unit of a bucket larger than CAP
+struct PlanParams {
+    uint32_t cap, t, tsub;
+};
+constexpr int G_RANK_MAX = 768;  // up to this many survivors per unit are ordered by counting instead of a bitonic sort
+
+struct __align__(16) Unit {
+    uint32_t skr_begin, skr_end;  // range of sorted records
+    uint32_t flags;               // bit 0: filtered (a slice of a bucket larger than CAP); bit 1: last slice (no upper bound)
+    uint32_t pad;
+    uint64_t lo, hi;              // filtered: keep k-mers whose 64-bit prefix p satisfies lo <= p < hi (hi ignored on the last slice)
+};
+constexpr uint32_t UNIT_FILTERED = 1u, UNIT_LAST = 2u;
+
+// ------------------------------------------------------------------ planning
+
+struct SkrCount {  // n of record i (word 2, bits 0-7)
+    const uint32_t *skr;
+    int nw;
+    __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return skr[i * nw + 2] & 0xffu; }
+};
+struct SkrRunHead {
+    const uint32_t *skr;
+    int nw;
+    __device__ __forceinline__ uint32_t operator()(uint64_t i) const {
+        return (i == 0 || skr[i * nw + 1] != skr[(i - 1) * nw + 1]) ? 1u : 0u;
+    }
+};
+
+__global__ void skr_run_starts_kernel(const uint32_t *__restrict__ skr, int nw, uint64_t n, const uint32_t *__restrict__ run_excl,
+                                      uint32_t *__restrict__ run_start) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t head = SkrRunHead{skr, nw}(i);
+    if (head) run_start[run_excl[i]] = (uint32_t)i;
+    if (i == n - 1) run_start[run_excl[i] + head] = (uint32_t)n;
+}
+
+struct RunView {
+    const uint32_t *run_start;    // [NR+1]
+    const uint32_t *inst_prefix;  // [n_skr+1]
+    __device__ __forceinline__ uint32_t size(uint64_t r) const { return inst_prefix[run_start[r + 1]] - inst_prefix[run_start[r]]; }
+};
+struct SmallSize {  // instances of run r if it is a small run, else 0
+    RunView rv;
+    PlanParams pp;
+    __device__ __forceinline__ uint32_t operator()(uint64_t r) const {
+        const uint32_t c = rv.size(r);
+        return c <= pp.t ? c : 0u;
+    }
+};
+__device__ __forceinline__ uint32_t units_of_big(uint32_t c, const PlanParams &pp) {
+    return c > pp.cap ? (c + pp.tsub - 1) / pp.tsub : 1u;  // slices of a bucket that does not fit one unit
+}
+struct UnitsOfRun {  // how many units start at run r
+    RunView rv;
+    const uint32_t *small_prefix;  // exclusive sum of SmallSize
+    PlanParams pp;
+    __device__ __forceinline__ uint32_t operator()(uint64_t r) const {
+        const uint32_t c = rv.size(r);
+        if (c > pp.t) return units_of_big(c, pp);
+        if (r == 0) return 1u;
+        if (rv.size(r - 1) > pp.t) return 1u;  // a big bucket closes the packing window
+        return (small_prefix[r] / pp.t != small_prefix[r - 1] / pp.t) ? 1u : 0u;
+    }
+};
+
+__global__ void fill_units_kernel(RunView rv, const uint32_t *__restrict__ small_prefix, const uint32_t *__restrict__ unit_base,
+                                  uint64_t n_runs, PlanParams pp, Unit *__restrict__ units) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_runs) return;
+    const uint32_t nu = UnitsOfRun{rv, small_prefix, pp}(r);
+    const uint32_t c = rv.size(r);
+    const uint32_t ub = unit_base[r];
+    if (c > pp.cap) {
+        // sliced bucket: split_big_runs_kernel fills the units (it needs a sample of the bucket's k-mers)
+    } else if (c > pp.t) {
+        units[ub] = Unit{rv.run_start[r], rv.run_start[r + 1], 0u, 0u, 0ull, 0ull};
+    } else {
+        // unit of this run = the latest head at or before it: exclusive base + own head flag - 1
+        const uint32_t u = ub + nu - 1;
+        if (nu) {
+            units[u].skr_begin = rv.run_start[r];
+            units[u].flags = 0;
+        }
+        atomicMax(&units[u].skr_end, rv.run_start[r + 1]);
+    }
+}
+
+// 64-bit prefix of the oriented k-mer of window w of a record: the top min(64, 2K) bits of the payload shifted left
+// by w bases, complemented when is_rev.  Monotone in the k-mer code, so slicing on it keeps k-mer order.
+template <int PW>
+__device__ __forceinline__ uint64_t window_prefix(const uint32_t *rec, uint32_t w, int K) {
+    const uint32_t bit = 2 * w, wi = bit >> 5, sh = bit & 31;
+    const uint32_t *pl = rec + 4;
+    auto word = [&](uint32_t i) -> uint32_t { return i < 2u * PW ? pl[i] : 0u; };
+    const uint32_t a = __funnelshift_l(word(wi + 1), word(wi), sh);
+    const uint32_t b = __funnelshift_l(word(wi + 2), word(wi + 1), sh);
+    uint64_t pre = ((uint64_t)a << 32) | b;
+    if ((rec[2] >> 8) & 1u) pre = ~pre;
+    if (2 * K < 64) pre &= ~0ull << (64 - 2 * K);
+    return pre;
+}
+
+constexpr int SPLIT_THREADS = 256;
+constexpr int SPLIT_SAMPLES = 2048;
+
+// One CTA per bucket larger than CAP: sample its k-mer prefixes evenly over the instances, sort the sample, and cut it
+// into P = ceil(c / TSUB) slices of equal sample count.
+template <int PW>
+__global__ void __launch_bounds__(SPLIT_THREADS)
+    split_big_runs_kernel(const uint32_t *__restrict__ skr, RunView rv, const uint32_t *__restrict__ unit_base, uint64_t n_runs, PlanParams pp,
+                          int K, Unit *__restrict__ units) {
+    constexpr int NW = SkrLayout<PW>::WORDS;
+    __shared__ uint64_t samp[SPLIT_SAMPLES];
+    for (uint64_t r = blockIdx.x; r < n_runs; r += gridDim.x) {
+        const uint32_t c = rv.size(r);
+        if (c <= pp.cap) continue;
+        const uint32_t a = rv.run_start[r], b = rv.run_start[r + 1];
+        const uint32_t base = rv.inst_prefix[a];
+        const uint32_t P = units_of_big(c, pp);
+        uint32_t S = 64;  // samples: a power of two, at least 32 per slice, at most SPLIT_SAMPLES
+        while (S < 32 * P && S < (uint32_t)SPLIT_SAMPLES) S <<= 1;
+        for (uint32_t t = threadIdx.x; t < S; t += SPLIT_THREADS) {
+            const uint32_t j = (uint32_t)(((uint64_t)(2 * t + 1) * c) / (2ull * S));  // instance index inside the bucket
+            uint32_t lo = a, hi = b - 1;  // last record whose first instance is <= j
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (rv.inst_prefix[mid] - base <= j) lo = mid;
+                else hi = mid - 1;
+            }
+            samp[t] = window_prefix<PW>(skr + (uint64_t)lo * NW, j - (rv.inst_prefix[lo] - base), K);
+        }
+        __syncthreads();
+        for (uint32_t k = 2; k <= S; k <<= 1) {
+            for (uint32_t jj = k >> 1; jj > 0; jj >>= 1) {
+                for (uint32_t idx = threadIdx.x; idx < S; idx += SPLIT_THREADS) {
+                    const uint32_t partner = idx ^ jj;
+                    if (partner > idx) {
+                        const uint64_t x = samp[idx], y = samp[partner];
+                        if ((x > y) == ((idx & k) == 0)) {
+                            samp[idx] = y;
+                            samp[partner] = x;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        const uint32_t ub = unit_base[r];
+        for (uint32_t p = threadIdx.x; p < P; p += SPLIT_THREADS) {
+            const uint64_t lo = p ? samp[(uint64_t)p * S / P] : 0ull;
+            const uint64_t hi = p + 1 < P ? samp[(uint64_t)(p + 1) * S / P] : 0ull;
+            units[ub + p] = Unit{a, b, UNIT_FILTERED | (p + 1 == P ? UNIT_LAST : 0u), 0u, lo, hi};
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ grouping kernel
+
+constexpr unsigned long long GL_VALUE_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long g_ld_volatile(const unsigned long long *p) {
+    return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+// chained scan over units carrying {surviving k-mers (31 bits), ids (31 bits)}: the aggregate is published as soon
+// as it is known, the exclusive prefix is resolved later (just before the unit writes its output), so the wait for
+// predecessors overlaps the unit's own ordering work.
+__device__ __forceinline__ void unit_publish(unsigned long long *state, uint32_t u, unsigned long long mine) {
+    atomicExch(&state[u], ((u == 0 ? 2ull : 1ull) << 62) | mine);
+}
+__device__ __forceinline__ unsigned long long unit_resolve(unsigned long long *state, uint32_t u, unsigned long long mine) {
+    if (u == 0) return 0;
+    unsigned long long sum = 0;
+    for (int64_t j = (int64_t)u - 1;; j--) {
+        unsigned long long v;
+        while (((v = g_ld_volatile(&state[j])) >> 62) == 0) __nanosleep(40);
+        sum += v & GL_VALUE_MASK;  // the two 31-bit fields cannot carry into each other: totals stay below 2^31
+        if ((v >> 62) == 2) break;
+    }
+    atomicExch(&state[u], (2ull << 62) | (sum + mine));
+    return sum;
+}
+__device__ __forceinline__ unsigned long long unit_lookback(unsigned long long *state, uint32_t u, unsigned long long mine) {
+    unit_publish(state, u, mine);
+    return unit_resolve(state, u, mine);
+}
+
+template <int NT>
+__device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t *total, uint32_t *warp_sums /* NT/32 + 1 */) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (unsigned)d) inc += o;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t s = lane < NT / 32 ? warp_sums[lane] : 0u;
+        uint32_t si = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, si, d);
+            if (lane >= (unsigned)d) si += o;
+        }
+        if (lane < NT / 32) warp_sums[lane] = si - s;
+        if (lane == NT / 32 - 1) warp_sums[NT / 32] = si;
+    }
+    __syncthreads();
+    const uint32_t res = inc - v + warp_sums[warp];
+    *total = warp_sums[NT / 32];
+    __syncthreads();
+    return res;
+}
+
+struct GroupOut {
+    uint64_t *kmer_codes;   // [S*KW]
+    uint32_t *kmer_mmer;    // [S]
+    uint64_t *kmer_id_off;  // [S+1]
+    int32_t *read_ids;      // [N]
+    uint64_t kmer_cap, id_cap;
+};
+struct GroupCounters {
+    unsigned long long distinct;
+    unsigned long long total_kmers, total_ids;  // written by the last unit
+    unsigned int overflow;
+    unsigned int ticket;
+    unsigned int n_units;
+    unsigned int pad;
+};
+
+template <int KW>
+__device__ __forceinline__ bool key_less(const uint64_t *key0, const uint64_t *key1, const uint32_t *mm, uint32_t a, uint32_t b) {
+    if (mm[a] != mm[b]) return mm[a] < mm[b];
+    if (key0[a] != key0[b]) return key0[a] < key0[b];
+    if (KW == 2) return key1[a] < key1[b];
+    return false;
+}
+
+template <int PW, int KW, int G_CAP, int G_THREADS>
+__global__ void __launch_bounds__(G_THREADS)
+    skr_group_kernel(const uint32_t *__restrict__ skr, const uint32_t *__restrict__ inst_prefix, const Unit *__restrict__ units, int K,
+                     int cutoff, const int32_t *__restrict__ ids_by_arrival, int32_t id_base, GroupOut out,
+                     unsigned long long *__restrict__ unit_state, GroupCounters *__restrict__ gc) {
+    constexpr int NW = SkrLayout<PW>::WORDS;
+    constexpr int G_HS = 2 * G_CAP;  // hash slots
+    constexpr int G_LOG_HS = G_CAP == 4096 ? 13 : (G_CAP == 2048 ? 12 : 11);
+    static_assert(G_CAP == 4096 || G_CAP == 2048 || G_CAP == 1024, "unit capacity");
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t *key0 = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *key1 = key0 + (KW == 2 ? G_CAP : 0);
+    uint32_t *mm = reinterpret_cast<uint32_t *>(key0 + KW * G_CAP);
+    uint32_t *arr = mm + G_CAP;
+    uint32_t *table = arr + G_CAP;  // G_HS slots; after grouping: [0,CAP) staged ids, [CAP, 2*CAP) id offsets of survivors
+    uint32_t *cnt = table + G_HS;
+    uint16_t *grp = reinterpret_cast<uint16_t *>(cnt + G_CAP);
+    uint16_t *rnk = grp + G_CAP;
+    uint16_t *surv = rnk + G_CAP;
+    uint32_t *stage_ids = table;
+    uint32_t *off = table + G_CAP;  // off[s], s < S <= CAP (the end of the last list is the unit's id total)
+    __shared__ uint32_t s_unit, s_count, s_nsurv, s_ndistinct, s_overflow, s_scan[G_THREADS / 32 + 1];
+    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_total_ids;
+
+    const uint32_t tid = threadIdx.x;
+    const uint64_t kmask0 = (2 * K >= 64 * KW) ? ~0ull : ((1ull << (2 * K - 64 * (KW - 1))) - 1);  // mask of the most significant word
+
+    for (;;) {
+        if (tid == 0) {
+            s_unit = atomicAdd(&gc->ticket, 1u);
+            s_count = 0;
+            s_nsurv = 0;
+            s_ndistinct = 0;
+            s_overflow = 0;
+        }
+        __syncthreads();
+        const uint32_t u = s_unit;
+        if (u >= gc->n_units) break;
+        const Unit un = units[u];
+        const uint32_t base_pref = inst_prefix[un.skr_begin];
+        const uint32_t n_cand = inst_prefix[un.skr_end] - base_pref;
+        const bool filtered = (un.flags & UNIT_FILTERED) != 0;
+        if (!filtered && n_cand > (uint32_t)G_CAP && tid == 0) s_overflow = 1;
+
+        // ---- zero the hash table and counters while records stream in
+        for (uint32_t i = tid; i < (uint32_t)G_HS; i += G_THREADS) table[i] = 0;
+        for (uint32_t i = tid; i < (uint32_t)G_CAP; i += G_THREADS) cnt[i] = 0;
+
+        // ---- expansion: one thread per record, rolling over its n windows
+        if (filtered || n_cand <= (uint32_t)G_CAP) {
+            for (uint32_t s = un.skr_begin + tid; s < un.skr_end; s += G_THREADS) {
+                const uint4 *p = reinterpret_cast<const uint4 *>(skr + (uint64_t)s * NW);
+                const uint4 h = p[0];
+                const uint32_t arrival = h.x, mmer = h.y, n = h.z & 0xffu;
+                const bool rev = (h.z >> 8) & 1u;
+                uint64_t w[PW];
+                {
+                    const uint4 a = p[1];
+                    w[0] = ((uint64_t)a.x << 32) | a.y;
+                    w[1] = ((uint64_t)a.z << 32) | a.w;
+                    if (PW == 4) {
+                        const uint4 b = p[2];
+                        w[PW - 2] = ((uint64_t)b.x << 32) | b.y;
+                        w[PW - 1] = ((uint64_t)b.z << 32) | b.w;
+                    }
+                }
+                const uint32_t pos0 = inst_prefix[s] - base_pref;
+                for (uint32_t t = 0; t < n; t++) {
+                    // oriented k-mer = top 2K bits of the remaining payload
+                    uint64_t k0, k1 = 0;
+                    if (KW == 1) {
+                        k0 = (2 * K == 64) ? w[0] : (w[0] >> (64 - 2 * K));
+                        if (rev) k0 = ~k0 & kmask0;
+                    } else {
+                        const int r = 128 - 2 * K;  // 0..62
+                        k0 = r ? (w[0] >> r) : w[0];
+                        k1 = r ? ((w[1] >> r) | (w[0] << (64 - r))) : w[1];
+                        if (rev) {
+                            k0 = ~k0 & kmask0;
+                            k1 = ~k1;
+                        }
+                    }
+                    bool keep = true;
+                    uint32_t pos = pos0 + t;
+                    if (filtered) {
+                        uint64_t pre = rev ? ~w[0] : w[0];  // 64-bit prefix of the oriented k-mer (same as window_prefix)
+                        if (2 * K < 64) pre &= ~0ull << (64 - 2 * K);
+                        keep = pre >= un.lo && ((un.flags & UNIT_LAST) || pre < un.hi);
+                        if (keep) {
+                            pos = atomicAdd(&s_count, 1u);
+                            if (pos >= (uint32_t)G_CAP) {
+                                keep = false;
+                                s_overflow = 1;
+                            }
+                        }
+                    }
+                    if (keep) {
+                        key0[pos] = k0;
+                        if (KW == 2) key1[pos] = k1;
+                        mm[pos] = mmer;
+                        arr[pos] = arrival;
+                    }
+                    // shift the payload left by one base
+#pragma unroll
+                    for (int q = 0; q < PW - 1; q++) w[q] = (w[q] << 2) | (w[q + 1] >> 62);
+                    w[PW - 1] <<= 2;
+                }
+            }
+        }
+        __syncthreads();
+        if (s_overflow) {  // give up on this unit (the whole batch will be redone by pipeline v1) but keep the chain alive
+            if (tid == 0) {
+                atomicExch(&gc->overflow, 1u);
+                (void)unit_lookback(unit_state, u, 0ull);
+            }
+            __syncthreads();
+            continue;
+        }
+        const uint32_t n_inst = filtered ? s_count : n_cand;
+
+        // ---- group: claim a slot with the instance index, compare keys through the instance arrays
+        for (uint32_t i = tid; i < n_inst; i += G_THREADS) {
+            const uint64_t k0 = key0[i], k1 = (KW == 2) ? key1[i] : 0ull;
+            const uint32_t m = mm[i];
+            uint64_t hx = (k0 ^ (k1 * 0x9E3779B97F4A7C15ull) ^ (((uint64_t)m << 32) | m)) * 0xD6E8FEB86659FD93ull;
+            uint32_t h = (uint32_t)(hx >> (64 - G_LOG_HS));
+            uint32_t rep;
+            for (;;) {
+                uint32_t cur = table[h];
+                if (cur == 0) {
+                    cur = atomicCAS(&table[h], 0u, i + 1);
+                    if (cur == 0) {
+                        rep = i;
+                        break;
+                    }
+                }
+                const uint32_t r = cur - 1;
+                if (key0[r] == k0 && (KW == 1 || key1[r] == k1) && mm[r] == m) {
+                    rep = r;
+                    break;
+                }
+                h = (h + 1) & (G_HS - 1);
+            }
+            grp[i] = (uint16_t)rep;
+            rnk[i] = (uint16_t)atomicAdd(&cnt[rep], 1u);
+        }
+        __syncthreads();
+
+        // ---- leaders and survivors (keep iff count > cutoff, binning.c:1102)
+        for (uint32_t i = tid; i < n_inst; i += G_THREADS) {
+            if (grp[i] == i) {
+                atomicAdd(&s_ndistinct, 1u);
+                if (cutoff < 0 || cnt[i] > (uint32_t)cutoff) surv[atomicAdd(&s_nsurv, 1u)] = (uint16_t)i;
+            }
+        }
+        __syncthreads();
+        const uint32_t S = s_nsurv;
+
+        // ---- survivors ascending by (m-mer, k-mer).  Usual case (a few hundred survivors): every survivor counts
+        // the survivors with a smaller key (keys are distinct, so ranks are a permutation) — no barriers inside;
+        // otherwise a bitonic sort of the instance indices, padded with 0xFFFF = +inf.
+        if (S <= (uint32_t)G_RANK_MAX) {
+            uint16_t *tmp = reinterpret_cast<uint16_t *>(stage_ids);  // the hash table is dead from here on
+            for (uint32_t s = tid; s < S; s += G_THREADS) {
+                const uint32_t i = surv[s];
+                const uint64_t k0 = key0[i], k1 = (KW == 2) ? key1[i] : 0ull;
+                const uint32_t m = mm[i];
+                uint32_t rank = 0;
+                for (uint32_t t = 0; t < S; t++) {
+                    const uint32_t j = surv[t];
+                    const uint32_t mj = mm[j];
+                    const uint64_t kj = key0[j];
+                    bool less = mj < m || (mj == m && kj < k0);
+                    if constexpr (KW == 2) less = less || (mj == m && kj == k0 && key1[j] < k1);
+                    rank += less ? 1u : 0u;
+                }
+                tmp[rank] = (uint16_t)i;
+            }
+            __syncthreads();
+            for (uint32_t s = tid; s < S; s += G_THREADS) surv[s] = tmp[s];
+            __syncthreads();
+        } else {
+            uint32_t n2 = 1;
+            while (n2 < S) n2 <<= 1;
+            for (uint32_t i = S + tid; i < n2; i += G_THREADS) surv[i] = 0xFFFFu;
+            __syncthreads();
+            for (uint32_t k = 2; k <= n2; k <<= 1) {
+                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                    for (uint32_t idx = tid; idx < n2; idx += G_THREADS) {
+                        const uint32_t partner = idx ^ j;
+                        if (partner > idx) {
+                            const uint32_t a = surv[idx], b = surv[partner];
+                            // a > b ?  (0xFFFF is larger than everything)
+                            const bool gt = (a == 0xFFFFu) ? (b != 0xFFFFu) : (b == 0xFFFFu ? false : key_less<KW>(key0, key1, mm, b, a));
+                            const bool asc = (idx & k) == 0;
+                            if (gt == asc) {
+                                surv[idx] = (uint16_t)b;
+                                surv[partner] = (uint16_t)a;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+
+        // ---- id offsets of the survivors (the hash table is dead from here on: its memory holds stage_ids / off)
+        {
+            uint32_t carry = 0;
+            for (uint32_t b0 = 0; b0 < S; b0 += G_THREADS) {
+                const uint32_t s = b0 + tid;
+                const uint32_t v = s < S ? cnt[surv[s]] : 0u;
+                uint32_t tot;
+                const uint32_t ex = block_excl_scan_u32<G_THREADS>(v, &tot, s_scan);
+                if (s < S) off[s] = carry + ex;
+                carry += tot;
+            }
+            if (tid == 0) {
+                s_total_ids = carry;
+                unit_publish(unit_state, u, ((unsigned long long)S << 31) | carry);
+                atomicAdd(&gc->distinct, (unsigned long long)s_ndistinct);
+            }
+        }
+        __syncthreads();
+        const uint32_t N = s_total_ids;
+
+        // ---- destination of every group: survivors get flag | length << 16 | offset, pruned leaders get 0
+        for (uint32_t i = tid; i < n_inst; i += G_THREADS)
+            if (grp[i] == i && !(cutoff < 0 || cnt[i] > (uint32_t)cutoff)) cnt[i] = 0;
+        __syncthreads();
+        for (uint32_t s = tid; s < S; s += G_THREADS) {
+            const uint32_t c = (s + 1 < S ? off[s + 1] : N) - off[s];
+            cnt[surv[s]] = 0x80000000u | (c << 16) | off[s];  // c <= CAP < 2^15, off < CAP <= 2^16
+        }
+        __syncthreads();
+        // ---- stage arrivals (unordered inside a list) ...
+        for (uint32_t i = tid; i < n_inst; i += G_THREADS) {
+            const uint32_t v = cnt[grp[i]];
+            if (v & 0x80000000u) stage_ids[(v & 0xffffu) + rnk[i]] = arr[i];
+        }
+        __syncthreads();
+        // ---- resolve the unit's output offsets (predecessors have had the whole ordering phase to publish)
+        if (tid == 0) {
+            s_base = unit_resolve(unit_state, u, ((unsigned long long)S << 31) | N);
+            if (u == gc->n_units - 1) {
+                gc->total_kmers = (s_base >> 31) + S;
+                gc->total_ids = (s_base & 0x7fffffffull) + N;
+            }
+        }
+        __syncthreads();
+        const uint64_t S_base = s_base >> 31, N_base = s_base & 0x7fffffffull;
+        if (S_base + S > out.kmer_cap || N_base + N > out.id_cap) {  // cannot happen with the caller's bounds; never write out of range
+            if (tid == 0) atomicExch(&gc->overflow, 2u);
+            __syncthreads();
+            continue;
+        }
+        // ---- ... then every instance finds its place in the newest-first list by counting the larger arrivals of
+        // its list (ties — the same read twice — by staging position) and writes its read id straight to HBM.
+        // The loads of one list are independent of each other, so nothing here is a dependent chain.
+        for (uint32_t i = tid; i < n_inst; i += G_THREADS) {
+            const uint32_t v = cnt[grp[i]];
+            if (!(v & 0x80000000u)) continue;
+            const uint32_t o = v & 0xffffu, c = (v >> 16) & 0x7fffu, a = arr[i], r = rnk[i];
+            const uint32_t *lst = stage_ids + o;
+            uint32_t rank = 0;
+            for (uint32_t y = 0; y < r; y++) rank += lst[y] >= a ? 1u : 0u;      // earlier staging position wins a tie
+            for (uint32_t y = r + 1; y < c; y++) rank += lst[y] > a ? 1u : 0u;
+            out.read_ids[N_base + o + rank] = ids_by_arrival ? ids_by_arrival[a] : id_base + (int32_t)a;
+        }
+
+        // ---- write the unit's slice of the flat table
+        for (uint32_t s = tid; s < S; s += G_THREADS) {
+            const uint32_t i = surv[s];
+            const uint64_t g = S_base + s;
+            out.kmer_codes[g * KW] = key0[i];
+            if (KW == 2) out.kmer_codes[g * KW + 1] = key1[i];
+            out.kmer_mmer[g] = mm[i];
+            out.kmer_id_off[g] = N_base + off[s];
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ bucket directory from the emitted k-mers
+
+struct KmerBucketHead {
+    const uint32_t *kmer_mmer;
+    __device__ __forceinline__ uint32_t operator()(uint64_t s) const { return (s == 0 || kmer_mmer[s] != kmer_mmer[s - 1]) ? 1u : 0u; }
+};
+
+__global__ void emit_buckets_kernel(const uint32_t *__restrict__ kmer_mmer, const uint32_t *__restrict__ bucket_excl, uint64_t n_kmers,
+                                    uint64_t n_ids, uint32_t *__restrict__ mmer_codes, uint64_t *__restrict__ mmer_kmer_off,
+                                    uint64_t *__restrict__ kmer_id_off) {
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_kmers) return;
+    const uint32_t head = KmerBucketHead{kmer_mmer}(s);
+    if (head) {
+        mmer_codes[bucket_excl[s]] = kmer_mmer[s];
+        mmer_kmer_off[bucket_excl[s]] = s;
+    }
+    if (s == n_kmers - 1) {
+        mmer_kmer_off[bucket_excl[s] + head] = n_kmers;
+        kmer_id_off[n_kmers] = n_ids;
+    }
+}
+
+__global__ void empty_table_kernel2(uint64_t *mmer_kmer_off, uint64_t *kmer_id_off) {
+    mmer_kmer_off[0] = 0;
+    kmer_id_off[0] = 0;
+}
+
+// ------------------------------------------------------------------ host side
+
+static int g_unit_cap() {  // GBIN_V2_CAP=2048|4096 selects the unit capacity (default 2048: three CTAs per SM)
+    static int cap = 0;
+    if (!cap) {
+        const char *e = getenv("GBIN_V2_CAP");
+        cap = (e && atoi(e) == 4096) ? 4096 : 2048;
+    }
+    return cap;
+}
+static PlanParams plan_params() {
+    const uint32_t cap = (uint32_t)g_unit_cap();
+    return PlanParams{cap, cap / 2, cap / 2};
+}
+
+size_t skr_group_smem_bytes(int KW) {
+    const size_t cap = (size_t)g_unit_cap();
+    return KW * cap * 8 + cap * 4 * 2 + 2 * cap * 4 + cap * 4 + cap * 2 * 3 + 64;
+}
+
+uint64_t skr_max_units(uint64_t n_inst, uint64_t n_runs) { return n_inst / (g_unit_cap() / 4) + 2 * n_runs + 8; }
+size_t skr_unit_bytes() { return sizeof(Unit); }
+
+// Phase A (needs n_skr on the host): instance prefix and m-mer run starts. *n_runs_dev receives the number of runs.
+int skr_plan_runs(const void *skr_sorted, uint64_t n_skr, int skr_words, uint32_t *inst_prefix /*[n+1]*/, uint32_t *run_excl /*[n]*/,
+                  uint32_t *run_start /*[n+1]*/, uint32_t *scratch, uint32_t *n_inst_dev, uint32_t *n_runs_dev, cudaStream_t st) {
+    const uint32_t *s = static_cast<const uint32_t *>(skr_sorted);
+    int l = 0;
+    l += exclusive_scan<uint32_t, SkrCount>(SkrCount{s, skr_words}, inst_prefix, n_skr, scratch, n_inst_dev, st);
+    cudaMemcpyAsync(inst_prefix + n_skr, n_inst_dev, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
+    l += exclusive_scan<uint32_t, SkrRunHead>(SkrRunHead{s, skr_words}, run_excl, n_skr, scratch, n_runs_dev, st);
+    skr_run_starts_kernel<<<(unsigned)((n_skr + 255) / 256), 256, 0, st>>>(s, skr_words, n_skr, run_excl, run_start);
+    return l + 1;
+}
+
+// Phase B (needs n_runs on the host): units. small_prefix / unit_base are [n_runs] scratch arrays.
+int skr_plan_units(const void *skr_sorted, int K, const uint32_t *inst_prefix, const uint32_t *run_start, uint64_t n_runs,
+                   uint32_t *small_prefix, uint32_t *unit_base, uint32_t *scratch, void *units, uint64_t max_units, void *gc_dev, int sm_count,
+                   cudaStream_t st) {
+    RunView rv{run_start, inst_prefix};
+    const PlanParams pp = plan_params();
+    GroupCounters *gc = static_cast<GroupCounters *>(gc_dev);
+    int l = 0;
+    cudaMemsetAsync(units, 0, sizeof(Unit) * max_units, st);
+    cudaMemsetAsync(gc, 0, sizeof(GroupCounters), st);
+    l += exclusive_scan<uint32_t, SmallSize>(SmallSize{rv, pp}, small_prefix, n_runs, scratch, nullptr, st);
+    l += exclusive_scan<uint32_t, UnitsOfRun>(UnitsOfRun{rv, small_prefix, pp}, unit_base, n_runs, scratch, &gc->n_units, st);
+    fill_units_kernel<<<(unsigned)((n_runs + 255) / 256), 256, 0, st>>>(rv, small_prefix, unit_base, n_runs, pp, static_cast<Unit *>(units));
+    const unsigned grid = (unsigned)(n_runs < (uint64_t)sm_count * 8 ? n_runs : (uint64_t)sm_count * 8);
+    const uint32_t *s = static_cast<const uint32_t *>(skr_sorted);
+    if (K <= 32) split_big_runs_kernel<2><<<grid, SPLIT_THREADS, 0, st>>>(s, rv, unit_base, n_runs, pp, K, static_cast<Unit *>(units));
+    else split_big_runs_kernel<4><<<grid, SPLIT_THREADS, 0, st>>>(s, rv, unit_base, n_runs, pp, K, static_cast<Unit *>(units));
+    return l + 2;
+}
+
+int skr_group_launch(const void *skr_sorted, int K, int cutoff, const uint32_t *inst_prefix, const void *units, unsigned long long *unit_state,
+                     uint64_t max_units, void *gc_dev, const int32_t *ids_by_arrival, int32_t id_base, uint64_t *kmer_codes,
+                     uint32_t *kmer_mmer, uint64_t *kmer_id_off, int32_t *read_ids, uint64_t kmer_cap, uint64_t id_cap, int sm_count,
+                     cudaStream_t st) {
+    const int KW = K <= 32 ? 1 : 2;
+    const size_t smem = skr_group_smem_bytes(KW);
+    cudaMemsetAsync(unit_state, 0, sizeof(unsigned long long) * max_units, st);
+    GroupOut out{kmer_codes, kmer_mmer, kmer_id_off, read_ids, kmer_cap, id_cap};
+    GroupCounters *gc = static_cast<GroupCounters *>(gc_dev);
+    const uint32_t *s = static_cast<const uint32_t *>(skr_sorted);
+    const Unit *un = static_cast<const Unit *>(units);
+    auto launch = [&](auto kern, int threads, int ctas_per_sm) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<sm_count * ctas_per_sm, threads, smem, st>>>(s, inst_prefix, un, K, cutoff, ids_by_arrival, id_base, out, unit_state, gc);
+    };
+    if (g_unit_cap() == 4096) {
+        if (KW == 1) launch(skr_group_kernel<2, 1, 4096, 512>, 512, 1);
+        else launch(skr_group_kernel<4, 2, 4096, 512>, 512, 1);
+    } else {
+        if (KW == 1) launch(skr_group_kernel<2, 1, 2048, 256>, 256, 3);
+        else launch(skr_group_kernel<4, 2, 2048, 256>, 256, 2);
+    }
+    return 1;
+}
+
+// Bucket directory over the n_kmers emitted k-mers. bucket_excl: [n_kmers] scratch. *n_buckets_dev receives B.
+int skr_emit_buckets(const uint32_t *kmer_mmer, uint64_t n_kmers, uint64_t n_ids, uint32_t *bucket_excl, uint32_t *scratch,
+                     uint32_t *mmer_codes, uint64_t *mmer_kmer_off, uint64_t *kmer_id_off, uint32_t *n_buckets_dev, cudaStream_t st) {
+    if (n_kmers == 0) {
+        cudaMemsetAsync(n_buckets_dev, 0, sizeof(uint32_t), st);
+        empty_table_kernel2<<<1, 1, 0, st>>>(mmer_kmer_off, kmer_id_off);
+        return 1;
+    }
+    int l = exclusive_scan<uint32_t, KmerBucketHead>(KmerBucketHead{kmer_mmer}, bucket_excl, n_kmers, scratch, n_buckets_dev, st);
+    emit_buckets_kernel<<<(unsigned)((n_kmers + 255) / 256), 256, 0, st>>>(kmer_mmer, bucket_excl, n_kmers, n_ids, mmer_codes, mmer_kmer_off,
+                                                                          kmer_id_off);
+    return l + 1;
+}
+
+}  // namespace gbin

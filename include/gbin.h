@@ -137,9 +137,18 @@ int gbin_table_to_host(gbin_ctx *ctx, const gbin_table *dev, gbin_table *host);
 
 int gbin_get_timings(const gbin_ctx *ctx, gbin_timings *out);
 
+/* Two device pipelines produce the same table:
+ *   2 (default): super-k-mer records -> stable sort by m-mer -> grouping/prune/emit in shared memory; a batch
+ *                that does not fit its shared-memory units (e.g. one k-mer with thousands of instances)
+ *                is transparently redone by pipeline 1;
+ *   1          : expanded k-mer instance records -> stable radix sort on (m-mer, k-mer) in HBM -> run-length/prune/emit.
+ * The environment variable GBIN_PIPELINE=1 selects pipeline 1 at context creation. */
+int gbin_set_pipeline(gbin_ctx *ctx, int pipeline);
+int gbin_get_pipeline_info(const gbin_ctx *ctx, int *configured, int *last_used, uint32_t *fallbacks);
+
 /* Optional per-kernel-class device timing (CUDA events around each launch on the call's stream),
  * accumulated over calls since it was enabled; what bench.py's roofline line is computed from. */
-#define GBIN_KERNEL_KINDS 8
+#define GBIN_KERNEL_KINDS 12
 typedef struct gbin_kernel_profile {
     float ms[GBIN_KERNEL_KINDS];          /* accumulated device time per kernel class */
     uint32_t launches[GBIN_KERNEL_KINDS]; /* kernels launched per class */
@@ -167,6 +176,21 @@ int gbin_partition_records_device(gbin_ctx *ctx, const void *d_records, uint64_t
  * scratch and is clobbered).  ids: device array mapping arrival -> read id, or NULL for id_base+arrival. */
 int gbin_group_records_device(gbin_ctx *ctx, void *d_records, uint64_t n, const int32_t *d_ids_by_arrival,
                               int32_t id_base, void *stream, gbin_table *out);
+
+/* Super-k-mer form of the staged path (pipeline 2): one record per signature segment — consecutive windows that
+ * keep one signature (binning.c:922) are one substring of K+n-1 bases.  Record layout (u32 words): arrival, m-mer
+ * code, n | is_rev << 8, first window index, then the bases 2 bits each MSB-first (4 words for K <= 32, else 8);
+ * 32 or 48 bytes.  About 1/5 of the bytes of the instance records for the same reads. */
+uint32_t gbin_skr_record_bytes(const gbin_ctx *ctx);
+int gbin_scan_skr_device(gbin_ctx *ctx, const gbin_reads *reads, uint32_t arrival_base, void *d_skr, uint64_t capacity, void *stream,
+                         uint64_t *n_skr_out, uint64_t *n_instances_out);
+int gbin_partition_skr_device(gbin_ctx *ctx, const void *d_skr, uint64_t n, uint32_t n_parts, void *d_out, void *stream,
+                              uint64_t *counts_host);
+/* Grouping + prune of n_skr records in arrival order (d_skr is clobbered). Fails with GBIN_E_STATE and
+ * *used_fallback = 1 when a shared-memory unit overflows (degenerate inputs); the caller then re-runs the batch
+ * through gbin_scan_reads_device / gbin_group_records_device. */
+int gbin_group_skr_device(gbin_ctx *ctx, void *d_skr, uint64_t n_skr, const int32_t *d_ids_by_arrival, int32_t id_base, void *stream,
+                          gbin_table *out, int *used_fallback);
 
 /* ---- host helpers ---- */
 

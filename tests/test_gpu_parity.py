@@ -77,8 +77,61 @@ def test_scan_stage_matches_process_read(case):
     b.close()
 
 
+def expand_skr(rec_words: np.ndarray, K: int):
+    """Host expansion of super-k-mer records (include/gbin.h layout) into per-window (mmer, arrival, khi, klo)."""
+    nw = rec_words.shape[1]
+    out = []
+    mask = (1 << (2 * K)) - 1
+    pbits = 32 * (nw - 4)
+    for r in rec_words:
+        arrival, mmer, meta, start = int(r[0]), int(r[1]), int(r[2]), int(r[3])
+        n, rev = meta & 0xff, (meta >> 8) & 1
+        payload = 0
+        for w in r[4:]:
+            payload = (payload << 32) | int(w)
+        for t in range(n):
+            k = (payload >> (pbits - 2 * K - 2 * t)) & mask
+            if rev:
+                k = ~k & mask
+            out.append((mmer, arrival, k >> 64, k & ((1 << 64) - 1), start + t))
+    return out
+
+
 @pytest.mark.parametrize("case", GPU_CASES, ids=lambda c: c["name"])
-def test_table_matches_oracle_and_reference_pin(case, tmp_path):
+def test_super_kmer_scan_matches_process_read(case):
+    """Pipeline-2 scan stage: expanding every super-k-mer record window by window reproduces the oracle's
+    per-window tuples in arrival order (so segments, orientation and m-mer codes are all right)."""
+    torch = torch_cuda()
+    data = O.load_case_bytes(case)
+    starts, lens = O.fgets_split(data, case["read_length_define"])
+    K, M = case["k"], case["m"]
+    if case["instances"] > 400000:
+        starts, lens = starts[:1200], lens[:1200]
+    tup, win = O.scan_all(data, starts, lens, K, M)
+    b = B.Binner(K, M, case["cutoff"])
+    rd, keep = dev_reads(torch, data, starts, lens)
+    rb = b.skr_record_bytes
+    assert rb == (32 if K <= 32 else 48)
+    buf = torch.zeros(max(len(tup), 1) * rb, dtype=torch.uint8, device="cuda")
+    n_skr, n_inst = b.scan_skr_device(rd, 0, buf, len(tup))
+    assert n_inst == len(tup)
+    words = buf[: n_skr * rb].cpu().numpy().view(np.uint32).reshape(n_skr, rb // 4)
+    got = expand_skr(words, K)
+    assert len(got) == len(tup)
+    np.testing.assert_array_equal(np.array([g[0] for g in got], dtype=np.uint32), tup["mmer"])
+    np.testing.assert_array_equal(np.array([g[1] for g in got], dtype=np.uint32), tup["arrival"])
+    np.testing.assert_array_equal(np.array([g[3] for g in got], dtype=np.uint64), tup["klo"])
+    np.testing.assert_array_equal(np.array([g[2] for g in got], dtype=np.uint64), tup["khi"])
+    # a segment ends exactly where the oracle's signature position changes (or the read ends)
+    seg_first = np.array([True] + [bool(win["sig_pos"][i] != win["sig_pos"][i - 1] or tup["arrival"][i] != tup["arrival"][i - 1])
+                                   for i in range(1, len(tup))]) if len(tup) else np.zeros(0, bool)
+    assert int(seg_first.sum()) == n_skr
+    b.close()
+
+
+@pytest.mark.parametrize("pipeline", [2, 1])
+@pytest.mark.parametrize("case", GPU_CASES, ids=lambda c: c["name"])
+def test_table_matches_oracle_and_reference_pin(case, pipeline, tmp_path):
     """Whole path through gbin_read_file_fgets + gbin_bin_reads_host: identical arrays to the oracle and
     the same md5 as the reference binary's sorted dump."""
     torch_cuda()
@@ -86,7 +139,7 @@ def test_table_matches_oracle_and_reference_pin(case, tmp_path):
     p = tmp_path / "reads.txt"
     p.write_bytes(data)
     d, starts, lens = B.read_file_fgets(str(p), case["read_length_define"])
-    b = B.Binner(case["k"], case["m"], case["cutoff"])
+    b = B.Binner(case["k"], case["m"], case["cutoff"], pipeline=pipeline)
     got = b.bin_host(d, len(starts), starts=starts, lens=lens)
     want = O.run(data, starts, lens, case["k"], case["m"], case["cutoff"])
     assert_tables_equal(got, want)
@@ -94,6 +147,14 @@ def test_table_matches_oracle_and_reference_pin(case, tmp_path):
     assert as_oracle_table(got).md5() == case["md5"]
     tm = b.timings()
     assert tm["kernel_launches"] > 0
+    info = b.pipeline_info()
+    assert info["configured"] == pipeline
+    if pipeline == 1 or case["instances"] == 0:
+        assert info["last_used"] == 1
+    elif case["name"] not in ("fuzz_polyA", "fuzz_ragged_k15"):
+        # homopolymers and 2-letter-alphabet reads hold single k-mers with more instances than a shared-memory unit:
+        # pipeline 2 detects the overflow and the batch is redone by pipeline 1
+        assert info["last_used"] == 2 and info["fallbacks"] == 0, info
     b.close()
 
 
@@ -137,15 +198,16 @@ def test_fixed_stride_form_and_explicit_ids():
     b.close()
 
 
+@pytest.mark.parametrize("pipeline", [2, 1])
 @pytest.mark.parametrize("K,M,cutoff,L", [(32, 15, 1, 80), (33, 8, 0, 90), (64, 15, 1, 200), (8, 4, 2, 40), (4, 2, 5, 30),
                                           (31, 4, -1, 60), (40, 13, 3, 150), (63, 2, 1, 100)])
-def test_key_width_and_parameter_edges(K, M, cutoff, L):
+def test_key_width_and_parameter_edges(K, M, cutoff, L, pipeline):
     """K = 32/33/64 (64-bit and 128-bit code boundaries), smallest/largest M, cutoff 0 / none."""
     torch_cuda()
     rs = synth.generate(1500, L, genome_len=2000, error_rate=0.01, seed=K * 100 + M, starts="uniform")
     starts = np.arange(rs.n_reads, dtype=np.uint64) * rs.stride
     lens = np.full(rs.n_reads, rs.read_len, dtype=np.uint32)
-    b = B.Binner(K, M, cutoff)
+    b = B.Binner(K, M, cutoff, pipeline=pipeline)
     got = b.bin_host(rs.buf, rs.n_reads, stride=rs.stride, read_len=rs.read_len)
     want = O.run(rs.as_bytes(), starts, lens, K, M, cutoff)
     assert want.n_kmers > 0
@@ -249,17 +311,53 @@ def test_reference_entry_points_process_read_prune_data():
     L.gbin_ref_reset(C.addressof(root))
 
 
-def test_medium_synthetic_cfg2_shape():
+@pytest.mark.parametrize("pipeline", [2, 1])
+def test_medium_synthetic_cfg2_shape(pipeline):
     """60 000 reads x 100 bp (4.2 M instances, 1026 sort tiles): multi-tile sort, multi-level scans."""
     torch_cuda()
     rs = synth.generate(60000, 100, error_rate=0.01, seed=20, starts="triangular")
     starts = np.arange(rs.n_reads, dtype=np.uint64) * rs.stride
     lens = np.full(rs.n_reads, rs.read_len, dtype=np.uint32)
-    b = B.Binner(31, 11, 1)
+    b = B.Binner(31, 11, 1, pipeline=pipeline)
     got = b.bin_host(rs.buf, rs.n_reads, stride=rs.stride, read_len=rs.read_len)
     want = O.run(rs.as_bytes(), starts, lens, 31, 11, 1)
     assert_tables_equal(got, want)
+    assert b.pipeline_info()["last_used"] == pipeline
     b.close()
+
+
+def test_homopolymer_batch_falls_back_to_the_hbm_pipeline():
+    """One k-mer with 210 000 instances cannot fit a shared-memory unit: pipeline 2 detects it and the batch is
+    redone by pipeline 1 — same table either way."""
+    torch_cuda()
+    poly = (b"A" * 100 + b"\n") * 3000
+    sp, lp = np.arange(3000, dtype=np.uint64) * 101, np.full(3000, 100, np.uint32)
+    b = B.Binner(31, 4, 1, pipeline=2)
+    t = b.bin_host(poly, 3000, stride=101, read_len=100)
+    assert_tables_equal(t, O.run(poly, sp, lp, 31, 4, 1))
+    info = b.pipeline_info()
+    assert info["last_used"] == 1 and info["fallbacks"] == 1
+    b.close()
+
+
+@pytest.mark.parametrize("n_reads,expect_v2", [(2500, True), (12000, False)])
+def test_deep_coverage_long_id_lists(n_reads, expect_v2):
+    """A tiny genome at ~125x / ~600x coverage: id lists of hundreds of entries and m-mer buckets larger than a
+    shared-memory unit (split by k-mer prefix).  At 600x a handful of k-mers with ~500 instances each no longer
+    spread evenly over the prefix sub-units, pipeline 2 reports the overflow and pipeline 1 redoes the batch."""
+    torch_cuda()
+    rs = synth.generate(n_reads, 100, genome_len=2000, error_rate=0.002, seed=77, starts="uniform")
+    starts = np.arange(rs.n_reads, dtype=np.uint64) * rs.stride
+    lens = np.full(rs.n_reads, rs.read_len, dtype=np.uint32)
+    for K, M in ((31, 11), (31, 4), (63, 15)):
+        b = B.Binner(K, M, 1, pipeline=2)
+        got = b.bin_host(rs.buf, rs.n_reads, stride=rs.stride, read_len=rs.read_len)
+        want = O.run(rs.as_bytes(), starts, lens, K, M, 1)
+        assert np.diff(want.kmer_id_off.astype(np.int64)).max() > (60 if expect_v2 else 200)
+        assert_tables_equal(got, want)
+        if expect_v2:
+            assert b.pipeline_info()["last_used"] == 2, (K, M, b.pipeline_info())
+        b.close()
 
 
 def check_table_invariants(t: B.HostTable, n_reads, W):

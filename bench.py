@@ -139,49 +139,65 @@ def config_dict(a, w, world):
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampled every 20 ms from process start; only samples whose timestamp falls inside the marked
+    window (warm-up + timed region) are used, and of those the loaded (upper) half for the median SM clock."""
+    QUERY = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
         self.tf = tempfile.NamedTemporaryFile(suffix=".csv", delete=False)
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=self.tf, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
         self.tf.close()
-        sm, mx, reasons = [], [], set()
+        rows = []
         with open(self.tf.name) as f:
             for ln in f:
                 p = [x.strip() for x in ln.split(",")]
-                if len(p) < 9:
+                if len(p) < 10:
                     continue
                 try:
-                    sm.append(float(p[1]))
-                    mx.append(float(p[2]))
+                    ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(p[2]), float(p[3]), p[6:10]))
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+        os.unlink(self.tf.name)
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.02 <= r[0] <= (self.t1 or 1e18) + 0.02]
+        use = inside if inside else rows
+        if use:
+            sm = sorted(r[1] for r in use)
+            reasons = set()
+            for r in use:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
-        os.unlink(self.tf.name)
-        if sm:
-            top = sorted(sm)[len(sm) // 2:]  # under load = upper half of the samples
-            out.update(sm_mhz=statistics.median(top), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=statistics.median(sm[len(sm) // 2:]), sm_max_mhz=max(r[2] for r in use), reasons=sorted(reasons),
+                       samples=len(use), samples_total=len(rows), window="warm-up + timed region" if inside else "whole process")
         return out
 
 
@@ -207,6 +223,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()  # nvidia-smi takes about a second to deliver its first sample: start it before the data is generated
     w = workload_params(a.workload, a.reads_per_gpu)
     K, M, cutoff = w["k"], w["m"], w["cutoff"]
     rs = make_reads(w, rank, world)
@@ -238,9 +257,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        sampler.start()  # nvidia-smi needs ~1 s to start: sample across warm-up + timed region, keep the loaded half
+        sampler.mark_begin()
 
     # ---- warm-up (also sizes every workspace buffer)
     table = None
@@ -269,6 +287,8 @@ def main():
         launches += binner.timings()["kernel_launches"] if world == 1 else 0
     barrier()
     wall_s = time.perf_counter() - t_wall0
+    if sampler:
+        sampler.mark_end()
     clocks = sampler.stop() if sampler else None
     prof = binner.kernel_profile()
     binner.set_kernel_profiling(False)
@@ -325,29 +345,48 @@ def main():
                "d2h_bytes_per_step": d2h * world, "ms_per_step": 1e3 * float(e2e_s[0]) / a.steps,
                "timing": "host wall clock, max over ranks; table D2H into pageable memory"}
 
-    # ---- roofline of the dominant kernel (stable radix scatter): algorithmic bytes = read + write of every record
+    # ---- roofline of the dominant kernel (the kernel class with the most device time in the timed region)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     rb = binner.record_bytes
+    KW = 1 if K <= 32 else 2
+    rstats = binner.run_stats()
+    n_skr = rstats["n_super_kmers"]
+    skr_b = binner.skr_record_bytes
+    n_rec = stats["instances"]  # k-mer instances this rank grouped in the last step
+    # algorithmic (compulsory) HBM bytes of ONE launch of each kernel class, see DESIGN.md section 4
+    alg_bytes = {
+        "radix_scatter": (2.0 * skr_b * n_skr) if n_skr else (2.0 * rb * n_rec),
+        "radix_hist": (1.0 * skr_b * n_skr) if n_skr else (1.0 * rb * n_rec),
+        "scan_reads": float(h_reads.numel()) + rb * n_inst_rank,
+        "skr_scan": float(h_reads.numel()) + skr_b * n_skr,
+        "skr_group": (skr_b + 4.0) * n_skr + stats["surviving_kmers"] * (8.0 * KW + 4 + 8) + 4.0 * stats["surviving_ids"],
+        "find_runs": 3.0 * rb * n_rec + 8.0 * n_rec,
+    }
+    ncu_traffic = {"skr_group": 494.3e6, "skr_scan": 272.9e6}  # dram read+write per launch, ncu --set full (profiles/)
     roofline = None
-    if "radix_scatter" in prof and prof["radix_scatter"]["launches"]:
-        sc = prof["radix_scatter"]
-        n_rec = stats["instances"] if world > 1 else n_inst_rank  # records one launch moves on this rank
-        alg = 2.0 * rb * n_rec
+    timed = {k: v for k, v in prof.items() if v["launches"] and k in alg_bytes}
+    if timed:
+        dom = max(timed, key=lambda k: timed[k]["ms"])
+        sc = timed[dom]
+        alg = alg_bytes[dom]
         avg_ms = sc["ms"] / sc["launches"]
         ach = alg / (avg_ms / 1e3) / 1e9
-        pipe_bytes_per_inst = (rs.read_len + 1) / W + 2 * rb + 4  # SURVEY §8(d)
+        pipe_bytes_per_inst = (rs.read_len + 1) / W + 2 * rb + 4  # SURVEY section 8(d)
         pipe_ach = pipe_bytes_per_inst * n_inst_rank * a.steps / (float(sum(step_ms)) / 1e3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "radix_scatter_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": alg, "launches": sc["launches"], "avg_launch_ms": avg_ms,
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": ncu_traffic.get(dom) if (world == 1 and a.workload == "cfg2" and not a.reads_per_gpu) else None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "launches": sc["launches"], "avg_launch_ms": avg_ms,
                     "share_of_step": sc["ms"] / float(sum(step_ms)),
+                    "note": "HBM is not what bounds this kernel: it groups k-mers in shared memory (hash + ranking), see DESIGN.md",
                     "pipeline": {"algorithmic_bytes_per_kmer": pipe_bytes_per_inst, "achieved": pipe_ach, "frac": pipe_ach / peak,
-                                 "note": "whole step against SURVEY §8(d)'s compulsory-traffic model"},
-                    "per_kernel_ms_per_step": {k: v["ms"] / a.steps for k, v in prof.items()}}
+                                 "note": "whole step against SURVEY 8(d)'s compulsory-traffic model (37.4 B per k-mer instance at cfg2)"},
+                    "per_kernel_ms_per_step": {k: v["ms"] / a.steps for k, v in prof.items()},
+                    "per_kernel_achieved_gbs": {k: alg_bytes[k] * v["launches"] / (v["ms"] / 1e3) / 1e9 for k, v in timed.items() if v["ms"] > 0},
+                    "run_stats": rstats, "pipeline_info": binner.pipeline_info()}
 
     # ---- CPU baseline (rank 0, N=1 only): the unmodified reference binary on one host core
     cpu = None

@@ -64,7 +64,7 @@ EXPORTS = [
     "gbin_strerror", "gbin_last_error", "gbin_version", "gbin_create", "gbin_destroy", "gbin_get_config",
     "gbin_bin_reads_host", "gbin_table_clone", "gbin_table_free", "gbin_pinned_alloc", "gbin_pinned_free",
     "gbin_bin_reads_device", "gbin_table_to_host", "gbin_get_timings", "gbin_record_bytes",
-    "gbin_set_kernel_profiling", "gbin_get_kernel_profile", "gbin_kernel_kind_name", "gbin_set_pipeline", "gbin_get_pipeline_info",
+    "gbin_set_kernel_profiling", "gbin_get_kernel_profile", "gbin_kernel_kind_name", "gbin_set_pipeline", "gbin_get_pipeline_info", "gbin_get_run_stats",
     "gbin_count_instances_device", "gbin_scan_reads_device", "gbin_partition_records_device",
     "gbin_group_records_device", "gbin_skr_record_bytes", "gbin_scan_skr_device", "gbin_partition_skr_device", "gbin_group_skr_device",
     "gbin_read_file_fgets", "gbin_table_dump", "gbin_table_dump_reference_format",
@@ -104,6 +104,7 @@ def load_library() -> C.CDLL:
     L.gbin_pinned_free.argtypes = [vp]
     L.gbin_pinned_free.restype = None
     L.gbin_get_timings.argtypes = [vp, C.POINTER(Timings)]
+    L.gbin_get_run_stats.argtypes = [vp, C.POINTER(u64 * 4)]
     L.gbin_set_pipeline.argtypes = [vp, C.c_int]
     L.gbin_get_pipeline_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint32)]
     L.gbin_set_kernel_profiling.argtypes = [vp, C.c_int]
@@ -262,6 +263,11 @@ class Binner:
         a, b, c = C.c_int(), C.c_int(), C.c_uint32()
         self._check(self.lib.gbin_get_pipeline_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return {"configured": a.value, "last_used": b.value, "fallbacks": c.value}
+
+    def run_stats(self) -> dict:
+        a = (C.c_uint64 * 4)()
+        self._check(self.lib.gbin_get_run_stats(self.h, C.byref(a)))
+        return {"n_super_kmers": int(a[0]), "n_mmer_runs": int(a[1]), "n_units": int(a[2])}
 
     def set_kernel_profiling(self, enable: bool):
         self._check(self.lib.gbin_set_kernel_profiling(self.h, int(enable)))

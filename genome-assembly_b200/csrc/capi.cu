@@ -97,6 +97,7 @@ struct gbin_ctx {
     int pipeline;        // 2: super-k-mer path with v1 as fallback (default); 1: v1 only
     int last_pipeline;   // which one produced the last table
     uint32_t fallbacks;  // v2 -> v1 fallbacks since creation
+    gbin_run_stats rs;   // sizes seen by the last pipeline-2 run
     // device-resident result
     DevBuf o_mmer_codes, o_mmer_kmer_off, o_kmer_codes, o_kmer_id_off, o_read_ids;
     // pinned host arena for results of the host path + small readbacks
@@ -315,7 +316,7 @@ int run_v2_scan(gbin_ctx *ctx, const gbin_reads *rd, uint64_t n, uint32_t max_le
     uint64_t n_skr = 0;
     for (int attempt = 0; attempt < 2; attempt++) {
         if (!ext) CU(ctx->skr_a.ensure((cap + 1) * NW * 4));
-        CU(ctx->tile_state.ensure((size_t)skr_scan_tiles(rd->n_reads, K, max_len) * 8 + 8));
+        CU(ctx->tile_state.ensure((size_t)skr_scan_tiles(rd->n_reads, K, M, max_len) * 8 + 8));
         CU(cudaMemsetAsync(dm->skr_counters, 0, sizeof dm->skr_counters, st));
         const bool on = ctx->prof.begin(KK_SKR_SCAN, st);
         const int ls = launch_skr_scan(rv, K, M, arrival_base, max_len, ext ? ext : ctx->skr_a.p, cap, ctx->tile_state.as<unsigned long long>(),
@@ -372,6 +373,8 @@ int run_v2_group(gbin_ctx *ctx, void *skr, void *twin, uint64_t n_skr, const int
     CU(cudaStreamSynchronize(st));
     const uint64_t n_runs = hm->n_runs_dev, n = hm->n_inst_dev;
     *n_inst_out = n;
+    ctx->rs.n_super_kmers = n_skr;
+    ctx->rs.n_mmer_runs = n_runs;
     const uint64_t max_units = skr_max_units(n, n_runs);
     CU(ctx->small_prefix.ensure((n_runs + 1) * 4));
     CU(ctx->unit_base.ensure((n_runs + 1) * 4));
@@ -400,6 +403,7 @@ int run_v2_group(gbin_ctx *ctx, void *skr, void *twin, uint64_t n_skr, const int
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(&hm->gc, &dm->gc, sizeof(SkrGroupCounters), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    ctx->rs.n_units = hm->gc.n_units;
     if (hm->gc.overflow) {  // a unit did not fit shared memory: this batch goes through pipeline v1
         ctx->fallbacks++;
         return GBIN_OK;
@@ -474,6 +478,7 @@ int bin_device_impl(gbin_ctx *ctx, const gbin_reads *rd, cudaStream_t st, gbin_t
         }
     }
     ctx->last_pipeline = 1;
+    memset(&ctx->rs, 0, sizeof ctx->rs);
     const size_t rb = sizeof(uint64_t) * ctx->KW + 8;
     CU(ctx->rec_a.ensure((n + 1) * rb));
     CU(ctx->rec_b.ensure((n + 1) * rb));
@@ -528,6 +533,7 @@ int gbin_create(const gbin_config *cfg, gbin_ctx **out) {
     if (const char *e = getenv("GBIN_PIPELINE")) ctx->pipeline = atoi(e) == 1 ? 1 : 2;
     ctx->last_pipeline = 0;
     ctx->fallbacks = 0;
+    memset(&ctx->rs, 0, sizeof ctx->rs);
     memset(&ctx->tm, 0, sizeof ctx->tm);
     ctx->prof.reset();
     cudaError_t e = cudaSetDevice(cfg->device);
@@ -607,6 +613,12 @@ static void finish_timings(gbin_ctx *ctx, int launches, bool host_path) {
     ctx->tm.total_ms = ms(0, host_path ? 5 : 4);
     ctx->tm.kernel_launches = (uint32_t)launches;
     ctx->prof.collect();
+}
+
+int gbin_get_run_stats(const gbin_ctx *ctx, gbin_run_stats *out) {
+    if (!ctx || !out) return GBIN_E_INVALID_ARG;
+    *out = ctx->rs;
+    return GBIN_OK;
 }
 
 int gbin_set_pipeline(gbin_ctx *ctx, int pipeline) {

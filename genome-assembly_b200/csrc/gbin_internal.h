@@ -79,7 +79,7 @@ int radix_partition_skr_by_owner(const void *in, void *out, uint64_t n, int skr_
 // ---- skr_scan.cu
 int launch_skr_scan(const ReadsView &rv, int K, int M, uint32_t arrival_base, uint32_t max_len, void *out, uint64_t capacity,
                     unsigned long long *tile_state, uint32_t *ticket, unsigned long long *counters, int sm_count, cudaStream_t st);
-uint32_t skr_scan_tiles(uint64_t n_reads, int K, uint32_t max_len);
+uint32_t skr_scan_tiles(uint64_t n_reads, int K, int M, uint32_t max_len);
 
 // ---- skr_group.cu (pipeline v2: plan units, group in shared memory, emit)
 struct SkrGroupCounters {  // mirror of GroupCounters in skr_group.cu

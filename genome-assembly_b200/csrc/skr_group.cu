@@ -20,15 +20,17 @@
 #include "gbin_device.cuh"
 #include "gbin_internal.h"
 #include "prefix_scan.cuh"
+#include "lookback.cuh"
 #include "skr.cuh"
 
 namespace gbin {
 
 // A unit holds at most CAP k-mer instances (template parameter of the kernel: 2048 or 4096).
-//   window  T    = CAP/2 : small buckets (<= T instances) are packed into windows of T
-//   sub-unit TSUB = CAP/2 : expected instances per sub-unit of a bucket larger than CAP
+//   small buckets (<= t = CAP/4 instances) are packed into windows of win = 3*CAP/4 instances of the small-bucket
+//   prefix space, so a packed unit holds less than win + t = CAP instances and is about 75 % full on average;
+//   a bucket with t < c <= CAP is a unit of its own; a larger one is cut into slices of about tsub = CAP/2.
 struct PlanParams {
-    uint32_t cap, t, tsub;
+    uint32_t cap, t, win, tsub;
 };
 constexpr int G_RANK_MAX = 768;  // up to this many survivors per unit are ordered by counting instead of a bitonic sort
 
@@ -89,7 +91,7 @@ struct UnitsOfRun {  // how many units start at run r
         if (c > pp.t) return units_of_big(c, pp);
         if (r == 0) return 1u;
         if (rv.size(r - 1) > pp.t) return 1u;  // a big bucket closes the packing window
-        return (small_prefix[r] / pp.t != small_prefix[r - 1] / pp.t) ? 1u : 0u;
+        return (small_prefix[r] / pp.win != small_prefix[r - 1] / pp.win) ? 1u : 0u;
     }
 };
 
@@ -187,34 +189,6 @@ __global__ void __launch_bounds__(SPLIT_THREADS)
 
 // ------------------------------------------------------------------ grouping kernel
 
-constexpr unsigned long long GL_VALUE_MASK = (1ull << 62) - 1;
-
-__device__ __forceinline__ unsigned long long g_ld_volatile(const unsigned long long *p) {
-    return *reinterpret_cast<const volatile unsigned long long *>(p);
-}
-// chained scan over units carrying {surviving k-mers (31 bits), ids (31 bits)}: the aggregate is published as soon
-// as it is known, the exclusive prefix is resolved later (just before the unit writes its output), so the wait for
-// predecessors overlaps the unit's own ordering work.
-__device__ __forceinline__ void unit_publish(unsigned long long *state, uint32_t u, unsigned long long mine) {
-    atomicExch(&state[u], ((u == 0 ? 2ull : 1ull) << 62) | mine);
-}
-__device__ __forceinline__ unsigned long long unit_resolve(unsigned long long *state, uint32_t u, unsigned long long mine) {
-    if (u == 0) return 0;
-    unsigned long long sum = 0;
-    for (int64_t j = (int64_t)u - 1;; j--) {
-        unsigned long long v;
-        while (((v = g_ld_volatile(&state[j])) >> 62) == 0) __nanosleep(40);
-        sum += v & GL_VALUE_MASK;  // the two 31-bit fields cannot carry into each other: totals stay below 2^31
-        if ((v >> 62) == 2) break;
-    }
-    atomicExch(&state[u], (2ull << 62) | (sum + mine));
-    return sum;
-}
-__device__ __forceinline__ unsigned long long unit_lookback(unsigned long long *state, uint32_t u, unsigned long long mine) {
-    unit_publish(state, u, mine);
-    return unit_resolve(state, u, mine);
-}
-
 template <int NT>
 __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t *total, uint32_t *warp_sums /* NT/32 + 1 */) {
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -282,13 +256,13 @@ __global__ void __launch_bounds__(G_THREADS)
     uint64_t *key1 = key0 + (KW == 2 ? G_CAP : 0);
     uint32_t *mm = reinterpret_cast<uint32_t *>(key0 + KW * G_CAP);
     uint32_t *arr = mm + G_CAP;
-    uint32_t *table = arr + G_CAP;  // G_HS slots; after grouping: [0,CAP) staged ids, [CAP, 2*CAP) id offsets of survivors
+    uint32_t *table = arr + G_CAP;  // G_HS slots; after grouping: [0,CAP) id offsets of survivors, [CAP,2*CAP) scratch / staged ids
     uint32_t *cnt = table + G_HS;
     uint16_t *grp = reinterpret_cast<uint16_t *>(cnt + G_CAP);
     uint16_t *rnk = grp + G_CAP;
     uint16_t *surv = rnk + G_CAP;
-    uint32_t *stage_ids = table;
-    uint32_t *off = table + G_CAP;  // off[s], s < S <= CAP (the end of the last list is the unit's id total)
+    uint32_t *off = table;                 // off[s], s < S <= CAP (the end of the last list is the unit's id total)
+    uint32_t *stage_ids = table + G_CAP;   // scratch; together with cnt (free once the offsets exist) 2*CAP words
     __shared__ uint32_t s_unit, s_count, s_nsurv, s_ndistinct, s_overflow, s_scan[G_THREADS / 32 + 1];
     __shared__ unsigned long long s_base;
     __shared__ uint32_t s_total_ids;
@@ -382,8 +356,9 @@ __global__ void __launch_bounds__(G_THREADS)
         if (s_overflow) {  // give up on this unit (the whole batch will be redone by pipeline v1) but keep the chain alive
             if (tid == 0) {
                 atomicExch(&gc->overflow, 1u);
-                (void)unit_lookback(unit_state, u, 0ull);
+                lkb_publish_aggregate(unit_state, u, 0ull);
             }
+            if (tid < 32) (void)lkb_resolve_warp<8>(unit_state, u, 0ull, tid);
             __syncthreads();
             continue;
         }
@@ -488,34 +463,33 @@ __global__ void __launch_bounds__(G_THREADS)
             }
             if (tid == 0) {
                 s_total_ids = carry;
-                unit_publish(unit_state, u, ((unsigned long long)S << 31) | carry);
+                lkb_publish_aggregate(unit_state, u, ((unsigned long long)S << 31) | carry);
                 atomicAdd(&gc->distinct, (unsigned long long)s_ndistinct);
             }
         }
         __syncthreads();
         const uint32_t N = s_total_ids;
 
-        // ---- destination of every group: survivors get flag | length << 16 | offset, pruned leaders get 0
-        for (uint32_t i = tid; i < n_inst; i += G_THREADS)
-            if (grp[i] == i && !(cutoff < 0 || cnt[i] > (uint32_t)cutoff)) cnt[i] = 0;
-        __syncthreads();
-        for (uint32_t s = tid; s < S; s += G_THREADS) {
-            const uint32_t c = (s + 1 < S ? off[s + 1] : N) - off[s];
-            cnt[surv[s]] = 0x80000000u | (c << 16) | off[s];  // c <= CAP < 2^15, off < CAP <= 2^16
+        // ---- every instance learns the index s of its surviving list (0xFFFF: pruned)
+        {
+            uint16_t *mapv = reinterpret_cast<uint16_t *>(stage_ids);  // leader index -> s
+            for (uint32_t sI = tid; sI < S; sI += G_THREADS) mapv[surv[sI]] = (uint16_t)sI;
+            __syncthreads();
+            for (uint32_t i = tid; i < n_inst; i += G_THREADS) {
+                const uint32_t rep = grp[i];
+                grp[i] = (cutoff < 0 || cnt[rep] > (uint32_t)cutoff) ? mapv[rep] : (uint16_t)0xFFFFu;
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        // ---- stage arrivals (unordered inside a list) ...
-        for (uint32_t i = tid; i < n_inst; i += G_THREADS) {
-            const uint32_t v = cnt[grp[i]];
-            if (v & 0x80000000u) stage_ids[(v & 0xffffu) + rnk[i]] = arr[i];
-        }
-        __syncthreads();
         // ---- resolve the unit's output offsets (predecessors have had the whole ordering phase to publish)
-        if (tid == 0) {
-            s_base = unit_resolve(unit_state, u, ((unsigned long long)S << 31) | N);
-            if (u == gc->n_units - 1) {
-                gc->total_kmers = (s_base >> 31) + S;
-                gc->total_ids = (s_base & 0x7fffffffull) + N;
+        if (tid < 32) {  // warp 0 walks back over the predecessors, 32 at a time
+            const unsigned long long base = lkb_resolve_warp<8>(unit_state, u, ((unsigned long long)S << 31) | N, tid);
+            if (tid == 0) {
+                s_base = base;
+                if (u == gc->n_units - 1) {
+                    gc->total_kmers = (base >> 31) + S;
+                    gc->total_ids = (base & 0x7fffffffull) + N;
+                }
             }
         }
         __syncthreads();
@@ -525,18 +499,68 @@ __global__ void __launch_bounds__(G_THREADS)
             __syncthreads();
             continue;
         }
-        // ---- ... then every instance finds its place in the newest-first list by counting the larger arrivals of
-        // its list (ties — the same read twice — by staging position) and writes its read id straight to HBM.
-        // The loads of one list are independent of each other, so nothing here is a dependent chain.
-        for (uint32_t i = tid; i < n_inst; i += G_THREADS) {
-            const uint32_t v = cnt[grp[i]];
-            if (!(v & 0x80000000u)) continue;
-            const uint32_t o = v & 0xffffu, c = (v >> 16) & 0x7fffu, a = arr[i], r = rnk[i];
-            const uint32_t *lst = stage_ids + o;
-            uint32_t rank = 0;
-            for (uint32_t y = 0; y < r; y++) rank += lst[y] >= a ? 1u : 0u;      // earlier staging position wins a tie
-            for (uint32_t y = r + 1; y < c; y++) rank += lst[y] > a ? 1u : 0u;
-            out.read_ids[N_base + o + rank] = ids_by_arrival ? ids_by_arrival[a] : id_base + (int32_t)a;
+        constexpr int NCH = G_CAP / 32;            // 32-instance chunks of a unit
+        constexpr int ITERS = G_CAP / G_THREADS;   // instances per thread
+        if (!filtered && S * NCH <= 2u * 2u * G_CAP) {
+            // ---- id lists, ordered path.  Instance positions of an unfiltered unit follow arrival order, so the place of
+            // an instance in its newest-first list is (members of the list in later chunks) + (members at a higher lane of
+            // its own chunk): a per-(list, chunk) count matrix filled with warp match, a suffix sum per list, done.
+            uint16_t *mat = reinterpret_cast<uint16_t *>(stage_ids);  // [S][NCH], spills into cnt (dead by now)
+            for (uint32_t x = tid; x < (S * NCH + 1) / 2; x += G_THREADS) reinterpret_cast<uint32_t *>(mat)[x] = 0u;
+            __syncthreads();
+            uint32_t within[ITERS];
+            const uint32_t lane = tid & 31, gt_mask = lane == 31 ? 0u : (0xffffffffu << (lane + 1));
+#pragma unroll
+            for (int it = 0; it < ITERS; it++) {
+                const uint32_t p = it * G_THREADS + tid;
+                const uint32_t sI = p < n_inst ? grp[p] : 0xFFFFu;
+                const bool act = sI != 0xFFFFu;
+                const unsigned amask = __ballot_sync(0xffffffffu, act);
+                within[it] = 0;
+                if (act) {
+                    const unsigned peers = __match_any_sync(amask, sI);
+                    within[it] = __popc(peers & gt_mask);
+                    if ((int)lane == __ffs(peers) - 1) mat[sI * NCH + (p >> 5)] = (uint16_t)__popc(peers);
+                }
+            }
+            __syncthreads();
+            for (uint32_t sI = tid; sI < S; sI += G_THREADS) {  // suffix sums over the chunks of list sI
+                uint32_t run = 0;
+                for (int ch = NCH - 1; ch >= 0; ch--) {
+                    const uint32_t c = mat[sI * NCH + ch];
+                    mat[sI * NCH + ch] = (uint16_t)run;
+                    run += c;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < ITERS; it++) {
+                const uint32_t p = it * G_THREADS + tid;
+                const uint32_t sI = p < n_inst ? grp[p] : 0xFFFFu;
+                if (sI != 0xFFFFu) {
+                    const uint32_t a = arr[p];
+                    out.read_ids[N_base + off[sI] + mat[sI * NCH + (p >> 5)] + within[it]] = ids_by_arrival ? ids_by_arrival[a] : id_base + (int32_t)a;
+                }
+            }
+        } else {
+            // ---- id lists, general path (slices of a big bucket, or very many lists): stage the arrivals of every list
+            // in the order the grouping happened to rank them, then every instance finds its place by counting the
+            // larger arrivals of its list (ties — the same read twice — by staging position).
+            for (uint32_t i = tid; i < n_inst; i += G_THREADS) {
+                const uint32_t sI = grp[i];
+                if (sI != 0xFFFFu) stage_ids[off[sI] + rnk[i]] = arr[i];
+            }
+            __syncthreads();
+            for (uint32_t i = tid; i < n_inst; i += G_THREADS) {
+                const uint32_t sI = grp[i];
+                if (sI == 0xFFFFu) continue;
+                const uint32_t o = off[sI], c = (sI + 1 < S ? off[sI + 1] : N) - o, a = arr[i], r = rnk[i];
+                const uint32_t *lst = stage_ids + o;
+                uint32_t rank = 0;
+                for (uint32_t y = 0; y < r; y++) rank += lst[y] >= a ? 1u : 0u;  // earlier staging position wins a tie
+                for (uint32_t y = r + 1; y < c; y++) rank += lst[y] > a ? 1u : 0u;
+                out.read_ids[N_base + o + rank] = ids_by_arrival ? ids_by_arrival[a] : id_base + (int32_t)a;
+            }
         }
 
         // ---- write the unit's slice of the flat table
@@ -592,7 +616,14 @@ static int g_unit_cap() {  // GBIN_V2_CAP=2048|4096 selects the unit capacity (d
 }
 static PlanParams plan_params() {
     const uint32_t cap = (uint32_t)g_unit_cap();
-    return PlanParams{cap, cap / 2, cap / 2};
+    static int eighths = 0;  // GBIN_V2_TSMALL = 1..4: small-bucket threshold in eighths of the capacity (default 4)
+    if (!eighths) {
+        const char *e = getenv("GBIN_V2_TSMALL");
+        eighths = e ? atoi(e) : 4;
+        if (eighths < 1 || eighths > 4) eighths = 4;
+    }
+    const uint32_t t = cap * eighths / 8;
+    return PlanParams{cap, t, cap - t, cap / 2};
 }
 
 size_t skr_group_smem_bytes(int KW) {

@@ -33,13 +33,27 @@ def split_reads_evenly(n_reads: int, world: int):
 
 
 class GpuStages:
-    """The product stages: scan / partition / group through the C ABI on torch-allocated HBM buffers."""
+    """The product stages: scan / partition / group through the C ABI on torch-allocated HBM buffers.
 
-    def __init__(self, binner: B.Binner):
+    form="skr" (default) exchanges super-k-mer records (pipeline 2: one 32/48-byte record per signature segment,
+    about a fifth of the bytes); form="records" exchanges expanded k-mer instance records (pipeline 1), which is
+    also what a batch is re-run with when a shared-memory unit of pipeline 2 overflows."""
+
+    def __init__(self, binner: B.Binner, form: str = "skr"):
+        assert form in ("skr", "records")
         self.b = binner
+        self.form = form
         self.device = torch.device("cuda", binner.device)
-        self.record_bytes = binner.record_bytes
+        self.record_bytes = binner.skr_record_bytes if form == "skr" else binner.record_bytes
         self.launches = 0  # kernels launched by the stages since construction
+
+    def fallback(self) -> "GpuStages":
+        """The stages a batch is re-run with after an overflow (None if already on the general path)."""
+        if self.form == "records":
+            return None
+        fb = GpuStages(self.b, "records")
+        fb.launches = self.launches
+        return fb
 
     def _count(self):
         self.launches += self.b.timings()["kernel_launches"]
@@ -52,6 +66,20 @@ class GpuStages:
 
     def scan(self, reads: B.CReads, arrival_base: int):
         n = self.b.count_instances_device(reads, self.stream())
+        if self.form == "skr":
+            cap = n // 4 + int(reads.n_reads) + 1024  # segments average ~10 windows; the call reports the exact need if this is short
+            while True:
+                rec = self.alloc_records(cap)
+                try:
+                    n_skr, n_inst = self.b.scan_skr_device(reads, arrival_base, rec, cap, self.stream())
+                    break
+                except B.GbinError as e:
+                    if e.code != B.GBIN_E_INVALID_ARG or cap >= n:
+                        raise
+                    cap = n
+            assert n_inst == n
+            self._count()
+            return rec, n_skr
         rec = self.alloc_records(n)
         got = self.b.scan_device(reads, arrival_base, rec, n, self.stream())
         assert got == n
@@ -60,12 +88,24 @@ class GpuStages:
 
     def partition(self, rec: torch.Tensor, n: int, parts: int):
         out = self.alloc_records(n)
-        counts = self.b.partition_device(rec, n, parts, out, self.stream())
+        if self.form == "skr":
+            counts = self.b.partition_skr_device(rec, n, parts, out, self.stream())
+        else:
+            counts = self.b.partition_device(rec, n, parts, out, self.stream())
         self._count()
         return out, counts
 
     def group(self, rec: torch.Tensor, n: int, id_base: int):
-        t = self.b.group_device(rec, n, None, id_base, self.stream())
+        """Returns the device table, or None when a shared-memory unit overflowed (form "skr" only)."""
+        if self.form == "skr":
+            try:
+                t = self.b.group_skr_device(rec, n, None, id_base, self.stream())
+            except B.GbinError as e:
+                if e.code != B.GBIN_E_STATE:
+                    raise
+                return None
+        else:
+            t = self.b.group_device(rec, n, None, id_base, self.stream())
         self._count()
         return t
 
@@ -92,6 +132,7 @@ class ShardedBinner:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.time_stages = time_stages
         self.stats = ExchangeStats()
+        self.fallbacks = 0
 
     def _ev(self):
         if not self.time_stages:
@@ -123,7 +164,32 @@ class ShardedBinner:
 
     def run(self, reads, arrival_base: int, id_base: int = 0):
         """reads: this rank's shard (device CReads); arrival_base: global index of its first read.
-        Returns the device table of the m-mer buckets this rank owns."""
+        Returns the device table of the m-mer buckets this rank owns.  If any rank reports an overflow of the
+        super-k-mer path, every rank re-runs the batch with the general (instance record) stages."""
+        table = self._run_once(reads, arrival_base, id_base)
+        ok = 0 if table is None else 1
+        if self.world > 1:
+            flag = torch.tensor([ok], dtype=torch.int32, device=self._flag_device())
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            ok = int(flag.item())
+        if ok:
+            return table
+        fb = self.stages.fallback() if hasattr(self.stages, "fallback") else None
+        if fb is None:
+            raise RuntimeError("grouping failed and no fallback stages are available")
+        self.fallbacks += 1
+        saved, self.stages = self.stages, fb
+        try:
+            table = self._run_once(reads, arrival_base, id_base)
+        finally:
+            saved.launches = fb.launches
+            self.stages = saved
+        return table
+
+    def _flag_device(self):
+        return getattr(self.stages, "device", torch.device("cpu"))
+
+    def _run_once(self, reads, arrival_base: int, id_base: int = 0):
         e0 = self._ev()
         rec, n = self.stages.scan(reads, arrival_base)
         e1 = self._ev()

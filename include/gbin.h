@@ -143,6 +143,14 @@ int gbin_get_timings(const gbin_ctx *ctx, gbin_timings *out);
  *                is transparently redone by pipeline 1;
  *   1          : expanded k-mer instance records -> stable radix sort on (m-mer, k-mer) in HBM -> run-length/prune/emit.
  * The environment variable GBIN_PIPELINE=1 selects pipeline 1 at context creation. */
+/* Sizes of the intermediate structures of the last pipeline-2 run (0 when pipeline 1 produced the table). */
+typedef struct gbin_run_stats {
+    uint64_t n_super_kmers; /* records emitted by the scan stage */
+    uint64_t n_mmer_runs;   /* distinct m-mer codes before the prune (level-1 buckets) */
+    uint64_t n_units;       /* shared-memory work units of the grouping kernel */
+    uint64_t reserved;
+} gbin_run_stats;
+int gbin_get_run_stats(const gbin_ctx *ctx, gbin_run_stats *out);
 int gbin_set_pipeline(gbin_ctx *ctx, int pipeline);
 int gbin_get_pipeline_info(const gbin_ctx *ctx, int *configured, int *last_used, uint32_t *fallbacks);
 

@@ -72,6 +72,7 @@ def main():
     ap.add_argument("--backend", default="gloo")
     ap.add_argument("--case", default="cfg5_small")
     ap.add_argument("--out", required=True)
+    ap.add_argument("--form", default="skr")
     a = ap.parse_args()
     dist.init_process_group(a.backend)
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -89,7 +90,7 @@ def main():
         local = int(os.environ.get("LOCAL_RANK", rank))
         torch.cuda.set_device(local)
         binner = B.Binner(K, M, cut, device=local)
-        stages = GpuStages(binner)
+        stages = GpuStages(binner, a.form)
         d = torch.from_numpy(np.frombuffer(data, dtype=np.uint8).copy()).cuda()
         s = torch.from_numpy(starts[lo:hi].astype(np.int64)).cuda()
         l = torch.from_numpy(lens[lo:hi].astype(np.int32)).cuda()
@@ -109,7 +110,7 @@ def main():
         got.assert_equal(want)
         assert got.md5() == case["md5"]
         with open(a.out, "w") as f:
-            f.write(f"OK world={world} kmers={got.n_kmers} sent={sb.stats.sent_records}\n")
+            f.write(f"OK world={world} kmers={got.n_kmers} sent={sb.stats.sent_records} fallbacks={sb.fallbacks}\n")
     dist.barrier()
     dist.destroy_process_group()
 

@@ -32,13 +32,16 @@ namespace gbin {
 struct PlanParams {
     uint32_t cap, t, win, tsub;
 };
-constexpr int G_RANK_MAX = 768;  // up to this many survivors per unit are ordered by counting instead of a bitonic sort
+constexpr int G_RANK_MAX = 512;  // up to this many survivors per unit are ordered by counting instead of a bitonic sort
+                                 // (their keys, 20 B each for 128-bit codes, plus a u16 rank array must fit the dead hash table: 16 KB at CAP 2048)
 
 struct __align__(16) Unit {
     uint32_t skr_begin, skr_end;  // range of sorted records
     uint32_t flags;               // bit 0: filtered (a slice of a bucket larger than CAP); bit 1: last slice (no upper bound)
-    uint32_t pad;
+    uint32_t base_pref;           // instance prefix of the first record
     uint64_t lo, hi;              // filtered: keep k-mers whose 64-bit prefix p satisfies lo <= p < hi (hi ignored on the last slice)
+    uint32_t n_cand;              // k-mer instances in the record range
+    uint32_t pad[3];
 };
 constexpr uint32_t UNIT_FILTERED = 1u, UNIT_LAST = 2u;
 
@@ -57,13 +60,30 @@ struct SkrRunHead {
     }
 };
 
-__global__ void skr_run_starts_kernel(const uint32_t *__restrict__ skr, int nw, uint64_t n, const uint32_t *__restrict__ run_excl,
-                                      uint32_t *__restrict__ run_start) {
+struct SkrCountAndHead {  // low half: windows of record i; high half: 1 if record i starts a new m-mer run
+    const uint32_t *skr;
+    int nw;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const {
+        return (uint64_t)SkrCount{skr, nw}(i) | ((uint64_t)SkrRunHead{skr, nw}(i) << 32);
+    }
+};
+
+// both[i] = exclusive {windows, run heads} before record i (packed u64).  Splits it into inst_prefix[] and run_start[].
+__global__ void skr_run_starts_kernel(const uint32_t *__restrict__ skr, int nw, uint64_t n, const uint64_t *__restrict__ both,
+                                      const uint64_t *__restrict__ total, uint32_t *__restrict__ inst_prefix, uint32_t *__restrict__ run_start,
+                                      uint32_t *__restrict__ n_inst_out, uint32_t *__restrict__ n_runs_out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t head = SkrRunHead{skr, nw}(i);
-    if (head) run_start[run_excl[i]] = (uint32_t)i;
-    if (i == n - 1) run_start[run_excl[i] + head] = (uint32_t)n;
+    const uint64_t b = both[i];
+    inst_prefix[i] = (uint32_t)b;
+    if (SkrRunHead{skr, nw}(i)) run_start[b >> 32] = (uint32_t)i;
+    if (i == n - 1) {
+        const uint64_t t = *total;
+        inst_prefix[n] = (uint32_t)t;
+        run_start[t >> 32] = (uint32_t)n;
+        *n_inst_out = (uint32_t)t;
+        *n_runs_out = (uint32_t)(t >> 32);
+    }
 }
 
 struct RunView {
@@ -95,8 +115,12 @@ struct UnitsOfRun {  // how many units start at run r
     }
 };
 
+struct GroupCounters;
+__device__ __forceinline__ unsigned int *big_counter(GroupCounters *gc);
+
 __global__ void fill_units_kernel(RunView rv, const uint32_t *__restrict__ small_prefix, const uint32_t *__restrict__ unit_base,
-                                  uint64_t n_runs, PlanParams pp, Unit *__restrict__ units) {
+                                  uint64_t n_runs, PlanParams pp, Unit *__restrict__ units, GroupCounters *__restrict__ gc,
+                                  uint32_t *__restrict__ big_list) {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_runs) return;
     const uint32_t nu = UnitsOfRun{rv, small_prefix, pp}(r);
@@ -104,16 +128,19 @@ __global__ void fill_units_kernel(RunView rv, const uint32_t *__restrict__ small
     const uint32_t ub = unit_base[r];
     if (c > pp.cap) {
         // sliced bucket: split_big_runs_kernel fills the units (it needs a sample of the bucket's k-mers)
+        big_list[atomicAdd(big_counter(gc), 1u)] = (uint32_t)r;
     } else if (c > pp.t) {
-        units[ub] = Unit{rv.run_start[r], rv.run_start[r + 1], 0u, 0u, 0ull, 0ull};
+        units[ub] = Unit{rv.run_start[r], rv.run_start[r + 1], 0u, rv.inst_prefix[rv.run_start[r]], 0ull, 0ull, c, {0u, 0u, 0u}};
     } else {
         // unit of this run = the latest head at or before it: exclusive base + own head flag - 1
         const uint32_t u = ub + nu - 1;
         if (nu) {
             units[u].skr_begin = rv.run_start[r];
             units[u].flags = 0;
+            units[u].base_pref = rv.inst_prefix[rv.run_start[r]];
         }
         atomicMax(&units[u].skr_end, rv.run_start[r + 1]);
+        atomicAdd(&units[u].n_cand, c);
     }
 }
 
@@ -139,13 +166,15 @@ constexpr int SPLIT_SAMPLES = 2048;
 // into P = ceil(c / TSUB) slices of equal sample count.
 template <int PW>
 __global__ void __launch_bounds__(SPLIT_THREADS)
-    split_big_runs_kernel(const uint32_t *__restrict__ skr, RunView rv, const uint32_t *__restrict__ unit_base, uint64_t n_runs, PlanParams pp,
-                          int K, Unit *__restrict__ units) {
+    split_big_runs_kernel(const uint32_t *__restrict__ skr, RunView rv, const uint32_t *__restrict__ unit_base,
+                          const uint32_t *__restrict__ big_list, const unsigned int *__restrict__ n_big, PlanParams pp, int K,
+                          Unit *__restrict__ units) {
     constexpr int NW = SkrLayout<PW>::WORDS;
     __shared__ uint64_t samp[SPLIT_SAMPLES];
-    for (uint64_t r = blockIdx.x; r < n_runs; r += gridDim.x) {
+    const uint32_t nb = *n_big;
+    for (uint32_t bi = blockIdx.x; bi < nb; bi += gridDim.x) {
+        const uint64_t r = big_list[bi];
         const uint32_t c = rv.size(r);
-        if (c <= pp.cap) continue;
         const uint32_t a = rv.run_start[r], b = rv.run_start[r + 1];
         const uint32_t base = rv.inst_prefix[a];
         const uint32_t P = units_of_big(c, pp);
@@ -181,7 +210,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS)
         for (uint32_t p = threadIdx.x; p < P; p += SPLIT_THREADS) {
             const uint64_t lo = p ? samp[(uint64_t)p * S / P] : 0ull;
             const uint64_t hi = p + 1 < P ? samp[(uint64_t)(p + 1) * S / P] : 0ull;
-            units[ub + p] = Unit{a, b, UNIT_FILTERED | (p + 1 == P ? UNIT_LAST : 0u), 0u, lo, hi};
+            units[ub + p] = Unit{a, b, UNIT_FILTERED | (p + 1 == P ? UNIT_LAST : 0u), base, lo, hi, c, {0u, 0u, 0u}};
         }
         __syncthreads();
     }
@@ -231,8 +260,10 @@ struct GroupCounters {
     unsigned int overflow;
     unsigned int ticket;
     unsigned int n_units;
-    unsigned int pad;
+    unsigned int n_big;  // buckets larger than a unit (work list of split_big_runs_kernel)
 };
+
+__device__ __forceinline__ unsigned int *big_counter(GroupCounters *gc) { return &gc->n_big; }
 
 template <int KW>
 __device__ __forceinline__ bool key_less(const uint64_t *key0, const uint64_t *key1, const uint32_t *mm, uint32_t a, uint32_t b) {
@@ -266,24 +297,30 @@ __global__ void __launch_bounds__(G_THREADS)
     __shared__ uint32_t s_unit, s_count, s_nsurv, s_ndistinct, s_overflow, s_scan[G_THREADS / 32 + 1];
     __shared__ unsigned long long s_base;
     __shared__ uint32_t s_total_ids;
+    __shared__ Unit s_un;
 
     const uint32_t tid = threadIdx.x;
     const uint64_t kmask0 = (2 * K >= 64 * KW) ? ~0ull : ((1ull << (2 * K - 64 * (KW - 1))) - 1);  // mask of the most significant word
 
+    // Units are handed out by an atomic ticket, taken only when the CTA is ready to start the unit: a ticket taken ahead
+    // of time would let later units overtake it, and their chained-scan resolve would then wait for it.
+    const uint32_t n_units = gc->n_units;
     for (;;) {
         if (tid == 0) {
             s_unit = atomicAdd(&gc->ticket, 1u);
+            if (s_unit < n_units) s_un = units[s_unit];
             s_count = 0;
             s_nsurv = 0;
             s_ndistinct = 0;
             s_overflow = 0;
+            s_total_ids = 0;
         }
         __syncthreads();
         const uint32_t u = s_unit;
-        if (u >= gc->n_units) break;
-        const Unit un = units[u];
-        const uint32_t base_pref = inst_prefix[un.skr_begin];
-        const uint32_t n_cand = inst_prefix[un.skr_end] - base_pref;
+        if (u >= n_units) break;
+        const Unit un = s_un;
+        const uint32_t base_pref = un.base_pref;
+        const uint32_t n_cand = un.n_cand;
         const bool filtered = (un.flags & UNIT_FILTERED) != 0;
         if (!filtered && n_cand > (uint32_t)G_CAP && tid == 0) s_overflow = 1;
 
@@ -396,31 +433,50 @@ __global__ void __launch_bounds__(G_THREADS)
         for (uint32_t i = tid; i < n_inst; i += G_THREADS) {
             if (grp[i] == i) {
                 atomicAdd(&s_ndistinct, 1u);
-                if (cutoff < 0 || cnt[i] > (uint32_t)cutoff) surv[atomicAdd(&s_nsurv, 1u)] = (uint16_t)i;
+                if (cutoff < 0 || cnt[i] > (uint32_t)cutoff) {
+                    surv[atomicAdd(&s_nsurv, 1u)] = (uint16_t)i;
+                    atomicAdd(&s_total_ids, cnt[i]);
+                }
             }
         }
         __syncthreads();
-        const uint32_t S = s_nsurv;
+        const uint32_t S = s_nsurv, N = s_total_ids;
+        // the unit's totals are known before any ordering work: publish them now so that successors rarely wait
+        if (tid == 0) {
+            lkb_publish_aggregate(unit_state, u, ((unsigned long long)S << 31) | N);
+            atomicAdd(&gc->distinct, (unsigned long long)s_ndistinct);
+        }
 
         // ---- survivors ascending by (m-mer, k-mer).  Usual case (a few hundred survivors): every survivor counts
         // the survivors with a smaller key (keys are distinct, so ranks are a permutation) — no barriers inside;
         // otherwise a bitonic sort of the instance indices, padded with 0xFFFF = +inf.
         if (S <= (uint32_t)G_RANK_MAX) {
-            uint16_t *tmp = reinterpret_cast<uint16_t *>(stage_ids);  // the hash table is dead from here on
+            // the hash table is dead from here on: its memory holds the survivors' keys side by side, so the ranking
+            // loop reads consecutive broadcast words instead of chasing surv[] -> key arrays
+            uint64_t *sk0 = reinterpret_cast<uint64_t *>(table);
+            uint64_t *sk1 = sk0 + (KW == 2 ? G_RANK_MAX : 0);
+            uint32_t *smm = reinterpret_cast<uint32_t *>(sk0 + KW * G_RANK_MAX);
+            uint16_t *tmp = reinterpret_cast<uint16_t *>(smm + G_RANK_MAX);
             for (uint32_t s = tid; s < S; s += G_THREADS) {
                 const uint32_t i = surv[s];
-                const uint64_t k0 = key0[i], k1 = (KW == 2) ? key1[i] : 0ull;
-                const uint32_t m = mm[i];
+                sk0[s] = key0[i];
+                if (KW == 2) sk1[s] = key1[i];
+                smm[s] = mm[i];
+            }
+            __syncthreads();
+            for (uint32_t s = tid; s < S; s += G_THREADS) {
+                const uint64_t k0 = sk0[s], k1 = (KW == 2) ? sk1[s] : 0ull;
+                const uint32_t m = smm[s];
                 uint32_t rank = 0;
+#pragma unroll 4
                 for (uint32_t t = 0; t < S; t++) {
-                    const uint32_t j = surv[t];
-                    const uint32_t mj = mm[j];
-                    const uint64_t kj = key0[j];
+                    const uint32_t mj = smm[t];
+                    const uint64_t kj = sk0[t];
                     bool less = mj < m || (mj == m && kj < k0);
-                    if constexpr (KW == 2) less = less || (mj == m && kj == k0 && key1[j] < k1);
+                    if constexpr (KW == 2) less = less || (mj == m && kj == k0 && sk1[t] < k1);
                     rank += less ? 1u : 0u;
                 }
-                tmp[rank] = (uint16_t)i;
+                tmp[rank] = surv[s];
             }
             __syncthreads();
             for (uint32_t s = tid; s < S; s += G_THREADS) surv[s] = tmp[s];
@@ -461,14 +517,8 @@ __global__ void __launch_bounds__(G_THREADS)
                 if (s < S) off[s] = carry + ex;
                 carry += tot;
             }
-            if (tid == 0) {
-                s_total_ids = carry;
-                lkb_publish_aggregate(unit_state, u, ((unsigned long long)S << 31) | carry);
-                atomicAdd(&gc->distinct, (unsigned long long)s_ndistinct);
-            }
         }
         __syncthreads();
-        const uint32_t N = s_total_ids;
 
         // ---- every instance learns the index s of its surviving list (0xFFFF: pruned)
         {
@@ -633,23 +683,23 @@ size_t skr_group_smem_bytes(int KW) {
 
 uint64_t skr_max_units(uint64_t n_inst, uint64_t n_runs) { return n_inst / (g_unit_cap() / 4) + 2 * n_runs + 8; }
 size_t skr_unit_bytes() { return sizeof(Unit); }
+uint64_t skr_max_big_runs(uint64_t n_inst) { return n_inst / (uint64_t)g_unit_cap() + 2; }
 
-// Phase A (needs n_skr on the host): instance prefix and m-mer run starts. *n_runs_dev receives the number of runs.
-int skr_plan_runs(const void *skr_sorted, uint64_t n_skr, int skr_words, uint32_t *inst_prefix /*[n+1]*/, uint32_t *run_excl /*[n]*/,
-                  uint32_t *run_start /*[n+1]*/, uint32_t *scratch, uint32_t *n_inst_dev, uint32_t *n_runs_dev, cudaStream_t st) {
+// Phase A (needs n_skr on the host): instance prefix and m-mer run starts in one fused scan.
+// both64: [n_skr + 1] u64 scratch; scratch64: prefix-scan scratch. *n_inst_dev / *n_runs_dev receive the totals.
+int skr_plan_runs(const void *skr_sorted, uint64_t n_skr, int skr_words, uint32_t *inst_prefix /*[n+1]*/, uint64_t *both64,
+                  uint32_t *run_start /*[n+1]*/, uint64_t *scratch64, uint32_t *n_inst_dev, uint32_t *n_runs_dev, cudaStream_t st) {
     const uint32_t *s = static_cast<const uint32_t *>(skr_sorted);
-    int l = 0;
-    l += exclusive_scan<uint32_t, SkrCount>(SkrCount{s, skr_words}, inst_prefix, n_skr, scratch, n_inst_dev, st);
-    cudaMemcpyAsync(inst_prefix + n_skr, n_inst_dev, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
-    l += exclusive_scan<uint32_t, SkrRunHead>(SkrRunHead{s, skr_words}, run_excl, n_skr, scratch, n_runs_dev, st);
-    skr_run_starts_kernel<<<(unsigned)((n_skr + 255) / 256), 256, 0, st>>>(s, skr_words, n_skr, run_excl, run_start);
+    int l = exclusive_scan<uint64_t, SkrCountAndHead>(SkrCountAndHead{s, skr_words}, both64, n_skr, scratch64, both64 + n_skr, st);
+    skr_run_starts_kernel<<<(unsigned)((n_skr + 255) / 256), 256, 0, st>>>(s, skr_words, n_skr, both64, both64 + n_skr, inst_prefix, run_start,
+                                                                          n_inst_dev, n_runs_dev);
     return l + 1;
 }
 
 // Phase B (needs n_runs on the host): units. small_prefix / unit_base are [n_runs] scratch arrays.
 int skr_plan_units(const void *skr_sorted, int K, const uint32_t *inst_prefix, const uint32_t *run_start, uint64_t n_runs,
-                   uint32_t *small_prefix, uint32_t *unit_base, uint32_t *scratch, void *units, uint64_t max_units, void *gc_dev, int sm_count,
-                   cudaStream_t st) {
+                   uint32_t *small_prefix, uint32_t *unit_base, uint32_t *scratch, void *units, uint64_t max_units, void *gc_dev,
+                   uint32_t *big_list, int sm_count, cudaStream_t st) {
     RunView rv{run_start, inst_prefix};
     const PlanParams pp = plan_params();
     GroupCounters *gc = static_cast<GroupCounters *>(gc_dev);
@@ -658,11 +708,14 @@ int skr_plan_units(const void *skr_sorted, int K, const uint32_t *inst_prefix, c
     cudaMemsetAsync(gc, 0, sizeof(GroupCounters), st);
     l += exclusive_scan<uint32_t, SmallSize>(SmallSize{rv, pp}, small_prefix, n_runs, scratch, nullptr, st);
     l += exclusive_scan<uint32_t, UnitsOfRun>(UnitsOfRun{rv, small_prefix, pp}, unit_base, n_runs, scratch, &gc->n_units, st);
-    fill_units_kernel<<<(unsigned)((n_runs + 255) / 256), 256, 0, st>>>(rv, small_prefix, unit_base, n_runs, pp, static_cast<Unit *>(units));
-    const unsigned grid = (unsigned)(n_runs < (uint64_t)sm_count * 8 ? n_runs : (uint64_t)sm_count * 8);
+    fill_units_kernel<<<(unsigned)((n_runs + 255) / 256), 256, 0, st>>>(rv, small_prefix, unit_base, n_runs, pp, static_cast<Unit *>(units), gc,
+                                                                       big_list);
+    const unsigned grid = (unsigned)sm_count * 4;
     const uint32_t *s = static_cast<const uint32_t *>(skr_sorted);
-    if (K <= 32) split_big_runs_kernel<2><<<grid, SPLIT_THREADS, 0, st>>>(s, rv, unit_base, n_runs, pp, K, static_cast<Unit *>(units));
-    else split_big_runs_kernel<4><<<grid, SPLIT_THREADS, 0, st>>>(s, rv, unit_base, n_runs, pp, K, static_cast<Unit *>(units));
+    if (K <= 32)
+        split_big_runs_kernel<2><<<grid, SPLIT_THREADS, 0, st>>>(s, rv, unit_base, big_list, &gc->n_big, pp, K, static_cast<Unit *>(units));
+    else
+        split_big_runs_kernel<4><<<grid, SPLIT_THREADS, 0, st>>>(s, rv, unit_base, big_list, &gc->n_big, pp, K, static_cast<Unit *>(units));
     return l + 2;
 }
 
@@ -681,9 +734,17 @@ int skr_group_launch(const void *skr_sorted, int K, int cutoff, const uint32_t *
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kern<<<sm_count * ctas_per_sm, threads, smem, st>>>(s, inst_prefix, un, K, cutoff, ids_by_arrival, id_base, out, unit_state, gc);
     };
+    static int thr = 0;  // GBIN_V2_THREADS=512: experiment with 512 threads per CTA at capacity 2048
+    if (!thr) {
+        const char *e = getenv("GBIN_V2_THREADS");
+        thr = (e && atoi(e) == 512) ? 512 : 256;
+    }
     if (g_unit_cap() == 4096) {
         if (KW == 1) launch(skr_group_kernel<2, 1, 4096, 512>, 512, 1);
         else launch(skr_group_kernel<4, 2, 4096, 512>, 512, 1);
+    } else if (thr == 512) {
+        if (KW == 1) launch(skr_group_kernel<2, 1, 2048, 512>, 512, 3);
+        else launch(skr_group_kernel<4, 2, 2048, 512>, 512, 2);
     } else {
         if (KW == 1) launch(skr_group_kernel<2, 1, 2048, 256>, 256, 3);
         else launch(skr_group_kernel<4, 2, 2048, 256>, 256, 2);

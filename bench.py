@@ -41,21 +41,32 @@ def parse_args():
     ap.add_argument("--impl", default="gbin", choices=["gbin", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--reads-per-gpu", type=int, default=0, help="override the workload's read count (debug)")
+    ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
+                    help="weak: every GPU holds the workload's read count (default for cfg2); strong: the workload's reads are split "
+                         "over the GPUs (default for cfg3-5, whose BASELINE sizes are totals)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
-def workload_params(name, reads_override=0):
+def workload_params(name, reads_override=0, scaling="auto", world=1):
+    """Per-GPU shape of the workload.  weak: n_reads per GPU = the workload's count; strong: the count is split."""
     from genome_assembly_b200 import synth
     w = dict(synth.WORKLOADS[name])
+    if scaling == "auto":
+        scaling = "weak" if name == "cfg2" else "strong"
+    w["scaling"] = scaling
+    w["total_reads"] = w["n_reads"] * world if scaling == "weak" else w["n_reads"]
+    if scaling == "strong":
+        w["n_reads"] = w["n_reads"] // world
     if reads_override:
         w["n_reads"] = reads_override
+        w["total_reads"] = reads_override * world
     return w
 
 
 def make_reads(w, rank, world):
-    """This rank's shard: config-shaped reads from one shared genome (world x the config's genome)."""
+    """This rank's shard: config-shaped reads from one shared genome (30x coverage over all ranks' reads)."""
     from genome_assembly_b200 import synth
     n = w["n_reads"]
     glen = synth.default_genome_len(n * world, w["read_len"])
@@ -103,7 +114,7 @@ def run_reference_arm(a):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    w = workload_params(a.workload, a.reads_per_gpu)
+    w = workload_params(a.workload, a.reads_per_gpu, a.scaling, max(a.gpus, 1))
     rs = make_reads(w, 0, max(a.gpus, 1))
     sample_reads = min(w["n_reads"], 40_000)  # ~2.8 M instances, a few seconds per step
     for _ in range(a.warmup):
@@ -118,21 +129,22 @@ def run_reference_arm(a):
     value = inst * a.steps / sum(inst / v for v in vals)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": 1e3 * wall / max(a.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64", "data": "synthetic",
+        "ms_per_step": 1e3 * wall / max(a.steps, 1), "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
+        "dtype": "u64" if w["k"] <= 32 else "u128", "data": "synthetic",
         "config": config_dict(a, w, max(a.gpus, 1)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ helpers
 
 def config_dict(a, w, world):
-    return {"workload": f"{a.workload}: {w['n_reads']} reads x {w['read_len']} bp per GPU, K={w['k']}, M={w['m']}, cutoff={w['cutoff']}, "
-                        f"{w['error_rate'] * 100:g}% substitutions, {w['starts']} starts, genome {world}x{w['n_reads'] * w['read_len'] // 30} bp",
+    return {"workload": f"{a.workload}: {w['n_reads']} reads x {w['read_len']} bp per GPU ({w['n_reads'] * world} in total, {w['scaling']} scaling), "
+                        f"K={w['k']}, M={w['m']}, cutoff={w['cutoff']}, {w['error_rate'] * 100:g}% substitutions, {w['starts']} starts, "
+                        f"genome {w['n_reads'] * world * w['read_len'] // 30} bp",
             "k": w["k"], "m": w["m"], "cutoff": w["cutoff"], "reads_per_gpu": w["n_reads"], "read_len": w["read_len"],
             "parallelism": f"reads split evenly over {world} GPU(s); records exchanged by owner = mmer % {world}" if world > 1 else "single GPU",
             "l2": "L2 flushed (256 MiB memset) before every timed step; per-step device times summed"}
@@ -201,8 +213,26 @@ class ClockSampler:
         return out
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line goes to the process's original stdout; everything else that libraries print on fd 1 (NCCL's
+    version banner, for instance) is diverted to stderr so that the driver can parse stdout as a single line."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     a = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference_arm(a)
         return
@@ -226,7 +256,7 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()  # nvidia-smi takes about a second to deliver its first sample: start it before the data is generated
-    w = workload_params(a.workload, a.reads_per_gpu)
+    w = workload_params(a.workload, a.reads_per_gpu, a.scaling, world)
     K, M, cutoff = w["k"], w["m"], w["cutoff"]
     rs = make_reads(w, rank, world)
     W = rs.read_len - K + 1
@@ -401,13 +431,13 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
             "dtype": "u64" if K <= 32 else "u128", "data": "synthetic",
             "config": config_dict(a, w, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu, "table": stats,
             "wall_s_timed_region": wall_s, "step_ms": step_ms,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -93,7 +93,7 @@ struct gbin_ctx {
     DevBuf group_of, run_start, surv_index, id_offset, surv_group, bucket_of;
     DevBuf misc;
     // pipeline v2 workspace
-    DevBuf skr_a, skr_b, tile_state, inst_prefix, run_excl, skr_run_start, small_prefix, unit_base, units, unit_state, o_kmer_mmer, bucket_excl, big_list;
+    DevBuf skr_a, skr_b, tile_state, inst_prefix, run_excl, skr_run_start, small_prefix, unit_base, units, unit_state, o_kmer_mmer, bucket_excl, big_list, big_k0, big_k1, big_arr;
     int pipeline;        // 2: super-k-mer path with v1 as fallback (default); 1: v1 only
     int last_pipeline;   // which one produced the last table
     uint32_t fallbacks;  // v2 -> v1 fallbacks since creation
@@ -380,12 +380,15 @@ int run_v2_group(gbin_ctx *ctx, void *skr, void *twin, uint64_t n_skr, const int
     CU(ctx->unit_base.ensure((n_runs + 1) * 4));
     CU(ctx->units.ensure(max_units * skr_unit_bytes()));
     CU(ctx->unit_state.ensure(max_units * 8));
-    CU(ctx->big_list.ensure(skr_max_big_runs(n) * 4));
+    CU(ctx->big_list.ensure(skr_max_big_runs(n) * 8));
+    CU(ctx->big_k0.ensure((n + 1) * 8));
+    if (KW == 2) CU(ctx->big_k1.ensure((n + 1) * 8));
+    CU(ctx->big_arr.ensure((n + 1) * 4));
     CU(ctx->scan_scratch.ensure(group_scan_scratch_bytes(n / 2 + n_runs + 1024)));
     on = ctx->prof.begin(KK_SKR_PLAN, st);
     lp = skr_plan_units(sorted, K, ctx->inst_prefix.as<uint32_t>(), ctx->skr_run_start.as<uint32_t>(), n_runs, ctx->small_prefix.as<uint32_t>(),
                         ctx->unit_base.as<uint32_t>(), ctx->scan_scratch.as<uint32_t>(), ctx->units.p, max_units, &dm->gc, ctx->big_list.as<uint32_t>(),
-                        ctx->sm_count, st);
+                        ctx->big_k0.as<uint64_t>(), ctx->big_k1.as<uint64_t>(), ctx->big_arr.as<uint32_t>(), ctx->sm_count, st);
     ctx->prof.end(on, lp, st);
     *launches += lp;
     CU(cudaGetLastError());
@@ -398,7 +401,7 @@ int run_v2_group(gbin_ctx *ctx, void *skr, void *twin, uint64_t n_skr, const int
     CU(ctx->o_read_ids.ensure((n + 1) * sizeof(int32_t)));
     on = ctx->prof.begin(KK_SKR_GROUP, st);
     lp = skr_group_launch(sorted, K, cutoff, ctx->inst_prefix.as<uint32_t>(), ctx->units.p, ctx->unit_state.as<unsigned long long>(), max_units,
-                          &dm->gc, d_ids, id_base, ctx->o_kmer_codes.as<uint64_t>(), ctx->o_kmer_mmer.as<uint32_t>(),
+                          &dm->gc, ctx->big_k0.as<uint64_t>(), ctx->big_k1.as<uint64_t>(), ctx->big_arr.as<uint32_t>(), d_ids, id_base, ctx->o_kmer_codes.as<uint64_t>(), ctx->o_kmer_mmer.as<uint32_t>(),
                           ctx->o_kmer_id_off.as<uint64_t>(), ctx->o_read_ids.as<int32_t>(), kmer_cap, n, ctx->sm_count, st);
     ctx->prof.end(on, lp, st);
     *launches += lp;
@@ -562,7 +565,7 @@ void gbin_destroy(gbin_ctx *ctx) {
                       &ctx->id_offset, &ctx->surv_group, &ctx->bucket_of, &ctx->misc, &ctx->o_mmer_codes, &ctx->o_mmer_kmer_off,
                       &ctx->o_kmer_codes, &ctx->o_kmer_id_off, &ctx->o_read_ids, &ctx->skr_a, &ctx->skr_b, &ctx->tile_state,
                       &ctx->inst_prefix, &ctx->run_excl, &ctx->skr_run_start, &ctx->small_prefix, &ctx->unit_base, &ctx->units,
-                      &ctx->unit_state, &ctx->o_kmer_mmer, &ctx->bucket_excl, &ctx->big_list};
+                      &ctx->unit_state, &ctx->o_kmer_mmer, &ctx->bucket_excl, &ctx->big_list, &ctx->big_k0, &ctx->big_k1, &ctx->big_arr};
     for (DevBuf *b : bufs) b->release();
     ctx->h_misc.release();
     ctx->h_result.release();

@@ -85,7 +85,7 @@ uint32_t skr_scan_tiles(uint64_t n_reads, int K, int M, uint32_t max_len);
 struct SkrGroupCounters {  // mirror of GroupCounters in skr_group.cu
     unsigned long long distinct;
     unsigned long long total_kmers, total_ids;
-    unsigned int overflow, ticket, n_units, n_big;
+    unsigned int overflow, ticket, n_units, n_big, big_inst, pad[3];
 };
 size_t skr_group_smem_bytes(int KW);
 uint64_t skr_max_units(uint64_t n_inst, uint64_t n_runs);
@@ -95,9 +95,9 @@ int skr_plan_runs(const void *skr_sorted, uint64_t n_skr, int skr_words, uint32_
 size_t skr_unit_bytes();
 int skr_plan_units(const void *skr_sorted, int K, const uint32_t *inst_prefix, const uint32_t *run_start, uint64_t n_runs,
                    uint32_t *small_prefix, uint32_t *unit_base, uint32_t *scratch, void *units, uint64_t max_units, void *gc_dev,
-                   uint32_t *big_list, int sm_count, cudaStream_t st);
+                   uint32_t *big_list, uint64_t *big_k0, uint64_t *big_k1, uint32_t *big_arr, int sm_count, cudaStream_t st);
 int skr_group_launch(const void *skr_sorted, int K, int cutoff, const uint32_t *inst_prefix, const void *units, unsigned long long *unit_state,
-                     uint64_t max_units, void *gc_dev, const int32_t *ids_by_arrival, int32_t id_base, uint64_t *kmer_codes,
+                     uint64_t max_units, void *gc_dev, uint64_t *big_k0, uint64_t *big_k1, uint32_t *big_arr, const int32_t *ids_by_arrival, int32_t id_base, uint64_t *kmer_codes,
                      uint32_t *kmer_mmer, uint64_t *kmer_id_off, int32_t *read_ids, uint64_t kmer_cap, uint64_t id_cap, int sm_count,
                      cudaStream_t st);
 int skr_emit_buckets(const uint32_t *kmer_mmer, uint64_t n_kmers, uint64_t n_ids, uint32_t *bucket_excl, uint32_t *scratch,

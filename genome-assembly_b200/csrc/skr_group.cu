@@ -4,9 +4,11 @@
 // two-level store (binning.c:1044-1049) is already formed and, inside a bucket, records are in arrival
 // order.  This file
 //   1. plans *units*: runs of whole m-mer buckets whose k-mer instances fit one CTA's shared memory
-//      (small buckets packed by windows of T instances; a bucket larger than CAP is range-partitioned
-//      on the 64-bit prefix of the oriented k-mer with splitters taken from a sorted sample of the
-//      bucket, which keeps ascending k-mer order across the slices);
+//      (small buckets packed by windows of T instances; a bucket larger than CAP is expanded ONCE into
+//      (k-mer, arrival) records in HBM, range-partitioned on the 64-bit prefix of the oriented k-mer:
+//      fine splitters come from a sorted sample of the bucket, exact fine counts are taken, and
+//      adjacent fine ranges are merged greedily into slices that fill a unit — ascending k-mer order
+//      is kept across the slices);
 //   2. runs a persistent kernel, one unit at a time per CTA, that expands the windows of every
 //      record (rolling 2-bit shift, complement when is_rev — binning.c:1029-1040), groups equal
 //      (m-mer, k-mer) keys with a shared-memory hash (level-2 zhash insert + ll_node push,
@@ -36,14 +38,14 @@ constexpr int G_RANK_MAX = 512;  // up to this many survivors per unit are order
                                  // (their keys, 20 B each for 128-bit codes, plus a u16 rank array must fit the dead hash table: 16 KB at CAP 2048)
 
 struct __align__(16) Unit {
-    uint32_t skr_begin, skr_end;  // range of sorted records
-    uint32_t flags;               // bit 0: filtered (a slice of a bucket larger than CAP); bit 1: last slice (no upper bound)
-    uint32_t base_pref;           // instance prefix of the first record
-    uint64_t lo, hi;              // filtered: keep k-mers whose 64-bit prefix p satisfies lo <= p < hi (hi ignored on the last slice)
-    uint32_t n_cand;              // k-mer instances in the record range
-    uint32_t pad[3];
+    uint32_t skr_begin, skr_end;  // range of sorted super-k-mer records; UNIT_RECORDS: range of expanded instance records
+    uint32_t flags;               // UNIT_RECORDS: a slice of a bucket larger than CAP, already expanded into the scratch arrays
+    uint32_t base_pref;           // instance prefix of the first super-k-mer record
+    uint32_t n_cand;              // k-mer instances of the unit
+    uint32_t mmer;                // UNIT_RECORDS: the bucket's m-mer code
+    uint32_t pad[2];
 };
-constexpr uint32_t UNIT_FILTERED = 1u, UNIT_LAST = 2u;
+constexpr uint32_t UNIT_RECORDS = 1u;
 
 // ------------------------------------------------------------------ planning
 
@@ -117,6 +119,7 @@ struct UnitsOfRun {  // how many units start at run r
 
 struct GroupCounters;
 __device__ __forceinline__ unsigned int *big_counter(GroupCounters *gc);
+__device__ __forceinline__ unsigned int *big_inst_counter(GroupCounters *gc);
 
 __global__ void fill_units_kernel(RunView rv, const uint32_t *__restrict__ small_prefix, const uint32_t *__restrict__ unit_base,
                                   uint64_t n_runs, PlanParams pp, Unit *__restrict__ units, GroupCounters *__restrict__ gc,
@@ -127,10 +130,12 @@ __global__ void fill_units_kernel(RunView rv, const uint32_t *__restrict__ small
     const uint32_t c = rv.size(r);
     const uint32_t ub = unit_base[r];
     if (c > pp.cap) {
-        // sliced bucket: split_big_runs_kernel fills the units (it needs a sample of the bucket's k-mers)
-        big_list[atomicAdd(big_counter(gc), 1u)] = (uint32_t)r;
+        // sliced bucket: partition_big_runs_kernel expands it into the scratch arrays and fills its units
+        const uint32_t bi = atomicAdd(big_counter(gc), 1u);
+        big_list[2 * bi] = (uint32_t)r;
+        big_list[2 * bi + 1] = atomicAdd(big_inst_counter(gc), c);  // its base in the scratch arrays
     } else if (c > pp.t) {
-        units[ub] = Unit{rv.run_start[r], rv.run_start[r + 1], 0u, rv.inst_prefix[rv.run_start[r]], 0ull, 0ull, c, {0u, 0u, 0u}};
+        units[ub] = Unit{rv.run_start[r], rv.run_start[r + 1], 0u, rv.inst_prefix[rv.run_start[r]], c, 0u, {0u, 0u}};
     } else {
         // unit of this run = the latest head at or before it: exclusive base + own head flag - 1
         const uint32_t u = ub + nu - 1;
@@ -144,8 +149,50 @@ __global__ void fill_units_kernel(RunView rv, const uint32_t *__restrict__ small
     }
 }
 
-// 64-bit prefix of the oriented k-mer of window w of a record: the top min(64, 2K) bits of the payload shifted left
-// by w bases, complemented when is_rev.  Monotone in the k-mer code, so slicing on it keeps k-mer order.
+// Calls f(t, k0, k1, prefix) for every window t of a super-k-mer record: the oriented k-mer code (top 2K bits of the payload
+// shifted left by t bases, complemented when is_rev — binning.c:1029-1040) and its 64-bit prefix (monotone in the code).
+template <int PW, int KW, typename F>
+__device__ __forceinline__ void for_each_window(const uint32_t *__restrict__ rec, int K, F &&f) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(rec);
+    const uint4 h = p[0];
+    const uint32_t n = h.z & 0xffu;
+    const bool rev = (h.z >> 8) & 1u;
+    const uint64_t kmask0 = (2 * K >= 64 * KW) ? ~0ull : ((1ull << (2 * K - 64 * (KW - 1))) - 1);  // mask of the most significant word
+    uint64_t w[PW];
+    {
+        const uint4 a = p[1];
+        w[0] = ((uint64_t)a.x << 32) | a.y;
+        w[1] = ((uint64_t)a.z << 32) | a.w;
+        if (PW == 4) {
+            const uint4 b = p[2];
+            w[PW - 2] = ((uint64_t)b.x << 32) | b.y;
+            w[PW - 1] = ((uint64_t)b.z << 32) | b.w;
+        }
+    }
+    for (uint32_t t = 0; t < n; t++) {
+        uint64_t k0, k1 = 0;
+        if (KW == 1) {
+            k0 = (2 * K == 64) ? w[0] : (w[0] >> (64 - 2 * K));
+            if (rev) k0 = ~k0 & kmask0;
+        } else {
+            const int r = 128 - 2 * K;  // 0..62
+            k0 = r ? (w[0] >> r) : w[0];
+            k1 = r ? ((w[1] >> r) | (w[0] << (64 - r))) : w[1];
+            if (rev) {
+                k0 = ~k0 & kmask0;
+                k1 = ~k1;
+            }
+        }
+        uint64_t pre = rev ? ~w[0] : w[0];
+        if (2 * K < 64) pre &= ~0ull << (64 - 2 * K);
+        f(t, k0, k1, pre);
+#pragma unroll
+        for (int q = 0; q < PW - 1; q++) w[q] = (w[q] << 2) | (w[q + 1] >> 62);  // next base
+        w[PW - 1] <<= 2;
+    }
+}
+
+// 64-bit prefix of the oriented k-mer of window w of a record (random access form of the above).
 template <int PW>
 __device__ __forceinline__ uint64_t window_prefix(const uint32_t *rec, uint32_t w, int K) {
     const uint32_t bit = 2 * w, wi = bit >> 5, sh = bit & 31;
@@ -159,28 +206,48 @@ __device__ __forceinline__ uint64_t window_prefix(const uint32_t *rec, uint32_t 
     return pre;
 }
 
-constexpr int SPLIT_THREADS = 256;
-constexpr int SPLIT_SAMPLES = 2048;
+constexpr int PART_THREADS = 256;
+constexpr int PART_SAMPLES = 2048;  // sorted sample of k-mer prefixes of one bucket
+constexpr int PART_FINE = 1024;     // fine ranges the bucket is counted into before they are merged into slices
+                                    // (32 KB of shared memory in total, so several buckets are in flight per SM)
 
-// One CTA per bucket larger than CAP: sample its k-mer prefixes evenly over the instances, sort the sample, and cut it
-// into P = ceil(c / TSUB) slices of equal sample count.
-template <int PW>
-__global__ void __launch_bounds__(SPLIT_THREADS)
-    split_big_runs_kernel(const uint32_t *__restrict__ skr, RunView rv, const uint32_t *__restrict__ unit_base,
-                          const uint32_t *__restrict__ big_list, const unsigned int *__restrict__ n_big, PlanParams pp, int K,
-                          Unit *__restrict__ units) {
+struct BigScratch {
+    uint64_t *k0, *k1;  // k-mer code words of the expanded instances (k1 only for 128-bit codes)
+    uint32_t *arr;      // their arrival indices
+};
+
+// One CTA per bucket larger than a unit.  (1) Sample the bucket's k-mer prefixes evenly over its instances and sort the
+// sample.  (2) Take fine splitters from it (fine ranges of about CAP/8 instances), expand every window once and count the
+// fine ranges exactly.  (3) Merge adjacent fine ranges greedily into slices of at most CAP instances — these are the
+// bucket's units, in ascending k-mer order.  (4) Expand again and scatter (k-mer, arrival) to the slice-major scratch.
+template <int PW, int KW>
+__global__ void __launch_bounds__(PART_THREADS)
+    partition_big_runs_kernel(const uint32_t *__restrict__ skr, RunView rv, const uint32_t *__restrict__ unit_base,
+                              const uint32_t *__restrict__ big_list, GroupCounters *__restrict__ gc, PlanParams pp, int K, BigScratch sc,
+                              Unit *__restrict__ units) {
     constexpr int NW = SkrLayout<PW>::WORDS;
-    __shared__ uint64_t samp[SPLIT_SAMPLES];
-    const uint32_t nb = *n_big;
+    extern __shared__ __align__(16) uint8_t part_smem[];
+    uint64_t *samp = reinterpret_cast<uint64_t *>(part_smem);         // [PART_SAMPLES]
+    uint64_t *spl = samp + PART_SAMPLES;                              // [PART_FINE] fine splitters (spl[0] unused)
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(spl + PART_FINE);    // [PART_FINE] fine counts, then scatter cursors
+    uint32_t *foff = cnt + PART_FINE;                                 // [PART_FINE + 1] exclusive prefix of the fine counts
+    __shared__ uint32_t s_bad;
+    const uint32_t nb = gc->n_big;
     for (uint32_t bi = blockIdx.x; bi < nb; bi += gridDim.x) {
-        const uint64_t r = big_list[bi];
+        const uint64_t r = big_list[2 * bi];
+        const uint32_t sbase = big_list[2 * bi + 1];
         const uint32_t c = rv.size(r);
         const uint32_t a = rv.run_start[r], b = rv.run_start[r + 1];
         const uint32_t base = rv.inst_prefix[a];
-        const uint32_t P = units_of_big(c, pp);
-        uint32_t S = 64;  // samples: a power of two, at least 32 per slice, at most SPLIT_SAMPLES
-        while (S < 32 * P && S < (uint32_t)SPLIT_SAMPLES) S <<= 1;
-        for (uint32_t t = threadIdx.x; t < S; t += SPLIT_THREADS) {
+        const uint32_t P = units_of_big(c, pp);  // unit slots reserved for this bucket
+        const uint32_t mmer = skr[(uint64_t)a * NW + 1];
+        uint32_t F = (c + pp.cap / 8 - 1) / (pp.cap / 8);  // fine ranges
+        if (F > (uint32_t)PART_FINE) F = PART_FINE;
+        uint32_t S = 128;  // samples: a power of two, about 8 per fine range, at most PART_SAMPLES
+        while (S < 8 * F && S < (uint32_t)PART_SAMPLES) S <<= 1;
+        if (threadIdx.x == 0) s_bad = 0;
+        // ---- (1) sample + sort
+        for (uint32_t t = threadIdx.x; t < S; t += PART_THREADS) {
             const uint32_t j = (uint32_t)(((uint64_t)(2 * t + 1) * c) / (2ull * S));  // instance index inside the bucket
             uint32_t lo = a, hi = b - 1;  // last record whose first instance is <= j
             while (lo < hi) {
@@ -193,7 +260,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS)
         __syncthreads();
         for (uint32_t k = 2; k <= S; k <<= 1) {
             for (uint32_t jj = k >> 1; jj > 0; jj >>= 1) {
-                for (uint32_t idx = threadIdx.x; idx < S; idx += SPLIT_THREADS) {
+                for (uint32_t idx = threadIdx.x; idx < S; idx += PART_THREADS) {
                     const uint32_t partner = idx ^ jj;
                     if (partner > idx) {
                         const uint64_t x = samp[idx], y = samp[partner];
@@ -206,11 +273,66 @@ __global__ void __launch_bounds__(SPLIT_THREADS)
                 __syncthreads();
             }
         }
-        const uint32_t ub = unit_base[r];
-        for (uint32_t p = threadIdx.x; p < P; p += SPLIT_THREADS) {
-            const uint64_t lo = p ? samp[(uint64_t)p * S / P] : 0ull;
-            const uint64_t hi = p + 1 < P ? samp[(uint64_t)(p + 1) * S / P] : 0ull;
-            units[ub + p] = Unit{a, b, UNIT_FILTERED | (p + 1 == P ? UNIT_LAST : 0u), base, lo, hi, c, {0u, 0u, 0u}};
+        // ---- (2) fine splitters and exact fine counts.  fine range f holds prefixes in [spl[f], spl[f+1])
+        for (uint32_t f = threadIdx.x; f < F; f += PART_THREADS) {
+            spl[f] = f ? samp[(uint64_t)f * S / F] : 0ull;
+            cnt[f] = 0;
+        }
+        __syncthreads();
+        auto fine_of = [&](uint64_t pre) -> uint32_t {  // number of splitters spl[1..F-1] that are <= pre
+            uint32_t lo = 0, hi = F - 1;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (spl[mid] <= pre) lo = mid;
+                else hi = mid - 1;
+            }
+            return lo;
+        };
+        for (uint32_t s = a + threadIdx.x; s < b; s += PART_THREADS)
+            for_each_window<PW, KW>(skr + (uint64_t)s * NW, K, [&](uint32_t, uint64_t, uint64_t, uint64_t pre) { atomicAdd(&cnt[fine_of(pre)], 1u); });
+        __syncthreads();
+        // ---- (3) greedy merge of adjacent fine ranges into slices of at most CAP instances (one thread: F is small)
+        if (threadIdx.x == 0) {
+            const uint32_t ub = unit_base[r];
+            uint32_t q = 0, run = 0, start = 0, acc = 0;
+            for (uint32_t f = 0; f < F; f++) {
+                const uint32_t cf = cnt[f];
+                foff[f] = acc;
+                if (cf > pp.cap) s_bad = 1;  // one fine range (one k-mer prefix, typically one k-mer) overflows a unit
+                if (run + cf > pp.cap) {
+                    if (q < P) units[ub + q] = Unit{sbase + start, sbase + acc, UNIT_RECORDS, 0u, run, mmer, {0u, 0u}};
+                    q++;
+                    start = acc;
+                    run = 0;
+                }
+                run += cf;
+                acc += cf;
+            }
+            foff[F] = acc;
+            if (q < P) units[ub + q] = Unit{sbase + start, sbase + acc, UNIT_RECORDS, 0u, run, mmer, {0u, 0u}};
+            q++;
+            if (q > P || acc != c) s_bad = 1;
+            for (; q < P; q++) units[ub + q] = Unit{sbase + acc, sbase + acc, UNIT_RECORDS, 0u, 0u, mmer, {0u, 0u}};  // unused slots: empty units
+        }
+        __syncthreads();
+        if (s_bad) {
+            if (threadIdx.x == 0) atomicExch(&gc->overflow, 4u);
+            __syncthreads();
+            continue;
+        }
+        for (uint32_t f = threadIdx.x; f < F; f += PART_THREADS) cnt[f] = 0;
+        __syncthreads();
+        // ---- (4) expand again and scatter to the slice-major scratch (order inside a fine range is arbitrary)
+        for (uint32_t s = a + threadIdx.x; s < b; s += PART_THREADS) {
+            const uint32_t *rec = skr + (uint64_t)s * NW;
+            const uint32_t arrival = rec[0];
+            for_each_window<PW, KW>(rec, K, [&](uint32_t, uint64_t k0, uint64_t k1, uint64_t pre) {
+                const uint32_t f = fine_of(pre);
+                const uint64_t pos = (uint64_t)sbase + foff[f] + atomicAdd(&cnt[f], 1u);
+                sc.k0[pos] = k0;
+                if (KW == 2) sc.k1[pos] = k1;
+                sc.arr[pos] = arrival;
+            });
         }
         __syncthreads();
     }
@@ -260,10 +382,13 @@ struct GroupCounters {
     unsigned int overflow;
     unsigned int ticket;
     unsigned int n_units;
-    unsigned int n_big;  // buckets larger than a unit (work list of split_big_runs_kernel)
+    unsigned int n_big;     // buckets larger than a unit (work list of partition_big_runs_kernel)
+    unsigned int big_inst;  // k-mer instances in those buckets (allocation cursor of the scratch arrays)
+    unsigned int pad[3];
 };
 
 __device__ __forceinline__ unsigned int *big_counter(GroupCounters *gc) { return &gc->n_big; }
+__device__ __forceinline__ unsigned int *big_inst_counter(GroupCounters *gc) { return &gc->big_inst; }
 
 template <int KW>
 __device__ __forceinline__ bool key_less(const uint64_t *key0, const uint64_t *key1, const uint32_t *mm, uint32_t a, uint32_t b) {
@@ -275,8 +400,8 @@ __device__ __forceinline__ bool key_less(const uint64_t *key0, const uint64_t *k
 
 template <int PW, int KW, int G_CAP, int G_THREADS>
 __global__ void __launch_bounds__(G_THREADS)
-    skr_group_kernel(const uint32_t *__restrict__ skr, const uint32_t *__restrict__ inst_prefix, const Unit *__restrict__ units, int K,
-                     int cutoff, const int32_t *__restrict__ ids_by_arrival, int32_t id_base, GroupOut out,
+    skr_group_kernel(const uint32_t *__restrict__ skr, const uint32_t *__restrict__ inst_prefix, const Unit *__restrict__ units, BigScratch sc,
+                     int K, int cutoff, const int32_t *__restrict__ ids_by_arrival, int32_t id_base, GroupOut out,
                      unsigned long long *__restrict__ unit_state, GroupCounters *__restrict__ gc) {
     constexpr int NW = SkrLayout<PW>::WORDS;
     constexpr int G_HS = 2 * G_CAP;  // hash slots
@@ -300,7 +425,6 @@ __global__ void __launch_bounds__(G_THREADS)
     __shared__ Unit s_un;
 
     const uint32_t tid = threadIdx.x;
-    const uint64_t kmask0 = (2 * K >= 64 * KW) ? ~0ull : ((1ull << (2 * K - 64 * (KW - 1))) - 1);  // mask of the most significant word
 
     // Units are handed out by an atomic ticket, taken only when the CTA is ready to start the unit: a ticket taken ahead
     // of time would let later units overtake it, and their chained-scan resolve would then wait for it.
@@ -321,71 +445,36 @@ __global__ void __launch_bounds__(G_THREADS)
         const Unit un = s_un;
         const uint32_t base_pref = un.base_pref;
         const uint32_t n_cand = un.n_cand;
-        const bool filtered = (un.flags & UNIT_FILTERED) != 0;
-        if (!filtered && n_cand > (uint32_t)G_CAP && tid == 0) s_overflow = 1;
+        const bool filtered = (un.flags & UNIT_RECORDS) != 0;  // a slice of a big bucket: instances arrive in arbitrary order
+        if (n_cand > (uint32_t)G_CAP && tid == 0) s_overflow = 1;
 
         // ---- zero the hash table and counters while records stream in
         for (uint32_t i = tid; i < (uint32_t)G_HS; i += G_THREADS) table[i] = 0;
         for (uint32_t i = tid; i < (uint32_t)G_CAP; i += G_THREADS) cnt[i] = 0;
 
-        // ---- expansion: one thread per record, rolling over its n windows
-        if (filtered || n_cand <= (uint32_t)G_CAP) {
-            for (uint32_t s = un.skr_begin + tid; s < un.skr_end; s += G_THREADS) {
-                const uint4 *p = reinterpret_cast<const uint4 *>(skr + (uint64_t)s * NW);
-                const uint4 h = p[0];
-                const uint32_t arrival = h.x, mmer = h.y, n = h.z & 0xffu;
-                const bool rev = (h.z >> 8) & 1u;
-                uint64_t w[PW];
-                {
-                    const uint4 a = p[1];
-                    w[0] = ((uint64_t)a.x << 32) | a.y;
-                    w[1] = ((uint64_t)a.z << 32) | a.w;
-                    if (PW == 4) {
-                        const uint4 b = p[2];
-                        w[PW - 2] = ((uint64_t)b.x << 32) | b.y;
-                        w[PW - 1] = ((uint64_t)b.z << 32) | b.w;
-                    }
+        if (n_cand <= (uint32_t)G_CAP) {
+            if (filtered) {
+                // ---- instances of a big bucket's slice were expanded by partition_big_runs_kernel: just load them
+                for (uint32_t i = tid; i < n_cand; i += G_THREADS) {
+                    const uint64_t g = (uint64_t)un.skr_begin + i;
+                    key0[i] = sc.k0[g];
+                    if (KW == 2) key1[i] = sc.k1[g];
+                    mm[i] = un.mmer;
+                    arr[i] = sc.arr[g];
                 }
-                const uint32_t pos0 = inst_prefix[s] - base_pref;
-                for (uint32_t t = 0; t < n; t++) {
-                    // oriented k-mer = top 2K bits of the remaining payload
-                    uint64_t k0, k1 = 0;
-                    if (KW == 1) {
-                        k0 = (2 * K == 64) ? w[0] : (w[0] >> (64 - 2 * K));
-                        if (rev) k0 = ~k0 & kmask0;
-                    } else {
-                        const int r = 128 - 2 * K;  // 0..62
-                        k0 = r ? (w[0] >> r) : w[0];
-                        k1 = r ? ((w[1] >> r) | (w[0] << (64 - r))) : w[1];
-                        if (rev) {
-                            k0 = ~k0 & kmask0;
-                            k1 = ~k1;
-                        }
-                    }
-                    bool keep = true;
-                    uint32_t pos = pos0 + t;
-                    if (filtered) {
-                        uint64_t pre = rev ? ~w[0] : w[0];  // 64-bit prefix of the oriented k-mer (same as window_prefix)
-                        if (2 * K < 64) pre &= ~0ull << (64 - 2 * K);
-                        keep = pre >= un.lo && ((un.flags & UNIT_LAST) || pre < un.hi);
-                        if (keep) {
-                            pos = atomicAdd(&s_count, 1u);
-                            if (pos >= (uint32_t)G_CAP) {
-                                keep = false;
-                                s_overflow = 1;
-                            }
-                        }
-                    }
-                    if (keep) {
+            } else {
+                // ---- expansion: one thread per super-k-mer record, rolling over its n windows
+                for (uint32_t s = un.skr_begin + tid; s < un.skr_end; s += G_THREADS) {
+                    const uint32_t *rec = skr + (uint64_t)s * NW;
+                    const uint32_t arrival = rec[0], mmer = rec[1];
+                    const uint32_t pos0 = inst_prefix[s] - base_pref;
+                    for_each_window<PW, KW>(rec, K, [&](uint32_t t, uint64_t k0, uint64_t k1, uint64_t) {
+                        const uint32_t pos = pos0 + t;
                         key0[pos] = k0;
                         if (KW == 2) key1[pos] = k1;
                         mm[pos] = mmer;
                         arr[pos] = arrival;
-                    }
-                    // shift the payload left by one base
-#pragma unroll
-                    for (int q = 0; q < PW - 1; q++) w[q] = (w[q] << 2) | (w[q + 1] >> 62);
-                    w[PW - 1] <<= 2;
+                    });
                 }
             }
         }
@@ -399,7 +488,7 @@ __global__ void __launch_bounds__(G_THREADS)
             __syncthreads();
             continue;
         }
-        const uint32_t n_inst = filtered ? s_count : n_cand;
+        const uint32_t n_inst = n_cand;
 
         // ---- group: claim a slot with the instance index, compare keys through the instance arrays
         for (uint32_t i = tid; i < n_inst; i += G_THREADS) {
@@ -699,7 +788,7 @@ int skr_plan_runs(const void *skr_sorted, uint64_t n_skr, int skr_words, uint32_
 // Phase B (needs n_runs on the host): units. small_prefix / unit_base are [n_runs] scratch arrays.
 int skr_plan_units(const void *skr_sorted, int K, const uint32_t *inst_prefix, const uint32_t *run_start, uint64_t n_runs,
                    uint32_t *small_prefix, uint32_t *unit_base, uint32_t *scratch, void *units, uint64_t max_units, void *gc_dev,
-                   uint32_t *big_list, int sm_count, cudaStream_t st) {
+                   uint32_t *big_list, uint64_t *big_k0, uint64_t *big_k1, uint32_t *big_arr, int sm_count, cudaStream_t st) {
     RunView rv{run_start, inst_prefix};
     const PlanParams pp = plan_params();
     GroupCounters *gc = static_cast<GroupCounters *>(gc_dev);
@@ -710,17 +799,22 @@ int skr_plan_units(const void *skr_sorted, int K, const uint32_t *inst_prefix, c
     l += exclusive_scan<uint32_t, UnitsOfRun>(UnitsOfRun{rv, small_prefix, pp}, unit_base, n_runs, scratch, &gc->n_units, st);
     fill_units_kernel<<<(unsigned)((n_runs + 255) / 256), 256, 0, st>>>(rv, small_prefix, unit_base, n_runs, pp, static_cast<Unit *>(units), gc,
                                                                        big_list);
-    const unsigned grid = (unsigned)sm_count * 4;
+    const unsigned grid = (unsigned)sm_count * 6;
+    const size_t part_smem = (size_t)PART_SAMPLES * 8 + (size_t)PART_FINE * 8 + (size_t)PART_FINE * 4 + ((size_t)PART_FINE + 1) * 4;
     const uint32_t *s = static_cast<const uint32_t *>(skr_sorted);
-    if (K <= 32)
-        split_big_runs_kernel<2><<<grid, SPLIT_THREADS, 0, st>>>(s, rv, unit_base, big_list, &gc->n_big, pp, K, static_cast<Unit *>(units));
-    else
-        split_big_runs_kernel<4><<<grid, SPLIT_THREADS, 0, st>>>(s, rv, unit_base, big_list, &gc->n_big, pp, K, static_cast<Unit *>(units));
+    BigScratch sc{big_k0, big_k1, big_arr};
+    if (K <= 32) {
+        cudaFuncSetAttribute(partition_big_runs_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem);
+        partition_big_runs_kernel<2, 1><<<grid, PART_THREADS, part_smem, st>>>(s, rv, unit_base, big_list, gc, pp, K, sc, static_cast<Unit *>(units));
+    } else {
+        cudaFuncSetAttribute(partition_big_runs_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem);
+        partition_big_runs_kernel<4, 2><<<grid, PART_THREADS, part_smem, st>>>(s, rv, unit_base, big_list, gc, pp, K, sc, static_cast<Unit *>(units));
+    }
     return l + 2;
 }
 
 int skr_group_launch(const void *skr_sorted, int K, int cutoff, const uint32_t *inst_prefix, const void *units, unsigned long long *unit_state,
-                     uint64_t max_units, void *gc_dev, const int32_t *ids_by_arrival, int32_t id_base, uint64_t *kmer_codes,
+                     uint64_t max_units, void *gc_dev, uint64_t *big_k0, uint64_t *big_k1, uint32_t *big_arr, const int32_t *ids_by_arrival, int32_t id_base, uint64_t *kmer_codes,
                      uint32_t *kmer_mmer, uint64_t *kmer_id_off, int32_t *read_ids, uint64_t kmer_cap, uint64_t id_cap, int sm_count,
                      cudaStream_t st) {
     const int KW = K <= 32 ? 1 : 2;
@@ -732,7 +826,8 @@ int skr_group_launch(const void *skr_sorted, int K, int cutoff, const uint32_t *
     const Unit *un = static_cast<const Unit *>(units);
     auto launch = [&](auto kern, int threads, int ctas_per_sm) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<sm_count * ctas_per_sm, threads, smem, st>>>(s, inst_prefix, un, K, cutoff, ids_by_arrival, id_base, out, unit_state, gc);
+        kern<<<sm_count * ctas_per_sm, threads, smem, st>>>(s, inst_prefix, un, BigScratch{big_k0, big_k1, big_arr}, K, cutoff, ids_by_arrival,
+                                                            id_base, out, unit_state, gc);
     };
     static int thr = 0;  // GBIN_V2_THREADS=512: experiment with 512 threads per CTA at capacity 2048
     if (!thr) {

@@ -360,6 +360,22 @@ def test_deep_coverage_long_id_lists(n_reads, expect_v2):
         b.close()
 
 
+def test_large_buckets_are_sliced_not_redone():
+    """19 M instances over a few thousand m-mer buckets (M=7): most buckets are several times larger than a shared-memory
+    unit and are range-partitioned on the k-mer prefix with sampled splitters; no slice may overflow (no fallback)."""
+    torch_cuda()
+    rs = synth.generate(150_000, 150, error_rate=0.01, seed=31, starts="uniform")
+    starts = np.arange(rs.n_reads, dtype=np.uint64) * rs.stride
+    lens = np.full(rs.n_reads, rs.read_len, dtype=np.uint32)
+    b = B.Binner(25, 7, 1, pipeline=2)
+    got = b.bin_host(rs.buf, rs.n_reads, stride=rs.stride, read_len=rs.read_len)
+    info, st = b.pipeline_info(), b.run_stats()
+    assert info["last_used"] == 2 and info["fallbacks"] == 0, (info, st)
+    assert st["n_units"] > 3 * st["n_mmer_runs"], st
+    assert_tables_equal(got, O.run(rs.as_bytes(), starts, lens, 25, 7, 1))
+    b.close()
+
+
 def check_table_invariants(t: B.HostTable, n_reads, W):
     """Size-independent properties of a pruned table (used at BASELINE's full sizes)."""
     assert t.n_instances == n_reads * W

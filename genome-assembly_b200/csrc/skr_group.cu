@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(PART_THREADS)
     uint32_t *cnt = reinterpret_cast<uint32_t *>(spl + PART_FINE);    // [PART_FINE] fine counts, then scatter cursors
     uint32_t *foff = cnt + PART_FINE;                                 // [PART_FINE + 1] exclusive prefix of the fine counts
     __shared__ uint32_t s_bad;
+    __shared__ uint16_t lut[258];  // lut[b] = fine range of the smallest prefix whose top byte is b
     const uint32_t nb = gc->n_big;
     for (uint32_t bi = blockIdx.x; bi < nb; bi += gridDim.x) {
         const uint64_t r = big_list[2 * bi];
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(PART_THREADS)
             cnt[f] = 0;
         }
         __syncthreads();
-        auto fine_of = [&](uint64_t pre) -> uint32_t {  // number of splitters spl[1..F-1] that are <= pre
+        auto fine_search = [&](uint64_t pre) -> uint32_t {  // number of splitters spl[1..F-1] that are <= pre
             uint32_t lo = 0, hi = F - 1;
             while (lo < hi) {
                 const uint32_t mid = (lo + hi + 1) >> 1;
@@ -287,6 +288,16 @@ __global__ void __launch_bounds__(PART_THREADS)
                 else hi = mid - 1;
             }
             return lo;
+        };
+        // a 256-entry table on the top byte of the prefix narrows the search to a step or two
+        for (uint32_t bb = threadIdx.x; bb < 257; bb += PART_THREADS) lut[bb] = bb < 256 ? (uint16_t)fine_search((uint64_t)bb << 56) : (uint16_t)(F - 1);
+        __syncthreads();
+        auto fine_of = [&](uint64_t pre) -> uint32_t {
+            const uint32_t bb = (uint32_t)(pre >> 56);
+            uint32_t f = lut[bb];
+            const uint32_t hi = lut[bb + 1];
+            while (f < hi && spl[f + 1] <= pre) f++;
+            return f;
         };
         for (uint32_t s = a + threadIdx.x; s < b; s += PART_THREADS)
             for_each_window<PW, KW>(skr + (uint64_t)s * NW, K, [&](uint32_t, uint64_t, uint64_t, uint64_t pre) { atomicAdd(&cnt[fine_of(pre)], 1u); });

@@ -29,6 +29,12 @@ template <int LKB_DEPTH>
 __device__ __forceinline__ unsigned long long lkb_resolve_warp(unsigned long long *state, uint32_t tile, unsigned long long mine,
                                                                uint32_t lane) {
     if (tile == 0) return 0ull;
+    // Cheap wait first: one lane polls the nearest predecessor until it has published anything at all (tiles finish in
+    // roughly ticket order, so this is where almost all of the waiting happens), then the warp evaluates the window.
+    if (lane == 0) {
+        while ((lkb_load(&state[tile - 1]) >> 62) == 0) __nanosleep(100);
+    }
+    __syncwarp();
     unsigned long long sum = 0;
     int64_t j = (int64_t)tile - 1;
     for (;;) {

@@ -396,7 +396,7 @@ def main():
         "skr_group": (skr_b + 4.0) * n_skr + stats["surviving_kmers"] * (8.0 * KW + 4 + 8) + 4.0 * stats["surviving_ids"],
         "find_runs": 3.0 * rb * n_rec + 8.0 * n_rec,
     }
-    ncu_traffic = {"skr_group": 494.3e6, "skr_scan": 272.9e6}  # dram read+write per launch, ncu --set full (profiles/)
+    ncu_traffic = {"skr_group": 500.1e6, "skr_scan": 277.3e6}  # dram read+write per launch, ncu --set full (profiles/)
     roofline = None
     timed = {k: v for k, v in prof.items() if v["launches"] and k in alg_bytes}
     if timed:

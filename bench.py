@@ -360,8 +360,8 @@ def main():
             d = h_reads.to(dev, non_blocking=True)
             rdx = B.Binner._reads(d, d.numel(), rs.n_reads, stride=rs.stride, read_len=rs.read_len, id_base=rank * rs.n_reads)
             tb = sharded.run(rdx, arrival_base=rank * rs.n_reads)
-            ht = binner.table_to_host(tb)
-            return int(ht.n_kmers * (8 * ht.kw + 8) + 8 + ht.n_ids * 4 + ht.n_buckets * 12 + 8)
+            ht = binner.table_to_pinned_raw(tb, stream)
+            return int(ht.n_kmers * (8 * ht.kmer_words + 8) + 8 + ht.n_ids * 4 + ht.n_buckets * 12 + 8)
         e2e_step()
         barrier()
         t0 = time.perf_counter()
@@ -373,7 +373,7 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
         e2e = {"value": n_inst_total * a.steps / float(e2e_s[0]), "unit": UNIT, "h2d_bytes_per_step": int(h_reads.numel()) * world,
                "d2h_bytes_per_step": d2h * world, "ms_per_step": 1e3 * float(e2e_s[0]) / a.steps,
-               "timing": "host wall clock, max over ranks; table D2H into pageable memory"}
+               "timing": "host wall clock, max over ranks; per rank: pinned H2D of its shard, sharded pipeline, D2H of its owner table into the pinned arena"}
 
     # ---- roofline of the dominant kernel (the kernel class with the most device time in the timed region)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")

@@ -63,7 +63,7 @@ class KernelProfile(C.Structure):
 EXPORTS = [
     "gbin_strerror", "gbin_last_error", "gbin_version", "gbin_create", "gbin_destroy", "gbin_get_config",
     "gbin_bin_reads_host", "gbin_table_clone", "gbin_table_free", "gbin_pinned_alloc", "gbin_pinned_free",
-    "gbin_bin_reads_device", "gbin_table_to_host", "gbin_get_timings", "gbin_record_bytes",
+    "gbin_bin_reads_device", "gbin_table_to_host", "gbin_table_to_pinned", "gbin_get_timings", "gbin_record_bytes",
     "gbin_set_kernel_profiling", "gbin_get_kernel_profile", "gbin_kernel_kind_name", "gbin_set_pipeline", "gbin_get_pipeline_info", "gbin_get_run_stats",
     "gbin_count_instances_device", "gbin_scan_reads_device", "gbin_partition_records_device",
     "gbin_group_records_device", "gbin_skr_record_bytes", "gbin_scan_skr_device", "gbin_partition_skr_device", "gbin_group_skr_device",
@@ -96,6 +96,7 @@ def load_library() -> C.CDLL:
     L.gbin_bin_reads_host.argtypes = [vp, C.POINTER(CReads), C.POINTER(CTable)]
     L.gbin_bin_reads_device.argtypes = [vp, C.POINTER(CReads), vp, C.POINTER(CTable)]
     L.gbin_table_to_host.argtypes = [vp, C.POINTER(CTable), C.POINTER(CTable)]
+    L.gbin_table_to_pinned.argtypes = [vp, C.POINTER(CTable), vp, C.POINTER(CTable)]
     L.gbin_table_clone.argtypes = [C.POINTER(CTable), C.POINTER(CTable)]
     L.gbin_table_free.argtypes = [C.POINTER(CTable)]
     L.gbin_table_free.restype = None
@@ -323,6 +324,12 @@ class Binner:
             return host_table_from_c(h)
         finally:
             self.lib.gbin_table_free(C.byref(h))
+
+    def table_to_pinned_raw(self, dev: CTable, stream=None) -> CTable:
+        """Device table -> the context's pinned arena (valid until the next host-table call); no numpy copies."""
+        h = CTable()
+        self._check(self.lib.gbin_table_to_pinned(self.h, C.byref(dev), stream, C.byref(h)))
+        return h
 
     # ---- staged device entry points
     def count_instances_device(self, reads: CReads, stream=None) -> int:

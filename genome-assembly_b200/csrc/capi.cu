@@ -74,6 +74,25 @@ struct Misc {  // small device-resident scalars
     unsigned long long skr_counters[4];  // [0] bad bases, [1] records, [2] instances
     SkrGroupCounters gc;
     uint32_t skr_ticket, n_inst_dev, n_runs_dev, n_buckets_dev;
+    uint32_t chunk_tickets[SKR_MAX_CHUNKS];
+    unsigned long long chunk_totals[SKR_MAX_CHUNKS];
+};
+
+// Host path only.  HostFeed: the reads are still in host memory; the scan stage copies them chunk by chunk on the copy
+// stream and scans every chunk as soon as it has landed.  HostSink: pinned destinations for the big arrays of the
+// table; finished chunks of the grouping are copied out on the second copy stream while later chunks are still running.
+struct HostFeed {
+    const char *src;     // host
+    char *dst;           // device
+    uint64_t bytes;
+    int chunks;
+};
+struct HostSink {
+    uint64_t *kmer_codes, *kmer_id_off;  // pinned; capacities in k-mers
+    int32_t *read_ids;                   // pinned; capacity in ids
+    uint64_t kmer_cap, id_cap;
+    uint64_t kmers_done, ids_done;       // what has been enqueued for copy so far
+    int chunks;
 };
 
 }  // namespace
@@ -83,6 +102,9 @@ struct gbin_ctx {
     int KW;
     int sm_count;
     cudaStream_t stream;
+    cudaStream_t st_h2d, st_d2h;  // copy streams of the host path (H2D of later read chunks / D2H of finished table chunks overlap the kernels)
+    cudaEvent_t ev_feed[SKR_MAX_CHUNKS], ev_chunk[SKR_MAX_CHUNKS], ev_copy;
+    int host_chunks;              // GBIN_HOST_CHUNKS (default 8; 1 = no overlap)
     char err[512];
     gbin_timings tm;
     cudaEvent_t ev[6];
@@ -101,7 +123,7 @@ struct gbin_ctx {
     // device-resident result
     DevBuf o_mmer_codes, o_mmer_kmer_off, o_kmer_codes, o_kmer_id_off, o_read_ids;
     // pinned host arena for results of the host path + small readbacks
-    HostBuf h_misc, h_result;
+    HostBuf h_misc, h_result, h_kmer_codes, h_kmer_id_off, h_read_ids;
     KernelProf prof;
 };
 
@@ -303,9 +325,10 @@ int run_group(gbin_ctx *ctx, void *recs, void *twin, uint64_t n, const int32_t *
 // ---- pipeline v2: super-k-mer records -> stable sort by m-mer -> grouping in shared memory
 
 // Scan stage: one record per signature segment, in arrival order, into ctx->skr_a (own == true) or into the
-// caller's buffer `ext` of `ext_cap` records.  *n_skr receives the record count.
+// caller's buffer `ext` of `ext_cap` records.  *n_skr receives the record count.  With a feed (host path, fixed-stride
+// reads) the reads arrive over PCIe in chunks on the copy stream and every chunk is scanned as soon as it is there.
 int run_v2_scan(gbin_ctx *ctx, const gbin_reads *rd, uint64_t n, uint32_t max_len, uint32_t arrival_base, void *ext, uint64_t ext_cap,
-                cudaStream_t st, uint64_t *n_skr_out, int *launches) {
+                cudaStream_t st, uint64_t *n_skr_out, int *launches, const HostFeed *feed = nullptr) {
     const int K = ctx->cfg.kmer_size, M = ctx->cfg.mmer_size;
     const int NW = K <= 32 ? 8 : 12;
     Misc *dm = ctx->misc.as<Misc>();
@@ -319,8 +342,20 @@ int run_v2_scan(gbin_ctx *ctx, const gbin_reads *rd, uint64_t n, uint32_t max_le
         CU(ctx->tile_state.ensure((size_t)skr_scan_tiles(rd->n_reads, K, M, max_len) * 8 + 8));
         CU(cudaMemsetAsync(dm->skr_counters, 0, sizeof dm->skr_counters, st));
         const bool on = ctx->prof.begin(KK_SKR_SCAN, st);
-        const int ls = launch_skr_scan(rv, K, M, arrival_base, max_len, ext ? ext : ctx->skr_a.p, cap, ctx->tile_state.as<unsigned long long>(),
-                                       &dm->skr_ticket, dm->skr_counters, ctx->sm_count, st);
+        int ls = 0;
+        const int chunks = (feed && attempt == 0) ? feed->chunks : 1;
+        for (int c = 0; c < chunks; c++) {
+            const uint64_t r0 = rd->n_reads * (uint64_t)c / chunks, r1 = rd->n_reads * (uint64_t)(c + 1) / chunks;
+            if (feed && attempt == 0) {
+                const uint64_t b0 = r0 * rd->stride, b1 = (c + 1 == chunks) ? feed->bytes : r1 * rd->stride;
+                if (b1 > b0) CU(cudaMemcpyAsync(feed->dst + b0, feed->src + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->st_h2d));
+                CU(cudaEventRecord(ctx->ev_feed[c], ctx->st_h2d));
+                CU(cudaStreamWaitEvent(st, ctx->ev_feed[c], 0));
+                if (c + 1 == chunks) CU(cudaEventRecord(ctx->ev[1], st));  // every byte of the reads is on the device
+            }
+            ls += launch_skr_scan(rv, r0, r1, K, M, arrival_base, max_len, ext ? ext : ctx->skr_a.p, cap, ctx->tile_state.as<unsigned long long>(),
+                                  &dm->skr_ticket, dm->skr_counters, ctx->sm_count, st);
+        }
         ctx->prof.end(on, ls, st);
         *launches += ls;
         CU(cudaGetLastError());
@@ -341,7 +376,7 @@ int run_v2_scan(gbin_ctx *ctx, const gbin_reads *rd, uint64_t n, uint32_t max_le
 // Sort + plan + group + emit over n_skr records in `skr` (clobbered; `twin` is the sort's second buffer).
 // *done = false when a unit overflowed and the batch must go through pipeline v1.
 int run_v2_group(gbin_ctx *ctx, void *skr, void *twin, uint64_t n_skr, const int32_t *d_ids, int32_t id_base, cudaStream_t st, gbin_table *out,
-                 int *launches, bool *done, uint64_t *n_inst_out) {
+                 int *launches, bool *done, uint64_t *n_inst_out, HostSink *sink = nullptr) {
     *done = false;
     const int K = ctx->cfg.kmer_size, M = ctx->cfg.mmer_size, cutoff = ctx->cfg.abundance_cutoff, KW = ctx->KW;
     const int NW = K <= 32 ? 8 : 12;
@@ -400,12 +435,37 @@ int run_v2_group(gbin_ctx *ctx, void *skr, void *twin, uint64_t n_skr, const int
     CU(ctx->o_kmer_id_off.ensure((kmer_cap + 2) * sizeof(uint64_t)));
     CU(ctx->o_read_ids.ensure((n + 1) * sizeof(int32_t)));
     on = ctx->prof.begin(KK_SKR_GROUP, st);
-    lp = skr_group_launch(sorted, K, cutoff, ctx->inst_prefix.as<uint32_t>(), ctx->units.p, ctx->unit_state.as<unsigned long long>(), max_units,
+    SkrGroupChunks ch{1u, dm->chunk_tickets, nullptr, nullptr, nullptr};
+    if (sink && sink->chunks > 1) {
+        ch.n = (uint32_t)sink->chunks;
+        ch.totals_dev = dm->chunk_totals;
+        ch.totals_host = hm->chunk_totals;
+        ch.done = ctx->ev_chunk;
+    }
+    lp = skr_group_launch(sorted, K, cutoff, ctx->inst_prefix.as<uint32_t>(), ctx->units.p, ctx->unit_state.as<unsigned long long>(), max_units, ch,
                           &dm->gc, ctx->big_k0.as<uint64_t>(), ctx->big_k1.as<uint64_t>(), ctx->big_arr.as<uint32_t>(), d_ids, id_base, ctx->o_kmer_codes.as<uint64_t>(), ctx->o_kmer_mmer.as<uint32_t>(),
                           ctx->o_kmer_id_off.as<uint64_t>(), ctx->o_read_ids.as<int32_t>(), kmer_cap, n, ctx->sm_count, st);
     ctx->prof.end(on, lp, st);
     *launches += lp;
     CU(cudaGetLastError());
+    if (ch.done) {
+        // Stream the finished part of the table to the host while later chunks are grouped: the output of units [0, u) is
+        // final once they have completed, and the flat table is written in unit order.
+        for (uint32_t c = 0; c < ch.n; c++) {
+            CU(cudaEventSynchronize(ctx->ev_chunk[c]));
+            const unsigned long long tot = hm->chunk_totals[c];
+            const uint64_t s1 = tot >> 31, n1 = tot & 0x7fffffffull;
+            if (s1 > sink->kmer_cap || n1 > sink->id_cap || s1 < sink->kmers_done || n1 < sink->ids_done) break;  // arena too small: the rest is copied at the end
+            const uint64_t s0 = sink->kmers_done, n0 = sink->ids_done;
+            if (s1 > s0) {
+                CU(cudaMemcpyAsync(sink->kmer_codes + s0 * KW, ctx->o_kmer_codes.as<uint64_t>() + s0 * KW, (s1 - s0) * KW * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->st_d2h));
+                CU(cudaMemcpyAsync(sink->kmer_id_off + s0, ctx->o_kmer_id_off.as<uint64_t>() + s0, (s1 - s0) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->st_d2h));
+            }
+            if (n1 > n0) CU(cudaMemcpyAsync(sink->read_ids + n0, ctx->o_read_ids.as<int32_t>() + n0, (n1 - n0) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->st_d2h));
+            sink->kmers_done = s1;
+            sink->ids_done = n1;
+        }
+    }
     CU(cudaMemcpyAsync(&hm->gc, &dm->gc, sizeof(SkrGroupCounters), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     ctx->rs.n_units = hm->gc.n_units;
@@ -450,37 +510,47 @@ int run_v2_group(gbin_ctx *ctx, void *skr, void *twin, uint64_t n_skr, const int
     return GBIN_OK;
 }
 
-int run_v2(gbin_ctx *ctx, const gbin_reads *rd, uint64_t n, uint32_t max_len, cudaStream_t st, gbin_table *out, int *launches, bool *done) {
+int run_v2(gbin_ctx *ctx, const gbin_reads *rd, uint64_t n, uint32_t max_len, cudaStream_t st, gbin_table *out, int *launches, bool *done,
+           const HostFeed *feed, HostSink *sink) {
     *done = false;
     if (n == 0 || n >= (1ull << 31)) return GBIN_OK;
     const int NW = ctx->cfg.kmer_size <= 32 ? 8 : 12;
     uint64_t n_skr = 0, n_chk = 0;
-    int rc = run_v2_scan(ctx, rd, n, max_len, 0, nullptr, 0, st, &n_skr, launches);
+    int rc = run_v2_scan(ctx, rd, n, max_len, 0, nullptr, 0, st, &n_skr, launches, feed);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[2], st));
     CU(ctx->skr_b.ensure((n_skr + 1) * NW * 4));
-    rc = run_v2_group(ctx, ctx->skr_a.p, ctx->skr_b.p, n_skr, rd->read_ids, rd->id_base, st, out, launches, done, &n_chk);
+    rc = run_v2_group(ctx, ctx->skr_a.p, ctx->skr_b.p, n_skr, rd->read_ids, rd->id_base, st, out, launches, done, &n_chk, sink);
     if (rc) return rc;
     if (n_chk != n) return fail(ctx, GBIN_E_CUDA, "internal: record windows sum to %llu, expected %llu", (unsigned long long)n_chk, (unsigned long long)n);
     return GBIN_OK;
 }
 
-int bin_device_impl(gbin_ctx *ctx, const gbin_reads *rd, cudaStream_t st, gbin_table *out, int *launches) {
+// feed: the reads have NOT been copied to rd->data yet (host path); whoever consumes them first issues the copy.
+int bin_device_impl(gbin_ctx *ctx, const gbin_reads *rd, cudaStream_t st, gbin_table *out, int *launches, const HostFeed *feed = nullptr,
+                    HostSink *sink = nullptr) {
     uint64_t n = 0;
     uint32_t max_len = 0;
     int rc = plan_reads(ctx, rd, st, &n, &max_len, launches);
     if (rc) return rc;
     if (max_len > GBIN_MAX_READ_LEN) return fail(ctx, GBIN_E_TOO_LARGE, "read length %u exceeds GBIN_MAX_READ_LEN", max_len);
     if (n >= (1ull << 32) - 8192) return fail(ctx, GBIN_E_TOO_LARGE, "%llu k-mer instances in one batch (limit 2^32)", (unsigned long long)n);
-    if (ctx->pipeline == 2) {
+    const bool v2 = ctx->pipeline == 2 && n != 0 && n < (1ull << 31);
+    if (feed && !v2) {  // nobody downstream streams the reads in: copy them in one piece
+        CU(cudaMemcpyAsync(feed->dst, feed->src, feed->bytes, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(ctx->ev[1], st));
+        feed = nullptr;
+    }
+    if (v2) {
         bool done = false;
-        rc = run_v2(ctx, rd, n, max_len, st, out, launches, &done);
+        rc = run_v2(ctx, rd, n, max_len, st, out, launches, &done, feed, sink);
         if (rc) return rc;
         if (done) {
             ctx->last_pipeline = 2;
             CU(cudaEventRecord(ctx->ev[4], st));
             return GBIN_OK;
         }
+        if (sink) sink->kmers_done = sink->ids_done = 0;  // what was streamed belongs to the abandoned attempt
     }
     ctx->last_pipeline = 1;
     memset(&ctx->rs, 0, sizeof ctx->rs);
@@ -544,7 +614,16 @@ int gbin_create(const gbin_config *cfg, gbin_ctx **out) {
     cudaError_t e = cudaSetDevice(cfg->device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->st_h2d, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->st_d2h, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev[i]);
+    for (int i = 0; i < SKR_MAX_CHUNKS && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_feed[i], cudaEventDisableTiming);
+    for (int i = 0; i < SKR_MAX_CHUNKS && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
+    ctx->host_chunks = 8;
+    if (const char *hc = getenv("GBIN_HOST_CHUNKS")) ctx->host_chunks = atoi(hc);
+    if (ctx->host_chunks < 1) ctx->host_chunks = 1;
+    if (ctx->host_chunks > SKR_MAX_CHUNKS) ctx->host_chunks = SKR_MAX_CHUNKS;
     if (e == cudaSuccess) e = ctx->misc.ensure(sizeof(Misc));
     if (e == cudaSuccess) e = ctx->h_misc.ensure(sizeof(Misc));
     if (e != cudaSuccess) {
@@ -569,8 +648,18 @@ void gbin_destroy(gbin_ctx *ctx) {
     for (DevBuf *b : bufs) b->release();
     ctx->h_misc.release();
     ctx->h_result.release();
+    ctx->h_kmer_codes.release();
+    ctx->h_kmer_id_off.release();
+    ctx->h_read_ids.release();
     ctx->prof.destroy();
     for (int i = 0; i < 6; i++) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < SKR_MAX_CHUNKS; i++) {
+        cudaEventDestroy(ctx->ev_feed[i]);
+        cudaEventDestroy(ctx->ev_chunk[i]);
+    }
+    cudaEventDestroy(ctx->ev_copy);
+    cudaStreamDestroy(ctx->st_h2d);
+    cudaStreamDestroy(ctx->st_d2h);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -676,18 +765,65 @@ int gbin_bin_reads_device(gbin_ctx *ctx, const gbin_reads *reads, void *stream, 
     return GBIN_OK;
 }
 
+// Copies what the sink has not streamed yet of the device table `dev` into the context's pinned arenas (regrown when too
+// small — then everything is copied) plus the bucket directory, and fills *out.  Work is enqueued on st; the caller syncs.
+static int table_to_pinned(gbin_ctx *ctx, const gbin_table &dev, HostSink *sink, cudaStream_t st, gbin_table *out) {
+    const uint64_t B = dev.n_buckets, S = dev.n_kmers, NS = dev.n_ids;
+    const int KW = dev.kmer_words;
+    uint64_t s0 = sink ? sink->kmers_done : 0, n0 = sink ? sink->ids_done : 0;
+    if (s0 > S || n0 > NS) s0 = n0 = 0;
+    if (s0 || n0) {  // the streamed copies must have landed before the arena is handed out
+        CU(cudaEventRecord(ctx->ev_copy, ctx->st_d2h));
+        CU(cudaStreamWaitEvent(st, ctx->ev_copy, 0));
+    }
+    const size_t need_kc = (S * KW + 1) * sizeof(uint64_t), need_ko = (S + 1) * sizeof(uint64_t), need_id = (NS + 1) * sizeof(int32_t);
+    if (need_kc > ctx->h_kmer_codes.cap || need_ko > ctx->h_kmer_id_off.cap || need_id > ctx->h_read_ids.cap) {
+        CU(cudaStreamSynchronize(ctx->st_d2h));  // regrowing frees the arenas: nothing may be in flight into them
+        CU(ctx->h_kmer_codes.ensure(need_kc));
+        CU(ctx->h_kmer_id_off.ensure(need_ko));
+        CU(ctx->h_read_ids.ensure(need_id));
+        s0 = n0 = 0;
+    }
+    const size_t sz_mo = (B + 1) * sizeof(uint64_t);
+    CU(ctx->h_result.ensure(sz_mo + (B + 1) * sizeof(uint32_t) + 64));
+    *out = dev;
+    out->on_device = 0;
+    out->ctx_owned = 1;
+    out->kmer_codes = static_cast<uint64_t *>(ctx->h_kmer_codes.p);
+    out->kmer_id_off = static_cast<uint64_t *>(ctx->h_kmer_id_off.p);
+    out->read_ids = static_cast<int32_t *>(ctx->h_read_ids.p);
+    out->mmer_kmer_off = static_cast<uint64_t *>(ctx->h_result.p);
+    out->mmer_codes = reinterpret_cast<uint32_t *>(static_cast<char *>(ctx->h_result.p) + sz_mo);
+    if (S > s0) CU(cudaMemcpyAsync(out->kmer_codes + s0 * KW, dev.kmer_codes + s0 * KW, (S - s0) * KW * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out->kmer_id_off + s0, dev.kmer_id_off + s0, (S + 1 - s0) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    if (NS > n0) CU(cudaMemcpyAsync(out->read_ids + n0, dev.read_ids + n0, (NS - n0) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out->mmer_kmer_off, dev.mmer_kmer_off, (B + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    if (B) CU(cudaMemcpyAsync(out->mmer_codes, dev.mmer_codes, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    return GBIN_OK;
+}
+
 int gbin_bin_reads_host(gbin_ctx *ctx, const gbin_reads *reads, gbin_table *out) {
     if (!ctx || !reads || !out) return GBIN_E_INVALID_ARG;
     CU(cudaSetDevice(ctx->cfg.device));
     cudaStream_t st = ctx->stream;
     int launches = 0;
     gbin_reads d = *reads;
+    HostFeed feed{};
+    bool use_feed = false;
     CU(cudaEventRecord(ctx->ev[0], st));
     if (reads->n_reads) {
         if (!reads->data || reads->data_bytes == 0) return fail(ctx, GBIN_E_INVALID_ARG, "host reads need data and data_bytes");
         CU(ctx->d_reads.ensure(reads->data_bytes + 64));
-        CU(cudaMemcpyAsync(ctx->d_reads.p, reads->data, reads->data_bytes, cudaMemcpyHostToDevice, st));
         d.data = ctx->d_reads.as<char>();
+        if (!reads->starts && reads->stride >= reads->read_len && (reads->n_reads - 1) * reads->stride + reads->read_len <= reads->data_bytes) {
+            // fixed stride: read ranges are byte ranges, so the copy is left to the scan stage, which overlaps it with the scan
+            feed = HostFeed{reads->data, ctx->d_reads.as<char>(), reads->data_bytes, ctx->host_chunks};
+            if (reads->n_reads < 4096u * (uint64_t)feed.chunks) feed.chunks = 1;
+            use_feed = true;
+            CU(cudaStreamWaitEvent(ctx->st_h2d, ctx->ev[0], 0));
+        } else {
+            CU(cudaMemcpyAsync(ctx->d_reads.p, reads->data, reads->data_bytes, cudaMemcpyHostToDevice, st));
+        }
         if (reads->starts) {
             if (!reads->lens) return fail(ctx, GBIN_E_INVALID_ARG, "ragged reads need lens");
             CU(ctx->d_starts.ensure(reads->n_reads * sizeof(uint64_t)));
@@ -712,36 +848,37 @@ int gbin_bin_reads_host(gbin_ctx *ctx, const gbin_reads *reads, gbin_table *out)
             d.read_ids = ctx->d_ids.as<int32_t>();
         }
     }
-    CU(cudaEventRecord(ctx->ev[1], st));
+    if (!use_feed) CU(cudaEventRecord(ctx->ev[1], st));
+    // the big arrays of the table are streamed into the pinned arenas as far as these reach (they are sized by the previous
+    // call, so the first call on a context copies everything at the end and later calls of similar size overlap the copy)
+    HostSink sink{static_cast<uint64_t *>(ctx->h_kmer_codes.p), static_cast<uint64_t *>(ctx->h_kmer_id_off.p), static_cast<int32_t *>(ctx->h_read_ids.p),
+                  0, 0, 0, 0, ctx->host_chunks};
+    sink.kmer_cap = ctx->h_kmer_codes.cap / (sizeof(uint64_t) * ctx->KW);
+    if (ctx->h_kmer_id_off.cap / sizeof(uint64_t) < sink.kmer_cap) sink.kmer_cap = ctx->h_kmer_id_off.cap / sizeof(uint64_t);
+    sink.id_cap = ctx->h_read_ids.cap / sizeof(int32_t);
     gbin_table dev;
-    int rc = bin_device_impl(ctx, &d, st, &dev, &launches);
+    int rc = bin_device_impl(ctx, &d, st, &dev, &launches, use_feed ? &feed : nullptr, &sink);
+    if (rc) {
+        cudaStreamSynchronize(ctx->st_h2d);
+        cudaStreamSynchronize(ctx->st_d2h);
+        return rc;
+    }
+    rc = table_to_pinned(ctx, dev, &sink, st, out);
     if (rc) return rc;
-    // D2H into the pinned arena
-    const uint64_t B = dev.n_buckets, S = dev.n_kmers, NS = dev.n_ids;
-    const int KW = dev.kmer_words;
-    const size_t sz_kc = (S * KW + 1) * sizeof(uint64_t), sz_ko = (S + 1) * sizeof(uint64_t), sz_mo = (B + 1) * sizeof(uint64_t);
-    const size_t sz_id = ((NS + 2) & ~1ull) * sizeof(int32_t), sz_mc = ((B + 2) & ~1ull) * sizeof(uint32_t);
-    CU(ctx->h_result.ensure(sz_kc + sz_ko + sz_mo + sz_id + sz_mc + 64));
-    char *h = static_cast<char *>(ctx->h_result.p);
-    *out = dev;
-    out->on_device = 0;
-    out->kmer_codes = reinterpret_cast<uint64_t *>(h);
-    h += sz_kc;
-    out->kmer_id_off = reinterpret_cast<uint64_t *>(h);
-    h += sz_ko;
-    out->mmer_kmer_off = reinterpret_cast<uint64_t *>(h);
-    h += sz_mo;
-    out->read_ids = reinterpret_cast<int32_t *>(h);
-    h += sz_id;
-    out->mmer_codes = reinterpret_cast<uint32_t *>(h);
-    CU(cudaMemcpyAsync(out->kmer_codes, dev.kmer_codes, S * KW * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(out->kmer_id_off, dev.kmer_id_off, (S + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(out->mmer_kmer_off, dev.mmer_kmer_off, (B + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(out->read_ids, dev.read_ids, NS * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(out->mmer_codes, dev.mmer_codes, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(ctx->ev[5], st));
     CU(cudaStreamSynchronize(st));
+    CU(cudaStreamSynchronize(ctx->st_d2h));
     finish_timings(ctx, launches, true);
+    return GBIN_OK;
+}
+
+int gbin_table_to_pinned(gbin_ctx *ctx, const gbin_table *dev, void *stream, gbin_table *host) {
+    if (!ctx || !dev || !host || !dev->on_device) return GBIN_E_INVALID_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    int rc = table_to_pinned(ctx, *dev, nullptr, st, host);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(st));
     return GBIN_OK;
 }
 
@@ -887,9 +1024,8 @@ int gbin_group_skr_device(gbin_ctx *ctx, void *d_skr, uint64_t n_skr, const int3
         int rc = run_v2_group(ctx, d_skr, ctx->skr_b.p, n_skr, d_ids_by_arrival, id_base, st, out, &launches, &done, &n);
         if (rc) return rc;
         if (!done) {
-            // overflow: expand the (sorted or unsorted, either is fine: expansion keeps per-record order and the v1 sort is
-            // stable on arrival only within equal keys, which requires arrival order) — records must be re-sorted by
-            // arrival first; simplest correct route: report it and let the caller re-run through the instance-record path.
+            // A unit overflowed (one k-mer with more instances than a unit holds).  The records were consumed by the sort,
+            // so the caller re-runs the batch from the reads through the instance-record entry points (pipeline 1).
             if (used_fallback) *used_fallback = 1;
             return fail(ctx, GBIN_E_STATE, "a shared-memory unit overflowed; re-run this batch through gbin_group_records_device");
         }

@@ -77,8 +77,10 @@ int radix_partition_skr_by_owner(const void *in, void *out, uint64_t n, int skr_
                                  cudaStream_t st);
 
 // ---- skr_scan.cu
-int launch_skr_scan(const ReadsView &rv, int K, int M, uint32_t arrival_base, uint32_t max_len, void *out, uint64_t capacity,
-                    unsigned long long *tile_state, uint32_t *ticket, unsigned long long *counters, int sm_count, cudaStream_t st);
+// Scans reads [read_begin, read_end) of rv; record offsets continue from counters[1] (zero it before the first launch).
+int launch_skr_scan(const ReadsView &rv, uint64_t read_begin, uint64_t read_end, int K, int M, uint32_t arrival_base, uint32_t max_len,
+                    void *out, uint64_t capacity, unsigned long long *tile_state, uint32_t *ticket, unsigned long long *counters, int sm_count,
+                    cudaStream_t st);
 uint32_t skr_scan_tiles(uint64_t n_reads, int K, int M, uint32_t max_len);
 
 // ---- skr_group.cu (pipeline v2: plan units, group in shared memory, emit)
@@ -96,8 +98,19 @@ size_t skr_unit_bytes();
 int skr_plan_units(const void *skr_sorted, int K, const uint32_t *inst_prefix, const uint32_t *run_start, uint64_t n_runs,
                    uint32_t *small_prefix, uint32_t *unit_base, uint32_t *scratch, void *units, uint64_t max_units, void *gc_dev,
                    uint32_t *big_list, uint64_t *big_k0, uint64_t *big_k1, uint32_t *big_arr, int sm_count, cudaStream_t st);
+// The grouping runs as ch.n consecutive launches over equal ranges of the unit list, one chained scan across them.
+// With totals_dev set, the end offsets of every chunk ({k-mers << 31 | ids}) are published after it (and copied to
+// totals_host / followed by the event done[c] when those are given), so the host can stream finished parts of the table.
+constexpr int SKR_MAX_CHUNKS = 16;
+struct SkrGroupChunks {
+    uint32_t n;                       // 1..SKR_MAX_CHUNKS
+    uint32_t *tickets;                // device, [n], zeroed by the launcher
+    unsigned long long *totals_dev;   // device, [n] or nullptr
+    unsigned long long *totals_host;  // pinned, [n] or nullptr
+    cudaEvent_t *done;                // [n] or nullptr
+};
 int skr_group_launch(const void *skr_sorted, int K, int cutoff, const uint32_t *inst_prefix, const void *units, unsigned long long *unit_state,
-                     uint64_t max_units, void *gc_dev, uint64_t *big_k0, uint64_t *big_k1, uint32_t *big_arr, const int32_t *ids_by_arrival, int32_t id_base, uint64_t *kmer_codes,
+                     uint64_t max_units, const SkrGroupChunks &ch, void *gc_dev, uint64_t *big_k0, uint64_t *big_k1, uint32_t *big_arr, const int32_t *ids_by_arrival, int32_t id_base, uint64_t *kmer_codes,
                      uint32_t *kmer_mmer, uint64_t *kmer_id_off, int32_t *read_ids, uint64_t kmer_cap, uint64_t id_cap, int sm_count,
                      cudaStream_t st);
 int skr_emit_buckets(const uint32_t *kmer_mmer, uint64_t n_kmers, uint64_t n_ids, uint32_t *bucket_excl, uint32_t *scratch,

@@ -413,7 +413,8 @@ template <int PW, int KW, int G_CAP, int G_THREADS>
 __global__ void __launch_bounds__(G_THREADS)
     skr_group_kernel(const uint32_t *__restrict__ skr, const uint32_t *__restrict__ inst_prefix, const Unit *__restrict__ units, BigScratch sc,
                      int K, int cutoff, const int32_t *__restrict__ ids_by_arrival, int32_t id_base, GroupOut out,
-                     unsigned long long *__restrict__ unit_state, GroupCounters *__restrict__ gc) {
+                     unsigned long long *__restrict__ unit_state, GroupCounters *__restrict__ gc, uint32_t chunk, uint32_t n_chunks,
+                     uint32_t *__restrict__ chunk_tickets) {
     constexpr int NW = SkrLayout<PW>::WORDS;
     constexpr int G_HS = 2 * G_CAP;  // hash slots
     constexpr int G_LOG_HS = G_CAP == 4096 ? 13 : (G_CAP == 2048 ? 12 : 11);
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(G_THREADS)
     uint16_t *surv = rnk + G_CAP;
     uint32_t *off = table;                 // off[s], s < S <= CAP (the end of the last list is the unit's id total)
     uint32_t *stage_ids = table + G_CAP;   // scratch; together with cnt (free once the offsets exist) 2*CAP words
-    __shared__ uint32_t s_unit, s_count, s_nsurv, s_ndistinct, s_overflow, s_scan[G_THREADS / 32 + 1];
+    __shared__ uint32_t s_unit, s_nsurv, s_ndistinct, s_overflow, s_scan[G_THREADS / 32 + 1];
     __shared__ unsigned long long s_base;
     __shared__ uint32_t s_total_ids;
     __shared__ Unit s_un;
@@ -439,12 +440,16 @@ __global__ void __launch_bounds__(G_THREADS)
 
     // Units are handed out by an atomic ticket, taken only when the CTA is ready to start the unit: a ticket taken ahead
     // of time would let later units overtake it, and their chained-scan resolve would then wait for it.
-    const uint32_t n_units = gc->n_units;
+    // One launch handles chunk `chunk` of `n_chunks` equal ranges of the unit list (the host path streams the finished part
+    // of the table to the host while later chunks are still being grouped); the chained scan runs across the launches.
+    const uint32_t n_units_all = gc->n_units;
+    const uint32_t unit_begin = (uint32_t)(((uint64_t)n_units_all * chunk) / n_chunks);
+    const uint32_t n_units = (uint32_t)(((uint64_t)n_units_all * (chunk + 1)) / n_chunks);  // this launch handles [unit_begin, n_units)
+    uint32_t *chunk_ticket = chunk_tickets + chunk;
     for (;;) {
         if (tid == 0) {
-            s_unit = atomicAdd(&gc->ticket, 1u);
+            s_unit = unit_begin + atomicAdd(chunk_ticket, 1u);
             if (s_unit < n_units) s_un = units[s_unit];
-            s_count = 0;
             s_nsurv = 0;
             s_ndistinct = 0;
             s_overflow = 0;
@@ -456,7 +461,7 @@ __global__ void __launch_bounds__(G_THREADS)
         const Unit un = s_un;
         const uint32_t base_pref = un.base_pref;
         const uint32_t n_cand = un.n_cand;
-        const bool filtered = (un.flags & UNIT_RECORDS) != 0;  // a slice of a big bucket: instances arrive in arbitrary order
+        const bool from_records = (un.flags & UNIT_RECORDS) != 0;  // a slice of a big bucket: its instances arrive in arbitrary order
         if (n_cand > (uint32_t)G_CAP && tid == 0) s_overflow = 1;
 
         // ---- zero the hash table and counters while records stream in
@@ -464,7 +469,7 @@ __global__ void __launch_bounds__(G_THREADS)
         for (uint32_t i = tid; i < (uint32_t)G_CAP; i += G_THREADS) cnt[i] = 0;
 
         if (n_cand <= (uint32_t)G_CAP) {
-            if (filtered) {
+            if (from_records) {
                 // ---- instances of a big bucket's slice were expanded by partition_big_runs_kernel: just load them
                 for (uint32_t i = tid; i < n_cand; i += G_THREADS) {
                     const uint64_t g = (uint64_t)un.skr_begin + i;
@@ -636,7 +641,7 @@ __global__ void __launch_bounds__(G_THREADS)
             const unsigned long long base = lkb_resolve_warp<8>(unit_state, u, ((unsigned long long)S << 31) | N, tid);
             if (tid == 0) {
                 s_base = base;
-                if (u == gc->n_units - 1) {
+                if (u == n_units_all - 1) {
                     gc->total_kmers = (base >> 31) + S;
                     gc->total_ids = (base & 0x7fffffffull) + N;
                 }
@@ -651,8 +656,8 @@ __global__ void __launch_bounds__(G_THREADS)
         }
         constexpr int NCH = G_CAP / 32;            // 32-instance chunks of a unit
         constexpr int ITERS = G_CAP / G_THREADS;   // instances per thread
-        if (!filtered && S * NCH <= 2u * 2u * G_CAP) {
-            // ---- id lists, ordered path.  Instance positions of an unfiltered unit follow arrival order, so the place of
+        if (!from_records && S * NCH <= 2u * 2u * G_CAP) {
+            // ---- id lists, ordered path.  Instance positions of a unit expanded from super-k-mer records follow arrival order, so the place of
             // an instance in its newest-first list is (members of the list in later chunks) + (members at a higher lane of
             // its own chunk): a per-(list, chunk) count matrix filled with warp match, a suffix sum per list, done.
             uint16_t *mat = reinterpret_cast<uint16_t *>(stage_ids);  // [S][NCH], spills into cnt (dead by now)
@@ -824,21 +829,37 @@ int skr_plan_units(const void *skr_sorted, int K, const uint32_t *inst_prefix, c
     return l + 2;
 }
 
+// After chunk `chunk` of the grouping has completed: its end offsets {surviving k-mers << 31 | ids} = the inclusive prefix of
+// its last unit (every unit of the chunk has resolved by then).  An empty prefix of the unit list yields 0.
+__global__ void publish_chunk_total_kernel(const unsigned long long *__restrict__ unit_state, const GroupCounters *__restrict__ gc, uint32_t chunk,
+                                           uint32_t n_chunks, unsigned long long *__restrict__ chunk_totals) {
+    const uint32_t end = (uint32_t)(((uint64_t)gc->n_units * (chunk + 1)) / n_chunks);
+    chunk_totals[chunk] = end ? (unit_state[end - 1] & LKB_VALUE_MASK) : 0ull;
+}
+
 int skr_group_launch(const void *skr_sorted, int K, int cutoff, const uint32_t *inst_prefix, const void *units, unsigned long long *unit_state,
-                     uint64_t max_units, void *gc_dev, uint64_t *big_k0, uint64_t *big_k1, uint32_t *big_arr, const int32_t *ids_by_arrival, int32_t id_base, uint64_t *kmer_codes,
+                     uint64_t max_units, const SkrGroupChunks &ch, void *gc_dev, uint64_t *big_k0, uint64_t *big_k1, uint32_t *big_arr, const int32_t *ids_by_arrival, int32_t id_base, uint64_t *kmer_codes,
                      uint32_t *kmer_mmer, uint64_t *kmer_id_off, int32_t *read_ids, uint64_t kmer_cap, uint64_t id_cap, int sm_count,
                      cudaStream_t st) {
     const int KW = K <= 32 ? 1 : 2;
     const size_t smem = skr_group_smem_bytes(KW);
     cudaMemsetAsync(unit_state, 0, sizeof(unsigned long long) * max_units, st);
+    cudaMemsetAsync(ch.tickets, 0, sizeof(uint32_t) * ch.n, st);
     GroupOut out{kmer_codes, kmer_mmer, kmer_id_off, read_ids, kmer_cap, id_cap};
     GroupCounters *gc = static_cast<GroupCounters *>(gc_dev);
     const uint32_t *s = static_cast<const uint32_t *>(skr_sorted);
     const Unit *un = static_cast<const Unit *>(units);
     auto launch = [&](auto kern, int threads, int ctas_per_sm) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<sm_count * ctas_per_sm, threads, smem, st>>>(s, inst_prefix, un, BigScratch{big_k0, big_k1, big_arr}, K, cutoff, ids_by_arrival,
-                                                            id_base, out, unit_state, gc);
+        for (uint32_t c = 0; c < ch.n; c++) {
+            kern<<<sm_count * ctas_per_sm, threads, smem, st>>>(s, inst_prefix, un, BigScratch{big_k0, big_k1, big_arr}, K, cutoff, ids_by_arrival,
+                                                                id_base, out, unit_state, gc, c, ch.n, ch.tickets);
+            if (ch.totals_dev) {
+                publish_chunk_total_kernel<<<1, 1, 0, st>>>(unit_state, gc, c, ch.n, ch.totals_dev);
+                if (ch.totals_host) cudaMemcpyAsync(ch.totals_host + c, ch.totals_dev + c, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+                if (ch.done) cudaEventRecord(ch.done[c], st);
+            }
+        }
     };
     static int thr = 0;  // GBIN_V2_THREADS=512: experiment with 512 threads per CTA at capacity 2048
     if (!thr) {
@@ -855,7 +876,7 @@ int skr_group_launch(const void *skr_sorted, int K, int cutoff, const uint32_t *
         if (KW == 1) launch(skr_group_kernel<2, 1, 2048, 256>, 256, 3);
         else launch(skr_group_kernel<4, 2, 2048, 256>, 256, 2);
     }
-    return 1;
+    return (int)(ch.totals_dev ? 2 * ch.n : ch.n);
 }
 
 // Bucket directory over the n_kmers emitted k-mers. bucket_excl: [n_kmers] scratch. *n_buckets_dev receives B.

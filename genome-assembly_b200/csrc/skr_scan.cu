@@ -91,8 +91,8 @@ __device__ __forceinline__ uint32_t skr_process_tile(const ReadsView &rv, const 
 
 template <int PW>
 __global__ void __launch_bounds__(SKR_WARPS * 32)
-    skr_scan_kernel(ReadsView rv, int K, int M, uint32_t arrival_base, uint32_t max_len, uint32_t rpw, uint32_t seg_cap, uint32_t ntiles,
-                    uint32_t *__restrict__ out, unsigned long long capacity, unsigned long long *__restrict__ tile_state,
+    skr_scan_kernel(ReadsView rv, uint64_t read_begin, int K, int M, uint32_t arrival_base, uint32_t max_len, uint32_t rpw, uint32_t seg_cap,
+                    uint32_t ntiles, uint32_t *__restrict__ out, unsigned long long capacity, unsigned long long *__restrict__ tile_state,
                     uint32_t *__restrict__ ticket, unsigned long long *__restrict__ counters /* [0] bad bases, [1] records, [2] instances */) {
     constexpr int NW = SkrLayout<PW>::WORDS;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -106,16 +106,19 @@ __global__ void __launch_bounds__(SKR_WARPS * 32)
     ws.stage = ws.segl + 2 * skr_len4(max_len);
     uint32_t nbad = 0;
     unsigned long long ninst = 0;
+    // records emitted by earlier launches over the same batch (the host path scans the reads in chunks while later
+    // chunks are still on their way over PCIe); rv.n_reads is the END of this launch's read range
+    const unsigned long long base0 = counters[1];
 
     for (;;) {
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(ticket, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= ntiles) break;
-        const uint64_t first = (uint64_t)tile * rpw;
+        const uint64_t first = read_begin + (uint64_t)tile * rpw;
         const uint32_t nseg = skr_process_tile<PW, false>(rv, ws, first, rpw, K, M, arrival_base, seg_cap, lane, out, 0ull, nbad, ninst);
         if (lane == 0) lkb_publish_aggregate(tile_state, tile, nseg);
-        const unsigned long long base = lkb_resolve_warp<1>(tile_state, tile, nseg, lane);
+        const unsigned long long base = base0 + lkb_resolve_warp<1>(tile_state, tile, nseg, lane);
         if (tile == ntiles - 1 && lane == 0) counters[1] = base + nseg;
         if (base + nseg <= capacity) {  // past the capacity only the total is produced (the caller re-runs)
             if (nseg <= seg_cap) {
@@ -153,14 +156,17 @@ static void skr_tile_shape(int K, int M, uint32_t max_len, uint32_t *rpw_out, ui
 
 // Host launcher.  tile_state must hold ntiles u64 (zeroed here), ticket one u32 (zeroed here).
 // Returns kernels launched; *ntiles_out = number of tiles.
-int launch_skr_scan(const ReadsView &rv, int K, int M, uint32_t arrival_base, uint32_t max_len, void *out, uint64_t capacity,
-                    unsigned long long *tile_state, uint32_t *ticket, unsigned long long *counters, int sm_count, cudaStream_t st) {
-    if (rv.n_reads == 0) return 0;
+int launch_skr_scan(const ReadsView &rv_all, uint64_t read_begin, uint64_t read_end, int K, int M, uint32_t arrival_base, uint32_t max_len,
+                    void *out, uint64_t capacity, unsigned long long *tile_state, uint32_t *ticket, unsigned long long *counters, int sm_count,
+                    cudaStream_t st) {
+    if (read_end <= read_begin) return 0;
+    ReadsView rv = rv_all;
+    rv.n_reads = read_end;  // the kernel treats n_reads as the end of its read range
     const int PW = skr_payload_units(K);
     const int NW = 4 + 2 * PW;
     uint32_t rpw, seg_cap;
     skr_tile_shape(K, M, max_len, &rpw, &seg_cap);
-    const uint32_t ntiles = (uint32_t)((rv.n_reads + rpw - 1) / rpw);
+    const uint32_t ntiles = (uint32_t)((read_end - read_begin + rpw - 1) / rpw);
     const size_t smem = (size_t)SKR_WARPS * skr_warp_smem(max_len, seg_cap, NW);
     cudaMemsetAsync(tile_state, 0, sizeof(unsigned long long) * ntiles, st);
     cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
@@ -168,11 +174,11 @@ int launch_skr_scan(const ReadsView &rv, int K, int M, uint32_t arrival_base, ui
     if (blocks > (ntiles + SKR_WARPS - 1) / SKR_WARPS) blocks = (ntiles + SKR_WARPS - 1) / SKR_WARPS;
     if (PW == 2) {
         cudaFuncSetAttribute(skr_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        skr_scan_kernel<2><<<blocks, SKR_WARPS * 32, smem, st>>>(rv, K, M, arrival_base, max_len, rpw, seg_cap, ntiles,
+        skr_scan_kernel<2><<<blocks, SKR_WARPS * 32, smem, st>>>(rv, read_begin, K, M, arrival_base, max_len, rpw, seg_cap, ntiles,
                                                                static_cast<uint32_t *>(out), capacity, tile_state, ticket, counters);
     } else {
         cudaFuncSetAttribute(skr_scan_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        skr_scan_kernel<4><<<blocks, SKR_WARPS * 32, smem, st>>>(rv, K, M, arrival_base, max_len, rpw, seg_cap, ntiles,
+        skr_scan_kernel<4><<<blocks, SKR_WARPS * 32, smem, st>>>(rv, read_begin, K, M, arrival_base, max_len, rpw, seg_cap, ntiles,
                                                                static_cast<uint32_t *>(out), capacity, tile_state, ticket, counters);
     }
     return 1;

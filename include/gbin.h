@@ -119,7 +119,10 @@ int gbin_get_config(const gbin_ctx *ctx, gbin_config *out);
 /* Whole hot path, HOST buffers: H2D copy of the reads, pack + window/signature scan (process_read,
  * binning.c:918-1040), grouping (the two-level zhash insert, binning.c:1044-1069), prune
  * (binning.c:1085-1144), D2H of the table into the context's pinned result arena (ctx_owned = 1:
- * valid until the next call on the context; gbin_table_clone makes an independent malloc'ed copy). */
+ * valid until the next call on the context; gbin_table_clone makes an independent malloc'ed copy).
+ * Fixed-stride reads are copied in GBIN_HOST_CHUNKS (default 8) pieces that are scanned as they land, and the
+ * finished part of the table is copied out while the rest is still being grouped (the arena is sized by the
+ * previous call, so the overlap starts with the second call of similar size on a context). */
 int gbin_bin_reads_host(gbin_ctx *ctx, const gbin_reads *reads, gbin_table *out);
 int gbin_table_clone(const gbin_table *host, gbin_table *out);
 void gbin_table_free(gbin_table *t);
@@ -134,6 +137,9 @@ int gbin_bin_reads_device(gbin_ctx *ctx, const gbin_reads *reads, void *stream, 
 
 /* Copies a device-resident table to freshly malloc'ed host arrays. */
 int gbin_table_to_host(gbin_ctx *ctx, const gbin_table *dev, gbin_table *host);
+/* Same into the context's page-locked result arena (ctx_owned = 1: valid until the next call on the context that
+ * produces a host table) — the fast way to bring a table produced by the staged / device entry points to the host. */
+int gbin_table_to_pinned(gbin_ctx *ctx, const gbin_table *dev, void *stream, gbin_table *host);
 
 int gbin_get_timings(const gbin_ctx *ctx, gbin_timings *out);
 

@@ -215,6 +215,33 @@ def test_key_width_and_parameter_edges(K, M, cutoff, L, pipeline):
     b.close()
 
 
+def test_host_path_streams_reads_in_and_table_out():
+    """gbin_bin_reads_host overlaps PCIe with the kernels: fixed-stride reads are copied and scanned in chunks, and from the
+    second call on a context the finished part of the table is copied out while the grouping continues.  Every call must give
+    the oracle's table, whatever the chunking, also when a larger batch follows a smaller one (arena regrowth)."""
+    torch_cuda()
+    rs = synth.generate(40_000, 100, error_rate=0.01, seed=11, starts="uniform")
+    K, M = 31, 11
+    n_small = 9000
+    want = {}
+    for n in (rs.n_reads, n_small):
+        starts = np.arange(n, dtype=np.uint64) * rs.stride
+        lens = np.full(n, rs.read_len, dtype=np.uint32)
+        want[n] = O.run(rs.buf[: n * rs.stride].tobytes(), starts, lens, K, M, 1)
+    b = B.Binner(K, M, 1)
+    for n in (n_small, rs.n_reads, rs.n_reads, n_small, rs.n_reads):
+        got = b.bin_host(rs.buf[: n * rs.stride], n, stride=rs.stride, read_len=rs.read_len)
+        assert_tables_equal(got, want[n])
+        assert b.pipeline_info()["last_used"] == 2
+    # device table -> pinned arena (what the multi-GPU end-to-end path uses)
+    torch = torch_cuda()
+    d = torch.from_numpy(rs.buf).cuda()
+    dev = b.bin_device_raw(B.Binner._reads(d, d.numel(), rs.n_reads, stride=rs.stride, read_len=rs.read_len),
+                           B.stream_handle(torch.cuda.current_stream()))
+    assert_tables_equal(B.host_table_from_c(b.table_to_pinned_raw(dev)), want[rs.n_reads])
+    b.close()
+
+
 def test_empty_and_degenerate_batches():
     torch_cuda()
     b = B.Binner(31, 4, 1)

@@ -103,4 +103,57 @@ __device__ __forceinline__ uint32_t warp_signature_hop(const uint32_t *wv, uint3
     return __reduce_min_sync(0xffffffffu, best_w == mx ? best_p : 0xffffffffu);
 }
 
+
+// ---- pipeline v2 scan: scores carry the strand bit, one hop = one REDUX
+
+// Whole warp: wr[p] = w(p) << 1 | is_rev(p) for every m-mer start p in [0, L-M]
+// (w(p) = max(s, 4^M-1-s) < 2^30, is_rev = the complement scored higher, binning.c:943,948).
+__device__ __forceinline__ void warp_mmer_scores_strand(const uint32_t *pk, uint32_t *wr, uint32_t L, int M, uint32_t FULL, uint32_t lane) {
+    const uint32_t down = 32u - 2u * (uint32_t)M;
+    for (uint32_t p = lane; p + M <= L; p += 32) {
+        const uint32_t bit = 2 * p, wi = bit >> 5, sh = bit & 31;
+        const uint32_t s = __funnelshift_l(pk[wi + 1], pk[wi], sh) >> down;
+        const uint32_t c = FULL - s;
+        wr[p] = c > s ? ((c << 1) | 1u) : (s << 1);
+    }
+    __syncwarp();
+}
+
+// One hop of the signature chain (binning.c:931-988 at a restart window i): the LEFTMOST position p in [i, i+C)
+// maximising w(p).  Whole warp.  Returns the offset of the signature from i; *w_rev = w(sig) << 1 | is_rev(sig).
+// PACKED: score, (inverted) offset and strand bit fit one 32-bit key, so the hop is a single REDUX.MAX
+// (needs 2M + 1 + OB <= 32 with OB = 5 offset bits when C <= 32, else 6).
+template <bool PACKED>
+__device__ __forceinline__ uint32_t warp_signature_hop_strand(const uint32_t *wr, uint32_t i, uint32_t C, uint32_t lane, uint32_t *w_rev) {
+    if (PACKED) {
+        if (C <= 32) {
+            const uint32_t v = lane < C ? wr[i + lane] : 0u;
+            const uint32_t key = ((v & ~1u) << 5) | ((31u - lane) << 1) | (v & 1u);
+            const uint32_t mx = __reduce_max_sync(0xffffffffu, key);
+            *w_rev = ((mx >> 6) << 1) | (mx & 1u);
+            return 31u - ((mx >> 1) & 31u);
+        }
+        const uint32_t v0 = wr[i + lane];  // C > 32: lanes cover offsets lane and lane + 32 (C <= 63)
+        const uint32_t v1 = lane + 32 < C ? wr[i + lane + 32] : 0u;
+        const uint32_t k0 = ((v0 & ~1u) << 6) | ((63u - lane) << 1) | (v0 & 1u);
+        const uint32_t k1 = ((v1 & ~1u) << 6) | ((31u - lane) << 1) | (v1 & 1u);
+        const uint32_t mx = __reduce_max_sync(0xffffffffu, max(k0, k1));
+        *w_rev = ((mx >> 7) << 1) | (mx & 1u);
+        return 63u - ((mx >> 1) & 63u);
+    }
+    uint32_t best = 0, best_off = 0;
+    for (uint32_t b = 0; b < C; b += 32) {
+        const uint32_t o = b + lane;
+        const uint32_t v = o < C ? wr[i + o] : 0u;
+        if ((v >> 1) > (best >> 1)) {  // strict: the earlier candidate survives ties
+            best = v;
+            best_off = o;
+        }
+    }
+    const uint32_t mx = __reduce_max_sync(0xffffffffu, best >> 1);
+    const uint32_t sel = __reduce_min_sync(0xffffffffu, (best >> 1) == mx ? ((best_off << 1) | (best & 1u)) : 0xffffffffu);
+    *w_rev = (mx << 1) | (sel & 1u);
+    return sel >> 1;
+}
+
 }  // namespace gbin

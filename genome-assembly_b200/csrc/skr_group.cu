@@ -351,6 +351,15 @@ __global__ void __launch_bounds__(PART_THREADS)
 
 // ------------------------------------------------------------------ grouping kernel
 
+// Named barriers of the grouping kernel: 0 = the whole CTA (workers + control warp), 1 = the workers only,
+// 2 = "the unit's totals are published" (workers arrive, the control warp waits).
+__device__ __forceinline__ void bar_workers(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_wait(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_all() { asm volatile("bar.sync 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Exclusive scan over the NT worker threads (barrier 1).
 template <int NT>
 __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t *total, uint32_t *warp_sums /* NT/32 + 1 */) {
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -361,7 +370,7 @@ __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t *to
         if (lane >= (unsigned)d) inc += o;
     }
     if (lane == 31) warp_sums[warp] = inc;
-    __syncthreads();
+    bar_workers(NT);
     if (warp == 0) {
         uint32_t s = lane < NT / 32 ? warp_sums[lane] : 0u;
         uint32_t si = s;
@@ -373,10 +382,10 @@ __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t *to
         if (lane < NT / 32) warp_sums[lane] = si - s;
         if (lane == NT / 32 - 1) warp_sums[NT / 32] = si;
     }
-    __syncthreads();
+    bar_workers(NT);
     const uint32_t res = inc - v + warp_sums[warp];
     *total = warp_sums[NT / 32];
-    __syncthreads();
+    bar_workers(NT);
     return res;
 }
 
@@ -409,13 +418,18 @@ __device__ __forceinline__ bool key_less(const uint64_t *key0, const uint64_t *k
     return false;
 }
 
+// The CTA = G_THREADS worker threads + one control warp.  The workers run the phases of a unit separated by barrier 1;
+// the control warp hides the latencies that are serial per unit: it resolves the unit's output offsets (chained scan over
+// units) while the workers order the survivors, and it takes the next ticket, fetches the next unit's descriptor and
+// prefetches its records into L2 while the workers write the unit's output.
 template <int PW, int KW, int G_CAP, int G_THREADS>
-__global__ void __launch_bounds__(G_THREADS)
+__global__ void __launch_bounds__(G_THREADS + 32)
     skr_group_kernel(const uint32_t *__restrict__ skr, const uint32_t *__restrict__ inst_prefix, const Unit *__restrict__ units, BigScratch sc,
                      int K, int cutoff, const int32_t *__restrict__ ids_by_arrival, int32_t id_base, GroupOut out,
                      unsigned long long *__restrict__ unit_state, GroupCounters *__restrict__ gc, uint32_t chunk, uint32_t n_chunks,
                      uint32_t *__restrict__ chunk_tickets) {
     constexpr int NW = SkrLayout<PW>::WORDS;
+    constexpr int ALL = G_THREADS + 32;
     constexpr int G_HS = 2 * G_CAP;  // hash slots
     constexpr int G_LOG_HS = G_CAP == 4096 ? 13 : (G_CAP == 2048 ? 12 : 11);
     static_assert(G_CAP == 4096 || G_CAP == 2048 || G_CAP == 1024, "unit capacity");
@@ -431,44 +445,90 @@ __global__ void __launch_bounds__(G_THREADS)
     uint16_t *surv = rnk + G_CAP;
     uint32_t *off = table;                 // off[s], s < S <= CAP (the end of the last list is the unit's id total)
     uint32_t *stage_ids = table + G_CAP;   // scratch; together with cnt (free once the offsets exist) 2*CAP words
-    __shared__ uint32_t s_unit, s_nsurv, s_ndistinct, s_overflow, s_scan[G_THREADS / 32 + 1];
-    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_nsurv, s_ndistinct, s_scan[G_THREADS / 32 + 1];
+    __shared__ unsigned long long s_base, s_agg;
     __shared__ uint32_t s_total_ids;
-    __shared__ Unit s_un;
+    __shared__ uint32_t s_uidx[2];
+    __shared__ Unit s_un[2];
 
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const bool ctrl = tid >= (uint32_t)G_THREADS;
 
-    // Units are handed out by an atomic ticket, taken only when the CTA is ready to start the unit: a ticket taken ahead
-    // of time would let later units overtake it, and their chained-scan resolve would then wait for it.
     // One launch handles chunk `chunk` of `n_chunks` equal ranges of the unit list (the host path streams the finished part
     // of the table to the host while later chunks are still being grouped); the chained scan runs across the launches.
     const uint32_t n_units_all = gc->n_units;
     const uint32_t unit_begin = (uint32_t)(((uint64_t)n_units_all * chunk) / n_chunks);
     const uint32_t n_units = (uint32_t)(((uint64_t)n_units_all * (chunk + 1)) / n_chunks);  // this launch handles [unit_begin, n_units)
     uint32_t *chunk_ticket = chunk_tickets + chunk;
-    for (;;) {
+
+    // Control warp: units are handed out by an atomic ticket, taken while the CTA writes the output of its current unit —
+    // a ticket taken much earlier would let later units overtake it, and their chained-scan resolve would then wait for it.
+    auto fetch_unit = [&](int slot) {
+        uint32_t u = 0;
+        if (lane == 0) u = unit_begin + atomicAdd(chunk_ticket, 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (lane == 0) s_uidx[slot] = u;
+        if (u >= n_units) return;
+        const uint32_t w = lane < 8 ? reinterpret_cast<const uint32_t *>(units + u)[lane] : 0u;
+        if (lane < 8) reinterpret_cast<uint32_t *>(&s_un[slot])[lane] = w;
+        const uint32_t b = __shfl_sync(0xffffffffu, w, 0), e = __shfl_sync(0xffffffffu, w, 1), fl = __shfl_sync(0xffffffffu, w, 2);
+        if (fl & UNIT_RECORDS) {
+            const char *p0 = reinterpret_cast<const char *>(sc.k0 + b), *p1 = reinterpret_cast<const char *>(sc.k0 + e);
+            for (const char *p = p0 + 128 * lane; p < p1; p += 128 * 32) prefetch_l2(p);
+            const char *q0 = reinterpret_cast<const char *>(sc.arr + b), *q1 = reinterpret_cast<const char *>(sc.arr + e);
+            for (const char *p = q0 + 128 * lane; p < q1; p += 128 * 32) prefetch_l2(p);
+            if (KW == 2) {
+                const char *r0 = reinterpret_cast<const char *>(sc.k1 + b), *r1 = reinterpret_cast<const char *>(sc.k1 + e);
+                for (const char *p = r0 + 128 * lane; p < r1; p += 128 * 32) prefetch_l2(p);
+            }
+        } else {
+            const char *p0 = reinterpret_cast<const char *>(skr + (uint64_t)b * NW), *p1 = reinterpret_cast<const char *>(skr + (uint64_t)e * NW);
+            for (const char *p = p0 + 128 * lane; p < p1; p += 128 * 32) prefetch_l2(p);
+            const char *q0 = reinterpret_cast<const char *>(inst_prefix + b), *q1 = reinterpret_cast<const char *>(inst_prefix + e);
+            for (const char *p = q0 + 128 * lane; p < q1; p += 128 * 32) prefetch_l2(p);
+        }
+    };
+
+    if (ctrl) fetch_unit(0);
+    bar_all();
+    for (int cur = 0;; cur ^= 1) {
+        const uint32_t u = s_uidx[cur];
+        if (u >= n_units) break;
+        const Unit un = s_un[cur];
+        const uint32_t n_cand = un.n_cand;
+        const bool too_big = n_cand > (uint32_t)G_CAP;  // cannot happen with the planner's bounds; the batch is then redone by pipeline v1
+
+        if (ctrl) {
+            bar_wait(2, ALL);  // the workers have published the unit's totals
+            const unsigned long long agg = s_agg;
+            const unsigned long long base = lkb_resolve_warp<8>(unit_state, u, agg, lane);
+            if (lane == 0) {
+                s_base = base;
+                if (u == n_units_all - 1) {
+                    gc->total_kmers = (base >> 31) + (agg >> 31);
+                    gc->total_ids = (base & 0x7fffffffull) + (agg & 0x7fffffffull);
+                }
+            }
+            bar_all();  // X: the unit's output offsets are known
+            fetch_unit(cur ^ 1);
+            bar_all();  // Y: the unit is done
+            continue;
+        }
+
+        // ================================================================ workers
+        const uint32_t base_pref = un.base_pref;
+        const bool from_records = (un.flags & UNIT_RECORDS) != 0;  // a slice of a big bucket: its instances arrive in arbitrary order
         if (tid == 0) {
-            s_unit = unit_begin + atomicAdd(chunk_ticket, 1u);
-            if (s_unit < n_units) s_un = units[s_unit];
             s_nsurv = 0;
             s_ndistinct = 0;
-            s_overflow = 0;
             s_total_ids = 0;
         }
-        __syncthreads();
-        const uint32_t u = s_unit;
-        if (u >= n_units) break;
-        const Unit un = s_un;
-        const uint32_t base_pref = un.base_pref;
-        const uint32_t n_cand = un.n_cand;
-        const bool from_records = (un.flags & UNIT_RECORDS) != 0;  // a slice of a big bucket: its instances arrive in arbitrary order
-        if (n_cand > (uint32_t)G_CAP && tid == 0) s_overflow = 1;
-
-        // ---- zero the hash table and counters while records stream in
-        for (uint32_t i = tid; i < (uint32_t)G_HS; i += G_THREADS) table[i] = 0;
-        for (uint32_t i = tid; i < (uint32_t)G_CAP; i += G_THREADS) cnt[i] = 0;
-
-        if (n_cand <= (uint32_t)G_CAP) {
+        // ---- zero the hash table and counters (contiguous: table, cnt) while records stream in
+        {
+            uint4 *z = reinterpret_cast<uint4 *>(table);
+            for (uint32_t i = tid; i < (uint32_t)(G_HS + G_CAP) / 4; i += G_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (!too_big) {
             if (from_records) {
                 // ---- instances of a big bucket's slice were expanded by partition_big_runs_kernel: just load them
                 for (uint32_t i = tid; i < n_cand; i += G_THREADS) {
@@ -494,14 +554,17 @@ __global__ void __launch_bounds__(G_THREADS)
                 }
             }
         }
-        __syncthreads();
-        if (s_overflow) {  // give up on this unit (the whole batch will be redone by pipeline v1) but keep the chain alive
+        bar_workers(G_THREADS);
+        if (too_big) {  // give up on this unit (the whole batch will be redone by pipeline v1) but keep the chain alive
             if (tid == 0) {
                 atomicExch(&gc->overflow, 1u);
+                s_agg = 0ull;
                 lkb_publish_aggregate(unit_state, u, 0ull);
             }
-            if (tid < 32) (void)lkb_resolve_warp<8>(unit_state, u, 0ull, tid);
-            __syncthreads();
+            __threadfence_block();
+            bar_arrive(2, ALL);
+            bar_all();  // X
+            bar_all();  // Y
             continue;
         }
         const uint32_t n_inst = n_cand;
@@ -510,19 +573,21 @@ __global__ void __launch_bounds__(G_THREADS)
         for (uint32_t i = tid; i < n_inst; i += G_THREADS) {
             const uint64_t k0 = key0[i], k1 = (KW == 2) ? key1[i] : 0ull;
             const uint32_t m = mm[i];
-            uint64_t hx = (k0 ^ (k1 * 0x9E3779B97F4A7C15ull) ^ (((uint64_t)m << 32) | m)) * 0xD6E8FEB86659FD93ull;
-            uint32_t h = (uint32_t)(hx >> (64 - G_LOG_HS));
+            uint32_t hx = ((uint32_t)k0 * 0x9E3779B1u) ^ ((uint32_t)(k0 >> 32) * 0x85EBCA77u) ^ (m * 0xC2B2AE3Du);
+            if (KW == 2) hx ^= ((uint32_t)k1 * 0x27D4EB2Fu) ^ ((uint32_t)(k1 >> 32) * 0x165667B1u);
+            hx *= 0x9E3779B1u;
+            uint32_t h = hx >> (32 - G_LOG_HS);
             uint32_t rep;
             for (;;) {
-                uint32_t cur = table[h];
-                if (cur == 0) {
-                    cur = atomicCAS(&table[h], 0u, i + 1);
-                    if (cur == 0) {
+                uint32_t c = table[h];
+                if (c == 0) {
+                    c = atomicCAS(&table[h], 0u, i + 1);
+                    if (c == 0) {
                         rep = i;
                         break;
                     }
                 }
-                const uint32_t r = cur - 1;
+                const uint32_t r = c - 1;
                 if (key0[r] == k0 && (KW == 1 || key1[r] == k1) && mm[r] == m) {
                     rep = r;
                     break;
@@ -532,25 +597,30 @@ __global__ void __launch_bounds__(G_THREADS)
             grp[i] = (uint16_t)rep;
             rnk[i] = (uint16_t)atomicAdd(&cnt[rep], 1u);
         }
-        __syncthreads();
+        bar_workers(G_THREADS);
 
         // ---- leaders and survivors (keep iff count > cutoff, binning.c:1102)
-        for (uint32_t i = tid; i < n_inst; i += G_THREADS) {
-            if (grp[i] == i) {
-                atomicAdd(&s_ndistinct, 1u);
-                if (cutoff < 0 || cnt[i] > (uint32_t)cutoff) {
-                    surv[atomicAdd(&s_nsurv, 1u)] = (uint16_t)i;
-                    atomicAdd(&s_total_ids, cnt[i]);
-                }
+        for (uint32_t i0 = 0; i0 < n_inst; i0 += G_THREADS) {
+            const uint32_t i = i0 + tid;
+            const bool leader = i < n_inst && grp[i] == i;
+            const unsigned lm = __ballot_sync(0xffffffffu, leader);
+            if (lane == 0 && lm) atomicAdd(&s_ndistinct, (uint32_t)__popc(lm));
+            if (leader && (cutoff < 0 || cnt[i] > (uint32_t)cutoff)) {
+                surv[atomicAdd(&s_nsurv, 1u)] = (uint16_t)i;
+                atomicAdd(&s_total_ids, cnt[i]);
             }
         }
-        __syncthreads();
+        bar_workers(G_THREADS);
         const uint32_t S = s_nsurv, N = s_total_ids;
-        // the unit's totals are known before any ordering work: publish them now so that successors rarely wait
+        // the unit's totals are known before any ordering work: publish them now so that successors rarely wait, and let the
+        // control warp resolve this unit's output offsets while the survivors are being ordered
         if (tid == 0) {
+            s_agg = ((unsigned long long)S << 31) | N;
             lkb_publish_aggregate(unit_state, u, ((unsigned long long)S << 31) | N);
             atomicAdd(&gc->distinct, (unsigned long long)s_ndistinct);
         }
+        __threadfence_block();
+        bar_arrive(2, ALL);
 
         // ---- survivors ascending by (m-mer, k-mer).  Usual case (a few hundred survivors): every survivor counts
         // the survivors with a smaller key (keys are distinct, so ranks are a permutation) — no barriers inside;
@@ -568,7 +638,7 @@ __global__ void __launch_bounds__(G_THREADS)
                 if (KW == 2) sk1[s] = key1[i];
                 smm[s] = mm[i];
             }
-            __syncthreads();
+            bar_workers(G_THREADS);
             for (uint32_t s = tid; s < S; s += G_THREADS) {
                 const uint64_t k0 = sk0[s], k1 = (KW == 2) ? sk1[s] : 0ull;
                 const uint32_t m = smm[s];
@@ -583,14 +653,14 @@ __global__ void __launch_bounds__(G_THREADS)
                 }
                 tmp[rank] = surv[s];
             }
-            __syncthreads();
+            bar_workers(G_THREADS);
             for (uint32_t s = tid; s < S; s += G_THREADS) surv[s] = tmp[s];
-            __syncthreads();
+            bar_workers(G_THREADS);
         } else {
             uint32_t n2 = 1;
             while (n2 < S) n2 <<= 1;
             for (uint32_t i = S + tid; i < n2; i += G_THREADS) surv[i] = 0xFFFFu;
-            __syncthreads();
+            bar_workers(G_THREADS);
             for (uint32_t k = 2; k <= n2; k <<= 1) {
                 for (uint32_t j = k >> 1; j > 0; j >>= 1) {
                     for (uint32_t idx = tid; idx < n2; idx += G_THREADS) {
@@ -606,7 +676,7 @@ __global__ void __launch_bounds__(G_THREADS)
                             }
                         }
                     }
-                    __syncthreads();
+                    bar_workers(G_THREADS);
                 }
             }
         }
@@ -623,78 +693,75 @@ __global__ void __launch_bounds__(G_THREADS)
                 carry += tot;
             }
         }
-        __syncthreads();
+        bar_workers(G_THREADS);
 
         // ---- every instance learns the index s of its surviving list (0xFFFF: pruned)
         {
             uint16_t *mapv = reinterpret_cast<uint16_t *>(stage_ids);  // leader index -> s
             for (uint32_t sI = tid; sI < S; sI += G_THREADS) mapv[surv[sI]] = (uint16_t)sI;
-            __syncthreads();
+            bar_workers(G_THREADS);
             for (uint32_t i = tid; i < n_inst; i += G_THREADS) {
                 const uint32_t rep = grp[i];
                 grp[i] = (cutoff < 0 || cnt[rep] > (uint32_t)cutoff) ? mapv[rep] : (uint16_t)0xFFFFu;
             }
-            __syncthreads();
+            bar_workers(G_THREADS);
         }
-        // ---- resolve the unit's output offsets (predecessors have had the whole ordering phase to publish)
-        if (tid < 32) {  // warp 0 walks back over the predecessors, 32 at a time
-            const unsigned long long base = lkb_resolve_warp<8>(unit_state, u, ((unsigned long long)S << 31) | N, tid);
-            if (tid == 0) {
-                s_base = base;
-                if (u == n_units_all - 1) {
-                    gc->total_kmers = (base >> 31) + S;
-                    gc->total_ids = (base & 0x7fffffffull) + N;
-                }
-            }
-        }
-        __syncthreads();
-        const uint64_t S_base = s_base >> 31, N_base = s_base & 0x7fffffffull;
-        if (S_base + S > out.kmer_cap || N_base + N > out.id_cap) {  // cannot happen with the caller's bounds; never write out of range
-            if (tid == 0) atomicExch(&gc->overflow, 2u);
-            __syncthreads();
-            continue;
-        }
-        constexpr int NCH = G_CAP / 32;            // 32-instance chunks of a unit
+
         constexpr int ITERS = G_CAP / G_THREADS;   // instances per thread
-        if (!from_records && S * NCH <= 2u * 2u * G_CAP) {
+        // rows of the (list, chunk) matrix below: one u16 per 32-instance chunk of the unit, padded to an odd number of
+        // 32-bit words so that the lanes of a warp (same chunk, different lists) fall into different banks
+        const uint32_t nch = (n_inst + 31) >> 5;
+        const uint32_t row_words = ((nch + 1) >> 1) | 1u, row = 2 * row_words;
+        const bool ordered = !from_records && S * row_words <= 2u * G_CAP;
+        bool fits = true;
+        uint64_t S_base = 0, N_base = 0;
+        if (ordered) {
             // ---- id lists, ordered path.  Instance positions of a unit expanded from super-k-mer records follow arrival order, so the place of
             // an instance in its newest-first list is (members of the list in later chunks) + (members at a higher lane of
             // its own chunk): a per-(list, chunk) count matrix filled with warp match, a suffix sum per list, done.
-            uint16_t *mat = reinterpret_cast<uint16_t *>(stage_ids);  // [S][NCH], spills into cnt (dead by now)
-            for (uint32_t x = tid; x < (S * NCH + 1) / 2; x += G_THREADS) reinterpret_cast<uint32_t *>(mat)[x] = 0u;
-            __syncthreads();
+            uint16_t *mat = reinterpret_cast<uint16_t *>(stage_ids);  // [S][row], spills into cnt (dead by now)
+            for (uint32_t x = tid; x < S * row_words; x += G_THREADS) reinterpret_cast<uint32_t *>(mat)[x] = 0u;
+            bar_workers(G_THREADS);
             uint32_t within[ITERS];
-            const uint32_t lane = tid & 31, gt_mask = lane == 31 ? 0u : (0xffffffffu << (lane + 1));
+            const uint32_t gt_mask = lane == 31 ? 0u : (0xffffffffu << (lane + 1));
 #pragma unroll
             for (int it = 0; it < ITERS; it++) {
                 const uint32_t p = it * G_THREADS + tid;
-                const uint32_t sI = p < n_inst ? grp[p] : 0xFFFFu;
-                const bool act = sI != 0xFFFFu;
-                const unsigned amask = __ballot_sync(0xffffffffu, act);
                 within[it] = 0;
-                if (act) {
-                    const unsigned peers = __match_any_sync(amask, sI);
-                    within[it] = __popc(peers & gt_mask);
-                    if ((int)lane == __ffs(peers) - 1) mat[sI * NCH + (p >> 5)] = (uint16_t)__popc(peers);
+                if (it * G_THREADS < n_inst) {
+                    const uint32_t sI = p < n_inst ? grp[p] : 0xFFFFu;
+                    const bool act = sI != 0xFFFFu;
+                    const unsigned amask = __ballot_sync(0xffffffffu, act);
+                    if (act) {
+                        const unsigned peers = __match_any_sync(amask, sI);
+                        within[it] = __popc(peers & gt_mask);
+                        if ((int)lane == __ffs(peers) - 1) mat[sI * row + (p >> 5)] = (uint16_t)__popc(peers);
+                    }
                 }
             }
-            __syncthreads();
+            bar_workers(G_THREADS);
             for (uint32_t sI = tid; sI < S; sI += G_THREADS) {  // suffix sums over the chunks of list sI
+                uint16_t *mrow = mat + sI * row;
                 uint32_t run = 0;
-                for (int ch = NCH - 1; ch >= 0; ch--) {
-                    const uint32_t c = mat[sI * NCH + ch];
-                    mat[sI * NCH + ch] = (uint16_t)run;
+                for (int ch = (int)nch - 1; ch >= 0; ch--) {
+                    const uint32_t c = mrow[ch];
+                    mrow[ch] = (uint16_t)run;
                     run += c;
                 }
             }
-            __syncthreads();
+            bar_all();  // X: the control warp has resolved the unit's output offsets (and the suffix sums are complete)
+            S_base = s_base >> 31;
+            N_base = s_base & 0x7fffffffull;
+            fits = S_base + S <= out.kmer_cap && N_base + N <= out.id_cap;  // always, with the caller's bounds; never write out of range
+            if (fits) {
 #pragma unroll
-            for (int it = 0; it < ITERS; it++) {
-                const uint32_t p = it * G_THREADS + tid;
-                const uint32_t sI = p < n_inst ? grp[p] : 0xFFFFu;
-                if (sI != 0xFFFFu) {
-                    const uint32_t a = arr[p];
-                    out.read_ids[N_base + off[sI] + mat[sI * NCH + (p >> 5)] + within[it]] = ids_by_arrival ? ids_by_arrival[a] : id_base + (int32_t)a;
+                for (int it = 0; it < ITERS; it++) {
+                    const uint32_t p = it * G_THREADS + tid;
+                    const uint32_t sI = p < n_inst ? grp[p] : 0xFFFFu;
+                    if (it * G_THREADS < n_inst && sI != 0xFFFFu) {
+                        const uint32_t a = arr[p];
+                        out.read_ids[N_base + off[sI] + mat[sI * row + (p >> 5)] + within[it]] = ids_by_arrival ? ids_by_arrival[a] : id_base + (int32_t)a;
+                    }
                 }
             }
         } else {
@@ -705,29 +772,37 @@ __global__ void __launch_bounds__(G_THREADS)
                 const uint32_t sI = grp[i];
                 if (sI != 0xFFFFu) stage_ids[off[sI] + rnk[i]] = arr[i];
             }
-            __syncthreads();
-            for (uint32_t i = tid; i < n_inst; i += G_THREADS) {
-                const uint32_t sI = grp[i];
-                if (sI == 0xFFFFu) continue;
-                const uint32_t o = off[sI], c = (sI + 1 < S ? off[sI + 1] : N) - o, a = arr[i], r = rnk[i];
-                const uint32_t *lst = stage_ids + o;
-                uint32_t rank = 0;
-                for (uint32_t y = 0; y < r; y++) rank += lst[y] >= a ? 1u : 0u;  // earlier staging position wins a tie
-                for (uint32_t y = r + 1; y < c; y++) rank += lst[y] > a ? 1u : 0u;
-                out.read_ids[N_base + o + rank] = ids_by_arrival ? ids_by_arrival[a] : id_base + (int32_t)a;
+            bar_all();  // X
+            S_base = s_base >> 31;
+            N_base = s_base & 0x7fffffffull;
+            fits = S_base + S <= out.kmer_cap && N_base + N <= out.id_cap;
+            if (fits) {
+                for (uint32_t i = tid; i < n_inst; i += G_THREADS) {
+                    const uint32_t sI = grp[i];
+                    if (sI == 0xFFFFu) continue;
+                    const uint32_t o = off[sI], c = (sI + 1 < S ? off[sI + 1] : N) - o, a = arr[i], r = rnk[i];
+                    const uint32_t *lst = stage_ids + o;
+                    uint32_t rank = 0;
+                    for (uint32_t y = 0; y < r; y++) rank += lst[y] >= a ? 1u : 0u;  // earlier staging position wins a tie
+                    for (uint32_t y = r + 1; y < c; y++) rank += lst[y] > a ? 1u : 0u;
+                    out.read_ids[N_base + o + rank] = ids_by_arrival ? ids_by_arrival[a] : id_base + (int32_t)a;
+                }
             }
         }
+        if (!fits && tid == 0) atomicExch(&gc->overflow, 2u);
 
         // ---- write the unit's slice of the flat table
-        for (uint32_t s = tid; s < S; s += G_THREADS) {
-            const uint32_t i = surv[s];
-            const uint64_t g = S_base + s;
-            out.kmer_codes[g * KW] = key0[i];
-            if (KW == 2) out.kmer_codes[g * KW + 1] = key1[i];
-            out.kmer_mmer[g] = mm[i];
-            out.kmer_id_off[g] = N_base + off[s];
+        if (fits) {
+            for (uint32_t s = tid; s < S; s += G_THREADS) {
+                const uint32_t i = surv[s];
+                const uint64_t g = S_base + s;
+                out.kmer_codes[g * KW] = key0[i];
+                if (KW == 2) out.kmer_codes[g * KW + 1] = key1[i];
+                out.kmer_mmer[g] = mm[i];
+                out.kmer_id_off[g] = N_base + off[s];
+            }
         }
-        __syncthreads();
+        bar_all();  // Y
     }
 }
 
@@ -852,7 +927,7 @@ int skr_group_launch(const void *skr_sorted, int K, int cutoff, const uint32_t *
     auto launch = [&](auto kern, int threads, int ctas_per_sm) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         for (uint32_t c = 0; c < ch.n; c++) {
-            kern<<<sm_count * ctas_per_sm, threads, smem, st>>>(s, inst_prefix, un, BigScratch{big_k0, big_k1, big_arr}, K, cutoff, ids_by_arrival,
+            kern<<<sm_count * ctas_per_sm, threads + 32, smem, st>>>(s, inst_prefix, un, BigScratch{big_k0, big_k1, big_arr}, K, cutoff, ids_by_arrival,
                                                                 id_base, out, unit_state, gc, c, ch.n, ch.tickets);
             if (ch.totals_dev) {
                 publish_chunk_total_kernel<<<1, 1, 0, st>>>(unit_state, gc, c, ch.n, ch.totals_dev);

@@ -275,7 +275,8 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     stages = GpuStages(binner)
-    sharded = ShardedBinner(stages, time_stages=False) if world > 1 else None
+    sharded = ShardedBinner(stages, time_stages=True) if world > 1 else None
+    stage_ms = {"scan": 0.0, "partition": 0.0, "exchange": 0.0, "group": 0.0}
 
     def step_device():
         if world == 1:
@@ -315,6 +316,10 @@ def main():
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1))
         launches += binner.timings()["kernel_launches"] if world == 1 else 0
+        if sharded is not None:
+            st_ = sharded.stats
+            for k_, v_ in (("scan", st_.scan_ms), ("partition", st_.partition_ms), ("exchange", st_.exchange_ms), ("group", st_.group_ms)):
+                stage_ms[k_] += v_ / a.steps
     barrier()
     wall_s = time.perf_counter() - t_wall0
     if sampler:
@@ -435,6 +440,8 @@ def main():
             "dtype": "u64" if K <= 32 else "u128", "data": "synthetic",
             "config": config_dict(a, w, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu, "table": stats,
+            "stage_ms_rank0": (dict(stage_ms, exchange_form=getattr(sharded, "exchange_kind", "nccl"),
+                                    sent_bytes_offrank=sharded.stats.sent_bytes_offrank) if sharded is not None else None),
             "wall_s_timed_region": wall_s, "step_ms": step_ms,
         }
         emit(line)

@@ -27,12 +27,12 @@ __device__ __forceinline__ void lkb_publish_aggregate(unsigned long long *state,
 // (the scan stage) use LKB_DEPTH = 1: their predecessors resolve quickly and a deeper window only adds L2 traffic.
 template <int LKB_DEPTH>
 __device__ __forceinline__ unsigned long long lkb_resolve_warp(unsigned long long *state, uint32_t tile, unsigned long long mine,
-                                                               uint32_t lane) {
+                                                               uint32_t lane, uint32_t sleep_ns = 100) {
     if (tile == 0) return 0ull;
     // Cheap wait first: one lane polls the nearest predecessor until it has published anything at all (tiles finish in
     // roughly ticket order, so this is where almost all of the waiting happens), then the warp evaluates the window.
     if (lane == 0) {
-        while ((lkb_load(&state[tile - 1]) >> 62) == 0) __nanosleep(100);
+        while ((lkb_load(&state[tile - 1]) >> 62) == 0) __nanosleep(sleep_ns);
     }
     __syncwarp();
     unsigned long long sum = 0;
@@ -68,7 +68,7 @@ __device__ __forceinline__ unsigned long long lkb_resolve_warp(unsigned long lon
         sum += part;
         if (done) break;
         j -= 32 * consumed;
-        if (retry) __nanosleep(64);
+        if (retry) __nanosleep(sleep_ns);
     }
     if (lane == 0) atomicExch(&state[tile], (2ull << 62) | (sum + mine));
     return sum;

@@ -1,13 +1,17 @@
 // skr_scan.cu — pipeline v2 scan stage: process_read's window/signature work (binning.c:918-1040)
 // emitting one super-k-mer record per signature segment instead of one record per window.
 //
-// One warp per read as in scan_reads.cu (pack in shared memory, signature chain by hops).  Every warp
-// works on tiles of RPW consecutive reads on its own (no CTA-wide barrier anywhere): it stages the
-// records of the tile in shared memory, obtains the tile's global output offset from a single-pass
-// chained scan over tiles (lookback.cuh; tiles are handed out in order by an atomic ticket so a
-// predecessor is always running), and the staged records leave the SM as one contiguous run of
-// 16-byte stores.  The output is therefore in arrival order (read-major, segment-minor) and
-// deterministic — the later stable sort by m-mer keeps arrival order per bucket.
+// One warp per read (pack in shared memory, then the signature chain by hops i -> sig+1; a hop is a
+// single REDUX.MAX over keys that carry score, inverted offset and strand bit).  Every warp works on
+// tiles of RPW consecutive reads on its own (no CTA-wide barrier anywhere): it stages the records of
+// the tile in shared memory, obtains the tile's global output offset from a single-pass chained scan
+// over tiles (lookback.cuh; tiles are handed out in order by an atomic ticket so a predecessor is
+// always running; the next ticket is already in flight while the look-back runs), and the staged
+// records leave the SM as one contiguous run of 16-byte stores.
+// The output is therefore in arrival order (read-major, segment-minor) and deterministic — the
+// later stable sort by m-mer keeps arrival order per bucket.
+#include <cstdlib>
+
 #include "gbin_device.cuh"
 #include "gbin_internal.h"
 #include "lookback.cuh"
@@ -17,23 +21,22 @@
 namespace gbin {
 
 constexpr int SKR_WARPS = 8;
-// per warp: packed words, m-mer scores, is_rev bit mask, segment list of the current read (2 words per segment), staged records;
-// every region is a multiple of 16 bytes
+// per warp: packed words, m-mer scores (with strand bit), segment list of the current read (2 words per segment), staged
+// records; every region is a multiple of 16 bytes
 __host__ __device__ inline uint32_t skr_len4(uint32_t max_len) { return (max_len + 3u) & ~3u; }
-__host__ __device__ inline uint32_t skr_mask_words(uint32_t max_len) { return ((max_len >> 5) + 1u + 3u) & ~3u; }
 __host__ __device__ inline uint32_t skr_warp_smem(uint32_t max_len, uint32_t seg_cap, int words) {
-    return 4 * scan_pk_words(max_len) + 4 * skr_len4(max_len) + 4 * skr_mask_words(max_len) + 8 * skr_len4(max_len) + 4 * seg_cap * words;
+    return 4 * scan_pk_words(max_len) + 4 * skr_len4(max_len) + 8 * skr_len4(max_len) + 4 * seg_cap * words;
 }
 
 // Per-warp scratch carved out of dynamic shared memory.
 struct WarpScratch {
-    uint32_t *pk, *wv, *revmask, *segl, *stage;
+    uint32_t *pk, *wr, *segl, *stage;
 };
 
-// One tile = rpw consecutive reads handled by one warp.  DIRECT = false: records are staged in shared memory (at most
-// seg_cap of them; the rest is only counted).  DIRECT = true: records are written straight to out + base (used to redo
-// a tile whose segments did not fit the staging area).  Returns the number of records of the tile.
-template <int PW, bool DIRECT>
+// One warp tile = rpw consecutive reads handled by one warp.  DIRECT = false: records are staged in shared memory (at
+// most seg_cap of them; the rest is only counted).  DIRECT = true: records are written straight to out + base (used to
+// redo a tile whose segments did not fit the staging area).  Returns the number of records of the tile.
+template <int PW, bool DIRECT, bool PACKED>
 __device__ __forceinline__ uint32_t skr_process_tile(const ReadsView &rv, const WarpScratch &ws, uint64_t first, uint32_t rpw, int K, int M,
                                                      uint32_t arrival_base, uint32_t seg_cap, uint32_t lane, uint32_t *__restrict__ out,
                                                      unsigned long long base, uint32_t &nbad, unsigned long long &ninst) {
@@ -52,18 +55,17 @@ __device__ __forceinline__ uint32_t skr_process_tile(const ReadsView &rv, const 
             nbad += bad;
             ninst += (lane == 0) ? W : 0;
         }
-        warp_mmer_scores_rev(ws.pk, ws.wv, ws.revmask, L, M, FULL, lane);
+        warp_mmer_scores_strand(ws.pk, ws.wr, L, M, FULL, lane);
         const uint32_t arrival = arrival_base + (uint32_t)r;
         // phase 1: the signature chain, one hop per segment; lane 0 notes the segments of this read
         uint32_t i = 0, nsr = 0;
         while (i < W) {
-            uint32_t mx;
-            const uint32_t sig = warp_signature_hop(ws.wv, i, C, lane, &mx);
-            const uint32_t rev = (ws.revmask[sig >> 5] >> (sig & 31)) & 1u;  // is_rev of the signature (binning.c:943,948)
+            uint32_t w_rev;  // w(sig) << 1 | is_rev of the signature (binning.c:943,948)
+            const uint32_t sig = i + warp_signature_hop_strand<PACKED>(ws.wr, i, C, lane, &w_rev);
             const uint32_t next = min(sig + 1, W);
             if (lane == 0) {
-                ws.segl[2 * nsr] = i | ((next - i) << 16) | (rev << 24);
-                ws.segl[2 * nsr + 1] = mx;
+                ws.segl[2 * nsr] = i | ((next - i) << 16) | ((w_rev & 1u) << 24);
+                ws.segl[2 * nsr + 1] = w_rev >> 1;
             }
             nsr++;
             i = next;
@@ -89,20 +91,20 @@ __device__ __forceinline__ uint32_t skr_process_tile(const ReadsView &rv, const 
     return nseg;
 }
 
-template <int PW>
+template <int PW, bool PACKED>
 __global__ void __launch_bounds__(SKR_WARPS * 32)
     skr_scan_kernel(ReadsView rv, uint64_t read_begin, int K, int M, uint32_t arrival_base, uint32_t max_len, uint32_t rpw, uint32_t seg_cap,
                     uint32_t ntiles, uint32_t *__restrict__ out, unsigned long long capacity, unsigned long long *__restrict__ tile_state,
-                    uint32_t *__restrict__ ticket, unsigned long long *__restrict__ counters /* [0] bad bases, [1] records, [2] instances */) {
+                    uint32_t *__restrict__ ticket, unsigned long long *__restrict__ counters /* [0] bad bases, [1] records, [2] instances */,
+                    uint32_t lkb_sleep) {
     constexpr int NW = SkrLayout<PW>::WORDS;
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *wbase = smem + (size_t)warp * skr_warp_smem(max_len, seg_cap, NW);
     WarpScratch ws;
     ws.pk = reinterpret_cast<uint32_t *>(wbase);
-    ws.wv = ws.pk + scan_pk_words(max_len);
-    ws.revmask = ws.wv + skr_len4(max_len);
-    ws.segl = ws.revmask + skr_mask_words(max_len);  // per segment of the current read: start | n << 16 | rev << 24, m-mer code
+    ws.wr = ws.pk + scan_pk_words(max_len);
+    ws.segl = ws.wr + skr_len4(max_len);  // per segment of the current read: start | n << 16 | rev << 24, m-mer code
     ws.stage = ws.segl + 2 * skr_len4(max_len);
     uint32_t nbad = 0;
     unsigned long long ninst = 0;
@@ -110,15 +112,14 @@ __global__ void __launch_bounds__(SKR_WARPS * 32)
     // chunks are still on their way over PCIe); rv.n_reads is the END of this launch's read range
     const unsigned long long base0 = counters[1];
 
-    for (;;) {
-        uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(ticket, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= ntiles) break;
+    uint32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(ticket, 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    while (tile < ntiles) {
         const uint64_t first = read_begin + (uint64_t)tile * rpw;
-        const uint32_t nseg = skr_process_tile<PW, false>(rv, ws, first, rpw, K, M, arrival_base, seg_cap, lane, out, 0ull, nbad, ninst);
+        const uint32_t nseg = skr_process_tile<PW, false, PACKED>(rv, ws, first, rpw, K, M, arrival_base, seg_cap, lane, out, 0ull, nbad, ninst);
         if (lane == 0) lkb_publish_aggregate(tile_state, tile, nseg);
-        const unsigned long long base = base0 + lkb_resolve_warp<1>(tile_state, tile, nseg, lane);
+        const unsigned long long base = base0 + lkb_resolve_warp<1>(tile_state, tile, nseg, lane, lkb_sleep);
         if (tile == ntiles - 1 && lane == 0) counters[1] = base + nseg;
         if (base + nseg <= capacity) {  // past the capacity only the total is produced (the caller re-runs)
             if (nseg <= seg_cap) {
@@ -127,10 +128,14 @@ __global__ void __launch_bounds__(SKR_WARPS * 32)
                 const uint32_t nvec = nseg * (NW / 4);
                 for (uint32_t v = lane; v < nvec; v += 32) dst[v] = src[v];
             } else {  // more segments than the staging area holds (rare): redo the tile, writing in place
-                (void)skr_process_tile<PW, true>(rv, ws, first, rpw, K, M, arrival_base, seg_cap, lane, out, base, nbad, ninst);
+                (void)skr_process_tile<PW, true, PACKED>(rv, ws, first, rpw, K, M, arrival_base, seg_cap, lane, out, base, nbad, ninst);
             }
         }
-        __syncwarp();
+        // the next ticket is taken only now: a ticket taken before the look-back lets later tiles overtake this warp's next
+        // tile, and their resolve then waits for it (measured: 1.5x slower)
+        uint32_t next_tile = 0;
+        if (lane == 0) next_tile = atomicAdd(ticket, 1u);
+        tile = __shfl_sync(0xffffffffu, next_tile, 0);
     }
     if (nbad) atomicAdd(&counters[0], (unsigned long long)nbad);
     if (ninst) atomicAdd(&counters[2], ninst);
@@ -141,12 +146,18 @@ __global__ void __launch_bounds__(SKR_WARPS * 32)
 static void skr_tile_shape(int K, int M, uint32_t max_len, uint32_t *rpw_out, uint32_t *seg_cap_out) {
     const int NW = skr_words(K);
     const uint32_t W = max_len >= (uint32_t)K ? max_len - K + 1 : 1;
-    const uint32_t budget = 4096u / (NW * 4u);  // records
+    static uint32_t stage_bytes = 0;  // GBIN_SCAN_STAGE_BYTES: staging budget per warp (experiments)
+    if (!stage_bytes) {
+        const char *e = getenv("GBIN_SCAN_STAGE_BYTES");
+        stage_bytes = e ? (uint32_t)atoi(e) : 4096u;
+        if (stage_bytes < 1024u || stage_bytes > 16384u) stage_bytes = 4096u;
+    }
+    const uint32_t budget = stage_bytes / (NW * 4u);  // records
     uint32_t per_read = (uint32_t)(1.6 * (double)W / ((K - M + 2) / 2.0)) + 2;
     if (per_read > W) per_read = W;
     uint32_t rpw = budget / per_read;
     if (rpw < 1) rpw = 1;
-    if (rpw > 8) rpw = 8;
+    if (rpw > stage_bytes / 512u) rpw = stage_bytes / 512u;  // 8 reads per tile at the default budget
     uint32_t cap = rpw * per_read;
     if (cap > budget) cap = budget;
     if (cap < 4) cap = 4;
@@ -154,8 +165,8 @@ static void skr_tile_shape(int K, int M, uint32_t max_len, uint32_t *rpw_out, ui
     *seg_cap_out = cap;
 }
 
-// Host launcher.  tile_state must hold ntiles u64 (zeroed here), ticket one u32 (zeroed here).
-// Returns kernels launched; *ntiles_out = number of tiles.
+// Host launcher.  tile_state must hold skr_scan_tiles() u64 (zeroed here), ticket one u32 (zeroed here).
+// Returns kernels launched.
 int launch_skr_scan(const ReadsView &rv_all, uint64_t read_begin, uint64_t read_end, int K, int M, uint32_t arrival_base, uint32_t max_len,
                     void *out, uint64_t capacity, unsigned long long *tile_state, uint32_t *ticket, unsigned long long *counters, int sm_count,
                     cudaStream_t st) {
@@ -172,14 +183,26 @@ int launch_skr_scan(const ReadsView &rv_all, uint64_t read_begin, uint64_t read_
     cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
     uint32_t blocks = (uint32_t)sm_count * 8;
     if (blocks > (ntiles + SKR_WARPS - 1) / SKR_WARPS) blocks = (ntiles + SKR_WARPS - 1) / SKR_WARPS;
+    // one-REDUX hops need score, inverted offset and strand bit in 32 bits (read_pack.cuh)
+    const bool packed = 2 * M + 1 + ((K - M + 1) <= 32 ? 5 : 6) <= 32;
+    // ns between polls of a predecessor tile that has not published yet: the kernel is bound by instruction issue, so a
+    // spinning warp takes issue slots from the warps that still compute (GBIN_SCAN_SLEEP overrides, for experiments)
+    static int lkb_sleep = -1;
+    if (lkb_sleep < 0) {
+        const char *e = getenv("GBIN_SCAN_SLEEP");
+        lkb_sleep = e ? atoi(e) : 400;
+    }
+    auto launch = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<blocks, SKR_WARPS * 32, smem, st>>>(rv, read_begin, K, M, arrival_base, max_len, rpw, seg_cap, ntiles, static_cast<uint32_t *>(out),
+                                                   capacity, tile_state, ticket, counters, (uint32_t)lkb_sleep);
+    };
     if (PW == 2) {
-        cudaFuncSetAttribute(skr_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        skr_scan_kernel<2><<<blocks, SKR_WARPS * 32, smem, st>>>(rv, read_begin, K, M, arrival_base, max_len, rpw, seg_cap, ntiles,
-                                                               static_cast<uint32_t *>(out), capacity, tile_state, ticket, counters);
+        if (packed) launch(skr_scan_kernel<2, true>);
+        else launch(skr_scan_kernel<2, false>);
     } else {
-        cudaFuncSetAttribute(skr_scan_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        skr_scan_kernel<4><<<blocks, SKR_WARPS * 32, smem, st>>>(rv, read_begin, K, M, arrival_base, max_len, rpw, seg_cap, ntiles,
-                                                               static_cast<uint32_t *>(out), capacity, tile_state, ticket, counters);
+        if (packed) launch(skr_scan_kernel<4, true>);
+        else launch(skr_scan_kernel<4, false>);
     }
     return 1;
 }

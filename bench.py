@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
                     help="weak: every GPU holds the workload's read count (default for cfg2); strong: the workload's reads are split "
                          "over the GPUs (default for cfg3-5, whose BASELINE sizes are totals)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="multi-GPU record exchange: peer = partition kernel stores into the owners' buffers over NVLink (default), nccl = all_to_all_single")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -275,7 +277,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     stages = GpuStages(binner)
-    sharded = ShardedBinner(stages, time_stages=True) if world > 1 else None
+    sharded = ShardedBinner(stages, time_stages=True, exchange=a.exchange) if world > 1 else None
     stage_ms = {"scan": 0.0, "partition": 0.0, "exchange": 0.0, "group": 0.0}
 
     def step_device():

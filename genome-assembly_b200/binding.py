@@ -66,7 +66,7 @@ EXPORTS = [
     "gbin_bin_reads_device", "gbin_table_to_host", "gbin_table_to_pinned", "gbin_get_timings", "gbin_record_bytes",
     "gbin_set_kernel_profiling", "gbin_get_kernel_profile", "gbin_kernel_kind_name", "gbin_set_pipeline", "gbin_get_pipeline_info", "gbin_get_run_stats",
     "gbin_count_instances_device", "gbin_scan_reads_device", "gbin_partition_records_device",
-    "gbin_group_records_device", "gbin_skr_record_bytes", "gbin_scan_skr_device", "gbin_partition_skr_device", "gbin_group_skr_device",
+    "gbin_group_records_device", "gbin_xchg_create", "gbin_xchg_attach", "gbin_xchg_exchange_skr", "gbin_xchg_destroy", "gbin_skr_record_bytes", "gbin_scan_skr_device", "gbin_partition_skr_device", "gbin_group_skr_device",
     "gbin_read_file_fgets", "gbin_table_dump", "gbin_table_dump_reference_format",
     "getval", "getbp", "getscore", "process_read", "prune_data", "gbin_ref_configure", "gbin_ref_last_status",
     "gbin_ref_reset", "gbin_table_to_zhash", "gbin_zhash_release",
@@ -123,6 +123,11 @@ def load_library() -> C.CDLL:
     L.gbin_scan_skr_device.argtypes = [vp, C.POINTER(CReads), u32, vp, u64, vp, C.POINTER(u64), C.POINTER(u64)]
     L.gbin_partition_skr_device.argtypes = [vp, vp, u64, u32, vp, vp, C.POINTER(u64)]
     L.gbin_group_skr_device.argtypes = [vp, vp, u64, vp, i32, vp, C.POINTER(CTable), C.POINTER(C.c_int)]
+    L.gbin_xchg_create.argtypes = [vp, u32, u32, u64, vp]
+    L.gbin_xchg_attach.argtypes = [vp, vp]
+    L.gbin_xchg_exchange_skr.argtypes = [vp, vp, u64, vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
+    L.gbin_xchg_destroy.argtypes = [vp]
+    L.gbin_xchg_destroy.restype = None
     L.gbin_read_file_fgets.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(vp),
                                        C.POINTER(u64)]
     L.gbin_table_dump.argtypes = [C.POINTER(CTable), C.c_char_p]
@@ -368,6 +373,27 @@ class Binner:
         fb = C.c_int()
         self._check(self.lib.gbin_group_skr_device(self.h, _ptr(d_skr), n_skr, _ptr(d_ids_by_arrival), id_base, stream, C.byref(t), C.byref(fb)))
         return t
+
+    # ---- owner exchange over peer memory (collective over the ranks whose contexts were attached to each other)
+    XCHG_HANDLE_BYTES = 192
+
+    def xchg_create(self, rank: int, world: int, capacity_records: int) -> bytes:
+        buf = C.create_string_buffer(self.XCHG_HANDLE_BYTES)
+        self._check(self.lib.gbin_xchg_create(self.h, rank, world, capacity_records, buf))
+        return buf.raw
+
+    def xchg_attach(self, all_handles: bytes):
+        self._check(self.lib.gbin_xchg_attach(self.h, C.c_char_p(all_handles)))
+
+    def xchg_exchange_skr(self, d_skr, n: int, world: int, stream=None):
+        """-> (device address of this rank's receive buffer, records received, records sent per owner)"""
+        recv, n_in = C.c_void_p(), C.c_uint64()
+        sent = (C.c_uint64 * 16)()
+        self._check(self.lib.gbin_xchg_exchange_skr(self.h, _ptr(d_skr), n, stream, C.byref(recv), C.byref(n_in), sent))
+        return int(recv.value or 0), int(n_in.value), [int(sent[i]) for i in range(world)]
+
+    def xchg_destroy(self):
+        self.lib.gbin_xchg_destroy(self.h)
 
     def group_device(self, d_records, n: int, d_ids_by_arrival=None, id_base: int = 0, stream=None) -> CTable:
         t = CTable()

@@ -120,6 +120,19 @@ struct gbin_ctx {
     int last_pipeline;   // which one produced the last table
     uint32_t fallbacks;  // v2 -> v1 fallbacks since creation
     gbin_run_stats rs;   // sizes seen by the last pipeline-2 run
+    // owner exchange over peer memory (multi-GPU, one process per GPU)
+    struct {
+        bool created = false, attached = false;
+        uint32_t rank = 0, world = 0, epoch = 0;
+        uint64_t cap = 0;
+        void *recv = nullptr;
+        XchgShared *sh = nullptr;
+        char **dst_tab = nullptr;
+        XchgResult *result = nullptr;
+        XchgPlan plan;
+        void *opened[2 * XCHG_MAX_WORLD];
+        int n_opened = 0;
+    } xg;
     // device-resident result
     DevBuf o_mmer_codes, o_mmer_kmer_off, o_kmer_codes, o_kmer_id_off, o_read_ids;
     // pinned host arena for results of the host path + small readbacks
@@ -625,7 +638,7 @@ int gbin_create(const gbin_config *cfg, gbin_ctx **out) {
     if (ctx->host_chunks < 1) ctx->host_chunks = 1;
     if (ctx->host_chunks > SKR_MAX_CHUNKS) ctx->host_chunks = SKR_MAX_CHUNKS;
     if (e == cudaSuccess) e = ctx->misc.ensure(sizeof(Misc));
-    if (e == cudaSuccess) e = ctx->h_misc.ensure(sizeof(Misc));
+    if (e == cudaSuccess) e = ctx->h_misc.ensure(sizeof(Misc) + sizeof(XchgResult));
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         delete ctx;
@@ -639,6 +652,7 @@ void gbin_destroy(gbin_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
+    gbin_xchg_destroy(ctx);
     DevBuf *bufs[] = {&ctx->d_reads, &ctx->d_starts, &ctx->d_lens, &ctx->d_ids, &ctx->rec_a, &ctx->rec_b, &ctx->radix_scratch,
                       &ctx->win_counts, &ctx->rec_off, &ctx->scan_scratch, &ctx->group_of, &ctx->run_start, &ctx->surv_index,
                       &ctx->id_offset, &ctx->surv_group, &ctx->bucket_of, &ctx->misc, &ctx->o_mmer_codes, &ctx->o_mmer_kmer_off,
@@ -960,6 +974,126 @@ int gbin_partition_records_device(gbin_ctx *ctx, const void *d_records, uint64_t
     CU(cudaStreamSynchronize(st));
     memcpy(counts_host, hm->part_counts, sizeof(uint64_t) * n_parts);
     ctx->tm.kernel_launches = (uint32_t)launches;
+    return GBIN_OK;
+}
+
+// ---------------------------------------------------------------- owner exchange over peer memory
+
+namespace {
+struct XchgHandle {  // what a rank publishes: GBIN_XCHG_HANDLE_BYTES
+    cudaIpcMemHandle_t recv, shared;
+    uint64_t cap;
+    uint32_t rank, world;
+    uint32_t record_bytes, magic;
+};
+static_assert(sizeof(XchgHandle) <= GBIN_XCHG_HANDLE_BYTES, "handle blob size");
+constexpr uint32_t XCHG_MAGIC = 0x67786331u;
+}  // namespace
+
+int gbin_xchg_create(gbin_ctx *ctx, uint32_t rank, uint32_t world, uint64_t capacity_records, void *handle_out) {
+    if (!ctx || !handle_out || world == 0 || world > (uint32_t)XCHG_MAX_WORLD || rank >= world || capacity_records == 0) return GBIN_E_INVALID_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    gbin_xchg_destroy(ctx);
+    auto &x = ctx->xg;
+    const size_t rb = gbin_skr_record_bytes(ctx);
+    CU(cudaMalloc(&x.recv, (capacity_records + 1) * rb));
+    CU(cudaMalloc(reinterpret_cast<void **>(&x.sh), sizeof(XchgShared)));
+    CU(cudaMalloc(reinterpret_cast<void **>(&x.dst_tab), sizeof(char *) * XCHG_MAX_WORLD));
+    CU(cudaMalloc(reinterpret_cast<void **>(&x.result), sizeof(XchgResult)));
+    CU(cudaMemset(x.sh, 0, sizeof(XchgShared)));
+    CU(cudaMemset(x.result, 0, sizeof(XchgResult)));
+    x.rank = rank;
+    x.world = world;
+    x.cap = capacity_records;
+    x.epoch = 0;
+    x.created = true;
+    XchgHandle h;
+    memset(&h, 0, sizeof h);
+    CU(cudaIpcGetMemHandle(&h.recv, x.recv));
+    CU(cudaIpcGetMemHandle(&h.shared, x.sh));
+    h.cap = capacity_records;
+    h.rank = rank;
+    h.world = world;
+    h.record_bytes = (uint32_t)rb;
+    h.magic = XCHG_MAGIC;
+    memset(handle_out, 0, GBIN_XCHG_HANDLE_BYTES);
+    memcpy(handle_out, &h, sizeof h);
+    return GBIN_OK;
+}
+
+int gbin_xchg_attach(gbin_ctx *ctx, const void *all_handles) {
+    if (!ctx || !all_handles || !ctx->xg.created) return GBIN_E_INVALID_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    auto &x = ctx->xg;
+    memset(&x.plan, 0, sizeof x.plan);
+    x.plan.rank = x.rank;
+    x.plan.world = x.world;
+    x.plan.dst_tab = x.dst_tab;
+    x.plan.result = x.result;
+    for (uint32_t r = 0; r < x.world; r++) {
+        XchgHandle h;
+        memcpy(&h, static_cast<const char *>(all_handles) + (size_t)r * GBIN_XCHG_HANDLE_BYTES, sizeof h);
+        if (h.magic != XCHG_MAGIC || h.rank != r || h.world != x.world || h.record_bytes != gbin_skr_record_bytes(ctx))
+            return fail(ctx, GBIN_E_INVALID_ARG, "exchange handle %u does not match this context (rank/world/record size)", r);
+        x.plan.cap[r] = h.cap;
+        if (r == x.rank) {
+            x.plan.peer_recv[r] = x.recv;
+            x.plan.peer_sh[r] = x.sh;
+            continue;
+        }
+        void *pr = nullptr, *ps = nullptr;
+        CU(cudaIpcOpenMemHandle(&pr, h.recv, cudaIpcMemLazyEnablePeerAccess));
+        x.opened[x.n_opened++] = pr;
+        CU(cudaIpcOpenMemHandle(&ps, h.shared, cudaIpcMemLazyEnablePeerAccess));
+        x.opened[x.n_opened++] = ps;
+        x.plan.peer_recv[r] = pr;
+        x.plan.peer_sh[r] = static_cast<XchgShared *>(ps);
+    }
+    x.attached = true;
+    return GBIN_OK;
+}
+
+void gbin_xchg_destroy(gbin_ctx *ctx) {
+    if (!ctx || !ctx->xg.created) return;
+    auto &x = ctx->xg;
+    cudaSetDevice(ctx->cfg.device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < x.n_opened; i++) cudaIpcCloseMemHandle(x.opened[i]);
+    x.n_opened = 0;
+    cudaFree(x.recv);
+    cudaFree(x.sh);
+    cudaFree(x.dst_tab);
+    cudaFree(x.result);
+    x.recv = nullptr;
+    x.sh = nullptr;
+    x.dst_tab = nullptr;
+    x.result = nullptr;
+    x.created = x.attached = false;
+    (void)cudaGetLastError();
+}
+
+int gbin_xchg_exchange_skr(gbin_ctx *ctx, const void *d_skr, uint64_t n, void *stream, void **d_recv_out, uint64_t *n_recv_out,
+                           uint64_t *sent_counts) {
+    if (!ctx || !d_recv_out || !n_recv_out || (n && !d_skr)) return GBIN_E_INVALID_ARG;
+    if (!ctx->xg.attached) return fail(ctx, GBIN_E_STATE, "gbin_xchg_exchange_skr before gbin_xchg_create / gbin_xchg_attach");
+    if (n >= (1ull << 32) - 8192) return fail(ctx, GBIN_E_TOO_LARGE, "too many records in one exchange call");
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    auto &x = ctx->xg;
+    CU(ctx->radix_scratch.ensure(radix_scratch_bytes(n)));
+    x.plan.epoch = ++x.epoch;
+    const int launches = radix_exchange_skr_by_owner(d_skr, n, ctx->cfg.kmer_size <= 32 ? 8 : 12, ctx->radix_scratch.p, x.plan, st);
+    CU(cudaGetLastError());
+    XchgResult *hr = reinterpret_cast<XchgResult *>(static_cast<char *>(ctx->h_misc.p) + sizeof(Misc));
+    CU(cudaMemcpyAsync(hr, x.result, sizeof(XchgResult), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->tm.kernel_launches = (uint32_t)launches;
+    if (sent_counts)
+        for (uint32_t r = 0; r < x.world; r++) sent_counts[r] = hr->sent[r];
+    if (hr->status == 2u) return fail(ctx, GBIN_E_CUDA, "owner exchange: a peer did not answer within the time limit");
+    if (hr->status == 1u) return fail(ctx, GBIN_E_TOO_LARGE, "owner exchange: a receive buffer is too small for this batch");
+    *d_recv_out = x.recv;
+    *n_recv_out = hr->n_in;
     return GBIN_OK;
 }
 

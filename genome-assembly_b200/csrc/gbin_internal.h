@@ -70,6 +70,29 @@ int radix_sort_records(void *a, void *b, uint64_t n, int KW, int K, int M, void 
 int radix_partition_by_owner(const void *in, void *out, uint64_t n, int KW, uint32_t n_parts, void *scratch, uint64_t *d_counts,
                              cudaStream_t st);
 
+// Owner exchange over peer memory (one process per GPU, CUDA IPC; see radix_sort.cu).
+constexpr int XCHG_MAX_WORLD = 16;
+struct XchgShared {  // one per rank, in device memory, mapped by every peer
+    unsigned long long counts[XCHG_MAX_WORLD * XCHG_MAX_WORLD];  // counts[s * XCHG_MAX_WORLD + d]: records rank s sends to owner d (row s written by rank s)
+    unsigned int count_flag[XCHG_MAX_WORLD];                     // epoch of rank s's row
+    unsigned int done_flag[XCHG_MAX_WORLD];                      // epoch: rank s has finished storing into this rank's receive buffer
+};
+struct XchgResult {  // device scalars of the last exchange
+    unsigned long long n_in;                  // records received
+    unsigned long long sent[XCHG_MAX_WORLD];  // records sent per owner
+    unsigned int status;                      // 0 ok, 1 an owner's receive buffer is too small (nothing was stored), 2 a peer did not answer
+    unsigned int pad;
+};
+struct XchgPlan {  // passed to the kernels by value
+    uint32_t rank, world, epoch, pad;
+    XchgShared *peer_sh[XCHG_MAX_WORLD];   // [rank] = own
+    void *peer_recv[XCHG_MAX_WORLD];       // receive buffers
+    unsigned long long cap[XCHG_MAX_WORLD];  // their capacities in records
+    char **dst_tab;                        // device, [XCHG_MAX_WORLD]: per-owner destinations of this exchange
+    XchgResult *result;                    // device
+};
+int radix_exchange_skr_by_owner(const void *in, uint64_t n, int skr_words, void *scratch, const XchgPlan &xp, cudaStream_t st);
+
 // v2: super-k-mer records (skr.cuh), sorted / partitioned on their m-mer code (word 1).
 int radix_sort_skr_by_mmer(void *a, void *b, uint64_t n, int skr_words, int M, void *scratch, bool *result_in_b, int *passes_out,
                            KernelProf *prof, cudaStream_t st);

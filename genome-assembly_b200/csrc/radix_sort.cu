@@ -102,13 +102,17 @@ __global__ void __launch_bounds__(RS_THREADS)
 template <int NU64>
 __global__ void __launch_bounds__(RS_THREADS)
     radix_scatter_kernel(const Blob<NU64> *__restrict__ in, Blob<NU64> *__restrict__ out, uint64_t n, DigitSel sel,
-                         const uint32_t *__restrict__ tile_off, uint32_t ntiles) {
+                         const uint32_t *__restrict__ tile_off, uint32_t ntiles, char *const *__restrict__ dst_tab) {
     constexpr int ITEMS = TileShape<NU64>::ITEMS, TILE = TileShape<NU64>::TILE;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     Blob<NU64> *exch = reinterpret_cast<Blob<NU64> *>(smem_raw);
     uint32_t *wc = reinterpret_cast<uint32_t *>(smem_raw + (size_t)TILE * sizeof(Blob<NU64>));  // [RS_WARPS][256]
     uint32_t *dstart = wc + RS_WARPS * RS_RADIX;
     uint32_t *goff = dstart + RS_RADIX;
+    // Owner exchange (dst_tab != nullptr, digit = owner < XCHG_MAX_WORLD): digit d's run goes to dst_tab[d], the owner's
+    // receive buffer (peer memory over NVLink) already offset so that the run lands behind the lower ranks' records.
+    __shared__ char *s_dst[XCHG_MAX_WORLD];
+    if (dst_tab && threadIdx.x < XCHG_MAX_WORLD) s_dst[threadIdx.x] = dst_tab[threadIdx.x];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t base = (uint64_t)blockIdx.x * TILE;
@@ -166,11 +170,108 @@ __global__ void __launch_bounds__(RS_THREADS)
         }
     }
     __syncthreads();
+    if (dst_tab) {
+        for (uint32_t i = tid; i < count; i += RS_THREADS) {
+            const Blob<NU64> r = exch[i];
+            const uint32_t d = digit_of<NU64>(r, sel);
+            char *bp = s_dst[d];
+            if (bp) store_blob<NU64>(reinterpret_cast<Blob<NU64> *>(bp) + (uint32_t)(goff[d] + i), r);
+        }
+        return;
+    }
     for (uint32_t i = tid; i < count; i += RS_THREADS) {
         const Blob<NU64> r = exch[i];
         const uint32_t d = digit_of<NU64>(r, sel);
         store_blob<NU64>(out + (uint32_t)(goff[d] + i), r);
     }
+}
+
+// ------------------------------------------------------------------ owner exchange over peer memory
+// One process per GPU; every rank maps every peer's receive buffer and XchgShared block (CUDA IPC, set up once by
+// capi.cu).  Per exchange (all on the rank's stream, no host round trip and no NCCL call):
+//   1. the usual per-tile histogram of digit = mmer % world and its scan (above);
+//   2. xchg_counts_kernel: this rank's per-owner counts go into row `rank` of every peer's count matrix, a flag with the
+//      exchange's epoch follows (release at system scope); the kernel then waits for every rank's row, derives where its
+//      records start inside each owner's buffer (behind the records of the lower ranks: arrival order is kept) and how
+//      many records it will receive itself;
+//   3. the scatter kernel stores every owner's run straight into that owner's buffer (NVLink peer stores);
+//   4. xchg_done_kernel: "my stores are done" to every peer, then waits for all peers' flags: the receive buffer is
+//      complete.  A rank publishes the counts of its NEXT exchange only after it has consumed its receive buffer (stream
+//      order), so waiting for all rows in step 2 also means every receive buffer is free again.
+// Waits are bounded (XCHG_TIMEOUT_CYCLES) so a missing peer yields an error code, not a hung GPU.
+
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+constexpr long long XCHG_TIMEOUT_CYCLES = 6000000000ll;  // about 3 s
+
+__device__ __forceinline__ bool xchg_wait_flag(const unsigned int *p, unsigned int epoch) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(p) != epoch) {
+        if (clock64() - t0 > XCHG_TIMEOUT_CYCLES) return false;
+        __nanosleep(200);
+    }
+    return true;
+}
+
+__global__ void xchg_counts_kernel(const uint32_t *__restrict__ tile_off, uint32_t ntiles, uint64_t n, XchgPlan xp, uint32_t rec_bytes) {
+    const uint32_t lane = threadIdx.x, G = xp.world, me = xp.rank;
+    unsigned long long cnt = 0, start = 0;
+    if (lane < G) {
+        start = n ? tile_off[(uint64_t)lane * ntiles] : 0;
+        const unsigned long long end = n ? ((lane + 1 < RS_RADIX) ? tile_off[(uint64_t)(lane + 1) * ntiles] : n) : 0;
+        cnt = end - start;
+        for (uint32_t p = 0; p < G; p++) xp.peer_sh[p]->counts[me * XCHG_MAX_WORLD + lane] = cnt;
+    }
+    __threadfence_system();
+    __syncwarp();
+    bool ok = true;
+    if (lane < G) {
+        st_release_sys(&xp.peer_sh[lane]->count_flag[me], xp.epoch);
+        ok = xchg_wait_flag(&xp.peer_sh[me]->count_flag[lane], xp.epoch);
+    }
+    const bool all_here = __all_sync(0xffffffffu, ok);
+    unsigned long long off = 0, tot = 0;
+    if (all_here && lane < G) {
+        for (uint32_t s = 0; s < G; s++) {
+            const unsigned long long c = ld_relaxed_sys_u64(&xp.peer_sh[me]->counts[s * XCHG_MAX_WORLD + lane]);
+            if (s < me) off += c;
+            tot += c;
+        }
+        ok = tot <= xp.cap[lane];
+    }
+    const bool fits = __all_sync(0xffffffffu, ok);
+    const unsigned long long n_in = __shfl_sync(0xffffffffu, tot, me);
+    if (lane < XCHG_MAX_WORLD)
+        xp.dst_tab[lane] = (all_here && fits && lane < G)
+                               ? reinterpret_cast<char *>(xp.peer_recv[lane]) + ((long long)off - (long long)start) * (long long)rec_bytes
+                               : nullptr;
+    if (lane < G) xp.result->sent[lane] = cnt;
+    if (lane == 0) {
+        xp.result->n_in = n_in;
+        xp.result->status = !all_here ? 2u : (fits ? 0u : 1u);
+    }
+}
+
+__global__ void xchg_done_kernel(XchgPlan xp) {
+    const uint32_t lane = threadIdx.x, G = xp.world, me = xp.rank;
+    __threadfence_system();
+    bool ok = true;
+    if (lane < G) {
+        st_release_sys(&xp.peer_sh[lane]->done_flag[me], xp.epoch);
+        ok = xchg_wait_flag(&xp.peer_sh[me]->done_flag[lane], xp.epoch);
+    }
+    if (!__all_sync(0xffffffffu, ok) && lane == 0) xp.result->status = 2u;
 }
 
 __global__ void part_counts_kernel(const uint32_t *__restrict__ tile_off, uint32_t ntiles, uint32_t nparts, uint64_t n,
@@ -199,10 +300,18 @@ size_t radix_scratch_bytes(uint64_t n) {
 }
 
 template <int NU64>
-static int one_pass(const void *in_v, void *out_v, uint64_t n, const DigitSel &sel, uint32_t *scratch, KernelProf *prof, cudaStream_t st) {
+static int one_pass(const void *in_v, void *out_v, uint64_t n, const DigitSel &sel, uint32_t *scratch, KernelProf *prof, cudaStream_t st,
+                    const XchgPlan *xp = nullptr) {
     const Blob<NU64> *in = static_cast<const Blob<NU64> *>(in_v);
     Blob<NU64> *out = static_cast<Blob<NU64> *>(out_v);
     constexpr int TILE = TileShape<NU64>::TILE;
+    if (n == 0) {
+        if (!xp) return 0;
+        // nothing to send: still take part in the count exchange and the completion barrier
+        xchg_counts_kernel<<<1, 32, 0, st>>>(scratch, 0, 0, *xp, (uint32_t)sizeof(Blob<NU64>));
+        xchg_done_kernel<<<1, 32, 0, st>>>(*xp);
+        return 2;
+    }
     const uint32_t nt = ntiles_of(n, TILE);
     const uint64_t table = (uint64_t)RS_RADIX * nt;
     uint32_t *tile_hist = scratch;
@@ -219,18 +328,26 @@ static int one_pass(const void *in_v, void *out_v, uint64_t n, const DigitSel &s
     const size_t smem = (size_t)TILE * sizeof(Blob<NU64>) + (RS_WARPS * RS_RADIX + 2 * RS_RADIX) * sizeof(uint32_t);
     cudaFuncSetAttribute(radix_scatter_kernel<NU64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     on = prof && prof->begin(KK_RADIX_SCATTER, st);
-    radix_scatter_kernel<NU64><<<nt, RS_THREADS, smem, st>>>(in, out, n, sel, tile_hist, nt);
+    if (xp) {  // counts to every peer, wait for theirs, per-owner destinations
+        xchg_counts_kernel<<<1, 32, 0, st>>>(tile_hist, nt, n, *xp, (uint32_t)sizeof(Blob<NU64>));
+        launches++;
+    }
+    radix_scatter_kernel<NU64><<<nt, RS_THREADS, smem, st>>>(in, out, n, sel, tile_hist, nt, xp ? xp->dst_tab : nullptr);
     if (prof) prof->end(on, 1, st);
+    if (xp) {
+        xchg_done_kernel<<<1, 32, 0, st>>>(*xp);
+        launches++;
+    }
     return launches + 1;
 }
 
 static int one_pass_any(int nu64, const void *in, void *out, uint64_t n, const DigitSel &sel, uint32_t *scratch, KernelProf *prof,
-                        cudaStream_t st) {
+                        cudaStream_t st, const XchgPlan *xp = nullptr) {
     switch (nu64) {
-        case 2: return one_pass<2>(in, out, n, sel, scratch, prof, st);
-        case 3: return one_pass<3>(in, out, n, sel, scratch, prof, st);
-        case 4: return one_pass<4>(in, out, n, sel, scratch, prof, st);
-        default: return one_pass<6>(in, out, n, sel, scratch, prof, st);
+        case 2: return one_pass<2>(in, out, n, sel, scratch, prof, st, xp);
+        case 3: return one_pass<3>(in, out, n, sel, scratch, prof, st, xp);
+        case 4: return one_pass<4>(in, out, n, sel, scratch, prof, st, xp);
+        default: return one_pass<6>(in, out, n, sel, scratch, prof, st, xp);
     }
 }
 
@@ -305,6 +422,12 @@ int radix_partition_skr_by_owner(const void *in, void *out, uint64_t n, int skr_
     const int launches = one_pass_any(nu64, in, out, n, DigitSel{0, 32, n_parts}, static_cast<uint32_t *>(scratch), nullptr, st);
     part_counts_kernel<<<1, RS_RADIX, 0, st>>>(static_cast<uint32_t *>(scratch), ntiles_any(nu64, n), n_parts, n, d_counts);
     return launches + 1;
+}
+
+// Owner partition of super-k-mer records fused with the exchange: see the notes above xchg_counts_kernel.
+int radix_exchange_skr_by_owner(const void *in, uint64_t n, int skr_words, void *scratch, const XchgPlan &xp, cudaStream_t st) {
+    // n == 0 still takes part in the count exchange and the completion barrier (one empty tile)
+    return one_pass_any(skr_words / 2, in, nullptr, n, DigitSel{0, 32, xp.world}, static_cast<uint32_t *>(scratch), nullptr, st, &xp);
 }
 
 }  // namespace gbin

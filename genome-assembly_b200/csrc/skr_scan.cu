@@ -142,22 +142,22 @@ __global__ void __launch_bounds__(SKR_WARPS * 32)
 }
 
 // Tile shape: rpw reads per warp and a staging area of seg_cap records, sized for 1.6x the expected number of segments
-// (a segment covers about (K-M+2)/2 windows) within a 4 KB budget per warp; tiles that exceed it are redone in place.
+// (a segment covers about (K-M+2)/2 windows) within a 6 KB budget per warp; tiles that exceed it are redone in place.
 static void skr_tile_shape(int K, int M, uint32_t max_len, uint32_t *rpw_out, uint32_t *seg_cap_out) {
     const int NW = skr_words(K);
     const uint32_t W = max_len >= (uint32_t)K ? max_len - K + 1 : 1;
     static uint32_t stage_bytes = 0;  // GBIN_SCAN_STAGE_BYTES: staging budget per warp (experiments)
     if (!stage_bytes) {
         const char *e = getenv("GBIN_SCAN_STAGE_BYTES");
-        stage_bytes = e ? (uint32_t)atoi(e) : 4096u;
-        if (stage_bytes < 1024u || stage_bytes > 16384u) stage_bytes = 4096u;
+        stage_bytes = e ? (uint32_t)atoi(e) : 6144u;
+        if (stage_bytes < 1024u || stage_bytes > 16384u) stage_bytes = 6144u;
     }
     const uint32_t budget = stage_bytes / (NW * 4u);  // records
     uint32_t per_read = (uint32_t)(1.6 * (double)W / ((K - M + 2) / 2.0)) + 2;
     if (per_read > W) per_read = W;
     uint32_t rpw = budget / per_read;
     if (rpw < 1) rpw = 1;
-    if (rpw > stage_bytes / 512u) rpw = stage_bytes / 512u;  // 8 reads per tile at the default budget
+    if (rpw > stage_bytes / 512u) rpw = stage_bytes / 512u;  // 12 reads per tile at the default budget
     uint32_t cap = rpw * per_read;
     if (cap > budget) cap = budget;
     if (cap < 4) cap = 4;
@@ -190,7 +190,7 @@ int launch_skr_scan(const ReadsView &rv_all, uint64_t read_begin, uint64_t read_
     static int lkb_sleep = -1;
     if (lkb_sleep < 0) {
         const char *e = getenv("GBIN_SCAN_SLEEP");
-        lkb_sleep = e ? atoi(e) : 400;
+        lkb_sleep = e ? atoi(e) : 800;
     }
     auto launch = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

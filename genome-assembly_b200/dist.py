@@ -95,7 +95,34 @@ class GpuStages:
         self._count()
         return out, counts
 
-    def group(self, rec: torch.Tensor, n: int, id_base: int):
+    # ---- partition fused with the exchange: records go straight into the owners' buffers over NVLink (peer stores)
+    def peer_exchange_setup(self, rank: int, world: int, capacity_records: int, group=None) -> bool:
+        """Collective.  Maps every rank's receive buffer into every other rank (CUDA IPC handles gathered over the process
+        group).  False when the form has no peer path (instance records use the NCCL all-to-all)."""
+        if self.form != "skr":
+            return False
+        mine = self.b.xchg_create(rank, world, capacity_records)
+        blobs = [None] * world
+        dist.all_gather_object(blobs, mine, group=group)
+        self.b.xchg_attach(b"".join(blobs))
+        dist.barrier(group=group)
+        self.peer_world = world
+        self.peer_capacity = capacity_records
+        return True
+
+    def peer_exchange(self, rec: torch.Tensor, n: int):
+        """Collective.  -> (receive buffer address, records received, records sent per owner), or None when some owner's
+        buffer was too small (every rank gets None; nothing was stored)."""
+        try:
+            out = self.b.xchg_exchange_skr(rec, n, self.peer_world, self.stream())
+        except B.GbinError as e:
+            if e.code != B.GBIN_E_TOO_LARGE:
+                raise
+            return None
+        self._count()
+        return out
+
+    def group(self, rec, n: int, id_base: int):
         """Returns the device table, or None when a shared-memory unit overflowed (form "skr" only)."""
         if self.form == "skr":
             try:
@@ -125,9 +152,13 @@ class ExchangeStats:
 class ShardedBinner:
     """Runs the hot path across the ranks of a torch.distributed process group."""
 
-    def __init__(self, stages, group=None, time_stages: bool = False):
+    def __init__(self, stages, group=None, time_stages: bool = False, exchange: str = "auto"):
+        """exchange: "peer" = the partition kernel stores into the owners' buffers over NVLink (CUDA IPC peer memory, the
+        default when the stages offer it), "nccl" = partition locally, then all_to_all_single."""
         self.stages = stages
         self.group = group
+        self.exchange_kind = "nccl" if exchange == "nccl" or not hasattr(stages, "peer_exchange_setup") else "peer"
+        self._peer_ready = False
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.time_stages = time_stages
@@ -186,6 +217,18 @@ class ShardedBinner:
             self.stages = saved
         return table
 
+    def _peer_path(self, n: int) -> bool:
+        """Collective decision (every rank evaluates the same conditions): set the peer exchange up on first use."""
+        if self.exchange_kind != "peer" or getattr(self.stages, "form", "") != "skr":
+            return False
+        if not self._peer_ready:
+            cap = torch.tensor([max(2 * n + 65536, getattr(self, "_peer_capacity_hint", 0))], dtype=torch.int64, device=self._flag_device())
+            dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=self.group)
+            self._peer_ready = self.stages.peer_exchange_setup(self.rank, self.world, int(cap.item()), self.group)
+            if not self._peer_ready:
+                self.exchange_kind = "nccl"
+        return self._peer_ready
+
     def _flag_device(self):
         return getattr(self.stages, "device", torch.device("cpu"))
 
@@ -196,6 +239,23 @@ class ShardedBinner:
         if self.world == 1:
             inbuf, n_in = rec, n
             e2 = e3 = e1
+        elif self._peer_path(n):
+            got = self.stages.peer_exchange(rec, n)
+            if got is None:  # an owner's buffer was too small: grow it for the next step, this step goes over NCCL
+                self._peer_ready = False
+                self._peer_capacity_hint = 2 * getattr(self.stages, "peer_capacity", n)
+                part, counts = self.stages.partition(rec, n, self.world)
+                e2 = self._ev()
+                inbuf, n_in = self.exchange(part, counts)
+                del part
+            else:
+                inbuf, n_in, counts = got
+                e2 = e1
+                self.stats.sent_records = sum(counts)
+                self.stats.recv_records = n_in
+                self.stats.sent_bytes_offrank = (sum(counts) - counts[self.rank]) * self.stages.record_bytes
+            self._keep_src = rec  # the peers read nothing from it, but the kernels that stored from it may still be in flight
+            e3 = self._ev()
         else:
             part, counts = self.stages.partition(rec, n, self.world)
             del rec

@@ -206,6 +206,23 @@ int gbin_partition_skr_device(gbin_ctx *ctx, const void *d_skr, uint64_t n, uint
 int gbin_group_skr_device(gbin_ctx *ctx, void *d_skr, uint64_t n_skr, const int32_t *d_ids_by_arrival, int32_t id_base, void *stream,
                           gbin_table *out, int *used_fallback);
 
+/* ---- owner exchange over peer memory (one process per GPU on one node) ----
+ * The partition by owner = mmer_code % world and the all-to-all are one step: every rank maps every
+ * peer's receive buffer (CUDA IPC) and the partition kernel stores each owner's records straight into that owner's buffer
+ * over NVLink, behind the records of the lower ranks (so arrival order is kept); counts and completion are exchanged
+ * through flags in peer memory.  Setup: every rank calls gbin_xchg_create, the GBIN_XCHG_HANDLE_BYTES blobs are gathered
+ * by the caller (any transport) into rank order and handed to gbin_xchg_attach on every rank.
+ * gbin_xchg_exchange_skr is collective: every rank of the world must call it once per step, on contexts attached to each
+ * other.  It returns this rank's receive buffer (owned by the context, valid until the next exchange) and record count;
+ * GBIN_E_TOO_LARGE means some owner's buffer was too small — nothing was stored anywhere and every rank gets the same
+ * error, so the caller can fall back to another transport for the step. */
+#define GBIN_XCHG_HANDLE_BYTES 192
+int gbin_xchg_create(gbin_ctx *ctx, uint32_t rank, uint32_t world, uint64_t capacity_records, void *handle_out);
+int gbin_xchg_attach(gbin_ctx *ctx, const void *all_handles);
+int gbin_xchg_exchange_skr(gbin_ctx *ctx, const void *d_skr, uint64_t n, void *stream, void **d_recv_out, uint64_t *n_recv_out,
+                           uint64_t *sent_counts);
+void gbin_xchg_destroy(gbin_ctx *ctx);
+
 /* ---- host helpers ---- */
 
 /* main's read loop (binning.c:1154-1166) over a file: fgets(buf, read_length_define), drop the last

@@ -73,6 +73,8 @@ def main():
     ap.add_argument("--case", default="cfg5_small")
     ap.add_argument("--out", required=True)
     ap.add_argument("--form", default="skr")
+    ap.add_argument("--exchange", default="auto", help="peer (partition kernel stores into the owners' buffers) or nccl")
+    ap.add_argument("--repeat", type=int, default=1, help="run the exchange this many times (epochs of the peer exchange)")
     a = ap.parse_args()
     dist.init_process_group(a.backend)
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -96,8 +98,11 @@ def main():
         l = torch.from_numpy(lens[lo:hi].astype(np.int32)).cuda()
         reads = B.Binner._reads(d, d.numel(), hi - lo, starts=s, lens=l)
         to_host = binner.table_to_host
-    sb = ShardedBinner(stages)
-    table = to_host(sb.run(reads, arrival_base=lo))
+    sb = ShardedBinner(stages, exchange=a.exchange)
+    for _ in range(a.repeat):
+        table = to_host(sb.run(reads, arrival_base=lo))
+    if a.exchange == "peer" and a.form == "skr":
+        assert sb.exchange_kind == "peer" and sb._peer_ready, "the peer exchange was not used"
     # every m-mer this rank holds is one it owns
     assert ((table.mmer_codes % world) == rank).all()
     gathered = [None] * world
@@ -110,7 +115,7 @@ def main():
         got.assert_equal(want)
         assert got.md5() == case["md5"]
         with open(a.out, "w") as f:
-            f.write(f"OK world={world} kmers={got.n_kmers} sent={sb.stats.sent_records} fallbacks={sb.fallbacks}\n")
+            f.write(f"OK world={world} kmers={got.n_kmers} sent={sb.stats.sent_records} fallbacks={sb.fallbacks} exchange={sb.exchange_kind}\n")
     dist.barrier()
     dist.destroy_process_group()
 

@@ -292,12 +292,17 @@ __global__ void __launch_bounds__(PART_THREADS)
         // a 256-entry table on the top byte of the prefix narrows the search to a step or two
         for (uint32_t bb = threadIdx.x; bb < 257; bb += PART_THREADS) lut[bb] = bb < 256 ? (uint16_t)fine_search((uint64_t)bb << 56) : (uint16_t)(F - 1);
         __syncthreads();
+        // the k-mers of a bucket share long prefixes (every window whose signature sits at offset j starts with j free bases
+        // followed by the m-mer itself), so the top byte alone leaves long candidate ranges: bisect inside the table's range
         auto fine_of = [&](uint64_t pre) -> uint32_t {
             const uint32_t bb = (uint32_t)(pre >> 56);
-            uint32_t f = lut[bb];
-            const uint32_t hi = lut[bb + 1];
-            while (f < hi && spl[f + 1] <= pre) f++;
-            return f;
+            uint32_t lo = lut[bb], hi = lut[bb + 1];  // the answer is the last f in [lo, hi] with spl[f] <= pre (spl[lo] <= pre holds)
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (spl[mid] <= pre) lo = mid;
+                else hi = mid - 1;
+            }
+            return lo;
         };
         for (uint32_t s = a + threadIdx.x; s < b; s += PART_THREADS)
             for_each_window<PW, KW>(skr + (uint64_t)s * NW, K, [&](uint32_t, uint64_t, uint64_t, uint64_t pre) { atomicAdd(&cnt[fine_of(pre)], 1u); });

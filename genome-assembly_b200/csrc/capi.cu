@@ -115,7 +115,7 @@ struct gbin_ctx {
     DevBuf group_of, run_start, surv_index, id_offset, surv_group, bucket_of;
     DevBuf misc;
     // pipeline v2 workspace
-    DevBuf skr_a, skr_b, tile_state, inst_prefix, run_excl, skr_run_start, small_prefix, unit_base, units, unit_state, o_kmer_mmer, bucket_excl, big_list, big_k0, big_k1, big_arr;
+    DevBuf skr_a, skr_b, tile_state, inst_prefix, run_excl, skr_run_start, small_prefix, unit_base, units, unit_state, o_kmer_mmer, bucket_excl, big_list, big_k0, big_k1, big_arr, stg_ids, stg_codes, stg_mmer, stg_off;
     int pipeline;        // 2: super-k-mer path with v1 as fallback (default); 1: v1 only
     int last_pipeline;   // which one produced the last table
     uint32_t fallbacks;  // v2 -> v1 fallbacks since creation
@@ -447,6 +447,10 @@ int run_v2_group(gbin_ctx *ctx, void *skr, void *twin, uint64_t n_skr, const int
     CU(ctx->o_kmer_mmer.ensure((kmer_cap + 1) * sizeof(uint32_t)));
     CU(ctx->o_kmer_id_off.ensure((kmer_cap + 2) * sizeof(uint64_t)));
     CU(ctx->o_read_ids.ensure((n + 1) * sizeof(int32_t)));
+    CU(ctx->stg_ids.ensure((n + 1) * sizeof(int32_t)));
+    CU(ctx->stg_codes.ensure((kmer_cap * KW + 1) * sizeof(uint64_t)));
+    CU(ctx->stg_mmer.ensure((kmer_cap + 1) * sizeof(uint32_t)));
+    CU(ctx->stg_off.ensure((kmer_cap + 1) * sizeof(uint32_t)));
     on = ctx->prof.begin(KK_SKR_GROUP, st);
     SkrGroupChunks ch{1u, dm->chunk_tickets, nullptr, nullptr, nullptr};
     if (sink && sink->chunks > 1) {
@@ -457,7 +461,8 @@ int run_v2_group(gbin_ctx *ctx, void *skr, void *twin, uint64_t n_skr, const int
     }
     lp = skr_group_launch(sorted, K, cutoff, ctx->inst_prefix.as<uint32_t>(), ctx->units.p, ctx->unit_state.as<unsigned long long>(), max_units, ch,
                           &dm->gc, ctx->big_k0.as<uint64_t>(), ctx->big_k1.as<uint64_t>(), ctx->big_arr.as<uint32_t>(), d_ids, id_base, ctx->o_kmer_codes.as<uint64_t>(), ctx->o_kmer_mmer.as<uint32_t>(),
-                          ctx->o_kmer_id_off.as<uint64_t>(), ctx->o_read_ids.as<int32_t>(), kmer_cap, n, ctx->sm_count, st);
+                          ctx->o_kmer_id_off.as<uint64_t>(), ctx->o_read_ids.as<int32_t>(), kmer_cap, n, ctx->stg_ids.as<int32_t>(), ctx->stg_codes.as<uint64_t>(),
+                          ctx->stg_mmer.as<uint32_t>(), ctx->stg_off.as<uint32_t>(), ctx->sm_count, st);
     ctx->prof.end(on, lp, st);
     *launches += lp;
     CU(cudaGetLastError());
@@ -658,7 +663,7 @@ void gbin_destroy(gbin_ctx *ctx) {
                       &ctx->id_offset, &ctx->surv_group, &ctx->bucket_of, &ctx->misc, &ctx->o_mmer_codes, &ctx->o_mmer_kmer_off,
                       &ctx->o_kmer_codes, &ctx->o_kmer_id_off, &ctx->o_read_ids, &ctx->skr_a, &ctx->skr_b, &ctx->tile_state,
                       &ctx->inst_prefix, &ctx->run_excl, &ctx->skr_run_start, &ctx->small_prefix, &ctx->unit_base, &ctx->units,
-                      &ctx->unit_state, &ctx->o_kmer_mmer, &ctx->bucket_excl, &ctx->big_list, &ctx->big_k0, &ctx->big_k1, &ctx->big_arr};
+                      &ctx->unit_state, &ctx->o_kmer_mmer, &ctx->bucket_excl, &ctx->big_list, &ctx->big_k0, &ctx->big_k1, &ctx->big_arr, &ctx->stg_ids, &ctx->stg_codes, &ctx->stg_mmer, &ctx->stg_off};
     for (DevBuf *b : bufs) b->release();
     ctx->h_misc.release();
     ctx->h_result.release();

@@ -40,7 +40,7 @@ constexpr int G_RANK_MAX = 512;  // up to this many survivors per unit are order
 struct __align__(16) Unit {
     uint32_t skr_begin, skr_end;  // range of sorted super-k-mer records; UNIT_RECORDS: range of expanded instance records
     uint32_t flags;               // UNIT_RECORDS: a slice of a bucket larger than CAP, already expanded into the scratch arrays
-    uint32_t base_pref;           // instance prefix of the first super-k-mer record
+    uint32_t base_pref;           // instance prefix of the unit's first k-mer instance (its coordinate in the staging arrays)
     uint32_t n_cand;              // k-mer instances of the unit
     uint32_t mmer;                // UNIT_RECORDS: the bucket's m-mer code
     uint32_t pad[2];
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(PART_THREADS)
                 foff[f] = acc;
                 if (cf > pp.cap) s_bad = 1;  // one fine range (one k-mer prefix, typically one k-mer) overflows a unit
                 if (run + cf > pp.cap) {
-                    if (q < P) units[ub + q] = Unit{sbase + start, sbase + acc, UNIT_RECORDS, 0u, run, mmer, {0u, 0u}};
+                    if (q < P) units[ub + q] = Unit{sbase + start, sbase + acc, UNIT_RECORDS, base + start, run, mmer, {0u, 0u}};
                     q++;
                     start = acc;
                     run = 0;
@@ -325,10 +325,10 @@ __global__ void __launch_bounds__(PART_THREADS)
                 acc += cf;
             }
             foff[F] = acc;
-            if (q < P) units[ub + q] = Unit{sbase + start, sbase + acc, UNIT_RECORDS, 0u, run, mmer, {0u, 0u}};
+            if (q < P) units[ub + q] = Unit{sbase + start, sbase + acc, UNIT_RECORDS, base + start, run, mmer, {0u, 0u}};
             q++;
             if (q > P || acc != c) s_bad = 1;
-            for (; q < P; q++) units[ub + q] = Unit{sbase + acc, sbase + acc, UNIT_RECORDS, 0u, 0u, mmer, {0u, 0u}};  // unused slots: empty units
+            for (; q < P; q++) units[ub + q] = Unit{sbase + acc, sbase + acc, UNIT_RECORDS, base + acc, 0u, mmer, {0u, 0u}};  // unused slots: empty units
         }
         __syncthreads();
         if (s_bad) {
@@ -400,6 +400,13 @@ struct GroupOut {
     uint64_t *kmer_id_off;  // [S+1]
     int32_t *read_ids;      // [N]
     uint64_t kmer_cap, id_cap;
+    // staging: a unit writes its part of the table at a place that depends on the unit alone (instance coordinate for ids,
+    // instance coordinate / (cutoff + 1) for k-mers), and the CTA moves it to its final place one unit later, when the
+    // chained scan over units has long resolved — nobody ever waits for a predecessor
+    int32_t *stg_ids;       // [id_cap]
+    uint64_t *stg_codes;    // [kmer_cap * KW]
+    uint32_t *stg_mmer;     // [kmer_cap]
+    uint32_t *stg_off;      // [kmer_cap] start of the k-mer's id list inside its unit
 };
 struct GroupCounters {
     unsigned long long distinct;
@@ -451,7 +458,7 @@ __global__ void __launch_bounds__(G_THREADS + 32)
     uint32_t *off = table;                 // off[s], s < S <= CAP (the end of the last list is the unit's id total)
     uint32_t *stage_ids = table + G_CAP;   // scratch; together with cnt (free once the offsets exist) 2*CAP words
     __shared__ uint32_t s_nsurv, s_ndistinct, s_scan[G_THREADS / 32 + 1];
-    __shared__ unsigned long long s_base, s_agg;
+    __shared__ unsigned long long s_agg;
     __shared__ uint32_t s_total_ids;
     __shared__ uint32_t s_uidx[2];
     __shared__ Unit s_un[2];
@@ -466,8 +473,8 @@ __global__ void __launch_bounds__(G_THREADS + 32)
     const uint32_t n_units = (uint32_t)(((uint64_t)n_units_all * (chunk + 1)) / n_chunks);  // this launch handles [unit_begin, n_units)
     uint32_t *chunk_ticket = chunk_tickets + chunk;
 
-    // Control warp: units are handed out by an atomic ticket, taken while the CTA writes the output of its current unit —
-    // a ticket taken much earlier would let later units overtake it, and their chained-scan resolve would then wait for it.
+    // Control warp: units are handed out by an atomic ticket, taken while the CTA orders and stages its current unit — a ticket
+    // taken much earlier would let later units overtake it, and their chained-scan resolve would then wait for it.
     auto fetch_unit = [&](int slot) {
         uint32_t u = 0;
         if (lane == 0) u = unit_begin + atomicAdd(chunk_ticket, 1u);
@@ -494,6 +501,50 @@ __global__ void __launch_bounds__(G_THREADS + 32)
         }
     };
 
+    // What the CTA still has to move from the staging arrays to its final place: the unit it finished last.
+    bool have_prev = false;
+    uint32_t prev_u = 0, prev_S = 0, prev_N = 0, prev_idb = 0, prev_kb = 0;
+    const uint32_t kdiv = cutoff >= 0 ? (uint32_t)cutoff + 1u : 1u;  // a surviving k-mer has more than `cutoff` instances
+
+    // Control warp, previous unit: resolve its output offsets from the chained scan over units — one unit late, so its
+    // predecessors have published long ago and nobody ever waits for a laggard (resolving at once and letting the workers
+    // wait at the end of the unit was measured 1.5x slower on batches with few survivors per unit)
+    auto resolve_prev = [&]() -> unsigned long long {
+        const unsigned long long agg = ((unsigned long long)prev_S << 31) | prev_N;
+        const unsigned long long base = lkb_resolve_warp<8>(unit_state, prev_u, agg, lane);  // the same value in every lane
+        if (lane == 0 && prev_u == n_units_all - 1) {
+            gc->total_kmers = (base >> 31) + prev_S;
+            gc->total_ids = (base & 0x7fffffffull) + prev_N;
+        }
+        return base;
+    };
+    // Control warp, previous unit: staging -> final place (the data is still in L2; eight loads in flight per lane)
+    auto move_prev = [&](unsigned long long pb) {
+        const uint64_t S_base = pb >> 31, N_base = pb & 0x7fffffffull;
+        if (S_base + prev_S > out.kmer_cap || N_base + prev_N > out.id_cap) {  // cannot happen with the caller's bounds; never write out of range
+            if (lane == 0) atomicExch(&gc->overflow, 2u);
+            return;
+        }
+        const int32_t *src = out.stg_ids + prev_idb;
+        int32_t *dst = out.read_ids + N_base;
+        uint32_t i = lane;
+        for (; i + 7 * 32 < prev_N; i += 8 * 32) {
+            int32_t v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = __ldcg(src + i + 32 * k);
+#pragma unroll
+            for (int k = 0; k < 8; k++) dst[i + 32 * k] = v[k];
+        }
+        for (; i < prev_N; i += 32) dst[i] = __ldcg(src + i);
+        for (uint32_t x = lane; x < prev_S; x += 32) {
+            const uint64_t g = S_base + x, q = (uint64_t)prev_kb + x;
+            out.kmer_codes[g * KW] = __ldcg(out.stg_codes + q * KW);
+            if (KW == 2) out.kmer_codes[g * KW + 1] = __ldcg(out.stg_codes + q * KW + 1);
+            out.kmer_mmer[g] = __ldcg(out.stg_mmer + q);
+            out.kmer_id_off[g] = N_base + __ldcg(out.stg_off + q);
+        }
+    };
+
     if (ctrl) fetch_unit(0);
     bar_all();
     for (int cur = 0;; cur ^= 1) {
@@ -502,21 +553,20 @@ __global__ void __launch_bounds__(G_THREADS + 32)
         const Unit un = s_un[cur];
         const uint32_t n_cand = un.n_cand;
         const bool too_big = n_cand > (uint32_t)G_CAP;  // cannot happen with the planner's bounds; the batch is then redone by pipeline v1
+        const uint32_t idb = un.base_pref, kb = un.base_pref / kdiv;  // this unit's places in the staging arrays
 
         if (ctrl) {
-            bar_wait(2, ALL);  // the workers have published the unit's totals
+            if (have_prev) move_prev(resolve_prev());  // while the workers expand and group this unit
+            bar_wait(2, ALL);                          // the workers have published this unit's totals
             const unsigned long long agg = s_agg;
-            const unsigned long long base = lkb_resolve_warp<8>(unit_state, u, agg, lane);
-            if (lane == 0) {
-                s_base = base;
-                if (u == n_units_all - 1) {
-                    gc->total_kmers = (base >> 31) + (agg >> 31);
-                    gc->total_ids = (base & 0x7fffffffull) + (agg & 0x7fffffffull);
-                }
-            }
-            bar_all();  // X: the unit's output offsets are known
             fetch_unit(cur ^ 1);
-            bar_all();  // Y: the unit is done
+            bar_all();  // Y: the unit is staged
+            have_prev = true;
+            prev_u = u;
+            prev_S = (uint32_t)(agg >> 31);
+            prev_N = (uint32_t)(agg & 0x7fffffffull);
+            prev_idb = idb;
+            prev_kb = kb;
             continue;
         }
 
@@ -568,8 +618,12 @@ __global__ void __launch_bounds__(G_THREADS + 32)
             }
             __threadfence_block();
             bar_arrive(2, ALL);
-            bar_all();  // X
             bar_all();  // Y
+            have_prev = true;
+            prev_u = u;
+            prev_S = prev_N = 0;
+            prev_idb = idb;
+            prev_kb = kb;
             continue;
         }
         const uint32_t n_inst = n_cand;
@@ -718,8 +772,6 @@ __global__ void __launch_bounds__(G_THREADS + 32)
         const uint32_t nch = (n_inst + 31) >> 5;
         const uint32_t row_words = ((nch + 1) >> 1) | 1u, row = 2 * row_words;
         const bool ordered = !from_records && S * row_words <= 2u * G_CAP;
-        bool fits = true;
-        uint64_t S_base = 0, N_base = 0;
         if (ordered) {
             // ---- id lists, ordered path.  Instance positions of a unit expanded from super-k-mer records follow arrival order, so the place of
             // an instance in its newest-first list is (members of the list in later chunks) + (members at a higher lane of
@@ -754,19 +806,14 @@ __global__ void __launch_bounds__(G_THREADS + 32)
                     run += c;
                 }
             }
-            bar_all();  // X: the control warp has resolved the unit's output offsets (and the suffix sums are complete)
-            S_base = s_base >> 31;
-            N_base = s_base & 0x7fffffffull;
-            fits = S_base + S <= out.kmer_cap && N_base + N <= out.id_cap;  // always, with the caller's bounds; never write out of range
-            if (fits) {
+            bar_workers(G_THREADS);
 #pragma unroll
-                for (int it = 0; it < ITERS; it++) {
-                    const uint32_t p = it * G_THREADS + tid;
-                    const uint32_t sI = p < n_inst ? grp[p] : 0xFFFFu;
-                    if (it * G_THREADS < n_inst && sI != 0xFFFFu) {
-                        const uint32_t a = arr[p];
-                        out.read_ids[N_base + off[sI] + mat[sI * row + (p >> 5)] + within[it]] = ids_by_arrival ? ids_by_arrival[a] : id_base + (int32_t)a;
-                    }
+            for (int it = 0; it < ITERS; it++) {
+                const uint32_t p = it * G_THREADS + tid;
+                const uint32_t sI = p < n_inst ? grp[p] : 0xFFFFu;
+                if (sI != 0xFFFFu) {
+                    const uint32_t a = arr[p];
+                    out.stg_ids[idb + off[sI] + mat[sI * row + (p >> 5)] + within[it]] = ids_by_arrival ? ids_by_arrival[a] : id_base + (int32_t)a;
                 }
             }
         } else {
@@ -777,38 +824,38 @@ __global__ void __launch_bounds__(G_THREADS + 32)
                 const uint32_t sI = grp[i];
                 if (sI != 0xFFFFu) stage_ids[off[sI] + rnk[i]] = arr[i];
             }
-            bar_all();  // X
-            S_base = s_base >> 31;
-            N_base = s_base & 0x7fffffffull;
-            fits = S_base + S <= out.kmer_cap && N_base + N <= out.id_cap;
-            if (fits) {
-                for (uint32_t i = tid; i < n_inst; i += G_THREADS) {
-                    const uint32_t sI = grp[i];
-                    if (sI == 0xFFFFu) continue;
-                    const uint32_t o = off[sI], c = (sI + 1 < S ? off[sI + 1] : N) - o, a = arr[i], r = rnk[i];
-                    const uint32_t *lst = stage_ids + o;
-                    uint32_t rank = 0;
-                    for (uint32_t y = 0; y < r; y++) rank += lst[y] >= a ? 1u : 0u;  // earlier staging position wins a tie
-                    for (uint32_t y = r + 1; y < c; y++) rank += lst[y] > a ? 1u : 0u;
-                    out.read_ids[N_base + o + rank] = ids_by_arrival ? ids_by_arrival[a] : id_base + (int32_t)a;
-                }
+            bar_workers(G_THREADS);
+            for (uint32_t i = tid; i < n_inst; i += G_THREADS) {
+                const uint32_t sI = grp[i];
+                if (sI == 0xFFFFu) continue;
+                const uint32_t o = off[sI], c = (sI + 1 < S ? off[sI + 1] : N) - o, a = arr[i], r = rnk[i];
+                const uint32_t *lst = stage_ids + o;
+                uint32_t rank = 0;
+                for (uint32_t y = 0; y < r; y++) rank += lst[y] >= a ? 1u : 0u;  // earlier staging position wins a tie
+                for (uint32_t y = r + 1; y < c; y++) rank += lst[y] > a ? 1u : 0u;
+                out.stg_ids[idb + o + rank] = ids_by_arrival ? ids_by_arrival[a] : id_base + (int32_t)a;
             }
         }
-        if (!fits && tid == 0) atomicExch(&gc->overflow, 2u);
 
-        // ---- write the unit's slice of the flat table
-        if (fits) {
-            for (uint32_t s = tid; s < S; s += G_THREADS) {
-                const uint32_t i = surv[s];
-                const uint64_t g = S_base + s;
-                out.kmer_codes[g * KW] = key0[i];
-                if (KW == 2) out.kmer_codes[g * KW + 1] = key1[i];
-                out.kmer_mmer[g] = mm[i];
-                out.kmer_id_off[g] = N_base + off[s];
-            }
+        // ---- stage the unit's slice of the flat table
+        for (uint32_t x = tid; x < S; x += G_THREADS) {
+            const uint32_t i = surv[x];
+            const uint64_t q = (uint64_t)kb + x;
+            out.stg_codes[q * KW] = key0[i];
+            if (KW == 2) out.stg_codes[q * KW + 1] = key1[i];
+            out.stg_mmer[q] = mm[i];
+            out.stg_off[q] = off[x];
         }
-        bar_all();  // Y
+        bar_all();  // Y: the unit is staged
+        have_prev = true;
+        prev_u = u;
+        prev_S = S;
+        prev_N = N;
+        prev_idb = idb;
+        prev_kb = kb;
     }
+    // ---- the last unit of this CTA
+    if (have_prev && ctrl) move_prev(resolve_prev());
 }
 
 // ------------------------------------------------------------------ bucket directory from the emitted k-mers
@@ -919,13 +966,13 @@ __global__ void publish_chunk_total_kernel(const unsigned long long *__restrict_
 
 int skr_group_launch(const void *skr_sorted, int K, int cutoff, const uint32_t *inst_prefix, const void *units, unsigned long long *unit_state,
                      uint64_t max_units, const SkrGroupChunks &ch, void *gc_dev, uint64_t *big_k0, uint64_t *big_k1, uint32_t *big_arr, const int32_t *ids_by_arrival, int32_t id_base, uint64_t *kmer_codes,
-                     uint32_t *kmer_mmer, uint64_t *kmer_id_off, int32_t *read_ids, uint64_t kmer_cap, uint64_t id_cap, int sm_count,
-                     cudaStream_t st) {
+                     uint32_t *kmer_mmer, uint64_t *kmer_id_off, int32_t *read_ids, uint64_t kmer_cap, uint64_t id_cap, int32_t *stg_ids, uint64_t *stg_codes,
+                     uint32_t *stg_mmer, uint32_t *stg_off, int sm_count, cudaStream_t st) {
     const int KW = K <= 32 ? 1 : 2;
     const size_t smem = skr_group_smem_bytes(KW);
     cudaMemsetAsync(unit_state, 0, sizeof(unsigned long long) * max_units, st);
     cudaMemsetAsync(ch.tickets, 0, sizeof(uint32_t) * ch.n, st);
-    GroupOut out{kmer_codes, kmer_mmer, kmer_id_off, read_ids, kmer_cap, id_cap};
+    GroupOut out{kmer_codes, kmer_mmer, kmer_id_off, read_ids, kmer_cap, id_cap, stg_ids, stg_codes, stg_mmer, stg_off};
     GroupCounters *gc = static_cast<GroupCounters *>(gc_dev);
     const uint32_t *s = static_cast<const uint32_t *>(skr_sorted);
     const Unit *un = static_cast<const Unit *>(units);

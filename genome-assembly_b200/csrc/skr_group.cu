@@ -442,9 +442,9 @@ __global__ void __launch_bounds__(G_THREADS + 32)
                      uint32_t *__restrict__ chunk_tickets) {
     constexpr int NW = SkrLayout<PW>::WORDS;
     constexpr int ALL = G_THREADS + 32;
-    constexpr int G_HS = 2 * G_CAP;  // hash slots
-    constexpr int G_LOG_HS = G_CAP == 4096 ? 13 : (G_CAP == 2048 ? 12 : 11);
-    static_assert(G_CAP == 4096 || G_CAP == 2048 || G_CAP == 1024, "unit capacity");
+    constexpr int G_LOG_HS = G_CAP > 2048 ? 13 : (G_CAP > 1024 ? 12 : 11);
+    constexpr int G_HS = 1 << G_LOG_HS;  // hash slots: the power of two in [2 CAP, 4 CAP)
+    static_assert(G_CAP % G_THREADS == 0 && G_CAP >= 1024 && G_CAP <= 4096, "unit capacity");
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t *key0 = reinterpret_cast<uint64_t *>(smem);
     uint64_t *key1 = key0 + (KW == 2 ? G_CAP : 0);
@@ -888,11 +888,12 @@ __global__ void empty_table_kernel2(uint64_t *mmer_kmer_off, uint64_t *kmer_id_o
 
 // ------------------------------------------------------------------ host side
 
-static int g_unit_cap() {  // GBIN_V2_CAP=2048|4096 selects the unit capacity (default 2048: three CTAs per SM)
+static int g_unit_cap() {  // GBIN_V2_CAP=1024|1280|2048|4096 selects the unit capacity (default 1280: four CTAs per SM; 2048: three)
     static int cap = 0;
     if (!cap) {
         const char *e = getenv("GBIN_V2_CAP");
-        cap = (e && atoi(e) == 4096) ? 4096 : 2048;
+        const int v = e ? atoi(e) : 1280;
+        cap = (v == 4096 || v == 2048 || v == 1024) ? v : 1280;
     }
     return cap;
 }
@@ -910,7 +911,8 @@ static PlanParams plan_params() {
 
 size_t skr_group_smem_bytes(int KW) {
     const size_t cap = (size_t)g_unit_cap();
-    return KW * cap * 8 + cap * 4 * 2 + 2 * cap * 4 + cap * 4 + cap * 2 * 3 + 64;
+    const size_t hs = cap > 2048 ? 8192 : (cap > 1024 ? 4096 : 2048);  // hash slots, as in the kernel
+    return KW * cap * 8 + cap * 4 * 2 + hs * 4 + cap * 4 + cap * 2 * 3 + 64;
 }
 
 uint64_t skr_max_units(uint64_t n_inst, uint64_t n_runs) { return n_inst / (g_unit_cap() / 4) + 2 * n_runs + 8; }
@@ -993,9 +995,16 @@ int skr_group_launch(const void *skr_sorted, int K, int cutoff, const uint32_t *
         const char *e = getenv("GBIN_V2_THREADS");
         thr = (e && atoi(e) == 512) ? 512 : 256;
     }
+    const int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));  // CTAs per SM that shared memory allows
     if (g_unit_cap() == 4096) {
         if (KW == 1) launch(skr_group_kernel<2, 1, 4096, 512>, 512, 1);
         else launch(skr_group_kernel<4, 2, 4096, 512>, 512, 1);
+    } else if (g_unit_cap() == 1280) {
+        if (KW == 1) launch(skr_group_kernel<2, 1, 1280, 256>, 256, per_sm < 4 ? per_sm : 4);
+        else launch(skr_group_kernel<4, 2, 1280, 256>, 256, per_sm < 4 ? per_sm : 4);
+    } else if (g_unit_cap() == 1024) {
+        if (KW == 1) launch(skr_group_kernel<2, 1, 1024, 256>, 256, per_sm < 4 ? per_sm : 4);
+        else launch(skr_group_kernel<4, 2, 1024, 256>, 256, per_sm < 4 ? per_sm : 4);
     } else if (thr == 512) {
         if (KW == 1) launch(skr_group_kernel<2, 1, 2048, 512>, 512, 3);
         else launch(skr_group_kernel<4, 2, 2048, 512>, 512, 2);

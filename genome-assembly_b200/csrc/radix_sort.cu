@@ -21,6 +21,9 @@ namespace gbin {
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_RADIX = 256;
+#ifndef RS_ITEMS_32B
+#define RS_ITEMS_32B 4
+#endif
 
 // A record seen as NU64 64-bit words (Rec<1>: 2, Rec<2>: 3, 32-byte super-k-mer: 4, 48-byte: 6).
 template <int NU64>
@@ -58,8 +61,8 @@ __device__ __forceinline__ void store_blob(Blob<NU64> *p, const Blob<NU64> &b) {
 }
 
 template <int NU64>
-struct TileShape {  // records per thread chosen so a thread keeps <= 64 registers of payload
-    static constexpr int ITEMS = NU64 <= 2 ? 16 : (NU64 <= 4 ? 8 : 4);
+struct TileShape {  // records per thread: GBIN_RS_ITEMS_* below (payload registers per thread = 2 * NU64 * ITEMS)
+    static constexpr int ITEMS = NU64 <= 2 ? 16 : (NU64 <= 4 ? RS_ITEMS_32B : 4);
     static constexpr int TILE = RS_THREADS * ITEMS;
 };
 

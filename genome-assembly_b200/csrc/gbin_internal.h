@@ -94,8 +94,9 @@ struct XchgPlan {  // passed to the kernels by value
 int radix_exchange_skr_by_owner(const void *in, uint64_t n, int skr_words, void *scratch, const XchgPlan &xp, cudaStream_t st);
 
 // v2: super-k-mer records (skr.cuh), sorted / partitioned on their m-mer code (word 1).
+// side_out (n u64, optional): {m-mer code << 32 | windows} of every record in sorted order, written by the last pass.
 int radix_sort_skr_by_mmer(void *a, void *b, uint64_t n, int skr_words, int M, void *scratch, bool *result_in_b, int *passes_out,
-                           KernelProf *prof, cudaStream_t st);
+                           uint64_t *side_out, KernelProf *prof, cudaStream_t st);
 int radix_partition_skr_by_owner(const void *in, void *out, uint64_t n, int skr_words, uint32_t n_parts, void *scratch, uint64_t *d_counts,
                                  cudaStream_t st);
 
@@ -115,7 +116,7 @@ struct SkrGroupCounters {  // mirror of GroupCounters in skr_group.cu
 size_t skr_group_smem_bytes(int KW);
 uint64_t skr_max_units(uint64_t n_inst, uint64_t n_runs);
 uint64_t skr_max_big_runs(uint64_t n_inst);
-int skr_plan_runs(const void *skr_sorted, uint64_t n_skr, int skr_words, uint32_t *inst_prefix, uint64_t *both64, uint32_t *run_start,
+int skr_plan_runs(const uint64_t *side, uint64_t n_skr, uint32_t *inst_prefix, uint64_t *both64, uint32_t *run_start,
                   uint64_t *scratch64, uint32_t *n_inst_dev, uint32_t *n_runs_dev, cudaStream_t st);
 size_t skr_unit_bytes();
 int skr_plan_units(const void *skr_sorted, int K, const uint32_t *inst_prefix, const uint32_t *run_start, uint64_t n_runs,

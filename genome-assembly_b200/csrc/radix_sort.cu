@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(RS_THREADS)
 template <int NU64>
 __global__ void __launch_bounds__(RS_THREADS)
     radix_scatter_kernel(const Blob<NU64> *__restrict__ in, Blob<NU64> *__restrict__ out, uint64_t n, DigitSel sel,
-                         const uint32_t *__restrict__ tile_off, uint32_t ntiles, char *const *__restrict__ dst_tab) {
+                         const uint32_t *__restrict__ tile_off, uint32_t ntiles, char *const *__restrict__ dst_tab, uint64_t *__restrict__ side) {
     constexpr int ITEMS = TileShape<NU64>::ITEMS, TILE = TileShape<NU64>::TILE;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     Blob<NU64> *exch = reinterpret_cast<Blob<NU64> *>(smem_raw);
@@ -185,7 +185,11 @@ __global__ void __launch_bounds__(RS_THREADS)
     for (uint32_t i = tid; i < count; i += RS_THREADS) {
         const Blob<NU64> r = exch[i];
         const uint32_t d = digit_of<NU64>(r, sel);
-        store_blob<NU64>(out + (uint32_t)(goff[d] + i), r);
+        const uint32_t pos = (uint32_t)(goff[d] + i);
+        store_blob<NU64>(out + pos, r);
+        // last pass of the super-k-mer sort: {m-mer code, windows} of every record in sorted order, 8 bytes instead of the
+        // whole record for the planning scans that follow
+        if (side) side[pos] = (r.w[0] & 0xffffffff00000000ull) | (r.w[1] & 0xffull);
     }
 }
 
@@ -304,7 +308,7 @@ size_t radix_scratch_bytes(uint64_t n) {
 
 template <int NU64>
 static int one_pass(const void *in_v, void *out_v, uint64_t n, const DigitSel &sel, uint32_t *scratch, KernelProf *prof, cudaStream_t st,
-                    const XchgPlan *xp = nullptr) {
+                    const XchgPlan *xp = nullptr, uint64_t *side = nullptr) {
     const Blob<NU64> *in = static_cast<const Blob<NU64> *>(in_v);
     Blob<NU64> *out = static_cast<Blob<NU64> *>(out_v);
     constexpr int TILE = TileShape<NU64>::TILE;
@@ -335,7 +339,7 @@ static int one_pass(const void *in_v, void *out_v, uint64_t n, const DigitSel &s
         xchg_counts_kernel<<<1, 32, 0, st>>>(tile_hist, nt, n, *xp, (uint32_t)sizeof(Blob<NU64>));
         launches++;
     }
-    radix_scatter_kernel<NU64><<<nt, RS_THREADS, smem, st>>>(in, out, n, sel, tile_hist, nt, xp ? xp->dst_tab : nullptr);
+    radix_scatter_kernel<NU64><<<nt, RS_THREADS, smem, st>>>(in, out, n, sel, tile_hist, nt, xp ? xp->dst_tab : nullptr, side);
     if (prof) prof->end(on, 1, st);
     if (xp) {
         xchg_done_kernel<<<1, 32, 0, st>>>(*xp);
@@ -345,12 +349,12 @@ static int one_pass(const void *in_v, void *out_v, uint64_t n, const DigitSel &s
 }
 
 static int one_pass_any(int nu64, const void *in, void *out, uint64_t n, const DigitSel &sel, uint32_t *scratch, KernelProf *prof,
-                        cudaStream_t st, const XchgPlan *xp = nullptr) {
+                        cudaStream_t st, const XchgPlan *xp = nullptr, uint64_t *side = nullptr) {
     switch (nu64) {
-        case 2: return one_pass<2>(in, out, n, sel, scratch, prof, st, xp);
-        case 3: return one_pass<3>(in, out, n, sel, scratch, prof, st, xp);
-        case 4: return one_pass<4>(in, out, n, sel, scratch, prof, st, xp);
-        default: return one_pass<6>(in, out, n, sel, scratch, prof, st, xp);
+        case 2: return one_pass<2>(in, out, n, sel, scratch, prof, st, xp, side);
+        case 3: return one_pass<3>(in, out, n, sel, scratch, prof, st, xp, side);
+        case 4: return one_pass<4>(in, out, n, sel, scratch, prof, st, xp, side);
+        default: return one_pass<6>(in, out, n, sel, scratch, prof, st, xp, side);
     }
 }
 
@@ -397,14 +401,15 @@ int radix_partition_by_owner(const void *in, void *out, uint64_t n, int KW, uint
 
 // v2: super-k-mer records (skr.cuh): word 1 (= high half of w[0]) is the m-mer code.
 int radix_sort_skr_by_mmer(void *a, void *b, uint64_t n, int skr_words, int M, void *scratch, bool *result_in_b, int *passes_out,
-                           KernelProf *prof, cudaStream_t st) {
+                           uint64_t *side_out, KernelProf *prof, cudaStream_t st) {
     *result_in_b = false;
     *passes_out = 0;
     if (n == 0) return 0;
     int launches = 0, passes = 0;
     void *src = a, *dst = b;
     for (int s = 0; s < 2 * M; s += 8) {
-        launches += one_pass_any(skr_words / 2, src, dst, n, DigitSel{0, 32 + s, 0}, static_cast<uint32_t *>(scratch), prof, st);
+        launches += one_pass_any(skr_words / 2, src, dst, n, DigitSel{0, 32 + s, 0}, static_cast<uint32_t *>(scratch), prof, st, nullptr,
+                                 s + 8 >= 2 * M ? side_out : nullptr);
         void *t = src;
         src = dst;
         dst = t;

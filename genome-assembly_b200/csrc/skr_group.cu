@@ -49,36 +49,32 @@ constexpr uint32_t UNIT_RECORDS = 1u;
 
 // ------------------------------------------------------------------ planning
 
-struct SkrCount {  // n of record i (word 2, bits 0-7)
-    const uint32_t *skr;
-    int nw;
-    __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return skr[i * nw + 2] & 0xffu; }
+// Planning reads the 8-byte side records the last sort pass wrote ({m-mer code << 32 | windows}, sorted order), not the records.
+struct SkrCount {  // windows of record i
+    const uint64_t *side;
+    __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return (uint32_t)side[i] & 0xffu; }
 };
 struct SkrRunHead {
-    const uint32_t *skr;
-    int nw;
-    __device__ __forceinline__ uint32_t operator()(uint64_t i) const {
-        return (i == 0 || skr[i * nw + 1] != skr[(i - 1) * nw + 1]) ? 1u : 0u;
-    }
+    const uint64_t *side;
+    __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return (i == 0 || (side[i] >> 32) != (side[i - 1] >> 32)) ? 1u : 0u; }
 };
 
 struct SkrCountAndHead {  // low half: windows of record i; high half: 1 if record i starts a new m-mer run
-    const uint32_t *skr;
-    int nw;
+    const uint64_t *side;
     __device__ __forceinline__ uint64_t operator()(uint64_t i) const {
-        return (uint64_t)SkrCount{skr, nw}(i) | ((uint64_t)SkrRunHead{skr, nw}(i) << 32);
+        return (uint64_t)SkrCount{side}(i) | ((uint64_t)SkrRunHead{side}(i) << 32);
     }
 };
 
 // both[i] = exclusive {windows, run heads} before record i (packed u64).  Splits it into inst_prefix[] and run_start[].
-__global__ void skr_run_starts_kernel(const uint32_t *__restrict__ skr, int nw, uint64_t n, const uint64_t *__restrict__ both,
+__global__ void skr_run_starts_kernel(const uint64_t *__restrict__ side, uint64_t n, const uint64_t *__restrict__ both,
                                       const uint64_t *__restrict__ total, uint32_t *__restrict__ inst_prefix, uint32_t *__restrict__ run_start,
                                       uint32_t *__restrict__ n_inst_out, uint32_t *__restrict__ n_runs_out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t b = both[i];
     inst_prefix[i] = (uint32_t)b;
-    if (SkrRunHead{skr, nw}(i)) run_start[b >> 32] = (uint32_t)i;
+    if (SkrRunHead{side}(i)) run_start[b >> 32] = (uint32_t)i;
     if (i == n - 1) {
         const uint64_t t = *total;
         inst_prefix[n] = (uint32_t)t;
@@ -921,12 +917,11 @@ uint64_t skr_max_big_runs(uint64_t n_inst) { return n_inst / (uint64_t)g_unit_ca
 
 // Phase A (needs n_skr on the host): instance prefix and m-mer run starts in one fused scan.
 // both64: [n_skr + 1] u64 scratch; scratch64: prefix-scan scratch. *n_inst_dev / *n_runs_dev receive the totals.
-int skr_plan_runs(const void *skr_sorted, uint64_t n_skr, int skr_words, uint32_t *inst_prefix /*[n+1]*/, uint64_t *both64,
-                  uint32_t *run_start /*[n+1]*/, uint64_t *scratch64, uint32_t *n_inst_dev, uint32_t *n_runs_dev, cudaStream_t st) {
-    const uint32_t *s = static_cast<const uint32_t *>(skr_sorted);
-    int l = exclusive_scan<uint64_t, SkrCountAndHead>(SkrCountAndHead{s, skr_words}, both64, n_skr, scratch64, both64 + n_skr, st);
-    skr_run_starts_kernel<<<(unsigned)((n_skr + 255) / 256), 256, 0, st>>>(s, skr_words, n_skr, both64, both64 + n_skr, inst_prefix, run_start,
-                                                                          n_inst_dev, n_runs_dev);
+int skr_plan_runs(const uint64_t *side, uint64_t n_skr, uint32_t *inst_prefix /*[n+1]*/, uint64_t *both64, uint32_t *run_start /*[n+1]*/,
+                  uint64_t *scratch64, uint32_t *n_inst_dev, uint32_t *n_runs_dev, cudaStream_t st) {
+    int l = exclusive_scan<uint64_t, SkrCountAndHead>(SkrCountAndHead{side}, both64, n_skr, scratch64, both64 + n_skr, st);
+    skr_run_starts_kernel<<<(unsigned)((n_skr + 255) / 256), 256, 0, st>>>(side, n_skr, both64, both64 + n_skr, inst_prefix, run_start, n_inst_dev,
+                                                                          n_runs_dev);
     return l + 1;
 }
 

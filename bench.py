@@ -11,7 +11,7 @@ owner with one NCCL all-to-all.
 
 One JSON line on stdout (rank 0).  `value` is device-resident throughput (inputs in HBM when the
 timed region starts), `e2e` goes through the public host-buffer call (pinned H2D + pipeline + D2H of
-the table inside the timed region), `roofline` is the dominant kernel (stable radix scatter) timed
+the table inside the timed region), `roofline` is the dominant kernel class (the shared-memory grouping kernel) timed
 live with CUDA events on its launching stream, `cpu_baseline` is the UNMODIFIED reference binary
 (oracle/_ref) on one host core over a bounded prefix of the same reads.
 """
@@ -403,7 +403,7 @@ def main():
         "skr_group": (skr_b + 4.0) * n_skr + stats["surviving_kmers"] * (8.0 * KW + 4 + 8) + 4.0 * stats["surviving_ids"],
         "find_runs": 3.0 * rb * n_rec + 8.0 * n_rec,
     }
-    ncu_traffic = {"skr_group": 500.1e6, "skr_scan": 277.3e6}  # dram read+write per launch, ncu --set full (profiles/)
+    ncu_traffic = {"skr_group": 868.2e6, "skr_scan": 271.0e6, "radix_scatter": 457.4e6}  # dram read+write per launch, ncu --set full (profiles/r1_final_kernels_raw.csv)
     roofline = None
     timed = {k: v for k, v in prof.items() if v["launches"] and k in alg_bytes}
     if timed:
@@ -418,7 +418,8 @@ def main():
                     "traffic": ncu_traffic.get(dom) if (world == 1 and a.workload == "cfg2" and not a.reads_per_gpu) else None,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "launches": sc["launches"], "avg_launch_ms": avg_ms,
                     "share_of_step": sc["ms"] / float(sum(step_ms)),
-                    "note": "HBM is not what bounds this kernel: it groups k-mers in shared memory (hash + ranking), see DESIGN.md",
+                    "note": "HBM is not what bounds this kernel: it groups k-mers in shared memory (hash, ranking, barriers between the phases of a unit); "
+                            "its DRAM traffic is about 1.6x the algorithmic bytes because every unit's output passes through staging arrays, see DESIGN.md 4.1",
                     "pipeline": {"algorithmic_bytes_per_kmer": pipe_bytes_per_inst, "achieved": pipe_ach, "frac": pipe_ach / peak,
                                  "note": "whole step against SURVEY 8(d)'s compulsory-traffic model (37.4 B per k-mer instance at cfg2)"},
                     "per_kernel_ms_per_step": {k: v["ms"] / a.steps for k, v in prof.items()},

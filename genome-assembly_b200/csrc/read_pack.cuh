@@ -66,24 +66,6 @@ __device__ __forceinline__ void warp_mmer_scores(const uint32_t *pk, uint32_t *w
     }
     __syncwarp();
 }
-// Same, and revmask[p / 32] bit (p % 32) = 1 iff the complement scored higher at p (is_rev, binning.c:943,948).
-__device__ __forceinline__ void warp_mmer_scores_rev(const uint32_t *pk, uint32_t *wv, uint32_t *revmask, uint32_t L, int M, uint32_t FULL,
-                                                     uint32_t lane) {
-    for (uint32_t p0 = 0; p0 + M <= L; p0 += 32) {
-        const uint32_t p = p0 + lane;
-        bool rev = false;
-        if (p + M <= L) {
-            const uint32_t s = mmer_at(pk, p, M);
-            const uint32_t c = FULL - s;
-            rev = c > s;
-            wv[p] = rev ? c : s;
-        }
-        const uint32_t m = __ballot_sync(0xffffffffu, rev);
-        if (lane == 0) revmask[p0 >> 5] = m;
-    }
-    __syncwarp();
-}
-
 // One hop of the signature chain (binning.c:931-988 at a restart window i): the LEFTMOST position
 // p in [i, i+C) maximising w(p).  Whole warp; returns sig, and w(sig) in *wmax.
 __device__ __forceinline__ uint32_t warp_signature_hop(const uint32_t *wv, uint32_t i, uint32_t C, uint32_t lane, uint32_t *wmax) {

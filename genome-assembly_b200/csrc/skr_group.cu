@@ -145,10 +145,11 @@ __global__ void fill_units_kernel(RunView rv, const uint32_t *__restrict__ small
     }
 }
 
-// Calls f(t, k0, k1, prefix) for every window t of a super-k-mer record: the oriented k-mer code (top 2K bits of the payload
-// shifted left by t bases, complemented when is_rev — binning.c:1029-1040) and its 64-bit prefix (monotone in the code).
+// Calls f(t, k0, k1, prefix) for the windows t = t0, t0 + step, ... of a super-k-mer record: the oriented k-mer code (top 2K bits
+// of the payload shifted left by t bases, complemented when is_rev — binning.c:1029-1040) and its 64-bit prefix (monotone in the
+// code).  step * 2 < 64.  (t0, step) = (0, 1) walks every window; the grouping kernel shares a record among several threads.
 template <int PW, int KW, typename F>
-__device__ __forceinline__ void for_each_window(const uint32_t *__restrict__ rec, int K, F &&f) {
+__device__ __forceinline__ void for_each_window_strided(const uint32_t *__restrict__ rec, int K, uint32_t t0, uint32_t step, F &&f) {
     const uint4 *p = reinterpret_cast<const uint4 *>(rec);
     const uint4 h = p[0];
     const uint32_t n = h.z & 0xffu;
@@ -165,7 +166,14 @@ __device__ __forceinline__ void for_each_window(const uint32_t *__restrict__ rec
             w[PW - 1] = ((uint64_t)b.z << 32) | b.w;
         }
     }
-    for (uint32_t t = 0; t < n; t++) {
+    auto advance = [&](uint32_t bases) {  // 0 < 2 * bases < 64
+        const uint32_t sh = 2 * bases;
+#pragma unroll
+        for (int q = 0; q < PW - 1; q++) w[q] = (w[q] << sh) | (w[q + 1] >> (64 - sh));
+        w[PW - 1] <<= sh;
+    };
+    if (t0) advance(t0);
+    for (uint32_t t = t0; t < n; t += step) {
         uint64_t k0, k1 = 0;
         if (KW == 1) {
             k0 = (2 * K == 64) ? w[0] : (w[0] >> (64 - 2 * K));
@@ -182,10 +190,12 @@ __device__ __forceinline__ void for_each_window(const uint32_t *__restrict__ rec
         uint64_t pre = rev ? ~w[0] : w[0];
         if (2 * K < 64) pre &= ~0ull << (64 - 2 * K);
         f(t, k0, k1, pre);
-#pragma unroll
-        for (int q = 0; q < PW - 1; q++) w[q] = (w[q] << 2) | (w[q + 1] >> 62);  // next base
-        w[PW - 1] <<= 2;
+        advance(step);
     }
+}
+template <int PW, int KW, typename F>
+__device__ __forceinline__ void for_each_window(const uint32_t *__restrict__ rec, int K, F &&f) {
+    for_each_window_strided<PW, KW>(rec, K, 0u, 1u, f);
 }
 
 // 64-bit prefix of the oriented k-mer of window w of a record (random access form of the above).
@@ -590,12 +600,16 @@ __global__ void __launch_bounds__(G_THREADS + 32)
                     arr[i] = sc.arr[g];
                 }
             } else {
-                // ---- expansion: one thread per super-k-mer record, rolling over its n windows
-                for (uint32_t s = un.skr_begin + tid; s < un.skr_end; s += G_THREADS) {
+                // ---- expansion: EXP_SUB threads share a super-k-mer record (a unit holds far fewer records than the CTA has
+                // threads), thread j of them rolling over the windows j, j + EXP_SUB, ...
+                constexpr uint32_t EXP_SUB = 4;
+                const uint32_t n_rec = un.skr_end - un.skr_begin;
+                for (uint32_t e = tid; e < n_rec * EXP_SUB; e += G_THREADS) {
+                    const uint32_t s = un.skr_begin + e / EXP_SUB;
                     const uint32_t *rec = skr + (uint64_t)s * NW;
                     const uint32_t arrival = rec[0], mmer = rec[1];
                     const uint32_t pos0 = inst_prefix[s] - base_pref;
-                    for_each_window<PW, KW>(rec, K, [&](uint32_t t, uint64_t k0, uint64_t k1, uint64_t) {
+                    for_each_window_strided<PW, KW>(rec, K, e % EXP_SUB, EXP_SUB, [&](uint32_t t, uint64_t k0, uint64_t k1, uint64_t) {
                         const uint32_t pos = pos0 + t;
                         key0[pos] = k0;
                         if (KW == 2) key1[pos] = k1;
@@ -985,11 +999,6 @@ int skr_group_launch(const void *skr_sorted, int K, int cutoff, const uint32_t *
             }
         }
     };
-    static int thr = 0;  // GBIN_V2_THREADS=512: experiment with 512 threads per CTA at capacity 2048
-    if (!thr) {
-        const char *e = getenv("GBIN_V2_THREADS");
-        thr = (e && atoi(e) == 512) ? 512 : 256;
-    }
     const int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));  // CTAs per SM that shared memory allows
     if (g_unit_cap() == 4096) {
         if (KW == 1) launch(skr_group_kernel<2, 1, 4096, 512>, 512, 1);
@@ -1000,12 +1009,9 @@ int skr_group_launch(const void *skr_sorted, int K, int cutoff, const uint32_t *
     } else if (g_unit_cap() == 1024) {
         if (KW == 1) launch(skr_group_kernel<2, 1, 1024, 256>, 256, per_sm < 4 ? per_sm : 4);
         else launch(skr_group_kernel<4, 2, 1024, 256>, 256, per_sm < 4 ? per_sm : 4);
-    } else if (thr == 512) {
-        if (KW == 1) launch(skr_group_kernel<2, 1, 2048, 512>, 512, 3);
-        else launch(skr_group_kernel<4, 2, 2048, 512>, 512, 2);
     } else {
-        if (KW == 1) launch(skr_group_kernel<2, 1, 2048, 256>, 256, 3);
-        else launch(skr_group_kernel<4, 2, 2048, 256>, 256, 2);
+        if (KW == 1) launch(skr_group_kernel<2, 1, 2048, 256>, 256, per_sm < 3 ? per_sm : 3);
+        else launch(skr_group_kernel<4, 2, 2048, 256>, 256, per_sm < 3 ? per_sm : 3);
     }
     return (int)(ch.totals_dev ? 2 * ch.n : ch.n);
 }

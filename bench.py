@@ -382,6 +382,27 @@ def main():
                "d2h_bytes_per_step": d2h * world, "ms_per_step": 1e3 * float(e2e_s[0]) / a.steps,
                "timing": "host wall clock, max over ranks; per rank: pinned H2D of its shard, sharded pipeline, D2H of its owner table into the pinned arena"}
 
+    # ---- input side: main's fgets loop on the device over this rank's file image (the reads buffer IS the
+    # file: one newline-terminated line per read), READ_LENGTH = L + 2 as for the synthetic configs
+    input_split = None
+    if world == 1 and not a.no_e2e:
+        rd_split = binner.split_reads_device(d_reads, d_reads.numel(), rs.read_len + 2, stream)
+        assert int(rd_split.n_reads) == rs.n_reads, (int(rd_split.n_reads), rs.n_reads)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ms = []
+        for _ in range(5):
+            flush.zero_()
+            ev0.record()
+            binner.split_reads_device(d_reads, d_reads.numel(), rs.read_len + 2, stream)
+            ev1.record()
+            ev1.synchronize()
+            ms.append(ev0.elapsed_time(ev1))
+        best = min(ms)
+        alg = 2.0 * d_reads.numel() + 12.0 * rs.n_reads + 8.0 * rs.n_reads  # image read twice (count, emit), newline positions, starts + lens
+        input_split = {"what": "gbin_split_reads_device: fgets-exact split of the file image into starts/lens on the device (includes its two host round trips)",
+                       "ms": best, "reads": rs.n_reads, "bytes": int(d_reads.numel()), "achieved_GBps": alg / (best / 1e3) / 1e9,
+                       "algorithmic_bytes": alg}
+
     # ---- roofline of the dominant kernel (the kernel class with the most device time in the timed region)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -442,7 +463,7 @@ def main():
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
             "dtype": "u64" if K <= 32 else "u128", "data": "synthetic",
             "config": config_dict(a, w, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cpu, "table": stats,
+            "roofline": roofline, "cpu_baseline": cpu, "table": stats, "input_split": input_split,
             "stage_ms_rank0": (dict(stage_ms, exchange_form=getattr(sharded, "exchange_kind", "nccl"),
                                     sent_bytes_offrank=sharded.stats.sent_bytes_offrank) if sharded is not None else None),
             "wall_s_timed_region": wall_s, "step_ms": step_ms,

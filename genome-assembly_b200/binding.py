@@ -67,7 +67,7 @@ EXPORTS = [
     "gbin_set_kernel_profiling", "gbin_get_kernel_profile", "gbin_kernel_kind_name", "gbin_set_pipeline", "gbin_get_pipeline_info", "gbin_get_run_stats",
     "gbin_count_instances_device", "gbin_scan_reads_device", "gbin_partition_records_device",
     "gbin_group_records_device", "gbin_xchg_create", "gbin_xchg_attach", "gbin_xchg_exchange_skr", "gbin_xchg_destroy", "gbin_skr_record_bytes", "gbin_scan_skr_device", "gbin_partition_skr_device", "gbin_group_skr_device",
-    "gbin_read_file_fgets", "gbin_table_dump", "gbin_table_dump_reference_format",
+    "gbin_split_reads_device", "gbin_copy_to_host", "gbin_bin_file_host", "gbin_read_file_fgets", "gbin_table_dump", "gbin_table_dump_reference_format",
     "getval", "getbp", "getscore", "process_read", "prune_data", "gbin_ref_configure", "gbin_ref_last_status",
     "gbin_ref_reset", "gbin_table_to_zhash", "gbin_zhash_release",
 ]
@@ -128,6 +128,9 @@ def load_library() -> C.CDLL:
     L.gbin_xchg_exchange_skr.argtypes = [vp, vp, u64, vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
     L.gbin_xchg_destroy.argtypes = [vp]
     L.gbin_xchg_destroy.restype = None
+    L.gbin_split_reads_device.argtypes = [vp, vp, u64, C.c_int, vp, C.POINTER(CReads)]
+    L.gbin_copy_to_host.argtypes = [vp, vp, vp, u64]
+    L.gbin_bin_file_host.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(CTable)]
     L.gbin_read_file_fgets.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(vp),
                                        C.POINTER(u64)]
     L.gbin_table_dump.argtypes = [C.POINTER(CTable), C.c_char_p]
@@ -335,6 +338,26 @@ class Binner:
         h = CTable()
         self._check(self.lib.gbin_table_to_pinned(self.h, C.byref(dev), stream, C.byref(h)))
         return h
+
+    # ---- main's read loop on the device
+    def split_reads_device(self, d_data, data_bytes: int, read_length_define: int, stream=None) -> CReads:
+        """fgets-style split of a file image in device memory -> ragged CReads with device pointers (context-owned)."""
+        rd = CReads()
+        self._check(self.lib.gbin_split_reads_device(self.h, _ptr(d_data), data_bytes, read_length_define, stream, C.byref(rd)))
+        return rd
+
+    def device_array(self, dev_ptr, n: int, dtype) -> np.ndarray:
+        """Host copy of n elements at a device address (context-owned device arrays)."""
+        out = np.zeros(n, dtype=dtype)
+        if n:
+            self._check(self.lib.gbin_copy_to_host(self.h, out.ctypes.data, int(dev_ptr), out.nbytes))
+        return out
+
+    def bin_file_host(self, path: str, read_length_define: int) -> HostTable:
+        """File -> pruned table: the file is split into reads on the device exactly as main's fgets loop does."""
+        t = CTable()
+        self._check(self.lib.gbin_bin_file_host(self.h, path.encode(), read_length_define, C.byref(t)))
+        return host_table_from_c(t)
 
     # ---- staged device entry points
     def count_instances_device(self, reads: CReads, stream=None) -> int:

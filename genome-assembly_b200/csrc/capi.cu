@@ -76,6 +76,7 @@ struct Misc {  // small device-resident scalars
     uint32_t skr_ticket, n_inst_dev, n_runs_dev, n_buckets_dev;
     uint32_t chunk_tickets[SKR_MAX_CHUNKS];
     unsigned long long chunk_totals[SKR_MAX_CHUNKS];
+    uint32_t split_n_nl, split_n_reads;
 };
 
 // Host path only.  HostFeed: the reads are still in host memory; the scan stage copies them chunk by chunk on the copy
@@ -136,7 +137,8 @@ struct gbin_ctx {
     // device-resident result
     DevBuf o_mmer_codes, o_mmer_kmer_off, o_kmer_codes, o_kmer_id_off, o_read_ids;
     // pinned host arena for results of the host path + small readbacks
-    HostBuf h_misc, h_result, h_kmer_codes, h_kmer_id_off, h_read_ids;
+    HostBuf h_misc, h_result, h_kmer_codes, h_kmer_id_off, h_read_ids, h_file;
+    DevBuf split_nl, split_tiles_buf, split_base;  // device-side fgets splitting
     KernelProf prof;
 };
 
@@ -671,6 +673,10 @@ void gbin_destroy(gbin_ctx *ctx) {
     ctx->h_kmer_codes.release();
     ctx->h_kmer_id_off.release();
     ctx->h_read_ids.release();
+    ctx->h_file.release();
+    ctx->split_nl.release();
+    ctx->split_tiles_buf.release();
+    ctx->split_base.release();
     ctx->prof.destroy();
     for (int i = 0; i < 6; i++) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < SKR_MAX_CHUNKS; i++) {
@@ -899,6 +905,123 @@ int gbin_table_to_pinned(gbin_ctx *ctx, const gbin_table *dev, void *stream, gbi
     int rc = table_to_pinned(ctx, *dev, nullptr, st, host);
     if (rc) return rc;
     CU(cudaStreamSynchronize(st));
+    return GBIN_OK;
+}
+
+
+// ---------------------------------------------------------------- main's read loop on the device
+
+namespace {
+// d_data: the file image in device memory.  Fills *out with the ragged-reads form (device pointers owned by the context).
+int split_reads_impl(gbin_ctx *ctx, const char *d_data, uint64_t size, int read_length_define, cudaStream_t st, gbin_reads *out, int *launches) {
+    if (read_length_define < 2) return fail(ctx, GBIN_E_INVALID_ARG, "READ_LENGTH must be at least 2 (fgets stores READ_LENGTH-1 bytes)");
+    memset(out, 0, sizeof *out);
+    out->data = d_data;
+    out->data_bytes = size;
+    if (size == 0) return GBIN_OK;
+    Misc *dm = ctx->misc.as<Misc>();
+    Misc *hm = static_cast<Misc *>(ctx->h_misc.p);
+    const uint8_t *data = reinterpret_cast<const uint8_t *>(d_data);
+    const uint32_t tiles = split_tiles(size);
+    const uint32_t cap = (uint32_t)read_length_define - 1u;
+    CU(ctx->split_tiles_buf.ensure(((size_t)tiles + scan_scratch_elems(tiles) + 16) * sizeof(uint32_t)));
+    uint32_t *tile_counts = ctx->split_tiles_buf.as<uint32_t>();
+    *launches += split_find_newlines(data, size, tile_counts, tile_counts + tiles, nullptr, &dm->split_n_nl, false, st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&hm->split_n_nl, &dm->split_n_nl, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    // the last line may lack its newline: it still is a line for fgets
+    char last = 0;
+    CU(cudaMemcpyAsync(&hm->pad, d_data + size - 1, 1, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(&last, &hm->pad, 1);
+    const uint64_t n_nl = hm->split_n_nl;
+    const uint64_t n_lines = n_nl + (last != '\n' ? 1 : 0);
+    if (n_lines >= (1ull << 32) - 1) return fail(ctx, GBIN_E_TOO_LARGE, "more than 2^32-1 lines in one file image");
+    CU(ctx->split_nl.ensure((n_nl + 1) * sizeof(uint64_t)));
+    *launches += split_find_newlines(data, size, tile_counts, nullptr, ctx->split_nl.as<uint64_t>(), nullptr, true, st);
+    CU(ctx->split_base.ensure((n_lines + 1) * sizeof(uint32_t)));
+    CU(ctx->scan_scratch.ensure(group_scan_scratch_bytes(n_lines)));
+    *launches += split_count_reads(ctx->split_nl.as<uint64_t>(), n_nl, size, cap, n_lines, ctx->split_base.as<uint32_t>(),
+                                   ctx->scan_scratch.as<uint32_t>(), &dm->split_n_reads, st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&hm->split_n_reads, &dm->split_n_reads, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const uint64_t n_reads = hm->split_n_reads;
+    CU(ctx->d_starts.ensure((n_reads + 1) * sizeof(uint64_t)));
+    CU(ctx->d_lens.ensure((n_reads + 1) * sizeof(uint32_t)));
+    *launches += split_emit_reads(ctx->split_nl.as<uint64_t>(), n_nl, size, cap, n_lines, ctx->split_base.as<uint32_t>(), ctx->d_starts.as<uint64_t>(),
+                                  ctx->d_lens.as<uint32_t>(), st);
+    CU(cudaGetLastError());
+    out->n_reads = n_reads;
+    out->starts = ctx->d_starts.as<uint64_t>();
+    out->lens = ctx->d_lens.as<uint32_t>();
+    out->max_read_len = cap > 1 ? cap - 1 : 1;  // a read is what one fgets call took, minus its last byte
+    return GBIN_OK;
+}
+}  // namespace
+
+int gbin_copy_to_host(gbin_ctx *ctx, void *host_dst, const void *device_src, uint64_t bytes) {
+    if (!ctx || (bytes && (!host_dst || !device_src))) return GBIN_E_INVALID_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (bytes) CU(cudaMemcpy(host_dst, device_src, bytes, cudaMemcpyDeviceToHost));
+    return GBIN_OK;
+}
+
+int gbin_split_reads_device(gbin_ctx *ctx, const char *d_data, uint64_t data_bytes, int read_length_define, void *stream, gbin_reads *out) {
+    if (!ctx || !out || (data_bytes && !d_data)) return GBIN_E_INVALID_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    int launches = 0;
+    int rc = split_reads_impl(ctx, d_data, data_bytes, read_length_define, st, out, &launches);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(st));
+    ctx->tm.kernel_launches = (uint32_t)launches;
+    return GBIN_OK;
+}
+
+int gbin_bin_file_host(gbin_ctx *ctx, const char *path, int read_length_define, gbin_table *out) {
+    if (!ctx || !path || !out) return GBIN_E_INVALID_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = ctx->stream;
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(ctx, GBIN_E_IO, "cannot open %s", path);
+    if (fseek(f, 0, SEEK_END) != 0) {
+        fclose(f);
+        return fail(ctx, GBIN_E_IO, "cannot seek in %s", path);
+    }
+    const long fsize = ftell(f);
+    rewind(f);
+    if (fsize < 0) {
+        fclose(f);
+        return fail(ctx, GBIN_E_IO, "cannot size %s", path);
+    }
+    const uint64_t size = (uint64_t)fsize;
+    cudaError_t e = ctx->h_file.ensure(size + 64);
+    if (e == cudaSuccess) e = ctx->d_reads.ensure(size + 64);
+    if (e != cudaSuccess) {
+        fclose(f);
+        (void)cudaGetLastError();
+        return fail(ctx, GBIN_E_NOMEM, "no room for the image of %s (%llu bytes)", path, (unsigned long long)size);
+    }
+    const size_t got = size ? fread(ctx->h_file.p, 1, size, f) : 0;
+    fclose(f);
+    if (got != size) return fail(ctx, GBIN_E_IO, "short read on %s", path);
+    int launches = 0;
+    CU(cudaEventRecord(ctx->ev[0], st));
+    if (size) CU(cudaMemcpyAsync(ctx->d_reads.p, ctx->h_file.p, size, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(ctx->ev[1], st));
+    gbin_reads rd;
+    int rc = split_reads_impl(ctx, ctx->d_reads.as<char>(), size, read_length_define, st, &rd, &launches);
+    if (rc) return rc;
+    gbin_table dev;
+    rc = bin_device_impl(ctx, &rd, st, &dev, &launches);
+    if (rc) return rc;
+    rc = table_to_pinned(ctx, dev, nullptr, st, out);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[5], st));
+    CU(cudaStreamSynchronize(st));
+    finish_timings(ctx, launches, true);
     return GBIN_OK;
 }
 

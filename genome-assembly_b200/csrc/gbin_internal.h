@@ -140,6 +140,15 @@ int skr_group_launch(const void *skr_sorted, int K, int cutoff, const uint32_t *
 int skr_emit_buckets(const uint32_t *kmer_mmer, uint64_t n_kmers, uint64_t n_ids, uint32_t *bucket_excl, uint32_t *scratch,
                      uint32_t *mmer_codes, uint64_t *mmer_kmer_off, uint64_t *kmer_id_off, uint32_t *n_buckets_dev, cudaStream_t st);
 
+// ---- split_reads.cu (main's fgets loop on the device)
+uint32_t split_tiles(uint64_t n);
+int split_find_newlines(const uint8_t *data, uint64_t n, uint32_t *tile_counts, uint32_t *scan_scratch, uint64_t *nl, uint32_t *n_nl_dev,
+                        bool emit, cudaStream_t st);
+int split_count_reads(const uint64_t *nl, uint64_t n_nl, uint64_t size, uint32_t cap, uint64_t n_lines, uint32_t *read_base, uint32_t *scan_scratch,
+                      uint32_t *n_reads_dev, cudaStream_t st);
+int split_emit_reads(const uint64_t *nl, uint64_t n_nl, uint64_t size, uint32_t cap, uint64_t n_lines, const uint32_t *read_base, uint64_t *starts,
+                     uint32_t *lens, cudaStream_t st);
+
 // ---- group_prune.cu
 struct GroupCounts {  // device-resident scalars, copied to the host between phases
     uint32_t n_distinct, n_kmers, n_buckets, pad;

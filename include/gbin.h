@@ -223,6 +223,18 @@ int gbin_xchg_exchange_skr(gbin_ctx *ctx, const void *d_skr, uint64_t n, void *s
                            uint64_t *sent_counts);
 void gbin_xchg_destroy(gbin_ctx *ctx);
 
+/* ---- main's read loop on the device (binning.c:1154-1166) ----
+ * Splits a file image in DEVICE memory into reads exactly as `while (fgets(read, read_length_define, file)) { read[--len] = 0; ... }`
+ * does: at most read_length_define-1 bytes per read, stopping after a newline, last byte dropped, one read (and id) per fgets
+ * return.  *out receives the ragged form with device pointers (data = d_data; starts/lens owned by the context, valid until
+ * the next split) ready for gbin_bin_reads_device.  Same result as gbin_read_file_fgets on the host. */
+int gbin_split_reads_device(gbin_ctx *ctx, const char *d_data, uint64_t data_bytes, int read_length_define, void *stream, gbin_reads *out);
+/* Plain device -> host copy of context-owned device arrays (device tables, the split's starts / lens). */
+int gbin_copy_to_host(gbin_ctx *ctx, void *host_dst, const void *device_src, uint64_t bytes);
+/* File -> table in one call: read the file into pinned memory, copy it to the device, split it there, run the hot path, copy
+ * the table to the context's pinned arena (ctx_owned = 1).  What `main` does up to and including prune_data. */
+int gbin_bin_file_host(gbin_ctx *ctx, const char *path, int read_length_define, gbin_table *out);
+
 /* ---- host helpers ---- */
 
 /* main's read loop (binning.c:1154-1166) over a file: fgets(buf, read_length_define), drop the last

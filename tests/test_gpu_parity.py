@@ -242,6 +242,43 @@ def test_host_path_streams_reads_in_and_table_out():
     b.close()
 
 
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c["name"])
+def test_device_side_fgets_split_matches_mains_read_loop(case):
+    """main's read loop (binning.c:1154-1166) on the device: same starts / lens as the host replay of fgets, for every
+    fixture (bundled reads.txt with READ_LENGTH 101: a 99-base read and an empty read per line; ragged lines, long lines,
+    missing trailing newline) and for a range of READ_LENGTH values around the line length."""
+    torch = torch_cuda()
+    data = O.load_case_bytes(case)
+    d = torch.from_numpy(np.frombuffer(data, dtype=np.uint8).copy()).cuda()
+    b = B.Binner(31, 11, 1)
+    for R in sorted({case["read_length_define"], 2, 3, 17, 100, 101, 102, 103, 4096}):
+        want_s, want_l = O.fgets_split(data, R)
+        rd = b.split_reads_device(d, d.numel(), R, B.stream_handle(torch.cuda.current_stream()))
+        n = int(rd.n_reads)
+        assert n == len(want_s), (R, n, len(want_s))
+        got_s = b.device_array(rd.starts, n, np.uint64)
+        got_l = b.device_array(rd.lens, n, np.uint32)
+        np.testing.assert_array_equal(got_s, want_s)
+        np.testing.assert_array_equal(got_l, want_l)
+    b.close()
+
+
+@pytest.mark.parametrize("case", [c for c in GPU_CASES if c["name"] in ("cfg1_reads", "cfg2_small", "fuzz_ragged_k25", "short_reads")], ids=lambda c: c["name"])
+def test_file_to_table_in_one_call(case, tmp_path):
+    """gbin_bin_file_host: file -> device -> split there -> hot path -> host table; equal to the oracle and the reference pin."""
+    torch_cuda()
+    data = O.load_case_bytes(case)
+    path = tmp_path / "reads.txt"
+    path.write_bytes(data)
+    starts, lens = O.fgets_split(data, case["read_length_define"])
+    want = O.run(data, starts, lens, case["k"], case["m"], case["cutoff"])
+    b = B.Binner(case["k"], case["m"], case["cutoff"])
+    got = b.bin_file_host(str(path), case["read_length_define"])
+    assert_tables_equal(got, want)
+    assert as_oracle_table(got).md5() == case["md5"]
+    b.close()
+
+
 def test_empty_and_degenerate_batches():
     torch_cuda()
     b = B.Binner(31, 4, 1)

@@ -47,13 +47,22 @@ __device__ __forceinline__ T block_exclusive_scan(T v, T *total) {
     return res;
 }
 
+// Both kernels read their tile striped (thread t takes elements t, t + 256, ...): consecutive threads touch consecutive
+// elements, whatever the input functor reads.  The scan kernel needs each thread's 16 elements to be consecutive for the
+// sequential part, so it passes the tile through shared memory (one pad element per 16 / 32 keeps the blocked accesses
+// spread over the banks).
+template <typename TOut>
+__device__ __forceinline__ uint32_t scan_pad(uint32_t p) {
+    return p + (sizeof(TOut) == 8 ? (p >> 4) : (p >> 5));
+}
+
 template <typename TOut, typename InOp>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(InOp in, TOut *__restrict__ block_sums, uint64_t n) {
-    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
     TOut s = 0;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; i++) {
-        const uint64_t j = base + i;
+        const uint64_t j = base + (uint64_t)i * SCAN_THREADS + threadIdx.x;
         if (j < n) s += (TOut)in(j);
     }
     TOut total;
@@ -64,24 +73,37 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(InOp in, TOut
 template <typename TOut, typename InOp>
 __global__ void __launch_bounds__(SCAN_THREADS)
     scan_apply_kernel(InOp in, TOut *__restrict__ out, const TOut *__restrict__ block_offsets, uint64_t n, TOut *__restrict__ total_out) {
-    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    __shared__ TOut ex[SCAN_TILE + SCAN_TILE / 16 + 1];
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        const uint32_t p = (uint32_t)i * SCAN_THREADS + threadIdx.x;
+        const uint64_t j = base + p;
+        ex[scan_pad<TOut>(p)] = j < n ? (TOut)in(j) : TOut(0);
+    }
+    __syncthreads();
     TOut v[SCAN_ITEMS];
     TOut s = 0;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; i++) {
-        const uint64_t j = base + i;
-        v[i] = j < n ? (TOut)in(j) : TOut(0);
+        v[i] = ex[scan_pad<TOut>(threadIdx.x * SCAN_ITEMS + i)];
         s += v[i];
     }
     TOut total;
     TOut run = block_exclusive_scan<TOut>(s, &total) + (block_offsets ? block_offsets[blockIdx.x] : TOut(0));
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; i++) {
-        const uint64_t j = base + i;
-        if (j < n) out[j] = run;
+        ex[scan_pad<TOut>(threadIdx.x * SCAN_ITEMS + i)] = run;
         run += v[i];
     }
     if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) *total_out = run;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        const uint32_t p = (uint32_t)i * SCAN_THREADS + threadIdx.x;
+        const uint64_t j = base + p;
+        if (j < n) out[j] = ex[scan_pad<TOut>(p)];
+    }
 }
 
 template <typename T>

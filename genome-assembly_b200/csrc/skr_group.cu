@@ -856,7 +856,8 @@ __global__ void __launch_bounds__(G_THREADS + 32)
             out.stg_mmer[q] = mm[i];
             out.stg_off[q] = off[x];
         }
-        bar_all();  // Y: the unit is staged
+        __threadfence();  // the staged unit is read back through L2 by the control warp (ld.cg): make the stores visible there first
+        bar_all();        // Y: the unit is staged
         have_prev = true;
         prev_u = u;
         prev_S = S;

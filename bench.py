@@ -148,7 +148,7 @@ def config_dict(a, w, world):
                         f"K={w['k']}, M={w['m']}, cutoff={w['cutoff']}, {w['error_rate'] * 100:g}% substitutions, {w['starts']} starts, "
                         f"genome {w['n_reads'] * world * w['read_len'] // 30} bp",
             "k": w["k"], "m": w["m"], "cutoff": w["cutoff"], "reads_per_gpu": w["n_reads"], "read_len": w["read_len"],
-            "parallelism": f"reads split evenly over {world} GPU(s); records exchanged by owner = mmer % {world}" if world > 1 else "single GPU",
+            "parallelism": f"reads split evenly over {world} GPU(s); records exchanged by owner = hash(mmer) -> [0, {world})" if world > 1 else "single GPU",
             "l2": "L2 flushed (256 MiB memset) before every timed step; per-step device times summed"}
 
 

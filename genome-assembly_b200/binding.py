@@ -66,7 +66,7 @@ EXPORTS = [
     "gbin_bin_reads_device", "gbin_table_to_host", "gbin_table_to_pinned", "gbin_get_timings", "gbin_record_bytes",
     "gbin_set_kernel_profiling", "gbin_get_kernel_profile", "gbin_kernel_kind_name", "gbin_set_pipeline", "gbin_get_pipeline_info", "gbin_get_run_stats",
     "gbin_count_instances_device", "gbin_scan_reads_device", "gbin_partition_records_device",
-    "gbin_group_records_device", "gbin_xchg_create", "gbin_xchg_attach", "gbin_xchg_exchange_skr", "gbin_xchg_destroy", "gbin_skr_record_bytes", "gbin_scan_skr_device", "gbin_partition_skr_device", "gbin_group_skr_device",
+    "gbin_group_records_device", "gbin_owner_of", "gbin_xchg_create", "gbin_xchg_attach", "gbin_xchg_exchange_skr", "gbin_xchg_destroy", "gbin_skr_record_bytes", "gbin_scan_skr_device", "gbin_partition_skr_device", "gbin_group_skr_device",
     "gbin_split_reads_device", "gbin_copy_to_host", "gbin_bin_file_host", "gbin_read_file_fgets", "gbin_table_dump", "gbin_table_dump_reference_format",
     "getval", "getbp", "getscore", "process_read", "prune_data", "gbin_ref_configure", "gbin_ref_last_status",
     "gbin_ref_reset", "gbin_table_to_zhash", "gbin_zhash_release",
@@ -123,6 +123,8 @@ def load_library() -> C.CDLL:
     L.gbin_scan_skr_device.argtypes = [vp, C.POINTER(CReads), u32, vp, u64, vp, C.POINTER(u64), C.POINTER(u64)]
     L.gbin_partition_skr_device.argtypes = [vp, vp, u64, u32, vp, vp, C.POINTER(u64)]
     L.gbin_group_skr_device.argtypes = [vp, vp, u64, vp, i32, vp, C.POINTER(CTable), C.POINTER(C.c_int)]
+    L.gbin_owner_of.argtypes = [u32, u32]
+    L.gbin_owner_of.restype = u32
     L.gbin_xchg_create.argtypes = [vp, u32, u32, u64, vp]
     L.gbin_xchg_attach.argtypes = [vp, vp]
     L.gbin_xchg_exchange_skr.argtypes = [vp, vp, u64, vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
@@ -200,6 +202,12 @@ def host_table_from_c(t: CTable) -> HostTable:
                      kmer_codes=_np_from(t.kmer_codes, t.n_kmers * t.kmer_words, np.uint64),
                      kmer_id_off=_np_from(t.kmer_id_off, t.n_kmers + 1, np.uint64),
                      read_ids=_np_from(t.read_ids, t.n_ids, np.int32))
+
+
+def owner_of(mmer_codes, parts: int) -> np.ndarray:
+    """gbin_owner_of for an array of m-mer codes: which of `parts` GPUs owns each bucket."""
+    m = np.asarray(mmer_codes).astype(np.uint64)
+    return ((((m * np.uint64(0x9E3779B1)) & np.uint64(0xFFFFFFFF)) * np.uint64(parts)) >> np.uint64(32)).astype(np.int64)
 
 
 CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy: explicit handle of the legacy default stream

@@ -1226,6 +1226,8 @@ int gbin_xchg_exchange_skr(gbin_ctx *ctx, const void *d_skr, uint64_t n, void *s
     return GBIN_OK;
 }
 
+uint32_t gbin_owner_of(uint32_t mmer_code, uint32_t n_parts) { return n_parts ? owner_of_mmer(mmer_code, n_parts) : 0u; }
+
 uint32_t gbin_skr_record_bytes(const gbin_ctx *ctx) { return ctx ? (ctx->cfg.kmer_size <= 32 ? 32u : 48u) : 0u; }
 
 int gbin_scan_skr_device(gbin_ctx *ctx, const gbin_reads *reads, uint32_t arrival_base, void *d_skr, uint64_t capacity, void *stream,

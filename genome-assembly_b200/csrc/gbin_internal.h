@@ -66,7 +66,7 @@ int launch_pack_reads(const ReadsView &rv, uint32_t words_per_read, uint32_t *pa
 size_t radix_scratch_bytes(uint64_t n);
 int radix_sort_records(void *a, void *b, uint64_t n, int KW, int K, int M, void *scratch, bool *result_in_b, int *passes_out,
                        KernelProf *prof, cudaStream_t st);
-// Stable partition by owner = mmer % n_parts: in -> out, part sizes to d_counts[n_parts] (device, u64).
+// Stable partition by owner = owner_of_mmer(mmer, n_parts): in -> out, part sizes to d_counts[n_parts] (device, u64).
 int radix_partition_by_owner(const void *in, void *out, uint64_t n, int KW, uint32_t n_parts, void *scratch, uint64_t *d_counts,
                              cudaStream_t st);
 

@@ -7,7 +7,7 @@
 //     scan stage emits records in arrival order, the records of one key stay in arrival order — which is
 //     what the linked list's head-insert order encodes (binning.c:1059-1069), read backwards;
 //   * pipeline v2: super-k-mer records sorted on the m-mer code only (level 1 of the two-level store).
-// With digit = mmer % n_parts the same pass is the stable owner partition of the multi-GPU path.
+// With digit = owner_of_mmer(mmer, n_parts) the same pass is the stable owner partition of the multi-GPU path.
 //
 // Per pass: (1) per-tile digit histogram, (2) exclusive scan of the [256][tiles] table,
 // (3) stable scatter: warp-level match ranking, tile-local reorder through shared memory so that
@@ -69,7 +69,7 @@ struct TileShape {  // records per thread: GBIN_RS_ITEMS_* below (payload regist
 struct DigitSel {
     int word64;    // which 64-bit word of the record holds the digit
     int shift;     // right shift inside that word
-    uint32_t mod;  // 0: digit = (word >> shift) & 0xff ; else digit = (u32)(word >> shift) % mod (owner partition)
+    uint32_t mod;  // 0: digit = (word >> shift) & 0xff ; else digit = owner_of_mmer((u32)(word >> shift), mod) (owner partition)
 };
 
 template <int NU64>
@@ -79,7 +79,7 @@ __device__ __forceinline__ uint32_t digit_of(const Blob<NU64> &r, const DigitSel
     for (int i = 1; i < NU64; i++)
         if (s.word64 == i) x = r.w[i];  // no dynamic indexing: keeps records in registers
     x >>= s.shift;
-    return s.mod ? (uint32_t)x % s.mod : (uint32_t)x & 0xffu;
+    return s.mod ? owner_of_mmer((uint32_t)x, s.mod) : (uint32_t)x & 0xffu;
 }
 
 template <int NU64>
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(RS_THREADS)
 // ------------------------------------------------------------------ owner exchange over peer memory
 // One process per GPU; every rank maps every peer's receive buffer and XchgShared block (CUDA IPC, set up once by
 // capi.cu).  Per exchange (all on the rank's stream, no host round trip and no NCCL call):
-//   1. the usual per-tile histogram of digit = mmer % world and its scan (above);
+//   1. the usual per-tile histogram of digit = owner_of_mmer(mmer, world) and its scan (above);
 //   2. xchg_counts_kernel: this rank's per-owner counts go into row `rank` of every peer's count matrix, a flag with the
 //      exchange's epoch follows (release at system scope); the kernel then waits for every rank's row, derives where its
 //      records start inside each owner's buffer (behind the records of the lower ranks: arrival order is kept) and how

@@ -2,7 +2,7 @@
 
     reads split evenly by contiguous id range (rank g holds arrival indices [base_g, base_g + n_g))
       -> scan stage on every rank (process_read's window/signature work, embarrassingly parallel)
-      -> stable partition of the k-mer instance records by owner = mmer_code % world
+      -> stable partition of the records by owner = gbin_owner_of(mmer_code, world) (a hash of the code)
       -> ONE personalised all-to-all-v of records (count exchange, then payload)
       -> sort / run-length / prune on the owner, which now holds whole m-mer buckets.
 

@@ -182,7 +182,10 @@ int gbin_count_instances_device(gbin_ctx *ctx, const gbin_reads *reads, void *st
  * d_records (capacity in records).  arrival = arrival_base + read index. */
 int gbin_scan_reads_device(gbin_ctx *ctx, const gbin_reads *reads, uint32_t arrival_base, void *d_records,
                            uint64_t capacity, void *stream, uint64_t *n_out);
-/* Stable partition of records by owner = mmer_code % n_parts into d_out;
+/* Owner of an m-mer bucket among n_parts GPUs: a multiplicative hash of the code, range-reduced
+ * ((code * 0x9E3779B1 mod 2^32) * n_parts) >> 32 — the plain remainder follows the skewed last bases of the signatures. */
+uint32_t gbin_owner_of(uint32_t mmer_code, uint32_t n_parts);
+/* Stable partition of records by owner = gbin_owner_of(mmer_code, n_parts) into d_out;
  * counts_host[p] receives the number of records of part p (parts are laid out in order). */
 int gbin_partition_records_device(gbin_ctx *ctx, const void *d_records, uint64_t n, uint32_t n_parts, void *d_out,
                                   void *stream, uint64_t *counts_host);
@@ -207,7 +210,7 @@ int gbin_group_skr_device(gbin_ctx *ctx, void *d_skr, uint64_t n_skr, const int3
                           gbin_table *out, int *used_fallback);
 
 /* ---- owner exchange over peer memory (one process per GPU on one node) ----
- * The partition by owner = mmer_code % world and the all-to-all are one step: every rank maps every
+ * The partition by owner = gbin_owner_of(mmer_code, world) and the all-to-all are one step: every rank maps every
  * peer's receive buffer (CUDA IPC) and the partition kernel stores each owner's records straight into that owner's buffer
  * over NVLink, behind the records of the lower ranks (so arrival order is kept); counts and completion are exchanged
  * through flags in peer memory.  Setup: every rank calls gbin_xchg_create, the GBIN_XCHG_HANDLE_BYTES blobs are gathered

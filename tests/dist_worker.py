@@ -51,7 +51,7 @@ class OracleStages:
 
     def partition(self, rec, n, parts):
         r = self._from_tensor(rec, n)
-        owner = r["mmer"] % parts
+        owner = B.owner_of(r["mmer"], parts)
         order = np.argsort(owner, kind="stable")
         return self._to_tensor(r[order]), [int((owner == p).sum()) for p in range(parts)]
 
@@ -104,7 +104,7 @@ def main():
     if a.exchange == "peer" and a.form == "skr":
         assert sb.exchange_kind == "peer" and sb._peer_ready, "the peer exchange was not used"
     # every m-mer this rank holds is one it owns
-    assert ((table.mmer_codes % world) == rank).all()
+    assert (B.owner_of(table.mmer_codes, world) == rank).all()
     gathered = [None] * world
     dist.gather_object(table, gathered if rank == 0 else None, dst=0)
     if rank == 0:

@@ -336,7 +336,7 @@ def test_owner_partition_is_stable_and_complete():
     assert b.scan_device(rd, 0, buf, n) == n
     for parts in (1, 2, 3, 8):
         counts = b.partition_device(buf, n, parts, out)
-        owner = tup["mmer"] % parts
+        owner = B.owner_of(tup["mmer"], parts)
         assert counts == [int((owner == p).sum()) for p in range(parts)]
         rec = records_to_numpy(torch, out, n, 1)
         order = np.argsort(owner, kind="stable")

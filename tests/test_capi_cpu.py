@@ -171,3 +171,22 @@ def test_zhash_adapter_and_dumps(name, tmp_path):
             e = e.contents.next
     L.gbin_zhash_release(C.byref(root))
     assert not root.entries
+
+
+def test_owner_function_host_and_numpy_agree_and_balance():
+    """gbin_owner_of (C, host) == binding.owner_of (numpy) == what the partition kernel computes (tests/test_gpu_parity.py
+    checks the kernel against the numpy form); every owner is in range and a uniform code space is spread evenly."""
+    import numpy as np
+    from genome_assembly_b200 import binding as B
+    L = B.load_library()
+    rng = np.random.default_rng(7)
+    codes = np.concatenate([rng.integers(0, 4 ** 15, size=4000, dtype=np.int64), np.arange(0, 64), np.array([4 ** 11 - 1, 4 ** 15 - 1, 2 ** 32 - 1])])
+    for parts in (1, 2, 3, 4, 7, 8, 16, 255):
+        want = B.owner_of(codes, parts)
+        got = np.array([L.gbin_owner_of(int(c), parts) for c in codes])
+        np.testing.assert_array_equal(got, want)
+        assert got.min() >= 0 and got.max() < parts
+    assert L.gbin_owner_of(12345, 0) == 0
+    dense = B.owner_of(np.arange(4 ** 9), 8)
+    share = np.bincount(dense, minlength=8) / dense.size
+    assert abs(share - 0.125).max() < 0.01

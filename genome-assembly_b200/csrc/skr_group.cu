@@ -27,7 +27,7 @@
 
 namespace gbin {
 
-// A unit holds at most CAP k-mer instances (template parameter of the kernel: 2048 or 4096).
+// A unit holds at most CAP k-mer instances (template parameter of the kernel: 1280 by default, 2048 or 4096).
 //   small buckets (<= t = CAP/4 instances) are packed into windows of win = 3*CAP/4 instances of the small-bucket
 //   prefix space, so a packed unit holds less than win + t = CAP instances and is about 75 % full on average;
 //   a bucket with t < c <= CAP is a unit of its own; a larger one is cut into slices of about tsub = CAP/2.
@@ -35,7 +35,7 @@ struct PlanParams {
     uint32_t cap, t, win, tsub;
 };
 constexpr int G_RANK_MAX = 512;  // up to this many survivors per unit are ordered by counting instead of a bitonic sort
-                                 // (their keys, 20 B each for 128-bit codes, plus a u16 rank array must fit the dead hash table: 16 KB at CAP 2048)
+                                 // (their keys, 20 B each for 128-bit codes, plus a u16 rank array must fit the dead hash table: 16 KB at CAP 1280 and 2048)
 
 struct __align__(16) Unit {
     uint32_t skr_begin, skr_end;  // range of sorted super-k-mer records; UNIT_RECORDS: range of expanded instance records
@@ -450,7 +450,8 @@ __global__ void __launch_bounds__(G_THREADS + 32)
     constexpr int ALL = G_THREADS + 32;
     constexpr int G_LOG_HS = G_CAP > 2048 ? 13 : (G_CAP > 1024 ? 12 : 11);
     constexpr int G_HS = 1 << G_LOG_HS;  // hash slots: the power of two in [2 CAP, 4 CAP)
-    static_assert(G_CAP % G_THREADS == 0 && G_CAP >= 1024 && G_CAP <= 4096, "unit capacity");
+    static_assert(G_CAP % G_THREADS == 0 && G_CAP > 1024 && G_CAP <= 4096, "unit capacity");
+    static_assert((size_t)G_RANK_MAX * (8 * KW + 4 + 2) <= (size_t)G_HS * 4, "the survivors' keys and ranks are laid over the dead hash table");
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t *key0 = reinterpret_cast<uint64_t *>(smem);
     uint64_t *key1 = key0 + (KW == 2 ? G_CAP : 0);
@@ -899,12 +900,12 @@ __global__ void empty_table_kernel2(uint64_t *mmer_kmer_off, uint64_t *kmer_id_o
 
 // ------------------------------------------------------------------ host side
 
-static int g_unit_cap() {  // GBIN_V2_CAP=1024|1280|2048|4096 selects the unit capacity (default 1280: four CTAs per SM; 2048: three)
+static int g_unit_cap() {  // GBIN_V2_CAP=1280|2048|4096 selects the unit capacity (default 1280: four CTAs per SM; 2048: three)
     static int cap = 0;
     if (!cap) {
         const char *e = getenv("GBIN_V2_CAP");
         const int v = e ? atoi(e) : 1280;
-        cap = (v == 4096 || v == 2048 || v == 1024) ? v : 1280;
+        cap = (v == 4096 || v == 2048) ? v : 1280;
     }
     return cap;
 }
@@ -1007,9 +1008,6 @@ int skr_group_launch(const void *skr_sorted, int K, int cutoff, const uint32_t *
     } else if (g_unit_cap() == 1280) {
         if (KW == 1) launch(skr_group_kernel<2, 1, 1280, 256>, 256, per_sm < 4 ? per_sm : 4);
         else launch(skr_group_kernel<4, 2, 1280, 256>, 256, per_sm < 4 ? per_sm : 4);
-    } else if (g_unit_cap() == 1024) {
-        if (KW == 1) launch(skr_group_kernel<2, 1, 1024, 256>, 256, per_sm < 4 ? per_sm : 4);
-        else launch(skr_group_kernel<4, 2, 1024, 256>, 256, per_sm < 4 ? per_sm : 4);
     } else {
         if (KW == 1) launch(skr_group_kernel<2, 1, 2048, 256>, 256, per_sm < 3 ? per_sm : 3);
         else launch(skr_group_kernel<4, 2, 2048, 256>, 256, per_sm < 3 ? per_sm : 3);

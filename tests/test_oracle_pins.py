@@ -84,3 +84,37 @@ def test_scan_trace_is_consistent():
             assert win["is_rev"][pos] == int(4 ** M - 1 - s[sig] > s[sig])
             pos += 1
     assert pos == len(tup)
+
+
+def _split_per_line(data: bytes, read_length_define: int):
+    """The per-line form of main's fgets loop that csrc/split_reads.cu evaluates in parallel: a line of l bytes (newline
+    included, or up to the end of the file) makes ceil(l / (R-1)) reads, piece k covering bytes [k(R-1), min((k+1)(R-1), l))
+    of the line minus its last byte."""
+    cap = read_length_define - 1
+    a = np.frombuffer(data, dtype=np.uint8)
+    nl = np.flatnonzero(a == 10)
+    ends = nl + 1
+    if len(a) and (len(nl) == 0 or nl[-1] != len(a) - 1):
+        ends = np.append(ends, len(a))
+    begins = np.concatenate([[0], ends[:-1]]) if len(ends) else np.zeros(0, np.int64)
+    starts, lens = [], []
+    for s0, e0 in zip(begins.tolist(), ends.tolist()):
+        for off in range(0, e0 - s0, cap):
+            starts.append(s0 + off)
+            lens.append(min(cap, e0 - s0 - off) - 1)
+    return np.array(starts, dtype=np.uint64), np.array(lens, dtype=np.uint32)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_per_line_split_equals_sequential_fgets(case):
+    """The decomposition the device-side splitter relies on (independent lines) gives exactly what the sequential replay of
+    fgets gives — on every fixture, for READ_LENGTH around and far from the line length, and on random bytes."""
+    data = O.load_case_bytes(case)[:200_000]
+    rng = np.random.default_rng(len(data))
+    noise = rng.choice(np.frombuffer(b"ACGT\nN", dtype=np.uint8), size=5000, p=[0.24, 0.24, 0.24, 0.24, 0.03, 0.01]).tobytes()
+    for blob in (data, noise, noise + b"ACGT", b"", b"\n", b"A", b"\n\n\nAC"):
+        for R in sorted({case["read_length_define"], 2, 3, 5, 64, 100, 101, 102, 4096}):
+            want_s, want_l = O.fgets_split(blob, R)
+            got_s, got_l = _split_per_line(blob, R)
+            np.testing.assert_array_equal(got_s, want_s)
+            np.testing.assert_array_equal(got_l, want_l)

@@ -67,7 +67,7 @@ EXPORTS = [
     "gbin_set_kernel_profiling", "gbin_get_kernel_profile", "gbin_kernel_kind_name", "gbin_set_pipeline", "gbin_get_pipeline_info", "gbin_get_run_stats",
     "gbin_count_instances_device", "gbin_scan_reads_device", "gbin_partition_records_device",
     "gbin_group_records_device", "gbin_owner_of", "gbin_xchg_create", "gbin_xchg_attach", "gbin_xchg_exchange_skr", "gbin_xchg_destroy", "gbin_skr_record_bytes", "gbin_scan_skr_device", "gbin_partition_skr_device", "gbin_group_skr_device",
-    "gbin_split_reads_device", "gbin_copy_to_host", "gbin_bin_file_host", "gbin_read_file_fgets", "gbin_table_dump", "gbin_table_dump_reference_format",
+    "gbin_split_reads_device", "gbin_copy_to_host", "gbin_bin_file_host", "gbin_read_file_fgets", "gbin_table_dump", "gbin_table_dump_reference_format", "gbin_table_dump_expanded_format",
     "getval", "getbp", "getscore", "process_read", "prune_data", "gbin_ref_configure", "gbin_ref_last_status",
     "gbin_ref_reset", "gbin_table_to_zhash", "gbin_zhash_release",
 ]
@@ -137,6 +137,7 @@ def load_library() -> C.CDLL:
                                        C.POINTER(u64)]
     L.gbin_table_dump.argtypes = [C.POINTER(CTable), C.c_char_p]
     L.gbin_table_dump_reference_format.argtypes = [C.POINTER(CTable), C.c_char_p]
+    L.gbin_table_dump_expanded_format.argtypes = [C.POINTER(CTable), C.c_char_p]
     L.getval.argtypes = [C.c_char]
     L.getval.restype = C.c_int
     L.getbp.argtypes = [C.c_int]

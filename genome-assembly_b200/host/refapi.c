@@ -211,6 +211,33 @@ int gbin_table_dump_reference_format(const gbin_table *t, const char *path)
     return GBIN_OK;
 }
 
+/* What print_kmer_read_ids (binning.c:792-823) prints once expand_read_id_list (binning.c:857-888) has given every base of
+ * every surviving k-mer its own copy of the k-mer's id list: m-mer line; per k-mer a key line and K lines of ids; a blank
+ * line after each bucket.  This is the layout generate_reads.py:14-62 parses. */
+int gbin_table_dump_expanded_format(const gbin_table *t, const char *path)
+{
+    if (!t || t->on_device) return GBIN_E_INVALID_ARG;
+    FILE *f = open_out(path);
+    if (!f) return GBIN_E_IO;
+    char mm[40], km[80];
+    for (uint64_t b = 0; b < t->n_buckets; b++) {
+        decode_code(0, t->mmer_codes[b], t->mmer_size, mm);
+        fprintf(f, "%s\n", mm);
+        for (uint64_t s = t->mmer_kmer_off[b]; s < t->mmer_kmer_off[b + 1]; s++) {
+            kmer_string(t, s, km);
+            fprintf(f, "%s\n", km);
+            for (int base = 0; base < t->kmer_size; base++) {
+                for (uint64_t q = t->kmer_id_off[s]; q < t->kmer_id_off[s + 1]; q++) fprintf(f, "%d ", t->read_ids[q]);
+                fputc('\n', f);
+            }
+        }
+        fputc('\n', f);
+    }
+    if (f != stdout) fclose(f);
+    else fflush(f);
+    return GBIN_OK;
+}
+
 /* ------------------------------------------------------------------ ZHashTable / ll_node adapter */
 
 /* zhash.c:171-182: h = (17*h + ch) % size over the key bytes — needed so that the reference's own

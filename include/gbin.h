@@ -249,6 +249,9 @@ int gbin_table_dump(const gbin_table *host, const char *path);
 /* Writes the table in print_kmer_read_ids's layout *before* expand_read_id_list (binning.c:792-823):
  * m-mer line, then per k-mer a key line and one line of ids, blank line after each bucket. */
 int gbin_table_dump_reference_format(const gbin_table *host, const char *path);
+/* Same after expand_read_id_list (binning.c:857-888): every base of a surviving k-mer carries its own copy of the id list,
+ * so print_kmer_read_ids prints K lines of ids per k-mer — the layout generate_reads.py:14-62 parses. */
+int gbin_table_dump_expanded_format(const gbin_table *host, const char *path);
 
 /* ---- the reference's own entry points (binning.c) ---- */
 struct ZHashTable;

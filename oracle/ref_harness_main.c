@@ -15,6 +15,9 @@
  *   ref_harness <reads-file>            dump to stdout, timings to stderr
  *   ref_harness <reads-file> --time     no dump; prints JSON timing line to stdout
  *   ref_harness <reads-file> --noprune  dump the table before prune_data
+ *   ref_harness <reads-file> --expanded the reference's own expand_read_id_list (binning.c:857-888) followed by its own
+ *                                       print_kmer_read_ids (binning.c:792-823) on the pruned table: the layout
+ *                                       generate_reads.py:14-62 parses (K id lines per k-mer)
  */
 #undef main
 #include <time.h>
@@ -28,7 +31,7 @@ static double hz_now(void)
 
 int main(int argc, char *argv[])
 {
-    int want_dump = 1, want_prune = 1;
+    int want_dump = 1, want_prune = 1, want_expanded = 0;
     if (argc < 2) {
         fprintf(stderr, "usage: %s <reads-file> [--time|--noprune]\n", argv[0]);
         return 2;
@@ -36,6 +39,7 @@ int main(int argc, char *argv[])
     for (int a = 2; a < argc; a++) {
         if (strcmp(argv[a], "--time") == 0) want_dump = 0;
         if (strcmp(argv[a], "--noprune") == 0) want_prune = 0;
+        if (strcmp(argv[a], "--expanded") == 0) want_expanded = 1;
     }
     FILE *file = fopen(argv[1], "r");
     if (!file) { perror(argv[1]); return 2; }
@@ -56,6 +60,11 @@ int main(int argc, char *argv[])
     if (want_prune) prune_data(hash_table);
     double t2 = hz_now();
     fclose(file);
+    if (want_expanded) {
+        expand_read_id_list(hash_table);
+        print_kmer_read_ids(hash_table);
+        return 0;
+    }
 
     long long survivors = 0, buckets = 0;
     struct ZHashEntry *mmer_entry, *kmer_entry;

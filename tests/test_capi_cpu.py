@@ -190,3 +190,45 @@ def test_owner_function_host_and_numpy_agree_and_balance():
     dense = B.owner_of(np.arange(4 ** 9), 8)
     share = np.bincount(dense, minlength=8) / dense.size
     assert abs(share - 0.125).max() < 0.01
+
+
+def _parse_expanded(text: bytes, K: int):
+    """{(mmer, kmer): K id lines} from the print_kmer_read_ids layout after expand_read_id_list."""
+    out = {}
+    for block in text.split(b"\n\n"):
+        lines = block.split(b"\n")
+        if not block.strip():
+            continue
+        mmer, rest = lines[0], lines[1:]
+        assert len(rest) % (K + 1) == 0, (mmer, len(rest))
+        for j in range(0, len(rest), K + 1):
+            key = (mmer, rest[j])
+            assert key not in out
+            out[key] = tuple(rest[j + 1: j + 1 + K])
+    return out
+
+
+@pytest.mark.parametrize("name", ["cfg1_reads", "cfg2_small"])
+def test_expanded_dump_equals_the_references_own_expand_and_print(name, tmp_path):
+    """gbin_table_dump_expanded_format against the UNMODIFIED reference running its own expand_read_id_list (binning.c:857-888)
+    and print_kmer_read_ids (binning.c:792-823) on its own pruned table (oracle/_ref harness, --expanded): same buckets, same
+    k-mers, the same K id lines per k-mer (the reference prints in hash-iteration order, so blocks are compared as sets)."""
+    import os
+    import subprocess
+    case = next(c for c in CASES if c["name"] == name)
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref",
+                       f"ref_K{case['k']}_M{case['m']}_C{case['cutoff']}_R{case['read_length_define']}")
+    if not os.path.exists(exe):
+        pytest.skip("reference harness not built")
+    data = O.load_case_bytes(case)
+    src = tmp_path / "reads.txt"
+    src.write_bytes(data)
+    ref = subprocess.run([exe, str(src), "--expanded"], capture_output=True, check=True).stdout
+    starts, lens = O.fgets_split(data, case["read_length_define"])
+    t = O.run(data, starts, lens, case["k"], case["m"], case["cutoff"])
+    ct, keep = c_table_from_oracle(t)
+    p = tmp_path / "expanded.txt"
+    assert B.load_library().gbin_table_dump_expanded_format(C.byref(ct), str(p).encode()) == 0
+    want, got = _parse_expanded(ref, case["k"]), _parse_expanded(p.read_bytes(), case["k"])
+    assert len(want) == case["surviving_kmers"]
+    assert got == want

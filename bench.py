@@ -78,15 +78,16 @@ def make_reads(w, rank, world):
 
 # ------------------------------------------------------------------------------------------ CPU reference leg
 
-def ref_binary(w):
-    name = f"ref_K{w['k']}_M{w['m']}_C{w['cutoff']}_R{w['read_len'] + 2}"
+def ref_binary(w, makefile_flags=False):
+    """-O2 build of the unmodified reference by default; makefile_flags: the build the reference's makefile makes (-g, no optimisation)."""
+    name = f"ref_K{w['k']}_M{w['m']}_C{w['cutoff']}_R{w['read_len'] + 2}" + ("_O0" if makefile_flags else "")
     return os.path.join(ROOT, "oracle", "_ref", name)
 
 
-def time_reference(w, rs, n_sample_reads):
+def time_reference(w, rs, n_sample_reads, makefile_flags=False):
     """Times the reference's own process_read loop + prune_data (binning.c:1158-1169) on the first
     n_sample_reads reads of the shard; returns (k-mers/s, dict)."""
-    exe = ref_binary(w)
+    exe = ref_binary(w, makefile_flags)
     n = min(n_sample_reads, rs.n_reads)
     inst = n * (rs.read_len - w["k"] + 1)
     with tempfile.NamedTemporaryFile(suffix=".txt", delete=False) as tf:
@@ -453,7 +454,14 @@ def main():
         try:
             v, info = time_reference(w, rs, 200_000)
             cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"],
-                   "seconds": info["seconds"], "host_cores_available": os.cpu_count()}
+                   "seconds": info["seconds"], "host_cores_available": os.cpu_count(), "build": "-O2"}
+            if os.path.exists(ref_binary(w, makefile_flags=True)):  # also with the reference makefile's own flags (-g)
+                try:
+                    v0, info0 = time_reference(w, rs, 50_000, makefile_flags=True)
+                    cpu["value_makefile_flags"] = v0
+                    cpu["makefile_flags_sample"] = f"first 50000 reads, built with -g as in the reference's makefile ({info0['seconds']:.1f} s)"
+                except Exception as e:  # noqa: BLE001
+                    cpu["makefile_flags_sample"] = f"unavailable: {type(e).__name__}: {e}"
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": f"{type(e).__name__}: {e}"}
 

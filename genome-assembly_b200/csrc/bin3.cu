@@ -1,0 +1,1078 @@
+// bin3.cu — pipeline v3: level 1 by reference, level 2 by one warp per unit.
+//
+// Input: the super-k-mer records of the scan stage, in arrival order (skr.cuh).  Stages:
+//   1. make_entries_kernel: one 8-byte entry {key << 32 | slot} per piece of a record (bin3.cuh) and the piece's
+//      window count (one byte per slot).  The records themselves never move again.
+//   2. radix_sort_entries (radix_sort.cu): stable LSD sort of the entries on the key = level 1 of the reference's
+//      two-level store (binning.c:1044-1049); inside a key entries stay in arrival order.
+//   3. planning (no atomics, no host round trip inside): instance prefix + atoms (runs of equal key) in one scan;
+//      units = packs of whole small atoms, single atoms, or the d-rounds of an atom larger than a unit.
+//   4. group3_kernel: every WARP owns one unit at a time — no CTA barrier anywhere.  The warp expands the windows of
+//      its pieces (rolling 2-bit shift, complement when is_rev — binning.c:1029-1040) into shared memory, groups
+//      equal (bucket, k-mer) keys with a hash whose slots hold instance indices (level-2 insert + ll_node push,
+//      binning.c:1052-1069), counts, prunes (count > ABUNDANCE_CUTOFF, binning.c:1094-1102), orders the survivors of
+//      every bucket by k-mer, orders every id list newest-first, obtains its place in the table from a two-level chained
+//      scan over units (aggregates are published right after the count, long before they are needed) and writes its part
+//      of the flat table ONCE, at its final place.
+//   5. span_reorder_kernel: atoms that were split into d-rounds come out round by round; their (few) surviving k-mers
+//      are sorted and their id lists moved from the staging arrays to the final place.
+//   6. skr_emit_buckets (skr_group.cu): bucket directory; buckets that lost all k-mers vanish (binning.c:1136-1142).
+#include "bin3.cuh"
+#include "gbin_device.cuh"
+#include "gbin_internal.h"
+#include "prefix_scan.cuh"
+
+namespace gbin {
+
+// ------------------------------------------------------------------ entries
+
+// h oriented bases starting at base j of the payload (2 bits per base, MSB first, 16 bases per u32 word).
+__device__ __forceinline__ uint32_t payload_bases(const uint32_t *pl, uint32_t nwords, uint32_t j, uint32_t h, bool rev) {
+    const uint32_t bit = 2 * j, wi = bit >> 5, sh = bit & 31;
+    const uint32_t a = wi < nwords ? pl[wi] : 0u, b = wi + 1 < nwords ? pl[wi + 1] : 0u;
+    uint32_t x = __funnelshift_l(b, a, sh);  // 16 bases starting at j
+    if (rev) x = ~x;
+    return h ? (x >> (32 - 2 * h)) : 0u;
+}
+
+template <int PW>
+__global__ void __launch_bounds__(256)
+    make_entries_kernel(const uint32_t *__restrict__ skr, uint64_t n_rec, KeyLayout kl, uint64_t *__restrict__ ent, uint8_t *__restrict__ piece_n,
+                        unsigned long long *__restrict__ n_real) {
+    constexpr int NW = SkrLayout<PW>::WORDS;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t real = 0;
+    if (i < n_rec) {
+        const uint4 h = *reinterpret_cast<const uint4 *>(skr + i * NW);
+        const uint32_t mmer = h.y, meta = h.z;
+        if (kl.nc == 1) {
+            ent[i] = ((uint64_t)mmer << 32) | (uint32_t)i;
+            piece_n[i] = (uint8_t)(meta & 0xffu);
+            real = 1;
+        } else {
+            const bool rev = (meta >> 8) & 1u;
+            const uint32_t so = (meta >> 16) & 0xffu;
+            const uint32_t *pl = skr + i * NW + 4;
+#pragma unroll
+            for (uint32_t c = 0; c < 2; c++) {
+                uint32_t t0, np;
+                piece_of(meta, c, kl, &t0, &np);
+                const uint32_t slot = (uint32_t)(2 * i + c);
+                uint32_t key = 0xffffffffu;
+                if (np) {
+                    const uint32_t fl = kl.h ? payload_bases(pl, 2 * PW, c == 0 ? so - kl.h : so + kl.M, kl.h, rev) : 0u;
+                    key = (mmer << kl.mshift) | (c << (2 * kl.h)) | fl;
+                    real++;
+                }
+                ent[slot] = ((uint64_t)key << 32) | slot;
+                piece_n[slot] = (uint8_t)np;
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) real += __shfl_xor_sync(0xffffffffu, real, d);
+    if ((threadIdx.x & 31) == 0 && real) atomicAdd(n_real, (unsigned long long)real);
+}
+
+int v3_make_entries(const void *skr, uint64_t n_rec, const KeyLayout &kl, uint64_t *ent, uint8_t *piece_n, unsigned long long *n_real_dev,
+                    cudaStream_t st) {
+    cudaMemsetAsync(n_real_dev, 0, sizeof(unsigned long long), st);
+    if (n_rec == 0) return 0;
+    const unsigned grid = (unsigned)((n_rec + 255) / 256);
+    if (kl.K <= 32) make_entries_kernel<2><<<grid, 256, 0, st>>>(static_cast<const uint32_t *>(skr), n_rec, kl, ent, piece_n, n_real_dev);
+    else make_entries_kernel<4><<<grid, 256, 0, st>>>(static_cast<const uint32_t *>(skr), n_rec, kl, ent, piece_n, n_real_dev);
+    return 1;
+}
+
+// ------------------------------------------------------------------ planning
+
+struct EntCountAndHead {  // low half: windows of sorted entry i; high half: 1 if it starts a new atom (run of equal key)
+    const uint64_t *ent;
+    const uint8_t *piece_n;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const {
+        const uint64_t e = ent[i];
+        const uint64_t head = (i == 0 || (e >> 32) != (ent[i - 1] >> 32)) ? 1ull : 0ull;
+        return (uint64_t)piece_n[(uint32_t)e] | (head << 32);
+    }
+};
+
+__global__ void v3_run_starts_kernel(const uint64_t *__restrict__ ent, uint64_t n, const uint64_t *__restrict__ both, const uint64_t *__restrict__ total,
+                                     uint32_t *__restrict__ inst_prefix, uint32_t *__restrict__ run_start, uint32_t *__restrict__ n_inst_out,
+                                     uint32_t *__restrict__ n_runs_out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t b = both[i];
+    inst_prefix[i] = (uint32_t)b;
+    if (i == 0 || (ent[i] >> 32) != (ent[i - 1] >> 32)) run_start[b >> 32] = (uint32_t)i;
+    if (i == n - 1) {
+        const uint64_t t = *total;
+        inst_prefix[n] = (uint32_t)t;
+        run_start[t >> 32] = (uint32_t)n;
+        *n_inst_out = (uint32_t)t;
+        *n_runs_out = (uint32_t)(t >> 32);
+    }
+}
+
+int v3_plan_runs(const uint64_t *ent, const uint8_t *piece_n, uint64_t n_ent, uint32_t *inst_prefix, uint64_t *both64, uint32_t *run_start,
+                 uint64_t *scratch64, uint32_t *n_inst_dev, uint32_t *n_runs_dev, cudaStream_t st) {
+    if (n_ent == 0) {
+        cudaMemsetAsync(n_inst_dev, 0, 4, st);
+        cudaMemsetAsync(n_runs_dev, 0, 4, st);
+        return 0;
+    }
+    int l = exclusive_scan<uint64_t, EntCountAndHead>(EntCountAndHead{ent, piece_n}, both64, n_ent, scratch64, both64 + n_ent, st);
+    v3_run_starts_kernel<<<(unsigned)((n_ent + 255) / 256), 256, 0, st>>>(ent, n_ent, both64, both64 + n_ent, inst_prefix, run_start, n_inst_dev,
+                                                                         n_runs_dev);
+    return l + 1;
+}
+
+// Packing: a unit is a run of consecutive atoms (so that unit order is key order) with at most `cap` instances, NB atoms
+// and EC entries — chosen greedily: an atom joins the current unit if it still fits, else it opens the next one.  Greedy
+// packing is a sequential recurrence; it is made parallel by restarting it at every block of PLAN_BLOCK atoms (one extra
+// partial unit per block, under 2 % of the units).  An atom with more than `cap` instances gets 2 * ceil(c / cap) + 1
+// round units (enough for a greedy cut of its d-histogram whenever no single d holds more than cap instances).
+constexpr int PLAN_BLOCK = 256;   // atoms walked by one thread
+constexpr int PLAN_CTA_BLOCKS = 32;
+struct Plan3 {
+    uint32_t cap, nb_max, ecap, max_rounds;
+};
+struct RunView3 {
+    const uint32_t *run_start;    // [NR+1]
+    const uint32_t *inst_prefix;  // [E+1]
+    __device__ __forceinline__ uint32_t size(uint64_t r) const { return inst_prefix[run_start[r + 1]] - inst_prefix[run_start[r]]; }
+};
+__host__ __device__ inline uint32_t rounds_of(uint32_t c, const Plan3 &pp) {
+    uint32_t r = 2 * ((c + pp.cap - 1) / pp.cap) + 1;
+    return r < pp.max_rounds ? r : pp.max_rounds;
+}
+
+// nunits[r] = units that start at atom r (low half) | 1 << 32 if the atom is split into rounds
+__global__ void __launch_bounds__(256)
+    v3_pack_kernel(RunView3 rv, uint64_t n_runs, Plan3 pp, uint64_t *__restrict__ nunits) {
+    __shared__ uint32_t s_c[PLAN_CTA_BLOCKS * PLAN_BLOCK];
+    __shared__ uint16_t s_e[PLAN_CTA_BLOCKS * PLAN_BLOCK];
+    const uint64_t first = (uint64_t)blockIdx.x * (PLAN_CTA_BLOCKS * PLAN_BLOCK);
+    for (uint32_t i = threadIdx.x; i < (uint32_t)(PLAN_CTA_BLOCKS * PLAN_BLOCK); i += blockDim.x) {
+        const uint64_t r = first + i;
+        uint32_t c = 0, e = 0;
+        if (r < n_runs) {
+            const uint32_t a = rv.run_start[r], b = rv.run_start[r + 1];
+            c = rv.inst_prefix[b] - rv.inst_prefix[a];
+            e = b - a;
+        }
+        s_c[i] = c;
+        s_e[i] = (uint16_t)(e > 0xffffu ? 0xffffu : e);
+    }
+    __syncthreads();
+    if (threadIdx.x >= (uint32_t)PLAN_CTA_BLOCKS) return;
+    // thread t walks block t; consecutive threads touch the same offset of consecutive blocks (stride PLAN_BLOCK + skew)
+    const uint32_t b0 = threadIdx.x * PLAN_BLOCK;
+    uint32_t cur_c = 0, cur_e = 0, cur_a = 0;
+    for (uint32_t i = 0; i < (uint32_t)PLAN_BLOCK; i++) {
+        const uint64_t r = first + b0 + i;
+        if (r >= n_runs) break;
+        const uint32_t c = s_c[b0 + i], e = s_e[b0 + i];
+        uint64_t out;
+        if (c > pp.cap) {
+            out = (uint64_t)rounds_of(c, pp) | (1ull << 32);
+            cur_a = 0;  // the next atom opens a unit
+        } else if (cur_a == 0 || cur_c + c > pp.cap || cur_e + e > pp.ecap || cur_a + 1 > pp.nb_max) {
+            out = 1ull;
+            cur_c = c;
+            cur_e = e;
+            cur_a = 1;
+        } else {
+            out = 0ull;
+            cur_c += c;
+            cur_e += e;
+            cur_a++;
+        }
+        nunits[r] = out;
+    }
+}
+
+struct G3Counters {
+    unsigned long long distinct;
+    unsigned long long total_kmers, total_ids;
+    unsigned int overflow;
+    unsigned int n_units, n_spans;
+    unsigned int pad;
+};
+
+__global__ void v3_head_runs_kernel(const uint64_t *__restrict__ nunits, const uint64_t *__restrict__ base, uint64_t n_runs, uint32_t *__restrict__ head_run) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_runs) return;
+    const uint32_t nu = (uint32_t)nunits[r];
+    const uint32_t ub = (uint32_t)base[r];
+    for (uint32_t j = 0; j < nu; j++) head_run[ub + j] = (uint32_t)r;
+}
+
+__global__ void v3_fill_units_kernel(RunView3 rv, const uint64_t *__restrict__ base, const uint64_t *__restrict__ totals, uint64_t n_runs, Plan3 pp,
+                                     const uint32_t *__restrict__ head_run, Unit3 *__restrict__ units, G3Counters *__restrict__ gc) {
+    const uint32_t n_units = (uint32_t)*totals;
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u == 0) {
+        gc->n_units = n_units;
+        gc->n_spans = (uint32_t)(*totals >> 32);
+    }
+    if (u >= n_units) return;
+    const uint32_t r0 = head_run[u];
+    const uint32_t c = rv.size(r0);
+    Unit3 un;
+    un.pad = 0;
+    un.ent_begin = rv.run_start[r0];
+    un.ibase = rv.inst_prefix[un.ent_begin];
+    if (c > pp.cap) {
+        un.ent_end = rv.run_start[r0 + 1];
+        un.n_inst = c;
+        un.round = u - (uint32_t)base[r0];
+        un.rounds = rounds_of(c, pp);
+        un.span = (uint32_t)(base[r0] >> 32);
+    } else {
+        const uint32_t r1 = (u + 1 < n_units) ? head_run[u + 1] : (uint32_t)n_runs;
+        un.ent_end = rv.run_start[r1];
+        un.n_inst = rv.inst_prefix[un.ent_end] - un.ibase;
+        un.round = 0;
+        un.rounds = 0;
+        un.span = 0;
+    }
+    units[u] = un;
+}
+
+// One warp per split atom: d-histogram of the atom (difference array over its pieces, then prefix), greedy cut into rounds of
+// consecutive d whose instances fit a unit.  Fills the atom's round units: d-range, instance coordinate, instances (0 = unused).
+__global__ void __launch_bounds__(128)
+    v3_round_cuts_kernel(const uint32_t *__restrict__ skr, int skr_words, const uint64_t *__restrict__ ent, KeyLayout kl, Unit3 *__restrict__ units,
+                         G3Counters *__restrict__ gc, uint32_t cap) {
+    __shared__ int s_hist[4][68];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int *dhist = s_hist[warp];
+    const uint32_t n_units = gc->n_units;
+    const uint32_t cls_mask = (uint32_t)(kl.nc - 1);
+    for (uint32_t u = blockIdx.x * 4 + warp; u < n_units; u += gridDim.x * 4) {
+        const Unit3 un = units[u];
+        if (un.rounds == 0 || un.round != 0) continue;
+        dhist[lane] = 0;
+        dhist[lane + 32] = 0;
+        if (lane < 4) dhist[64 + lane] = 0;
+        __syncwarp();
+        const uint32_t n_ent = un.ent_end - un.ent_begin;
+        for (uint32_t e = lane; e < n_ent; e += 32) {
+            const uint32_t slot = (uint32_t)ent[un.ent_begin + e];
+            const uint32_t meta = skr[(uint64_t)(slot >> kl.cshift) * skr_words + 2];
+            uint32_t t0, np;
+            piece_of(meta, slot & cls_mask, kl, &t0, &np);
+            if (np) {
+                const int so = (int)((meta >> 16) & 0xffu);
+                atomicAdd(&dhist[so - (int)(t0 + np - 1)], 1);  // smallest d of the piece
+                atomicAdd(&dhist[so - (int)t0 + 1], -1);        // one past its largest d
+            }
+        }
+        __syncwarp();
+        const int a = dhist[2 * lane], b = dhist[2 * lane + 1];
+        int incl = a + b;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += o;
+        }
+        __syncwarp();
+        dhist[2 * lane] = incl - b;  // instances with d = 2 * lane
+        dhist[2 * lane + 1] = incl;  // instances with d = 2 * lane + 1
+        __syncwarp();
+        if (lane == 0) {
+            uint32_t rnd = 0, acc = 0, before = 0;
+            int lo = 0;
+            bool bad = false;
+            auto emit = [&](int hi) {
+                if (rnd < un.rounds) {
+                    Unit3 &w = units[u + rnd];
+                    w.span = (uint32_t)lo | ((uint32_t)hi << 8);
+                    w.ibase = un.ibase + before;
+                    w.n_inst = acc;
+                } else {
+                    bad = true;
+                }
+            };
+            for (int d = 0; d < 64; d++) {
+                const uint32_t c = (uint32_t)dhist[d];
+                if (c > cap) bad = true;
+                if (acc + c > cap) {
+                    emit(d - 1);
+                    rnd++;
+                    lo = d;
+                    before += acc;
+                    acc = 0;
+                }
+                acc += c;
+            }
+            emit(63);
+            for (uint32_t j = rnd + 1; j < un.rounds; j++) {  // unused rounds
+                units[u + j].n_inst = 0;
+                units[u + j].ibase = un.ibase + un.n_inst;
+            }
+            if (bad) atomicExch(&gc->overflow, 1u);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ the grouping kernel
+
+struct UnitOut3 {  // what a unit reports: its place in the staging arrays and its totals
+    uint32_t ibase;  // instance coordinate of the unit's first instance = where its ids are staged; its k-mers are staged at ibase / kdiv
+    uint32_t S, N;   // surviving k-mers, ids
+    uint32_t pad;
+};
+
+// Units never wait for each other: a unit writes its part of the table into staging arrays at a place that depends on the
+// unit alone (ids at its instance coordinate, k-mers at that coordinate divided by cutoff + 1 — disjoint because a surviving
+// k-mer has more than `cutoff` instances), and reports its totals.  One scan over the totals and finalize3_kernel then put
+// everything at its final place.
+struct G3Stage {
+    uint64_t *codes;  // [kmer_cap * KW]
+    uint32_t *mmer;   // [kmer_cap]
+    uint32_t *loff;   // [kmer_cap] start of the k-mer's id list inside its unit
+    int32_t *ids;     // [id_cap]
+    UnitOut3 *unit_out;
+    uint64_t kmer_cap, id_cap;
+    uint32_t kdiv;
+};
+
+template <int PW>
+struct Payload {
+    uint64_t w[PW];
+    __device__ __forceinline__ void set(const uint4 &a, const uint4 &b) {
+        w[0] = ((uint64_t)a.x << 32) | a.y;
+        w[1] = ((uint64_t)a.z << 32) | a.w;
+        if (PW == 4) {
+            w[PW - 2] = ((uint64_t)b.x << 32) | b.y;
+            w[PW - 1] = ((uint64_t)b.z << 32) | b.w;
+        }
+    }
+    __device__ __forceinline__ void advance(uint32_t bases) {  // 0 < 2 * bases < 64
+        const uint32_t sh = 2 * bases;
+#pragma unroll
+        for (int q = 0; q < PW - 1; q++) w[q] = (w[q] << sh) | (w[q + 1] >> (64 - sh));
+        w[PW - 1] <<= sh;
+    }
+    __device__ __forceinline__ void skip(uint32_t bases) {  // any number of bases
+        while (bases >= 31) {
+            advance(31);
+            bases -= 31;
+        }
+        if (bases) advance(bases);
+    }
+};
+
+// Oriented k-mer code of the window at the front of the payload (top 2K bits), complemented when rev (binning.c:1029-1040).
+template <int PW, int KW>
+__device__ __forceinline__ void front_kmer(const Payload<PW> &pl, int K, bool rev, uint64_t kmask0, uint64_t *k0, uint64_t *k1) {
+    if (KW == 1) {
+        uint64_t a = (2 * K == 64) ? pl.w[0] : (pl.w[0] >> (64 - 2 * K));
+        if (rev) a = ~a & kmask0;
+        *k0 = a;
+        *k1 = 0;
+    } else {
+        const int r = 128 - 2 * K;  // 0..62
+        uint64_t a = r ? (pl.w[0] >> r) : pl.w[0];
+        uint64_t b = r ? ((pl.w[1] >> r) | (pl.w[0] << (64 - r))) : pl.w[1];
+        if (rev) {
+            a = ~a & kmask0;
+            b = ~b;
+        }
+        *k0 = a;
+        *k1 = b;
+    }
+}
+
+template <int WCAP, int KW>
+struct WarpLayout {  // per-warp shared memory; every region is a multiple of 16 bytes
+    static constexpr int NB_MAX = WCAP / 8;  // buckets of a packed unit
+    static constexpr int ECAP = WCAP / 4;    // entries of a packed unit (an atom with more entries is a unit of its own)
+    static constexpr int BSTART_BYTES = ((NB_MAX + 1) * 2 + 15) / 16 * 16;
+    static constexpr int BYTES = KW * WCAP * 8 /*keys*/ + WCAP * 4 /*table*/ + WCAP * 2 /*cnt*/ + WCAP * 2 /*grp*/ + WCAP * 2 /*rk*/ + WCAP /*eix*/ + BSTART_BYTES +
+                                 NB_MAX * 4 /*bmm*/ + ECAP * 4 /*eid*/ + ECAP /*ebk*/;
+};
+
+__device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, uint32_t lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (uint32_t)d) v += o;
+    }
+    return v;
+}
+
+constexpr int G3_WARPS = 5;  // warps (= units in flight) per CTA
+constexpr int G3_U = 4;  // instances per lane that are in flight together in the instance-major phases
+
+template <int PW, int KW, int WCAP, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+    group3_kernel(const uint32_t *__restrict__ skr, const uint64_t *__restrict__ ent, const Unit3 *__restrict__ units, KeyLayout kl, int cutoff,
+                  const int32_t *__restrict__ ids_by_arrival, int32_t id_base, G3Stage out, G3Counters *__restrict__ gc,
+                  const uint32_t *__restrict__ chunk_bounds, uint32_t chunk, uint32_t *__restrict__ chunk_tickets) {
+    constexpr int NW = SkrLayout<PW>::WORDS;
+    constexpr int HS = 2 * WCAP;  // hash slots (u16 each)
+    constexpr int LOG_HS = WCAP == 512 ? 10 : 11;
+    constexpr int U = G3_U;
+    static_assert(WCAP == 512 || WCAP == 1024, "unit capacity");
+    static_assert((1 << LOG_HS) == HS, "hash size");
+    using WL = WarpLayout<WCAP, KW>;
+    constexpr int NB_MAX = WL::NB_MAX, ECAP = WL::ECAP;
+    extern __shared__ __align__(16) uint8_t smem3[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *wb = smem3 + (size_t)warp * WL::BYTES;
+    uint64_t *key0 = reinterpret_cast<uint64_t *>(wb);
+    uint64_t *key1 = key0 + (KW == 2 ? WCAP : 0);
+    uint16_t *tbl16 = reinterpret_cast<uint16_t *>(key0 + KW * WCAP);  // [2 * WCAP] hash slots: instance index + 1 of the group's leader
+    uint32_t *cnt32 = reinterpret_cast<uint32_t *>(tbl16 + 2 * WCAP);  // [WCAP / 2] words = [WCAP] u16: instances per group, later the END of its id list
+    uint16_t *cnt16 = reinterpret_cast<uint16_t *>(cnt32);
+    uint16_t *grp = cnt16 + WCAP;                                      // [WCAP] leader (first inserted instance) of every instance's group
+    uint16_t *rk = grp + WCAP;                                         // [WCAP] rank of the instance inside its group, in position order
+    uint8_t *eix = reinterpret_cast<uint8_t *>(rk + WCAP);             // [WCAP] entry of the instance (packed units)
+    uint16_t *bstart = reinterpret_cast<uint16_t *>(eix + WCAP);       // [NB_MAX + 1] first instance of every bucket of the unit
+    uint32_t *bmm = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(bstart) + WL::BSTART_BYTES);  // [NB_MAX] its m-mer code
+    int32_t *eid = reinterpret_cast<int32_t *>(bmm + NB_MAX);          // [ECAP] read id of every entry
+    uint8_t *ebk = reinterpret_cast<uint8_t *>(eid + ECAP);            // [ECAP] bucket ordinal of every entry
+    // after the grouping the hash table is dead: its memory holds the survivor lists, then the unit's ids
+    uint16_t *surv = tbl16;                               // [WCAP] instance index of every surviving leader, ascending
+    uint16_t *sorted = surv + WCAP;                       // [WCAP] the same in table order
+    int32_t *idbuf = reinterpret_cast<int32_t *>(tbl16);  // [WCAP] the unit's ids in output order
+
+    const int K = kl.K;
+    const uint64_t kmask0 = (2 * K >= 64 * KW) ? ~0ull : ((1ull << (2 * K - 64 * (KW - 1))) - 1);
+    const uint32_t unit_begin = chunk_bounds[chunk], unit_end = chunk_bounds[chunk + 1];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t cls_mask = (uint32_t)(kl.nc - 1);
+
+    uint32_t u = 0;
+    if (lane == 0) u = unit_begin + atomicAdd(&chunk_tickets[chunk], 1u);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    while (u < unit_end) {
+        Unit3 un;
+        {
+            const uint32_t wv = lane < 8 ? reinterpret_cast<const uint32_t *>(units + u)[lane] : 0u;
+            un.ent_begin = __shfl_sync(0xffffffffu, wv, 0);
+            un.ent_end = __shfl_sync(0xffffffffu, wv, 1);
+            un.n_inst = __shfl_sync(0xffffffffu, wv, 2);
+            un.round = __shfl_sync(0xffffffffu, wv, 3);
+            un.rounds = __shfl_sync(0xffffffffu, wv, 4);
+            un.span = __shfl_sync(0xffffffffu, wv, 5);
+            un.ibase = __shfl_sync(0xffffffffu, wv, 6);
+        }
+        // the next ticket is taken now and read at the end of the unit (units do not depend on each other)
+        uint32_t u_next = 0;
+        if (lane == 0) u_next = unit_begin + atomicAdd(&chunk_tickets[chunk], 1u);
+        const uint32_t u_cur = u;
+        const bool is_round = un.rounds != 0;
+        const uint32_t n_ent = un.ent_end - un.ent_begin;
+        // packed: the unit's entries fit the per-entry tables and every instance remembers its entry; otherwise (a round of a split
+        // atom, or one atom of very many entries) the unit is ONE bucket and the id pass walks the entries again
+        const bool packed = !is_round && n_ent <= (uint32_t)ECAP;
+        if (is_round && un.n_inst == 0) {  // a round the cut did not need
+            if (lane == 0) out.unit_out[u_cur] = UnitOut3{un.ibase, 0u, 0u, 0u};
+            u = __shfl_sync(0xffffffffu, u_next, 0);
+            continue;
+        }
+
+        // ---- zero the hash table and the counters (contiguous)
+        {
+            uint4 *z = reinterpret_cast<uint4 *>(tbl16);
+            for (uint32_t i = lane; i < (uint32_t)(WCAP * 4 + WCAP * 2) / 16; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncwarp();
+
+        // ---- round units: the planner cut the atom's instances by ranges of d; mine is [dlo, dhi]
+        int dlo = 0, dhi = 63;
+        const uint32_t ibase = un.ibase;
+        bool bad = false;
+        if (is_round) {
+            dlo = (int)(un.span & 0xffu);
+            dhi = (int)((un.span >> 8) & 0xffu);
+        }
+
+        // ---- expansion: lane = entry.  Instance positions follow entry order (= key order, arrival order inside a key).
+        uint32_t n_inst = 0, n_bkt = 0;
+        if (!bad) {
+            uint32_t carry_pos = 0, carry_ord = 0, prev_mm = 0xffffffffu;
+            for (uint32_t e0 = 0; e0 < n_ent; e0 += 32) {
+                const uint32_t e = e0 + lane;
+                uint32_t np = 0, t0 = 0, mm = 0xffffffffu, arrival = 0;
+                bool rev = false;
+                uint4 ha = make_uint4(0u, 0u, 0u, 0u), pa = ha, pb = ha;
+                if (e < n_ent) {
+                    const uint64_t en = ent[un.ent_begin + e];
+                    const uint32_t slot = (uint32_t)en;
+                    mm = (uint32_t)(en >> 32) >> kl.mshift;
+                    const uint4 *rp = reinterpret_cast<const uint4 *>(skr + (uint64_t)(slot >> kl.cshift) * NW);
+                    ha = rp[0];  // the whole record at once: header and payload
+                    pa = rp[1];
+                    if (PW == 4) pb = rp[2];
+                    arrival = ha.x;
+                    const uint32_t meta = ha.z;
+                    rev = (meta >> 8) & 1u;
+                    piece_of(meta, slot & cls_mask, kl, &t0, &np);
+                    if (is_round && np) {  // windows with dlo <= so - t <= dhi
+                        const int so = (int)((meta >> 16) & 0xffu);
+                        int a = so - dhi, b = so - dlo;  // t in [a, b]
+                        if (a < (int)t0) a = (int)t0;
+                        if (b > (int)(t0 + np - 1)) b = (int)(t0 + np - 1);
+                        if (dlo > dhi || b < a) np = 0;
+                        else {
+                            t0 = (uint32_t)a;
+                            np = (uint32_t)(b - a + 1);
+                        }
+                    }
+                }
+                // buckets (runs of equal m-mer code) of the unit and instance positions
+                uint32_t pm = __shfl_up_sync(0xffffffffu, mm, 1);
+                if (lane == 0) pm = prev_mm;
+                const bool head = e < n_ent && mm != pm;
+                const uint32_t hs = warp_incl_scan_u32(head ? 1u : 0u, lane);
+                const uint32_t ps = warp_incl_scan_u32(np, lane);
+                const uint32_t ord = carry_ord + hs - 1;  // bucket ordinal of this entry
+                const uint32_t pos0 = carry_pos + ps - np;
+                if (head && ord < (uint32_t)NB_MAX) {
+                    bstart[ord] = (uint16_t)pos0;
+                    bmm[ord] = mm;
+                }
+                carry_ord += __shfl_sync(0xffffffffu, hs, 31);
+                carry_pos += __shfl_sync(0xffffffffu, ps, 31);
+                prev_mm = __shfl_sync(0xffffffffu, mm, 31);
+                if (carry_pos > (uint32_t)WCAP || carry_ord > (uint32_t)NB_MAX || (!packed && carry_ord > 1u)) {  // cannot happen with the planner's bounds
+                    bad = true;
+                    break;
+                }
+                if (packed && e < n_ent) {
+                    eid[e] = ids_by_arrival ? ids_by_arrival[arrival] : id_base + (int32_t)arrival;
+                    ebk[e] = (uint8_t)ord;
+                }
+                if (np) {
+                    Payload<PW> pl;
+                    pl.set(pa, pb);
+                    pl.skip(t0);
+                    for (uint32_t i = 0; i < np; i++) {
+                        uint64_t k0, k1;
+                        front_kmer<PW, KW>(pl, K, rev, kmask0, &k0, &k1);
+                        key0[pos0 + i] = k0;
+                        if (KW == 2) key1[pos0 + i] = k1;
+                        if (packed) eix[pos0 + i] = (uint8_t)e;
+                        pl.advance(1);
+                    }
+                }
+            }
+            n_inst = carry_pos;
+            n_bkt = carry_ord;
+            if (!bad && lane == 0) bstart[n_bkt] = (uint16_t)n_inst;
+        }
+        __syncwarp();
+        if (bad) {  // give up on this unit: the batch is redone by another pipeline
+            if (lane == 0) {
+                atomicExch(&gc->overflow, 1u);
+                out.unit_out[u_cur] = UnitOut3{ibase, 0u, 0u, 0u};
+            }
+            u = __shfl_sync(0xffffffffu, u_next, 0);
+            continue;
+        }
+
+        // ---- group: claim a slot with the instance index, compare keys through the instance arrays.  U instances per lane are in
+        // flight together.  The rank of an instance inside its group follows position order: 32 positions per step, the peers of a
+        // step are ranked by lane, the steps by the order in which their counter updates are issued.
+        for (uint32_t b0 = 0; b0 < n_inst; b0 += 32 * U) {
+            uint64_t k0[U], k1[U];
+            uint32_t lo[U], hi[U], idx[U], rep[U], cur[U];
+            bool valid[U];
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                const uint32_t p = b0 + j * 32 + lane;
+                valid[j] = p < n_inst;
+                k0[j] = valid[j] ? key0[p] : 0ull;
+                k1[j] = (KW == 2 && valid[j]) ? key1[p] : 0ull;
+                uint32_t o = 0;
+                if (packed && valid[j]) o = ebk[eix[p]];
+                lo[j] = bstart[o];  // instances of the same bucket: positions [lo, hi)
+                hi[j] = bstart[o + 1];
+                uint32_t hx = ((uint32_t)k0[j] * 0x9E3779B1u) ^ ((uint32_t)(k0[j] >> 32) * 0x85EBCA77u) ^ (o * 0xC2B2AE3Du);
+                if (KW == 2) hx ^= ((uint32_t)k1[j] * 0x27D4EB2Fu) ^ ((uint32_t)(k1[j] >> 32) * 0x165667B1u);
+                hx *= 0x9E3779B1u;
+                idx[j] = hx >> (32 - LOG_HS);
+                rep[j] = 0xffffffffu;
+            }
+#pragma unroll
+            for (int j = 0; j < U; j++) cur[j] = valid[j] ? tbl16[idx[j]] : 0u;
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                if (valid[j] && cur[j] == 0) {
+                    const uint32_t p = b0 + j * 32 + lane;
+                    const uint32_t old = atomicCAS(&tbl16[idx[j]], (unsigned short)0, (unsigned short)(p + 1));
+                    if (old == 0) rep[j] = p;
+                    else cur[j] = old;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                if (valid[j] && rep[j] == 0xffffffffu) {
+                    const uint32_t r = cur[j] - 1;
+                    if (r >= lo[j] && r < hi[j] && key0[r] == k0[j] && (KW == 1 || key1[r] == k1[j])) rep[j] = r;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                if (valid[j] && rep[j] == 0xffffffffu) {  // the slot holds another key: probe on
+                    const uint32_t p = b0 + j * 32 + lane;
+                    uint32_t ix = (idx[j] + 1) & (HS - 1);
+                    for (;;) {
+                        uint32_t c = tbl16[ix];
+                        if (c == 0) {
+                            c = atomicCAS(&tbl16[ix], (unsigned short)0, (unsigned short)(p + 1));
+                            if (c == 0) {
+                                rep[j] = p;
+                                break;
+                            }
+                        }
+                        const uint32_t r = c - 1;
+                        if (r >= lo[j] && r < hi[j] && key0[r] == k0[j] && (KW == 1 || key1[r] == k1[j])) {
+                            rep[j] = r;
+                            break;
+                        }
+                        ix = (ix + 1) & (HS - 1);
+                    }
+                }
+            }
+            // ranks: all matches first, then all counter updates (issued in position order), then the broadcasts
+            unsigned peers[U];
+            uint32_t c[U];
+#pragma unroll
+            for (int j = 0; j < U; j++) peers[j] = __match_any_sync(0xffffffffu, valid[j] ? rep[j] : (0x10000u + lane));
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                c[j] = 0;
+                if (valid[j] && (int)lane == __ffs(peers[j]) - 1) {
+                    const uint32_t sh = 16u * (rep[j] & 1u);
+                    c[j] = (atomicAdd(&cnt32[rep[j] >> 1], (uint32_t)__popc(peers[j]) << sh) >> sh) & 0xffffu;
+                }
+                __syncwarp();  // the updates of step j must be issued before those of step j + 1 (diverged lanes could run ahead)
+            }
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                c[j] = __shfl_sync(0xffffffffu, c[j], __ffs(peers[j]) - 1);
+                if (valid[j]) {
+                    const uint32_t p = b0 + j * 32 + lane;
+                    grp[p] = (uint16_t)rep[j];
+                    rk[p] = (uint16_t)(c[j] + __popc(peers[j] & lt_mask));
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- leaders and survivors (keep iff count > cutoff, binning.c:1102); survivors are listed by ascending position
+        uint32_t S = 0, N = 0, D = 0;
+        for (uint32_t b0 = 0; b0 < n_inst; b0 += 32 * U) {
+            bool leader[U];
+            uint32_t c[U];
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                const uint32_t p = b0 + j * 32 + lane;
+                leader[j] = p < n_inst && grp[p] == p;
+            }
+#pragma unroll
+            for (int j = 0; j < U; j++) c[j] = leader[j] ? cnt16[b0 + j * 32 + lane] : 0u;
+#pragma unroll
+            for (int j = 0; j < U; j++) {
+                const uint32_t p = b0 + j * 32 + lane;
+                const bool sv = leader[j] && (cutoff < 0 || c[j] > (uint32_t)cutoff);
+                const unsigned lm = __ballot_sync(0xffffffffu, leader[j]), sm = __ballot_sync(0xffffffffu, sv);
+                if (sv) surv[S + __popc(sm & lt_mask)] = (uint16_t)p;
+                else if (leader[j]) cnt16[p] = 0xffffu;  // pruned
+                S += __popc(sm);
+                D += __popc(lm);
+                N += sv ? c[j] : 0u;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) N += __shfl_xor_sync(0xffffffffu, N, d);
+        const uint64_t kbase = ibase / out.kdiv;
+        const bool oob = (uint64_t)ibase + N > out.id_cap || kbase + S > out.kmer_cap;  // cannot happen with the caller's bounds; never write out of range
+        if (lane == 0) {
+            out.unit_out[u_cur] = UnitOut3{ibase, oob ? 0u : S, oob ? 0u : N, 0u};
+            atomicAdd(&gc->distinct, (unsigned long long)D);
+            if (oob) atomicExch(&gc->overflow, 2u);
+        }
+        __syncwarp();
+        if (oob) {
+            u = __shfl_sync(0xffffffffu, u_next, 0);
+            continue;
+        }
+
+        // ---- table order: buckets ascend with position already; inside a bucket every survivor counts the smaller keys
+        for (uint32_t x0 = 0; x0 < S; x0 += 32) {
+            const uint32_t x = x0 + lane;
+            if (x < S) {
+                const uint32_t p = surv[x];
+                uint32_t a = 0, a2 = S;
+                if (n_bkt > 1) {
+                    const uint32_t o = ebk[eix[p]];
+                    const uint32_t blo = bstart[o], bhi = bstart[o + 1];
+                    uint32_t b = S;  // first survivor with position >= blo
+                    while (a < b) {
+                        const uint32_t m = (a + b) >> 1;
+                        if (surv[m] < blo) a = m + 1;
+                        else b = m;
+                    }
+                    uint32_t b2 = S;  // first survivor with position >= bhi
+                    a2 = a;
+                    while (a2 < b2) {
+                        const uint32_t m = (a2 + b2) >> 1;
+                        if (surv[m] < bhi) a2 = m + 1;
+                        else b2 = m;
+                    }
+                }
+                const uint64_t k0 = key0[p], k1 = (KW == 2) ? key1[p] : 0ull;
+                uint32_t rank = a;
+                for (uint32_t t = a; t < a2; t++) {
+                    const uint32_t q = surv[t];
+                    const uint64_t q0 = key0[q];
+                    bool less = q0 < k0;
+                    if constexpr (KW == 2) less = less || (q0 == k0 && key1[q] < k1);
+                    rank += less ? 1u : 0u;
+                }
+                sorted[rank] = (uint16_t)p;
+            }
+        }
+        __syncwarp();
+
+        // ---- list offsets in table order: cnt[leader] becomes the END of its list inside the unit
+        {
+            uint32_t carry = 0;
+            for (uint32_t x0 = 0; x0 < S; x0 += 32) {
+                const uint32_t x = x0 + lane;
+                const uint32_t p = x < S ? sorted[x] : 0u;
+                const uint32_t c = x < S ? cnt16[p] : 0u;
+                const uint32_t inc = warp_incl_scan_u32(c, lane);
+                if (x < S) cnt16[p] = (uint16_t)(carry + inc);
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+        }
+        __syncwarp();
+
+        // ---- k-mers in table order, staged
+        for (uint32_t x0 = 0; x0 < S; x0 += 32) {
+            const uint32_t x = x0 + lane;
+            if (x < S) {
+                const uint32_t p = sorted[x];
+                const uint32_t beg = x ? cnt16[sorted[x - 1]] : 0u;
+                const uint64_t g = kbase + x;
+                out.codes[g * KW] = key0[p];
+                if (KW == 2) out.codes[g * KW + 1] = key1[p];
+                out.mmer[g] = bmm[n_bkt > 1 ? ebk[eix[p]] : 0u];
+                out.loff[g] = beg;
+            }
+        }
+        __syncwarp();  // surv / sorted are dead from here on: the table's memory becomes the id buffer
+
+        // ---- ids, newest first (binning.c:1059-1069): an instance's place = end of its list - 1 - its rank.  The unit's ids are
+        // collected in shared memory and leave as one coalesced run.
+        if (N) {
+            if (packed) {
+                for (uint32_t b0 = 0; b0 < n_inst; b0 += 32 * U) {
+                    uint32_t end[U], r[U];
+                    int32_t id[U];
+#pragma unroll
+                    for (int j = 0; j < U; j++) {
+                        const uint32_t p = b0 + j * 32 + lane;
+                        end[j] = 0xffffu;
+                        r[j] = 0;
+                        id[j] = 0;
+                        if (p < n_inst) {
+                            end[j] = cnt16[grp[p]];
+                            r[j] = rk[p];
+                            id[j] = eid[eix[p]];
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < U; j++)
+                        if (end[j] != 0xffffu) idbuf[end[j] - 1u - r[j]] = id[j];
+                }
+            } else {  // lane = entry (the read id belongs to the record)
+                uint32_t carry_pos = 0;
+                for (uint32_t e0 = 0; e0 < n_ent; e0 += 32) {
+                    const uint32_t e = e0 + lane;
+                    uint32_t np = 0, arrival = 0;
+                    if (e < n_ent) {
+                        const uint32_t slot = (uint32_t)ent[un.ent_begin + e];
+                        const uint32_t *rec = skr + (uint64_t)(slot >> kl.cshift) * NW;
+                        const uint32_t meta = rec[2];
+                        arrival = rec[0];
+                        uint32_t t0;
+                        piece_of(meta, slot & cls_mask, kl, &t0, &np);
+                        if (is_round && np) {
+                            const int so = (int)((meta >> 16) & 0xffu);
+                            int a = so - dhi, b = so - dlo;
+                            if (a < (int)t0) a = (int)t0;
+                            if (b > (int)(t0 + np - 1)) b = (int)(t0 + np - 1);
+                            np = (dlo > dhi || b < a) ? 0u : (uint32_t)(b - a + 1);
+                        }
+                    }
+                    const uint32_t ps = warp_incl_scan_u32(np, lane);
+                    const uint32_t pos0 = carry_pos + ps - np;
+                    carry_pos += __shfl_sync(0xffffffffu, ps, 31);
+                    if (np) {
+                        const int32_t id = ids_by_arrival ? ids_by_arrival[arrival] : id_base + (int32_t)arrival;
+                        for (uint32_t i = 0; i < np; i++) {
+                            const uint32_t p = pos0 + i;
+                            const uint32_t end = cnt16[grp[p]];
+                            if (end != 0xffffu) idbuf[end - 1u - rk[p]] = id;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            int32_t *dst = out.ids + ibase;
+            for (uint32_t i = lane; i < N; i += 32) dst[i] = idbuf[i];
+        }
+        __syncwarp();
+        u = __shfl_sync(0xffffffffu, u_next, 0);
+    }
+}
+
+// ------------------------------------------------------------------ finalize: staging -> final place
+
+struct UnitSN {  // {S << 32 | N} of the units of one chunk, 0 elsewhere
+    const UnitOut3 *uo;
+    const uint32_t *chunk_bounds;
+    uint32_t chunk;
+    __device__ __forceinline__ uint64_t operator()(uint64_t u) const {
+        if (u < chunk_bounds[chunk] || u >= chunk_bounds[chunk + 1]) return 0ull;
+        return ((uint64_t)uo[u].S << 32) | uo[u].N;
+    }
+};
+
+// totals[c] = totals[c - 1] + what chunk c emitted, as {k-mers << 32 | ids} (totals[-1] = 0)
+__global__ void v3_chunk_total_kernel(const uint64_t *__restrict__ chunk_sum, uint32_t chunk, unsigned long long *__restrict__ totals, G3Counters *__restrict__ gc,
+                                      uint32_t n_chunks) {
+    const unsigned long long t = (chunk ? totals[chunk - 1] : 0ull) + *chunk_sum;
+    totals[chunk] = t;
+    if (chunk + 1 == n_chunks) {
+        gc->total_kmers = t >> 32;
+        gc->total_ids = t & 0xffffffffull;
+    }
+}
+
+struct G3Final {
+    uint64_t *kmer_codes;   // [S * KW]
+    uint32_t *kmer_mmer;    // [S]
+    uint64_t *kmer_id_off;  // [S + 1]
+    int32_t *read_ids;      // [N]
+};
+
+// One warp per unit: copy its staged k-mers and ids to their place in the table (place = totals of all units before it).  The
+// round units of a split atom are handled together by the warp that takes the atom's first round: the rounds are sorted runs of
+// distinct k-mers, so a k-mer's place inside the atom = its index in its own run + the number of smaller k-mers in every other run.
+template <int KW>
+__global__ void __launch_bounds__(128)
+    finalize3_kernel(const Unit3 *__restrict__ units, const uint64_t *__restrict__ unit_excl, const unsigned long long *__restrict__ totals, G3Stage st,
+                     G3Final fin, const uint32_t *__restrict__ chunk_bounds, uint32_t chunk, uint32_t *__restrict__ tickets) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t unit_begin = chunk_bounds[chunk], unit_end = chunk_bounds[chunk + 1];
+    const unsigned long long base = chunk ? totals[chunk - 1] : 0ull;
+    const uint64_t S0 = base >> 32, N0 = base & 0xffffffffull;
+    for (;;) {
+        uint32_t u = 0;
+        if (lane == 0) u = unit_begin + atomicAdd(&tickets[chunk], 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= unit_end) break;
+        const Unit3 un = units[u];
+        const uint64_t ex = unit_excl[u];
+        const uint64_t Sb = S0 + (ex >> 32), Nb = N0 + (ex & 0xffffffffull);
+        if (un.rounds == 0) {
+            const UnitOut3 uo = st.unit_out[u];
+            const uint64_t kb = uo.ibase / st.kdiv;
+            for (uint32_t x = lane; x < uo.S; x += 32) {
+                fin.kmer_codes[(Sb + x) * KW] = st.codes[(kb + x) * KW];
+                if (KW == 2) fin.kmer_codes[(Sb + x) * KW + 1] = st.codes[(kb + x) * KW + 1];
+                fin.kmer_mmer[Sb + x] = st.mmer[kb + x];
+                fin.kmer_id_off[Sb + x] = Nb + st.loff[kb + x];
+            }
+            const int32_t *src = st.ids + uo.ibase;
+            int32_t *dst = fin.read_ids + Nb;
+            for (uint32_t i = lane; i < uo.N; i += 32) dst[i] = src[i];
+            continue;
+        }
+        if (un.round != 0) continue;  // handled with the atom's first round
+        const uint32_t R = un.rounds;
+        // pass 1: every k-mer's place inside the atom; its list length goes to kmer_id_off at that place
+        uint32_t S_tot = 0;
+        for (uint32_t j = 0; j < R; j++) S_tot += st.unit_out[u + j].S;
+        const uint32_t mm = S_tot ? st.mmer[st.unit_out[u].ibase / st.kdiv + 0] : 0u;  // every round of the atom has the same m-mer; round 0 may be empty:
+        uint32_t mmer = mm;
+        if (S_tot && st.unit_out[u].S == 0) {
+            for (uint32_t j = 1; j < R; j++) {
+                const UnitOut3 o = st.unit_out[u + j];
+                if (o.S) {
+                    mmer = st.mmer[o.ibase / st.kdiv];
+                    break;
+                }
+            }
+        }
+        for (uint32_t j = 0; j < R; j++) {
+            const UnitOut3 uj = st.unit_out[u + j];
+            const uint64_t kbj = uj.ibase / st.kdiv;
+            for (uint32_t x = lane; x < uj.S; x += 32) {
+                const uint64_t k0 = st.codes[(kbj + x) * KW], k1 = KW == 2 ? st.codes[(kbj + x) * KW + 1] : 0ull;
+                uint32_t rank = x;
+                for (uint32_t j2 = 0; j2 < R; j2++) {
+                    if (j2 == j) continue;
+                    const UnitOut3 u2 = st.unit_out[u + j2];
+                    const uint64_t kb2 = u2.ibase / st.kdiv;
+                    uint32_t a = 0, b = u2.S;  // keys of run j2 smaller than mine
+                    while (a < b) {
+                        const uint32_t m = (a + b) >> 1;
+                        const uint64_t q0 = st.codes[(kb2 + m) * KW];
+                        bool less = q0 < k0;
+                        if constexpr (KW == 2) less = less || (q0 == k0 && st.codes[(kb2 + m) * KW + 1] < k1);
+                        if (less) a = m + 1;
+                        else b = m;
+                    }
+                    rank += a;
+                }
+                const uint32_t cnt = (x + 1 < uj.S ? st.loff[kbj + x + 1] : uj.N) - st.loff[kbj + x];
+                fin.kmer_codes[(Sb + rank) * KW] = k0;
+                if (KW == 2) fin.kmer_codes[(Sb + rank) * KW + 1] = k1;
+                fin.kmer_mmer[Sb + rank] = mmer;
+                fin.kmer_id_off[Sb + rank] = cnt;
+                st.mmer[kbj + x] = rank;  // remembered for pass 3 (the staged m-mer is not needed any more)
+            }
+        }
+        __syncwarp();
+        __threadfence();
+        // pass 2: list lengths -> offsets (in place)
+        uint64_t carry = Nb;
+        for (uint32_t x0 = 0; x0 < S_tot; x0 += 32) {
+            const uint32_t x = x0 + lane;
+            const uint32_t c = x < S_tot ? (uint32_t)fin.kmer_id_off[Sb + x] : 0u;
+            const uint32_t inc = warp_incl_scan_u32(c, lane);
+            if (x < S_tot) fin.kmer_id_off[Sb + x] = carry + inc - c;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        __syncwarp();
+        __threadfence();
+        // pass 3: lists, eight lanes per list
+        for (uint32_t j = 0; j < R; j++) {
+            const UnitOut3 uj = st.unit_out[u + j];
+            const uint64_t kbj = uj.ibase / st.kdiv;
+            for (uint32_t x = lane >> 3; x < uj.S; x += 4) {
+                const uint32_t lo = st.loff[kbj + x];
+                const uint32_t cnt = (x + 1 < uj.S ? st.loff[kbj + x + 1] : uj.N) - lo;
+                const uint32_t rank = st.mmer[kbj + x];
+                const int32_t *src = st.ids + uj.ibase + lo;
+                int32_t *dst = fin.read_ids + fin.kmer_id_off[Sb + rank];
+                for (uint32_t i = lane & 7u; i < cnt; i += 8) dst[i] = src[i];
+            }
+        }
+    }
+}
+
+// chunk_bounds[c] = first unit of chunk c, moved back to the first round of a split atom so that no atom straddles two chunks.
+__global__ void v3_chunk_bounds_kernel(const Unit3 *__restrict__ units, const G3Counters *__restrict__ gc, uint32_t n_chunks, uint32_t *__restrict__ chunk_bounds) {
+    const uint32_t nu = gc->n_units;
+    for (uint32_t c = 0; c <= n_chunks; c++) {
+        uint32_t b = (uint32_t)(((uint64_t)nu * c) / n_chunks);
+        if (c == n_chunks) b = nu;
+        else if (b < nu && units[b].rounds != 0) b -= units[b].round;
+        chunk_bounds[c] = b;
+    }
+}
+
+// ------------------------------------------------------------------ host side
+
+// cap: instances per unit, 512 or 1024 (gbin_set_tuning "v3_cap")
+static Plan3 v3_plan_params(const KeyLayout &kl, int cap_i) {
+    const uint32_t cap = cap_i == 512 ? 512u : 1024u;
+    return Plan3{cap, cap / 8, cap / 4, (uint32_t)(kl.K - kl.M + 1)};  // NB_MAX and ECAP of WarpLayout
+}
+
+uint64_t v3_max_units(uint64_t n_inst, uint64_t n_runs, int cap) {
+    const uint64_t c = cap == 512 ? 512 : 1024;
+    // packed units: two consecutive ones hold more than cap instances, or cap / 4 entries, or cap / 8 atoms; + one per plan block; rounds: 2c/cap + 3 per atom
+    return 2 * (n_inst / c) + 2 * (n_inst / (c / 4)) / 1 + 2 * (n_runs / (c / 8)) + n_runs / PLAN_BLOCK + 3 * n_runs + 16;
+}
+size_t v3_unit_bytes() { return sizeof(Unit3); }
+size_t v3_unit_out_bytes() { return sizeof(UnitOut3); }
+size_t v3_counters_bytes() { return sizeof(G3Counters); }
+
+struct PtrIn64 {
+    const uint64_t *p;
+    __device__ __forceinline__ uint64_t operator()(uint64_t j) const { return p[j]; }
+};
+
+// Units over the n_runs atoms.  nunits64 / base64: [n_runs + 1] u64 scratch each; head_run: [max_units].
+int v3_plan_units(const void *skr, const uint64_t *ent, const KeyLayout &kl, int cap, const uint32_t *inst_prefix, const uint32_t *run_start, uint64_t n_runs, uint64_t *nunits64, uint64_t *base64,
+                  uint32_t *head_run, void *scratch, void *units, uint64_t max_units, void *gc_dev, uint32_t n_chunks, uint32_t *chunk_bounds, cudaStream_t st) {
+    RunView3 rv{run_start, inst_prefix};
+    const Plan3 pp = v3_plan_params(kl, cap);
+    G3Counters *gc = static_cast<G3Counters *>(gc_dev);
+    cudaMemsetAsync(gc, 0, sizeof(G3Counters), st);
+    int l = 0;
+    if (n_runs) {
+        const uint64_t per_cta = (uint64_t)PLAN_CTA_BLOCKS * PLAN_BLOCK;
+        v3_pack_kernel<<<(unsigned)((n_runs + per_cta - 1) / per_cta), 256, 0, st>>>(rv, n_runs, pp, nunits64);
+        l += 1 + exclusive_scan<uint64_t, PtrIn64>(PtrIn64{nunits64}, base64, n_runs, static_cast<uint64_t *>(scratch), base64 + n_runs, st);
+        v3_head_runs_kernel<<<(unsigned)((n_runs + 255) / 256), 256, 0, st>>>(nunits64, base64, n_runs, head_run);
+        v3_fill_units_kernel<<<(unsigned)((max_units + 255) / 256), 256, 0, st>>>(rv, base64, base64 + n_runs, n_runs, pp, head_run, static_cast<Unit3 *>(units), gc);
+        v3_round_cuts_kernel<<<592, 128, 0, st>>>(static_cast<const uint32_t *>(skr), kl.K <= 32 ? 8 : 12, ent, kl, static_cast<Unit3 *>(units), gc, pp.cap);
+        l += 3;
+    }
+    v3_chunk_bounds_kernel<<<1, 1, 0, st>>>(static_cast<const Unit3 *>(units), gc, n_chunks, chunk_bounds);
+    return l + 1;
+}
+
+size_t v3_group_smem_bytes(int KW, int cap) {
+    const size_t per_warp = cap == 512 ? (KW == 1 ? WarpLayout<512, 1>::BYTES : WarpLayout<512, 2>::BYTES)
+                                       : (KW == 1 ? WarpLayout<1024, 1>::BYTES : WarpLayout<1024, 2>::BYTES);
+    return per_warp * G3_WARPS;
+}
+
+int v3_group_launch(const void *skr, const uint64_t *ent, const void *units, const KeyLayout &kl, int cap, int cutoff, const int32_t *ids_by_arrival, int32_t id_base,
+                    const V3Out &o, uint64_t max_units, uint64_t *unit_excl, void *scan_scratch, void *gc_dev, const V3Chunks &ch, int sm_count, KernelProf *prof,
+                    cudaStream_t st) {
+    const int KW = kl.K <= 32 ? 1 : 2;
+    constexpr int WARPS = G3_WARPS;
+    const size_t smem = v3_group_smem_bytes(KW, cap);
+    cudaMemsetAsync(ch.tickets, 0, sizeof(uint32_t) * 2 * ch.n, st);
+    const uint32_t kdiv = cutoff >= 0 ? (uint32_t)cutoff + 1u : 1u;
+    G3Stage stg{o.stg_codes, o.stg_mmer, o.stg_loff, o.stg_ids, static_cast<UnitOut3 *>(o.unit_out), o.kmer_cap, o.id_cap, kdiv};
+    G3Final fin{o.kmer_codes, o.kmer_mmer, o.kmer_id_off, o.read_ids};
+    G3Counters *gc = static_cast<G3Counters *>(gc_dev);
+    const uint32_t *sk = static_cast<const uint32_t *>(skr);
+    const Unit3 *un = static_cast<const Unit3 *>(units);
+    int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    int launches = 0;
+    auto launch = [&](auto kern, auto fin_kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        for (uint32_t c = 0; c < ch.n; c++) {
+            bool on = prof && prof->begin(KK_SKR_GROUP, st);
+            kern<<<sm_count * per_sm, WARPS * 32, smem, st>>>(sk, ent, un, kl, cutoff, ids_by_arrival, id_base, stg, gc, ch.bounds, c, ch.tickets);
+            if (prof) prof->end(on, 1, st);
+            on = prof && prof->begin(KK_V3_SPAN, st);
+            int l = exclusive_scan<uint64_t, UnitSN>(UnitSN{stg.unit_out, ch.bounds, c}, unit_excl, max_units, static_cast<uint64_t *>(scan_scratch), ch.chunk_sum, st);
+            v3_chunk_total_kernel<<<1, 1, 0, st>>>(ch.chunk_sum, c, ch.totals_dev, gc, ch.n);
+            fin_kern<<<sm_count * 8, 128, 0, st>>>(un, unit_excl, ch.totals_dev, stg, fin, ch.bounds, c, ch.tickets + ch.n);
+            if (prof) prof->end(on, l + 2, st);
+            launches += l + 3;
+            if (ch.totals_host) cudaMemcpyAsync(ch.totals_host + c, ch.totals_dev + c, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+            if (ch.done) cudaEventRecord(ch.done[c], st);
+        }
+    };
+    if (KW == 1) {
+        if (cap == 512) launch(group3_kernel<2, 1, 512, WARPS>, finalize3_kernel<1>);
+        else launch(group3_kernel<2, 1, 1024, WARPS>, finalize3_kernel<1>);
+    } else {
+        if (cap == 512) launch(group3_kernel<4, 2, 512, WARPS>, finalize3_kernel<2>);
+        else launch(group3_kernel<4, 2, 1024, WARPS>, finalize3_kernel<2>);
+    }
+    return launches;
+}
+
+}  // namespace gbin

@@ -77,6 +77,12 @@ struct Misc {  // small device-resident scalars
     uint32_t chunk_tickets[SKR_MAX_CHUNKS];
     unsigned long long chunk_totals[SKR_MAX_CHUNKS];
     uint32_t split_n_nl, split_n_reads;
+    // pipeline v3
+    V3Counters gc3;
+    unsigned long long n_real_entries;
+    uint32_t chunk_bounds[SKR_MAX_CHUNKS + 1];
+    uint32_t v3_tickets[2 * SKR_MAX_CHUNKS];
+    uint64_t v3_chunk_sum;
 };
 
 // Host path only.  HostFeed: the reads are still in host memory; the scan stage copies them chunk by chunk on the copy
@@ -117,7 +123,10 @@ struct gbin_ctx {
     DevBuf misc;
     // pipeline v2 workspace
     DevBuf skr_a, skr_b, tile_state, inst_prefix, run_excl, skr_run_start, small_prefix, unit_base, units, unit_state, o_kmer_mmer, bucket_excl, big_list, big_k0, big_k1, big_arr, stg_ids, stg_codes, stg_mmer, stg_off, skr_side;
-    int pipeline;        // 2: super-k-mer path with v1 as fallback (default); 1: v1 only
+    // pipeline v3 workspace
+    DevBuf ent_a, ent_b, piece_n, v3_base64, v3_head_run, v3_unit_out, v3_unit_excl;
+    int v3_h, v3_nc, v3_cap;  // key layout and unit capacity of pipeline 3 (gbin_set_tuning; GBIN_V3_H / GBIN_V3_NC / GBIN_V3_CAP)
+    int pipeline;        // 3: sort by reference + warp units, falling back to 2, then 1 (default); 2: super-k-mer path with v1 as fallback; 1: v1 only
     int last_pipeline;   // which one produced the last table
     uint32_t fallbacks;  // v2 -> v1 fallbacks since creation
     gbin_run_stats rs;   // sizes seen by the last pipeline-2 run
@@ -531,18 +540,197 @@ int run_v2_group(gbin_ctx *ctx, void *skr, void *twin, uint64_t n_skr, const int
     return GBIN_OK;
 }
 
+// ---- pipeline v3: entries sorted by reference, one warp per unit, table written once (bin3.cu)
+// The records in `skr` are read, not moved.  *done = false when a unit or a span overflowed (the batch then goes through
+// pipeline 2, which sorts the records themselves).
+int run_v3_group(gbin_ctx *ctx, const void *skr, uint64_t n_skr, const int32_t *d_ids, int32_t id_base, cudaStream_t st, gbin_table *out, int *launches,
+                 bool *done, uint64_t *n_inst_out, HostSink *sink = nullptr) {
+    *done = false;
+    const int K = ctx->cfg.kmer_size, M = ctx->cfg.mmer_size, cutoff = ctx->cfg.abundance_cutoff, KW = ctx->KW;
+    Misc *dm = ctx->misc.as<Misc>();
+    Misc *hm = static_cast<Misc *>(ctx->h_misc.p);
+    const KeyLayout kl = make_key_layout(K, M, ctx->v3_h, ctx->v3_nc);
+    if (n_skr >= (1ull << (32 - kl.cshift))) return GBIN_OK;  // slots are 32-bit
+
+    // ---- entries + level 1: stable sort of the entries by key
+    const uint64_t n_slots = n_skr << kl.cshift;
+    CU(ctx->ent_a.ensure((n_slots + 2) * 8));
+    CU(ctx->ent_b.ensure((n_slots + 2) * 8));
+    CU(ctx->piece_n.ensure(n_slots + 16));
+    bool on = ctx->prof.begin(KK_V3_ENTRIES, st);
+    int lp = v3_make_entries(skr, n_skr, kl, ctx->ent_a.as<uint64_t>(), ctx->piece_n.as<uint8_t>(), &dm->n_real_entries, st);
+    ctx->prof.end(on, lp, st);
+    *launches += lp;
+    CU(cudaGetLastError());
+    CU(ctx->radix_scratch.ensure(radix_scratch_bytes(n_slots)));
+    bool in_b = false;
+    int passes = 0;
+    *launches += radix_sort_entries(ctx->ent_a.p, ctx->ent_b.p, n_slots, kl.key_bits, ctx->radix_scratch.p, &in_b, &passes, &ctx->prof, st);
+    CU(cudaGetLastError());
+    ctx->tm.sort_passes = (uint32_t)passes;
+    const uint64_t *ent = in_b ? ctx->ent_b.as<uint64_t>() : ctx->ent_a.as<uint64_t>();
+    CU(cudaEventRecord(ctx->ev[3], st));
+    uint64_t n_ent = n_slots;
+    if (kl.nc == 2) {  // empty pieces carry the all-ones key and sort behind everything: plan over the real ones only
+        CU(cudaMemcpyAsync(&hm->n_real_entries, &dm->n_real_entries, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        n_ent = hm->n_real_entries;
+    }
+
+    // ---- plan: instance prefix, atoms, units
+    CU(ctx->inst_prefix.ensure((n_ent + 2) * 4));
+    CU(ctx->run_excl.ensure((n_ent + 2) * 8));
+    CU(ctx->skr_run_start.ensure((n_ent + 2) * 4));
+    CU(ctx->scan_scratch.ensure(group_scan_scratch_bytes(n_ent)));
+    on = ctx->prof.begin(KK_SKR_PLAN, st);
+    lp = v3_plan_runs(ent, ctx->piece_n.as<uint8_t>(), n_ent, ctx->inst_prefix.as<uint32_t>(), ctx->run_excl.as<uint64_t>(), ctx->skr_run_start.as<uint32_t>(),
+                      ctx->scan_scratch.as<uint64_t>(), &dm->n_inst_dev, &dm->n_runs_dev, st);
+    ctx->prof.end(on, lp, st);
+    *launches += lp;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&hm->n_inst_dev, &dm->n_inst_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const uint64_t n_runs = hm->n_runs_dev, n = hm->n_inst_dev;
+    *n_inst_out = n;
+    ctx->rs.n_super_kmers = n_skr;
+    ctx->rs.n_mmer_runs = n_runs;
+    const uint64_t max_units = v3_max_units(n, n_runs, ctx->v3_cap);
+    CU(ctx->small_prefix.ensure((n_runs + 2) * 8));
+    CU(ctx->v3_base64.ensure((n_runs + 2) * 8));
+    CU(ctx->v3_head_run.ensure((max_units + 1) * 4));
+    CU(ctx->units.ensure(max_units * v3_unit_bytes()));
+    CU(ctx->v3_unit_out.ensure(max_units * v3_unit_out_bytes()));
+    CU(ctx->v3_unit_excl.ensure((max_units + 1) * 8));
+    CU(ctx->scan_scratch.ensure(group_scan_scratch_bytes(n_runs + max_units + 1024)));
+    V3Chunks ch{1u, dm->v3_tickets, dm->chunk_bounds, &dm->v3_chunk_sum, dm->chunk_totals, nullptr, nullptr};
+    if (sink && sink->chunks > 1) {
+        ch.n = (uint32_t)sink->chunks;
+        ch.totals_host = hm->chunk_totals;
+        ch.done = ctx->ev_chunk;
+    }
+    on = ctx->prof.begin(KK_SKR_PLAN, st);
+    lp = v3_plan_units(skr, ent, kl, ctx->v3_cap, ctx->inst_prefix.as<uint32_t>(), ctx->skr_run_start.as<uint32_t>(), n_runs, ctx->small_prefix.as<uint64_t>(),
+                       ctx->v3_base64.as<uint64_t>(), ctx->v3_head_run.as<uint32_t>(), ctx->scan_scratch.p, ctx->units.p, max_units, &dm->gc3, ch.n, dm->chunk_bounds, st);
+    ctx->prof.end(on, lp, st);
+    *launches += lp;
+    CU(cudaGetLastError());
+
+    // ---- level 2 + prune + emit.  Output bounds: a surviving k-mer has more than `cutoff` instances.
+    const uint64_t kmer_cap = cutoff >= 0 ? n / ((uint64_t)cutoff + 1) + 1 : n + 1;
+    CU(ctx->o_kmer_codes.ensure((kmer_cap * KW + 1) * sizeof(uint64_t)));
+    CU(ctx->o_kmer_mmer.ensure((kmer_cap + 1) * sizeof(uint32_t)));
+    CU(ctx->o_kmer_id_off.ensure((kmer_cap + 2) * sizeof(uint64_t)));
+    CU(ctx->o_read_ids.ensure((n + 1) * sizeof(int32_t)));
+    CU(ctx->stg_ids.ensure((n + 1) * sizeof(int32_t)));
+    CU(ctx->stg_codes.ensure((kmer_cap * KW + 1) * sizeof(uint64_t)));
+    CU(ctx->stg_mmer.ensure((kmer_cap + 1) * sizeof(uint32_t)));
+    CU(ctx->stg_off.ensure((kmer_cap + 1) * sizeof(uint32_t)));
+    V3Out vo{ctx->o_kmer_codes.as<uint64_t>(), ctx->o_kmer_mmer.as<uint32_t>(), ctx->o_kmer_id_off.as<uint64_t>(), ctx->o_read_ids.as<int32_t>(), kmer_cap, n,
+             ctx->stg_codes.as<uint64_t>(), ctx->stg_mmer.as<uint32_t>(), ctx->stg_off.as<uint32_t>(), ctx->stg_ids.as<int32_t>(), ctx->v3_unit_out.p};
+    lp = v3_group_launch(skr, ent, ctx->units.p, kl, ctx->v3_cap, cutoff, d_ids, id_base, vo, max_units, ctx->v3_unit_excl.as<uint64_t>(), ctx->scan_scratch.p,
+                         &dm->gc3, ch, ctx->sm_count, &ctx->prof, st);
+    *launches += lp;
+    CU(cudaGetLastError());
+    if (ch.done) {
+        // Stream the finished part of the table to the host while later chunks are grouped: the output of the units of a chunk
+        // (and of the split atoms inside it) is final once the chunk's two launches have completed.
+        for (uint32_t c = 0; c < ch.n; c++) {
+            CU(cudaEventSynchronize(ctx->ev_chunk[c]));
+            const unsigned long long tot = hm->chunk_totals[c];
+            const uint64_t s1 = tot >> 32, n1 = tot & 0xffffffffull;
+            if (s1 > sink->kmer_cap || n1 > sink->id_cap || s1 < sink->kmers_done || n1 < sink->ids_done) break;  // arena too small: the rest is copied at the end
+            const uint64_t s0 = sink->kmers_done, n0 = sink->ids_done;
+            if (s1 > s0) {
+                CU(cudaMemcpyAsync(sink->kmer_codes + s0 * KW, ctx->o_kmer_codes.as<uint64_t>() + s0 * KW, (s1 - s0) * KW * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->st_d2h));
+                CU(cudaMemcpyAsync(sink->kmer_id_off + s0, ctx->o_kmer_id_off.as<uint64_t>() + s0, (s1 - s0) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->st_d2h));
+            }
+            if (n1 > n0) CU(cudaMemcpyAsync(sink->read_ids + n0, ctx->o_read_ids.as<int32_t>() + n0, (n1 - n0) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->st_d2h));
+            sink->kmers_done = s1;
+            sink->ids_done = n1;
+        }
+    }
+    CU(cudaMemcpyAsync(&hm->gc3, &dm->gc3, sizeof(V3Counters), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->rs.n_units = hm->gc3.n_units;
+    ctx->rs.reserved = hm->gc3.n_spans;
+    if (hm->gc3.overflow) {  // not done: the caller falls back
+        snprintf(ctx->err, sizeof ctx->err, "pipeline 3 gave the batch up (code %u: a (bucket, d) class larger than a unit)", hm->gc3.overflow);
+        return GBIN_OK;
+    }
+    const uint64_t S = hm->gc3.total_kmers, NS = hm->gc3.total_ids;
+
+    // ---- bucket directory
+    CU(ctx->bucket_excl.ensure((S + 1) * 4));
+    CU(ctx->o_mmer_codes.ensure((S + 1) * sizeof(uint32_t)));
+    CU(ctx->o_mmer_kmer_off.ensure((S + 2) * sizeof(uint64_t)));
+    CU(ctx->scan_scratch.ensure(group_scan_scratch_bytes(S + 1024)));
+    on = ctx->prof.begin(KK_EMIT, st);
+    lp = skr_emit_buckets(ctx->o_kmer_mmer.as<uint32_t>(), S, NS, ctx->bucket_excl.as<uint32_t>(), ctx->scan_scratch.as<uint32_t>(),
+                          ctx->o_mmer_codes.as<uint32_t>(), ctx->o_mmer_kmer_off.as<uint64_t>(), ctx->o_kmer_id_off.as<uint64_t>(),
+                          &dm->n_buckets_dev, st);
+    ctx->prof.end(on, lp, st);
+    *launches += lp;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&hm->n_buckets_dev, &dm->n_buckets_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+
+    memset(out, 0, sizeof *out);
+    out->kmer_size = K;
+    out->mmer_size = M;
+    out->abundance_cutoff = cutoff;
+    out->kmer_words = KW;
+    out->on_device = 1;
+    out->ctx_owned = 1;
+    out->n_instances = n;
+    out->n_distinct = hm->gc3.distinct;
+    out->n_kmers = S;
+    out->n_ids = NS;
+    out->n_buckets = hm->n_buckets_dev;
+    out->mmer_codes = ctx->o_mmer_codes.as<uint32_t>();
+    out->mmer_kmer_off = ctx->o_mmer_kmer_off.as<uint64_t>();
+    out->kmer_codes = ctx->o_kmer_codes.as<uint64_t>();
+    out->kmer_id_off = ctx->o_kmer_id_off.as<uint64_t>();
+    out->read_ids = ctx->o_read_ids.as<int32_t>();
+    *done = true;
+    return GBIN_OK;
+}
+
+// Group stage of the super-k-mer pipelines: v3 first (when configured), then v2.  *used receives the pipeline that made the table.
+int run_skr_group(gbin_ctx *ctx, void *skr, uint64_t n_skr, const int32_t *d_ids, int32_t id_base, cudaStream_t st, gbin_table *out, int *launches, bool *done,
+                  uint64_t *n_inst_out, HostSink *sink, int *used) {
+    *done = false;
+    const int NW = ctx->cfg.kmer_size <= 32 ? 8 : 12;
+    if (ctx->pipeline >= 3) {
+        int rc = run_v3_group(ctx, skr, n_skr, d_ids, id_base, st, out, launches, done, n_inst_out, sink);
+        if (rc) return rc;
+        if (*done) {
+            *used = 3;
+            return GBIN_OK;
+        }
+        ctx->fallbacks++;
+        if (sink) {  // what was streamed belongs to the abandoned attempt
+            CU(cudaStreamSynchronize(ctx->st_d2h));
+            sink->kmers_done = sink->ids_done = 0;
+        }
+    }
+    CU(ctx->skr_b.ensure((n_skr + 1) * NW * 4));
+    int rc = run_v2_group(ctx, skr, ctx->skr_b.p, n_skr, d_ids, id_base, st, out, launches, done, n_inst_out, sink);
+    if (rc) return rc;
+    if (*done) *used = 2;
+    return GBIN_OK;
+}
+
 int run_v2(gbin_ctx *ctx, const gbin_reads *rd, uint64_t n, uint32_t max_len, cudaStream_t st, gbin_table *out, int *launches, bool *done,
-           const HostFeed *feed, HostSink *sink) {
+           const HostFeed *feed, HostSink *sink, int *used) {
     *done = false;
     if (n == 0 || n >= (1ull << 31)) return GBIN_OK;
-    const int NW = ctx->cfg.kmer_size <= 32 ? 8 : 12;
     uint64_t n_skr = 0, n_chk = 0;
     int rc = run_v2_scan(ctx, rd, n, max_len, 0, nullptr, 0, st, &n_skr, launches, feed);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[2], st));
-    CU(ctx->skr_b.ensure((n_skr + 1) * NW * 4));
-    rc = run_v2_group(ctx, ctx->skr_a.p, ctx->skr_b.p, n_skr, rd->read_ids, rd->id_base, st, out, launches, done, &n_chk, sink);
+    rc = run_skr_group(ctx, ctx->skr_a.p, n_skr, rd->read_ids, rd->id_base, st, out, launches, done, &n_chk, sink, used);
     if (rc) return rc;
+    if (!*done) return GBIN_OK;
     if (n_chk != n) return fail(ctx, GBIN_E_CUDA, "internal: record windows sum to %llu, expected %llu", (unsigned long long)n_chk, (unsigned long long)n);
     return GBIN_OK;
 }
@@ -556,7 +744,7 @@ int bin_device_impl(gbin_ctx *ctx, const gbin_reads *rd, cudaStream_t st, gbin_t
     if (rc) return rc;
     if (max_len > GBIN_MAX_READ_LEN) return fail(ctx, GBIN_E_TOO_LARGE, "read length %u exceeds GBIN_MAX_READ_LEN", max_len);
     if (n >= (1ull << 32) - 8192) return fail(ctx, GBIN_E_TOO_LARGE, "%llu k-mer instances in one batch (limit 2^32)", (unsigned long long)n);
-    const bool v2 = ctx->pipeline == 2 && n != 0 && n < (1ull << 31);
+    const bool v2 = ctx->pipeline >= 2 && n != 0 && n < (1ull << 31);
     if (feed && !v2) {  // nobody downstream streams the reads in: copy them in one piece
         CU(cudaMemcpyAsync(feed->dst, feed->src, feed->bytes, cudaMemcpyHostToDevice, st));
         CU(cudaEventRecord(ctx->ev[1], st));
@@ -564,14 +752,18 @@ int bin_device_impl(gbin_ctx *ctx, const gbin_reads *rd, cudaStream_t st, gbin_t
     }
     if (v2) {
         bool done = false;
-        rc = run_v2(ctx, rd, n, max_len, st, out, launches, &done, feed, sink);
+        int used = 2;
+        rc = run_v2(ctx, rd, n, max_len, st, out, launches, &done, feed, sink, &used);
         if (rc) return rc;
         if (done) {
-            ctx->last_pipeline = 2;
+            ctx->last_pipeline = used;
             CU(cudaEventRecord(ctx->ev[4], st));
             return GBIN_OK;
         }
-        if (sink) sink->kmers_done = sink->ids_done = 0;  // what was streamed belongs to the abandoned attempt
+        if (sink) {  // what was streamed belongs to the abandoned attempt; nothing may still be in flight into the arenas
+            CU(cudaStreamSynchronize(ctx->st_d2h));
+            sink->kmers_done = sink->ids_done = 0;
+        }
     }
     ctx->last_pipeline = 1;
     memset(&ctx->rs, 0, sizeof ctx->rs);
@@ -625,8 +817,17 @@ int gbin_create(const gbin_config *cfg, gbin_ctx **out) {
     ctx->cfg = *cfg;
     ctx->KW = cfg->kmer_size <= 32 ? 1 : 2;
     ctx->err[0] = 0;
-    ctx->pipeline = 2;
-    if (const char *e = getenv("GBIN_PIPELINE")) ctx->pipeline = atoi(e) == 1 ? 1 : 2;
+    ctx->pipeline = 3;
+    if (const char *e = getenv("GBIN_PIPELINE")) {
+        const int v = atoi(e);
+        ctx->pipeline = (v >= 1 && v <= 3) ? v : 3;
+    }
+    ctx->v3_h = 0;
+    ctx->v3_nc = 1;
+    if (const char *e = getenv("GBIN_V3_NC")) ctx->v3_nc = atoi(e) == 2 ? 2 : 1;
+    if (const char *e = getenv("GBIN_V3_H")) ctx->v3_h = atoi(e);
+    ctx->v3_cap = 1024;
+    if (const char *e = getenv("GBIN_V3_CAP")) ctx->v3_cap = atoi(e) == 512 ? 512 : 1024;
     ctx->last_pipeline = 0;
     ctx->fallbacks = 0;
     memset(&ctx->rs, 0, sizeof ctx->rs);
@@ -666,7 +867,8 @@ void gbin_destroy(gbin_ctx *ctx) {
                       &ctx->id_offset, &ctx->surv_group, &ctx->bucket_of, &ctx->misc, &ctx->o_mmer_codes, &ctx->o_mmer_kmer_off,
                       &ctx->o_kmer_codes, &ctx->o_kmer_id_off, &ctx->o_read_ids, &ctx->skr_a, &ctx->skr_b, &ctx->tile_state,
                       &ctx->inst_prefix, &ctx->run_excl, &ctx->skr_run_start, &ctx->small_prefix, &ctx->unit_base, &ctx->units,
-                      &ctx->unit_state, &ctx->o_kmer_mmer, &ctx->bucket_excl, &ctx->big_list, &ctx->big_k0, &ctx->big_k1, &ctx->big_arr, &ctx->stg_ids, &ctx->stg_codes, &ctx->stg_mmer, &ctx->stg_off, &ctx->skr_side};
+                      &ctx->unit_state, &ctx->o_kmer_mmer, &ctx->bucket_excl, &ctx->big_list, &ctx->big_k0, &ctx->big_k1, &ctx->big_arr, &ctx->stg_ids, &ctx->stg_codes, &ctx->stg_mmer, &ctx->stg_off, &ctx->skr_side,
+                      &ctx->ent_a, &ctx->ent_b, &ctx->piece_n, &ctx->v3_base64, &ctx->v3_head_run, &ctx->v3_unit_out, &ctx->v3_unit_excl};
     for (DevBuf *b : bufs) b->release();
     ctx->h_misc.release();
     ctx->h_result.release();
@@ -742,8 +944,28 @@ int gbin_get_run_stats(const gbin_ctx *ctx, gbin_run_stats *out) {
 }
 
 int gbin_set_pipeline(gbin_ctx *ctx, int pipeline) {
-    if (!ctx || (pipeline != 1 && pipeline != 2)) return GBIN_E_INVALID_ARG;
+    if (!ctx || pipeline < 1 || pipeline > 3) return GBIN_E_INVALID_ARG;
     ctx->pipeline = pipeline;
+    return GBIN_OK;
+}
+
+int gbin_set_tuning(gbin_ctx *ctx, const char *name, int value) {
+    if (!ctx || !name) return GBIN_E_INVALID_ARG;
+    if (!strcmp(name, "v3_cap")) {
+        if (value != 512 && value != 1024) return GBIN_E_INVALID_ARG;
+        ctx->v3_cap = value;
+    } else if (!strcmp(name, "v3_nc")) {
+        if (value != 1 && value != 2) return GBIN_E_INVALID_ARG;
+        ctx->v3_nc = value;
+    } else if (!strcmp(name, "v3_h")) {
+        if (value < 0 || value > 15) return GBIN_E_INVALID_ARG;
+        ctx->v3_h = value;
+    } else if (!strcmp(name, "host_chunks")) {
+        if (value < 1 || value > SKR_MAX_CHUNKS) return GBIN_E_INVALID_ARG;
+        ctx->host_chunks = value;
+    } else {
+        return GBIN_E_INVALID_ARG;
+    }
     return GBIN_OK;
 }
 
@@ -773,7 +995,7 @@ int gbin_get_kernel_profile(const gbin_ctx *ctx, gbin_kernel_profile *out) {
 
 const char *gbin_kernel_kind_name(int kind) {
     static const char *names[] = {"scan_reads", "radix_hist", "radix_tile_scan", "radix_scatter", "find_runs", "prune_offsets", "emit_table",
-                                  "skr_scan", "skr_plan", "skr_group"};
+                                  "skr_scan", "skr_plan", "skr_group", "v3_entries", "v3_span"};
     return (kind >= 0 && kind < KK_COUNT) ? names[kind] : "";
 }
 
@@ -1284,9 +1506,9 @@ int gbin_group_skr_device(gbin_ctx *ctx, void *d_skr, uint64_t n_skr, const int3
     CU(cudaEventRecord(ctx->ev[2], st));
     bool done = false;
     uint64_t n = 0;
+    int used = 2;
     if (n_skr) {
-        CU(ctx->skr_b.ensure((n_skr + 1) * NW * 4));
-        int rc = run_v2_group(ctx, d_skr, ctx->skr_b.p, n_skr, d_ids_by_arrival, id_base, st, out, &launches, &done, &n);
+        int rc = run_skr_group(ctx, d_skr, n_skr, d_ids_by_arrival, id_base, st, out, &launches, &done, &n, nullptr, &used);
         if (rc) return rc;
         if (!done) {
             // A unit overflowed (one k-mer with more instances than a unit holds).  The records were consumed by the sort,
@@ -1303,7 +1525,7 @@ int gbin_group_skr_device(gbin_ctx *ctx, void *d_skr, uint64_t n_skr, const int3
     CU(cudaEventRecord(ctx->ev[4], st));
     CU(cudaStreamSynchronize(st));
     finish_timings(ctx, launches, false);
-    ctx->last_pipeline = 2;
+    ctx->last_pipeline = used;
     return GBIN_OK;
 }
 

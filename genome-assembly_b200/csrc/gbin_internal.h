@@ -4,13 +4,14 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "bin3.cuh"
 #include "gbin_device.cuh"
 
 namespace gbin {
 
 // Per-kernel-class device timing (CUDA events on the launching stream), for the roofline numbers
 // bench.py reports.  Disabled by default; when disabled begin/end cost one branch.
-enum KernelKind { KK_SCAN = 0, KK_RADIX_HIST, KK_RADIX_TILESCAN, KK_RADIX_SCATTER, KK_RUNS, KK_PRUNE, KK_EMIT, KK_SKR_SCAN, KK_SKR_PLAN, KK_SKR_GROUP, KK_COUNT };
+enum KernelKind { KK_SCAN = 0, KK_RADIX_HIST, KK_RADIX_TILESCAN, KK_RADIX_SCATTER, KK_RUNS, KK_PRUNE, KK_EMIT, KK_SKR_SCAN, KK_SKR_PLAN, KK_SKR_GROUP, KK_V3_ENTRIES, KK_V3_SPAN, KK_COUNT };
 struct KernelProf {
     static constexpr int MAX_REGIONS = 256;
     bool enabled = false;
@@ -139,6 +140,51 @@ int skr_group_launch(const void *skr_sorted, int K, int cutoff, const uint32_t *
                      uint32_t *stg_mmer, uint32_t *stg_off, int sm_count, cudaStream_t st);
 int skr_emit_buckets(const uint32_t *kmer_mmer, uint64_t n_kmers, uint64_t n_ids, uint32_t *bucket_excl, uint32_t *scratch,
                      uint32_t *mmer_codes, uint64_t *mmer_kmer_off, uint64_t *kmer_id_off, uint32_t *n_buckets_dev, cudaStream_t st);
+
+// ---- bin3.cu (pipeline v3: sort by reference, one warp per unit, table written once at its final place)
+int radix_sort_entries(void *a, void *b, uint64_t n, int key_bits, void *scratch, bool *result_in_b, int *passes_out, KernelProf *prof,
+                       cudaStream_t st);
+int v3_make_entries(const void *skr, uint64_t n_rec, const KeyLayout &kl, uint64_t *ent, uint8_t *piece_n, unsigned long long *n_real_dev,
+                    cudaStream_t st);
+int v3_plan_runs(const uint64_t *ent, const uint8_t *piece_n, uint64_t n_ent, uint32_t *inst_prefix, uint64_t *both64, uint32_t *run_start,
+                 uint64_t *scratch64, uint32_t *n_inst_dev, uint32_t *n_runs_dev, cudaStream_t st);
+uint64_t v3_max_units(uint64_t n_inst, uint64_t n_runs, int cap);
+size_t v3_unit_bytes();
+size_t v3_unit_out_bytes();
+size_t v3_counters_bytes();
+struct V3Counters {  // mirror of G3Counters in bin3.cu
+    unsigned long long distinct, total_kmers, total_ids;
+    unsigned int overflow, n_units, n_spans, pad;
+};
+int v3_plan_units(const void *skr, const uint64_t *ent, const KeyLayout &kl, int cap, const uint32_t *inst_prefix, const uint32_t *run_start, uint64_t n_runs, uint64_t *nunits64, uint64_t *base64,
+                  uint32_t *head_run, void *scratch, void *units, uint64_t max_units, void *gc_dev, uint32_t n_chunks, uint32_t *chunk_bounds, cudaStream_t st);
+struct V3Out {
+    // the flat table
+    uint64_t *kmer_codes;
+    uint32_t *kmer_mmer;
+    uint64_t *kmer_id_off;
+    int32_t *read_ids;
+    // staging (unit-local places) and what every unit reports
+    uint64_t kmer_cap, id_cap;
+    uint64_t *stg_codes;
+    uint32_t *stg_mmer;
+    uint32_t *stg_loff;
+    int32_t *stg_ids;
+    void *unit_out;
+};
+struct V3Chunks {
+    uint32_t n;                       // 1..SKR_MAX_CHUNKS launches over consecutive ranges of the unit list
+    uint32_t *tickets;                // device, [2 * n], zeroed by the launcher
+    uint32_t *bounds;                 // device, [n + 1], filled by v3_plan_units
+    uint64_t *chunk_sum;              // device scalar (scratch)
+    unsigned long long *totals_dev;   // device, [n]: {k-mers << 32 | ids} emitted up to the end of every chunk
+    unsigned long long *totals_host;  // pinned, [n] or nullptr
+    cudaEvent_t *done;                // [n] or nullptr
+};
+size_t v3_group_smem_bytes(int KW, int cap);
+int v3_group_launch(const void *skr, const uint64_t *ent, const void *units, const KeyLayout &kl, int cap, int cutoff, const int32_t *ids_by_arrival, int32_t id_base,
+                    const V3Out &o, uint64_t max_units, uint64_t *unit_excl, void *scan_scratch, void *gc_dev, const V3Chunks &ch, int sm_count, KernelProf *prof,
+                    cudaStream_t st);
 
 // ---- split_reads.cu (main's fgets loop on the device)
 uint32_t split_tiles(uint64_t n);

@@ -189,7 +189,9 @@ __global__ void __launch_bounds__(RS_THREADS)
         store_blob<NU64>(out + pos, r);
         // last pass of the super-k-mer sort: {m-mer code, windows} of every record in sorted order, 8 bytes instead of the
         // whole record for the planning scans that follow
-        if (side) side[pos] = (r.w[0] & 0xffffffff00000000ull) | (r.w[1] & 0xffull);
+        if constexpr (NU64 >= 2) {
+            if (side) side[pos] = (r.w[0] & 0xffffffff00000000ull) | (r.w[1] & 0xffull);
+        }
     }
 }
 
@@ -294,6 +296,7 @@ static inline uint32_t ntiles_of(uint64_t n, int tile) { return (uint32_t)((n + 
 
 static uint32_t ntiles_any(int nu64, uint64_t n) {
     switch (nu64) {
+        case 1: return ntiles_of(n, TileShape<1>::TILE);
         case 2: return ntiles_of(n, TileShape<2>::TILE);
         case 3: return ntiles_of(n, TileShape<3>::TILE);
         case 4: return ntiles_of(n, TileShape<4>::TILE);
@@ -351,6 +354,7 @@ static int one_pass(const void *in_v, void *out_v, uint64_t n, const DigitSel &s
 static int one_pass_any(int nu64, const void *in, void *out, uint64_t n, const DigitSel &sel, uint32_t *scratch, KernelProf *prof,
                         cudaStream_t st, const XchgPlan *xp = nullptr, uint64_t *side = nullptr) {
     switch (nu64) {
+        case 1: return one_pass<1>(in, out, n, sel, scratch, prof, st, xp, side);
         case 2: return one_pass<2>(in, out, n, sel, scratch, prof, st, xp, side);
         case 3: return one_pass<3>(in, out, n, sel, scratch, prof, st, xp, side);
         case 4: return one_pass<4>(in, out, n, sel, scratch, prof, st, xp, side);
@@ -410,6 +414,27 @@ int radix_sort_skr_by_mmer(void *a, void *b, uint64_t n, int skr_words, int M, v
     for (int s = 0; s < 2 * M; s += 8) {
         launches += one_pass_any(skr_words / 2, src, dst, n, DigitSel{0, 32 + s, 0}, static_cast<uint32_t *>(scratch), prof, st, nullptr,
                                  s + 8 >= 2 * M ? side_out : nullptr);
+        void *t = src;
+        src = dst;
+        dst = t;
+        passes++;
+    }
+    *result_in_b = (src == b);
+    *passes_out = passes;
+    return launches;
+}
+
+// v3: 8-byte entries {key << 32 | slot} sorted on the low `key_bits` bits of the key (stable, so entries of one key keep
+// their order: slots ascend with arrival).
+int radix_sort_entries(void *a, void *b, uint64_t n, int key_bits, void *scratch, bool *result_in_b, int *passes_out, KernelProf *prof,
+                       cudaStream_t st) {
+    *result_in_b = false;
+    *passes_out = 0;
+    if (n == 0) return 0;
+    int launches = 0, passes = 0;
+    void *src = a, *dst = b;
+    for (int s = 0; s < key_bits; s += 8) {
+        launches += one_pass_any(1, src, dst, n, DigitSel{0, 32 + s, 0}, static_cast<uint32_t *>(scratch), prof, st);
         void *t = src;
         src = dst;
         dst = t;

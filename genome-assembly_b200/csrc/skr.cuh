@@ -6,7 +6,8 @@
 //
 //   word 0        arrival index of the read
 //   word 1        m-mer bucket code  w(sig) = max(s, 4^M-1-s)
-//   word 2        n (bits 0-7: windows in the segment, 1..K-M+1 <= 63) | is_rev << 8
+//   word 2        n (bits 0-7: windows in the segment, 1..K-M+1 <= 63) | is_rev << 8 | so << 16 (bits 16-21: offset of the
+//                 signature m-mer from the segment's first base; window t holds it at offset d = so - t, 0 <= d <= K-M)
 //   word 3        start: index of the segment's first window in the read (diagnostic / parity)
 //   word 4..      the K+n-1 bases, 2 bits each, MSB first, 16 bases per word, zero padded
 //

@@ -64,7 +64,7 @@ __device__ __forceinline__ uint32_t skr_process_tile(const ReadsView &rv, const 
             const uint32_t sig = i + warp_signature_hop_strand<PACKED>(ws.wr, i, C, lane, &w_rev);
             const uint32_t next = min(sig + 1, W);
             if (lane == 0) {
-                ws.segl[2 * nsr] = i | ((next - i) << 16) | ((w_rev & 1u) << 24);
+                ws.segl[2 * nsr] = i | ((next - i) << 16) | ((w_rev & 1u) << 24) | ((sig - i) << 25);  // sig - i <= K-M <= 62
                 ws.segl[2 * nsr + 1] = w_rev >> 1;
             }
             nsr++;
@@ -75,13 +75,13 @@ __device__ __forceinline__ uint32_t skr_process_tile(const ReadsView &rv, const 
         for (uint32_t e = lane; e < nsr * NW; e += 32) {
             const uint32_t sg = e / NW, j = e - sg * NW;
             const uint32_t info = ws.segl[2 * sg], mx = ws.segl[2 * sg + 1];
-            const uint32_t st0 = info & 0xffffu, n = (info >> 16) & 0xffu, rev = (info >> 24) & 1u;
+            const uint32_t st0 = info & 0xffffu, n = (info >> 16) & 0xffu, rev = (info >> 24) & 1u, so = (info >> 25) & 0x3fu;
             const uint32_t jp = j >= 4 ? j - 4 : 0;
             const uint32_t bit = 2 * st0, wi = (bit >> 5) + jp, sh = bit & 31;
             uint32_t word = __funnelshift_l(ws.pk[wi + 1], ws.pk[wi], sh);
             const int keep = 2 * (int)(K + n - 1) - 32 * (int)jp;  // valid payload bits in this word
             word = keep >= 32 ? word : (keep <= 0 ? 0u : (word & (0xffffffffu << (32 - keep))));
-            word = j == 0 ? arrival : (j == 1 ? mx : (j == 2 ? (n | (rev << 8)) : (j == 3 ? st0 : word)));
+            word = j == 0 ? arrival : (j == 1 ? mx : (j == 2 ? (n | (rev << 8) | (so << 16)) : (j == 3 ? st0 : word)));
             if (DIRECT) out[(base + nseg + sg) * NW + j] = word;
             else if (nseg + sg < seg_cap) ws.stage[(nseg + sg) * NW + j] = word;
         }

@@ -158,6 +158,12 @@ typedef struct gbin_run_stats {
 } gbin_run_stats;
 int gbin_get_run_stats(const gbin_ctx *ctx, gbin_run_stats *out);
 int gbin_set_pipeline(gbin_ctx *ctx, int pipeline);
+/* Tuning knobs (tests and experiments; every setting produces the same table):
+ *   "v3_cap" 512|1024      k-mer instances per work unit of pipeline 3 (default 1024)
+ *   "v3_nc"  1|2           pieces per super-k-mer record: 1 = key is the m-mer code; 2 = windows split by the signature's offset
+ *   "v3_h"   0..           with v3_nc = 2: bases next to the signature that extend the level-1 key (clamped to what K, M allow)
+ *   "host_chunks" 1..16    pieces in which gbin_bin_reads_host streams reads in / the table out */
+int gbin_set_tuning(gbin_ctx *ctx, const char *name, int value);
 int gbin_get_pipeline_info(const gbin_ctx *ctx, int *configured, int *last_used, uint32_t *fallbacks);
 
 /* Optional per-kernel-class device timing (CUDA events around each launch on the call's stream),

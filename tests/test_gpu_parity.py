@@ -129,7 +129,7 @@ def test_super_kmer_scan_matches_process_read(case):
     b.close()
 
 
-@pytest.mark.parametrize("pipeline", [2, 1])
+@pytest.mark.parametrize("pipeline", [3, 2, 1])
 @pytest.mark.parametrize("case", GPU_CASES, ids=lambda c: c["name"])
 def test_table_matches_oracle_and_reference_pin(case, pipeline, tmp_path):
     """Whole path through gbin_read_file_fgets + gbin_bin_reads_host: identical arrays to the oracle and
@@ -153,8 +153,12 @@ def test_table_matches_oracle_and_reference_pin(case, pipeline, tmp_path):
         assert info["last_used"] == 1
     elif case["name"] not in ("fuzz_polyA", "fuzz_ragged_k15"):
         # homopolymers and 2-letter-alphabet reads hold single k-mers with more instances than a shared-memory unit:
-        # pipeline 2 detects the overflow and the batch is redone by pipeline 1
-        assert info["last_used"] == 2 and info["fallbacks"] == 0, info
+        # pipelines 3 and 2 detect the overflow and the batch is redone by the next pipeline down
+        if pipeline == 3 and case["m"] <= 5:
+            # few, huge m-mer buckets: a (bucket, d) class can exceed a unit of pipeline 3, the batch then goes to pipeline 2
+            assert info["last_used"] in (3, 2), info
+        else:
+            assert info["last_used"] == pipeline and info["fallbacks"] == 0, info
     b.close()
 
 
@@ -198,7 +202,7 @@ def test_fixed_stride_form_and_explicit_ids():
     b.close()
 
 
-@pytest.mark.parametrize("pipeline", [2, 1])
+@pytest.mark.parametrize("pipeline", [3, 2, 1])
 @pytest.mark.parametrize("K,M,cutoff,L", [(32, 15, 1, 80), (33, 8, 0, 90), (64, 15, 1, 200), (8, 4, 2, 40), (4, 2, 5, 30),
                                           (31, 4, -1, 60), (40, 13, 3, 150), (63, 2, 1, 100)])
 def test_key_width_and_parameter_edges(K, M, cutoff, L, pipeline):
@@ -232,7 +236,7 @@ def test_host_path_streams_reads_in_and_table_out():
     for n in (n_small, rs.n_reads, rs.n_reads, n_small, rs.n_reads):
         got = b.bin_host(rs.buf[: n * rs.stride], n, stride=rs.stride, read_len=rs.read_len)
         assert_tables_equal(got, want[n])
-        assert b.pipeline_info()["last_used"] == 2
+        assert b.pipeline_info()["last_used"] == 3
     # device table -> pinned arena (what the multi-GPU end-to-end path uses)
     torch = torch_cuda()
     d = torch.from_numpy(rs.buf).cuda()
@@ -375,7 +379,7 @@ def test_reference_entry_points_process_read_prune_data():
     L.gbin_ref_reset(C.addressof(root))
 
 
-@pytest.mark.parametrize("pipeline", [2, 1])
+@pytest.mark.parametrize("pipeline", [3, 2, 1])
 def test_medium_synthetic_cfg2_shape(pipeline):
     """60 000 reads x 100 bp (4.2 M instances, 1026 sort tiles): multi-tile sort, multi-level scans."""
     torch_cuda()
@@ -390,18 +394,41 @@ def test_medium_synthetic_cfg2_shape(pipeline):
     b.close()
 
 
-def test_homopolymer_batch_falls_back_to_the_hbm_pipeline():
-    """One k-mer with 210 000 instances cannot fit a shared-memory unit: pipeline 2 detects it and the batch is
+@pytest.mark.parametrize("pipeline", [3, 2])
+def test_homopolymer_batch_falls_back_to_the_hbm_pipeline(pipeline):
+    """One k-mer with 210 000 instances cannot fit a shared-memory unit: pipelines 3 and 2 detect it and the batch is
     redone by pipeline 1 — same table either way."""
     torch_cuda()
     poly = (b"A" * 100 + b"\n") * 3000
     sp, lp = np.arange(3000, dtype=np.uint64) * 101, np.full(3000, 100, np.uint32)
-    b = B.Binner(31, 4, 1, pipeline=2)
+    b = B.Binner(31, 4, 1, pipeline=pipeline)
     t = b.bin_host(poly, 3000, stride=101, read_len=100)
     assert_tables_equal(t, O.run(poly, sp, lp, 31, 4, 1))
     info = b.pipeline_info()
-    assert info["last_used"] == 1 and info["fallbacks"] == 1
+    assert info["last_used"] == 1 and info["fallbacks"] == pipeline - 1
     b.close()
+
+
+@pytest.mark.parametrize("cap", [1024, 512])
+@pytest.mark.parametrize("n_reads", [2500, 12000])
+def test_deep_coverage_rounds_and_spans(n_reads, cap):
+    """Pipeline 3 on a tiny genome at ~125x / ~600x coverage: every m-mer bucket is larger than a unit, so it is grouped in
+    d-rounds (ranges of the signature's offset inside the k-mer) by several warps and put back in k-mer order by the span
+    pass; id lists hold hundreds of entries."""
+    torch_cuda()
+    rs = synth.generate(n_reads, 100, genome_len=2000, error_rate=0.002, seed=77, starts="uniform")
+    starts = np.arange(rs.n_reads, dtype=np.uint64) * rs.stride
+    lens = np.full(rs.n_reads, rs.read_len, dtype=np.uint32)
+    for K, M in ((31, 11), (31, 4), (63, 15)):
+        b = B.Binner(K, M, 1, pipeline=3)
+        b.set_tuning("v3_cap", cap)
+        got = b.bin_host(rs.buf, rs.n_reads, stride=rs.stride, read_len=rs.read_len)
+        want = O.run(rs.as_bytes(), starts, lens, K, M, 1)
+        assert_tables_equal(got, want)
+        info = b.pipeline_info()
+        if n_reads == 2500:  # no (bucket, d) class exceeds a unit: no fallback
+            assert info["last_used"] == 3 and info["fallbacks"] == 0, (K, M, cap, info)
+        b.close()
 
 
 @pytest.mark.parametrize("n_reads,expect_v2", [(2500, True), (12000, False)])
@@ -436,6 +463,22 @@ def test_large_buckets_are_sliced_not_redone():
     info, st = b.pipeline_info(), b.run_stats()
     assert info["last_used"] == 2 and info["fallbacks"] == 0, (info, st)
     assert st["n_units"] > 3 * st["n_mmer_runs"], st
+    assert_tables_equal(got, O.run(rs.as_bytes(), starts, lens, 25, 7, 1))
+    b.close()
+
+
+@pytest.mark.parametrize("cap", [1024, 512])
+def test_v3_large_buckets_in_rounds(cap):
+    """Pipeline 3 on the same 19 M instances: buckets of ~15 000 instances are cut into d-rounds; a (bucket, d) class that
+    exceeds a unit sends the batch to pipeline 2.  Either way the table is the oracle's."""
+    torch_cuda()
+    rs = synth.generate(150_000, 150, error_rate=0.01, seed=31, starts="uniform")
+    starts = np.arange(rs.n_reads, dtype=np.uint64) * rs.stride
+    lens = np.full(rs.n_reads, rs.read_len, dtype=np.uint32)
+    b = B.Binner(25, 7, 1, pipeline=3)
+    b.set_tuning("v3_cap", cap)
+    got = b.bin_host(rs.buf, rs.n_reads, stride=rs.stride, read_len=rs.read_len)
+    assert b.pipeline_info()["last_used"] in (3, 2)
     assert_tables_equal(got, O.run(rs.as_bytes(), starts, lens, 25, 7, 1))
     b.close()
 

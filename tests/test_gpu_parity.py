@@ -426,7 +426,7 @@ def test_deep_coverage_rounds_and_spans(n_reads, cap):
         want = O.run(rs.as_bytes(), starts, lens, K, M, 1)
         assert_tables_equal(got, want)
         info = b.pipeline_info()
-        if n_reads == 2500:  # no (bucket, d) class exceeds a unit: no fallback
+        if n_reads == 2500 and M > 4:  # no (bucket, d) class exceeds a unit: no fallback (M = 4 has a few huge buckets)
             assert info["last_used"] == 3 and info["fallbacks"] == 0, (K, M, cap, info)
         b.close()
 

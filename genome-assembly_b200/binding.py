@@ -105,7 +105,7 @@ def load_library() -> C.CDLL:
     L.gbin_pinned_free.argtypes = [vp]
     L.gbin_pinned_free.restype = None
     L.gbin_get_timings.argtypes = [vp, C.POINTER(Timings)]
-    L.gbin_get_run_stats.argtypes = [vp, C.POINTER(u64 * 4)]
+    L.gbin_get_run_stats.argtypes = [vp, C.POINTER(u64 * 5)]
     L.gbin_set_pipeline.argtypes = [vp, C.c_int]
     L.gbin_set_tuning.argtypes = [vp, C.c_char_p, C.c_int]
     L.gbin_get_pipeline_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint32)]
@@ -287,9 +287,10 @@ class Binner:
         return {"configured": a.value, "last_used": b.value, "fallbacks": c.value}
 
     def run_stats(self) -> dict:
-        a = (C.c_uint64 * 4)()
+        a = (C.c_uint64 * 5)()
         self._check(self.lib.gbin_get_run_stats(self.h, C.byref(a)))
-        return {"n_super_kmers": int(a[0]), "n_mmer_runs": int(a[1]), "n_units": int(a[2])}
+        return {"n_super_kmers": int(a[0]), "n_mmer_runs": int(a[1]), "n_units": int(a[2]), "n_lsd_kmers": int(a[3]),
+                "key_nc": int(a[4]) & 0xffffffff, "key_h": int(a[4]) >> 32}
 
     def set_kernel_profiling(self, enable: bool):
         self._check(self.lib.gbin_set_kernel_profiling(self.h, int(enable)))

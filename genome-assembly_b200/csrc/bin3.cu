@@ -69,9 +69,15 @@ __global__ void __launch_bounds__(256)
             }
         }
     }
+    if (kl.nc == 1) return;  // every slot is real: the host knows the count
+    __shared__ uint32_t s_real;
+    if (threadIdx.x == 0) s_real = 0;
+    __syncthreads();
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) real += __shfl_xor_sync(0xffffffffu, real, d);
-    if ((threadIdx.x & 31) == 0 && real) atomicAdd(n_real, (unsigned long long)real);
+    if ((threadIdx.x & 31) == 0 && real) atomicAdd(&s_real, real);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_real) atomicAdd(n_real, (unsigned long long)s_real);
 }
 
 int v3_make_entries(const void *skr, uint64_t n_rec, const KeyLayout &kl, uint64_t *ent, uint8_t *piece_n, unsigned long long *n_real_dev,
@@ -146,48 +152,92 @@ __host__ __device__ inline uint32_t rounds_of(uint32_t c, const Plan3 &pp) {
     return r < pp.max_rounds ? r : pp.max_rounds;
 }
 
-// nunits[r] = units that start at atom r (low half) | 1 << 32 if the atom is split into rounds
-__global__ void __launch_bounds__(256)
-    v3_pack_kernel(RunView3 rv, uint64_t n_runs, Plan3 pp, uint64_t *__restrict__ nunits) {
-    __shared__ uint32_t s_c[PLAN_CTA_BLOCKS * PLAN_BLOCK];
-    __shared__ uint16_t s_e[PLAN_CTA_BLOCKS * PLAN_BLOCK];
-    const uint64_t first = (uint64_t)blockIdx.x * (PLAN_CTA_BLOCKS * PLAN_BLOCK);
-    for (uint32_t i = threadIdx.x; i < (uint32_t)(PLAN_CTA_BLOCKS * PLAN_BLOCK); i += blockDim.x) {
-        const uint64_t r = first + i;
-        uint32_t c = 0, e = 0;
-        if (r < n_runs) {
-            const uint32_t a = rv.run_start[r], b = rv.run_start[r + 1];
-            c = rv.inst_prefix[b] - rv.inst_prefix[a];
-            e = b - a;
+// Per atom (run of equal key): instances, entries and m-mer code, for the packer.
+__global__ void v3_atoms_kernel(RunView3 rv, const uint64_t *__restrict__ ent, uint64_t n_runs, int mshift, uint32_t *__restrict__ atom_c,
+                                uint32_t *__restrict__ atom_e, uint32_t *__restrict__ atom_mm) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_runs) return;
+    const uint32_t a = rv.run_start[r], b = rv.run_start[r + 1];
+    atom_c[r] = rv.inst_prefix[b] - rv.inst_prefix[a];
+    atom_e[r] = b - a;
+    atom_mm[r] = (uint32_t)(ent[a] >> 32) >> mshift;
+}
+
+// nunits[r] = units that start at atom r (low half) | ATOM_ROUNDS if the atom is split into rounds.
+// spanlen[r] = 0: the atom's bucket fits a unit; L > 0 at the first atom of a bucket that is a span of L units; SPAN_MEMBER at the
+// other atoms of such a bucket.  A bucket (run of atoms with one m-mer code) is packed whole when it fits a unit; otherwise it
+// becomes a span: units that hold nothing but this bucket — its atoms packed greedily, atoms larger than a unit cut into rounds.
+// One thread walks PLAN_BLOCK atoms' worth of buckets: from the first bucket that starts at or after its block to the end of the
+// bucket that straddles the block's end.
+constexpr uint64_t ATOM_ROUNDS = 1ull << 32;
+constexpr uint32_t SPAN_MEMBER = 0xfffffffeu;       // a further unit of a short span (merged by the warp of its first unit)
+constexpr uint32_t SPAN_MEMBER_LONG = 0xffffffffu;  // a unit of a long span (put in order by the global sort)
+constexpr uint32_t SPAN_SHORT_MAX = 8;              // units of a short span
+__global__ void __launch_bounds__(128)
+    v3_pack_kernel(const uint32_t *__restrict__ atom_c, const uint32_t *__restrict__ atom_e, const uint32_t *__restrict__ atom_mm, uint64_t n_runs, Plan3 pp,
+                   uint64_t *__restrict__ nunits, uint32_t *__restrict__ spanlen) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t r = t * PLAN_BLOCK;
+    const uint64_t stop = r + PLAN_BLOCK < n_runs ? r + PLAN_BLOCK : n_runs;
+    if (r >= n_runs) return;
+    if (r > 0)
+        while (r < n_runs && atom_mm[r] == atom_mm[r - 1]) r++;  // that bucket belongs to the previous walker
+    uint32_t cur_c = 0, cur_e = 0, cur_b = 0;
+    while (r < stop) {
+        const uint32_t mm = atom_mm[r];
+        uint64_t q = r;
+        uint64_t cb = 0, eb = 0;
+        do {
+            cb += atom_c[q];
+            eb += atom_e[q];
+            q++;
+        } while (q < n_runs && atom_mm[q] == mm);
+        if (cb <= pp.cap && eb <= pp.ecap) {  // the whole bucket is one item
+            if (cur_b == 0 || cur_c + cb > pp.cap || cur_e + eb > pp.ecap || cur_b + 1 > pp.nb_max) {
+                nunits[r] = 1ull;
+                cur_c = (uint32_t)cb;
+                cur_e = (uint32_t)eb;
+                cur_b = 1;
+            } else {
+                nunits[r] = 0ull;
+                cur_c += (uint32_t)cb;
+                cur_e += (uint32_t)eb;
+                cur_b++;
+            }
+            spanlen[r] = 0;
+            for (uint64_t a = r + 1; a < q; a++) {
+                nunits[a] = 0ull;
+                spanlen[a] = 0;
+            }
+        } else {  // a span
+            cur_b = 0;  // the next bucket opens a unit
+            uint32_t L = 0, sc = 0, se = 0;
+            bool open = false;
+            for (uint64_t a = r; a < q; a++) {
+                const uint32_t c = atom_c[a], e = atom_e[a];
+                if (c > pp.cap) {
+                    const uint32_t R = rounds_of(c, pp);
+                    nunits[a] = (uint64_t)R | ATOM_ROUNDS;
+                    L += R;
+                    open = false;
+                } else if (!open || sc + c > pp.cap || se + e > pp.ecap) {
+                    nunits[a] = 1ull;
+                    L++;
+                    sc = c;
+                    se = e;
+                    open = true;
+                } else {
+                    nunits[a] = 0ull;
+                    sc += c;
+                    se += e;
+                }
+                spanlen[a] = SPAN_MEMBER;
+            }
+            spanlen[r] = L;
+            if (L > SPAN_SHORT_MAX)
+                for (uint64_t a = r + 1; a < q; a++) spanlen[a] = SPAN_MEMBER_LONG;
         }
-        s_c[i] = c;
-        s_e[i] = (uint16_t)(e > 0xffffu ? 0xffffu : e);
-    }
-    __syncthreads();
-    if (threadIdx.x >= (uint32_t)PLAN_CTA_BLOCKS) return;
-    // thread t walks block t; consecutive threads touch the same offset of consecutive blocks (stride PLAN_BLOCK + skew)
-    const uint32_t b0 = threadIdx.x * PLAN_BLOCK;
-    uint32_t cur_c = 0, cur_e = 0, cur_a = 0;
-    for (uint32_t i = 0; i < (uint32_t)PLAN_BLOCK; i++) {
-        const uint64_t r = first + b0 + i;
-        if (r >= n_runs) break;
-        const uint32_t c = s_c[b0 + i], e = s_e[b0 + i];
-        uint64_t out;
-        if (c > pp.cap) {
-            out = (uint64_t)rounds_of(c, pp) | (1ull << 32);
-            cur_a = 0;  // the next atom opens a unit
-        } else if (cur_a == 0 || cur_c + c > pp.cap || cur_e + e > pp.ecap || cur_a + 1 > pp.nb_max) {
-            out = 1ull;
-            cur_c = c;
-            cur_e = e;
-            cur_a = 1;
-        } else {
-            out = 0ull;
-            cur_c += c;
-            cur_e += e;
-            cur_a++;
-        }
-        nunits[r] = out;
+        r = q;
     }
 }
 
@@ -197,6 +247,7 @@ struct G3Counters {
     unsigned int overflow;
     unsigned int n_units, n_spans;
     unsigned int pad;
+    unsigned long long lsd_kmers, lsd_ids;  // surviving k-mers / ids of the spans that are put in order by the global sort
 };
 
 __global__ void v3_head_runs_kernel(const uint64_t *__restrict__ nunits, const uint64_t *__restrict__ base, uint64_t n_runs, uint32_t *__restrict__ head_run) {
@@ -207,8 +258,9 @@ __global__ void v3_head_runs_kernel(const uint64_t *__restrict__ nunits, const u
     for (uint32_t j = 0; j < nu; j++) head_run[ub + j] = (uint32_t)r;
 }
 
-__global__ void v3_fill_units_kernel(RunView3 rv, const uint64_t *__restrict__ base, const uint64_t *__restrict__ totals, uint64_t n_runs, Plan3 pp,
-                                     const uint32_t *__restrict__ head_run, Unit3 *__restrict__ units, G3Counters *__restrict__ gc) {
+__global__ void v3_fill_units_kernel(RunView3 rv, const uint64_t *__restrict__ nunits, const uint32_t *__restrict__ spanlen, const uint64_t *__restrict__ base,
+                                     const uint64_t *__restrict__ totals, uint64_t n_runs, const uint32_t *__restrict__ head_run, Unit3 *__restrict__ units,
+                                     G3Counters *__restrict__ gc) {
     const uint32_t n_units = (uint32_t)*totals;
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u == 0) {
@@ -217,25 +269,28 @@ __global__ void v3_fill_units_kernel(RunView3 rv, const uint64_t *__restrict__ b
     }
     if (u >= n_units) return;
     const uint32_t r0 = head_run[u];
-    const uint32_t c = rv.size(r0);
+    const uint64_t nu = nunits[r0];
+    const uint32_t ub = (uint32_t)base[r0];
     Unit3 un;
-    un.pad = 0;
+    un.drange = 0u | (63u << 8);
     un.ent_begin = rv.run_start[r0];
     un.ibase = rv.inst_prefix[un.ent_begin];
-    if (c > pp.cap) {
+    if (nu & ATOM_ROUNDS) {
         un.ent_end = rv.run_start[r0 + 1];
-        un.n_inst = c;
-        un.round = u - (uint32_t)base[r0];
-        un.rounds = rounds_of(c, pp);
-        un.span = (uint32_t)(base[r0] >> 32);
+        un.n_inst = rv.inst_prefix[un.ent_end] - un.ibase;
+        un.round = u - ub;
+        un.rounds = (uint32_t)nu;
     } else {
         const uint32_t r1 = (u + 1 < n_units) ? head_run[u + 1] : (uint32_t)n_runs;
         un.ent_end = rv.run_start[r1];
         un.n_inst = rv.inst_prefix[un.ent_end] - un.ibase;
         un.round = 0;
         un.rounds = 0;
-        un.span = 0;
     }
+    const uint32_t sl = spanlen[r0];
+    // the head atom of a span carries its length; its first unit is the span's head, its further (round) units are members
+    if (sl == 0 || sl == SPAN_MEMBER || sl == SPAN_MEMBER_LONG) un.span_len = sl;
+    else un.span_len = u == ub ? sl : (sl > SPAN_SHORT_MAX ? SPAN_MEMBER_LONG : SPAN_MEMBER);
     units[u] = un;
 }
 
@@ -287,7 +342,7 @@ __global__ void __launch_bounds__(128)
             auto emit = [&](int hi) {
                 if (rnd < un.rounds) {
                     Unit3 &w = units[u + rnd];
-                    w.span = (uint32_t)lo | ((uint32_t)hi << 8);
+                    w.drange = (uint32_t)lo | ((uint32_t)hi << 8);
                     w.ibase = un.ibase + before;
                     w.n_inst = acc;
                 } else {
@@ -407,7 +462,7 @@ __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, uint32_t lane
 constexpr int G3_WARPS = 5;  // warps (= units in flight) per CTA
 constexpr int G3_U = 4;  // instances per lane that are in flight together in the instance-major phases
 
-template <int PW, int KW, int WCAP, int WARPS>
+template <int PW, int KW, int WCAP, int WARPS, int U>
 __global__ void __launch_bounds__(WARPS * 32)
     group3_kernel(const uint32_t *__restrict__ skr, const uint64_t *__restrict__ ent, const Unit3 *__restrict__ units, KeyLayout kl, int cutoff,
                   const int32_t *__restrict__ ids_by_arrival, int32_t id_base, G3Stage out, G3Counters *__restrict__ gc,
@@ -415,7 +470,6 @@ __global__ void __launch_bounds__(WARPS * 32)
     constexpr int NW = SkrLayout<PW>::WORDS;
     constexpr int HS = 2 * WCAP;  // hash slots (u16 each)
     constexpr int LOG_HS = WCAP == 512 ? 10 : 11;
-    constexpr int U = G3_U;
     static_assert(WCAP == 512 || WCAP == 1024, "unit capacity");
     static_assert((1 << LOG_HS) == HS, "hash size");
     using WL = WarpLayout<WCAP, KW>;
@@ -458,7 +512,7 @@ __global__ void __launch_bounds__(WARPS * 32)
             un.n_inst = __shfl_sync(0xffffffffu, wv, 2);
             un.round = __shfl_sync(0xffffffffu, wv, 3);
             un.rounds = __shfl_sync(0xffffffffu, wv, 4);
-            un.span = __shfl_sync(0xffffffffu, wv, 5);
+            un.drange = __shfl_sync(0xffffffffu, wv, 5);
             un.ibase = __shfl_sync(0xffffffffu, wv, 6);
         }
         // the next ticket is taken now and read at the end of the unit (units do not depend on each other)
@@ -488,8 +542,8 @@ __global__ void __launch_bounds__(WARPS * 32)
         const uint32_t ibase = un.ibase;
         bool bad = false;
         if (is_round) {
-            dlo = (int)(un.span & 0xffu);
-            dhi = (int)((un.span >> 8) & 0xffu);
+            dlo = (int)(un.drange & 0xffu);
+            dhi = (int)((un.drange >> 8) & 0xffu);
         }
 
         // ---- expansion: lane = entry.  Instance positions follow entry order (= key order, arrival order inside a key).
@@ -850,12 +904,17 @@ struct UnitSN {  // {S << 32 | N} of the units of one chunk, 0 elsewhere
 
 // totals[c] = totals[c - 1] + what chunk c emitted, as {k-mers << 32 | ids} (totals[-1] = 0)
 __global__ void v3_chunk_total_kernel(const uint64_t *__restrict__ chunk_sum, uint32_t chunk, unsigned long long *__restrict__ totals, G3Counters *__restrict__ gc,
-                                      uint32_t n_chunks) {
+                                      uint32_t n_chunks, int which) {
     const unsigned long long t = (chunk ? totals[chunk - 1] : 0ull) + *chunk_sum;
     totals[chunk] = t;
     if (chunk + 1 == n_chunks) {
-        gc->total_kmers = t >> 32;
-        gc->total_ids = t & 0xffffffffull;
+        if (which == 0) {
+            gc->total_kmers = t >> 32;
+            gc->total_ids = t & 0xffffffffull;
+        } else {
+            gc->lsd_kmers = t >> 32;
+            gc->lsd_ids = t & 0xffffffffull;
+        }
     }
 }
 
@@ -869,117 +928,239 @@ struct G3Final {
 // One warp per unit: copy its staged k-mers and ids to their place in the table (place = totals of all units before it).  The
 // round units of a split atom are handled together by the warp that takes the atom's first round: the rounds are sorted runs of
 // distinct k-mers, so a k-mer's place inside the atom = its index in its own run + the number of smaller k-mers in every other run.
+// Long spans: every unit of the span appends its surviving k-mers to the arrays of the global sort, at a place given by a scan
+// over the units of long spans (so a span's records are contiguous, spans in key order, and the sort by (m-mer, k-mer) permutes
+// records only inside their span).  Indexed by the place p of a record BEFORE the sort: where its id list is staged and how long
+// it is; indexed by a place q AFTER the sort: the k-mer's index in the table and what to add to the running list offset.
+struct G3Lsd {
+    const uint64_t *excl;  // [units] {k-mers << 32 | ids} of the long-span units before this one
+    void *rec;             // Rec<KW> [n]
+    uint32_t *src_off;     // [n] staging coordinate of the record's id list
+    uint32_t *cnt;         // [n] its length
+    uint32_t *fidx;        // [n] table index of the k-mer that ends up at this place
+    uint32_t *nadj;        // [n] ids before the span that are not in long spans
+    uint64_t cap;
+};
+
+struct UnitSNLong {  // {S << 32 | N} of the units of long spans of one chunk, 0 elsewhere
+    const UnitOut3 *uo;
+    const Unit3 *units;
+    const uint32_t *chunk_bounds;
+    uint32_t chunk;
+    __device__ __forceinline__ uint64_t operator()(uint64_t u) const {
+        if (u < chunk_bounds[chunk] || u >= chunk_bounds[chunk + 1]) return 0ull;
+        const uint32_t sl = units[u].span_len;
+        if (sl != SPAN_MEMBER_LONG && (sl <= SPAN_SHORT_MAX || sl == SPAN_MEMBER)) return 0ull;
+        return ((uint64_t)uo[u].S << 32) | uo[u].N;
+    }
+};
+
+// One warp per unit: copy its staged k-mers and ids to their place in the table (place = totals of all units before it).
+// Short span: the warp of its first unit merges the units' runs — they hold distinct k-mers, each run ascending, so a k-mer's
+// place inside the span = its index in its own run + the number of smaller k-mers in every other run.
 template <int KW>
-__global__ void __launch_bounds__(128)
-    finalize3_kernel(const Unit3 *__restrict__ units, const uint64_t *__restrict__ unit_excl, const unsigned long long *__restrict__ totals, G3Stage st,
-                     G3Final fin, const uint32_t *__restrict__ chunk_bounds, uint32_t chunk, uint32_t *__restrict__ tickets) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t unit_begin = chunk_bounds[chunk], unit_end = chunk_bounds[chunk + 1];
-    const unsigned long long base = chunk ? totals[chunk - 1] : 0ull;
-    const uint64_t S0 = base >> 32, N0 = base & 0xffffffffull;
-    for (;;) {
-        uint32_t u = 0;
-        if (lane == 0) u = unit_begin + atomicAdd(&tickets[chunk], 1u);
-        u = __shfl_sync(0xffffffffu, u, 0);
-        if (u >= unit_end) break;
-        const Unit3 un = units[u];
-        const uint64_t ex = unit_excl[u];
-        const uint64_t Sb = S0 + (ex >> 32), Nb = N0 + (ex & 0xffffffffull);
-        if (un.rounds == 0) {
-            const UnitOut3 uo = st.unit_out[u];
-            const uint64_t kb = uo.ibase / st.kdiv;
-            for (uint32_t x = lane; x < uo.S; x += 32) {
-                fin.kmer_codes[(Sb + x) * KW] = st.codes[(kb + x) * KW];
-                if (KW == 2) fin.kmer_codes[(Sb + x) * KW + 1] = st.codes[(kb + x) * KW + 1];
-                fin.kmer_mmer[Sb + x] = st.mmer[kb + x];
-                fin.kmer_id_off[Sb + x] = Nb + st.loff[kb + x];
+__device__ __forceinline__ void finalize3_unit(const Unit3 *__restrict__ units, const uint64_t *__restrict__ unit_excl, unsigned long long base,
+                                               unsigned long long lsd_base, const G3Stage &st, const G3Final &fin, const G3Lsd &ls, G3Counters *gc, uint32_t u,
+                                               uint32_t lane) {
+    const uint32_t span_len = units[u].span_len;
+    const uint64_t ex = unit_excl[u];
+    const UnitOut3 uo = st.unit_out[u];
+    const uint64_t Sb = (base >> 32) + (ex >> 32), Nb = (base & 0xffffffffull) + (ex & 0xffffffffull);
+    if (span_len == 0) {
+        // everything is loaded before anything is stored: one round trip to memory per batch of loads
+        const uint64_t kb = uo.ibase / st.kdiv;
+        for (uint32_t x0 = 0; x0 < uo.S; x0 += 128) {
+            uint64_t c0[4], c1[4];
+            uint32_t mm[4], lo[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t x = x0 + q * 32 + lane;
+                if (x < uo.S) {
+                    c0[q] = st.codes[(kb + x) * KW];
+                    if (KW == 2) c1[q] = st.codes[(kb + x) * KW + 1];
+                    mm[q] = st.mmer[kb + x];
+                    lo[q] = st.loff[kb + x];
+                }
             }
-            const int32_t *src = st.ids + uo.ibase;
-            int32_t *dst = fin.read_ids + Nb;
-            for (uint32_t i = lane; i < uo.N; i += 32) dst[i] = src[i];
-            continue;
-        }
-        if (un.round != 0) continue;  // handled with the atom's first round
-        const uint32_t R = un.rounds;
-        // pass 1: every k-mer's place inside the atom; its list length goes to kmer_id_off at that place
-        uint32_t S_tot = 0;
-        for (uint32_t j = 0; j < R; j++) S_tot += st.unit_out[u + j].S;
-        const uint32_t mm = S_tot ? st.mmer[st.unit_out[u].ibase / st.kdiv + 0] : 0u;  // every round of the atom has the same m-mer; round 0 may be empty:
-        uint32_t mmer = mm;
-        if (S_tot && st.unit_out[u].S == 0) {
-            for (uint32_t j = 1; j < R; j++) {
-                const UnitOut3 o = st.unit_out[u + j];
-                if (o.S) {
-                    mmer = st.mmer[o.ibase / st.kdiv];
-                    break;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t x = x0 + q * 32 + lane;
+                if (x < uo.S) {
+                    fin.kmer_codes[(Sb + x) * KW] = c0[q];
+                    if (KW == 2) fin.kmer_codes[(Sb + x) * KW + 1] = c1[q];
+                    fin.kmer_mmer[Sb + x] = mm[q];
+                    fin.kmer_id_off[Sb + x] = Nb + lo[q];
                 }
             }
         }
-        for (uint32_t j = 0; j < R; j++) {
-            const UnitOut3 uj = st.unit_out[u + j];
-            const uint64_t kbj = uj.ibase / st.kdiv;
-            for (uint32_t x = lane; x < uj.S; x += 32) {
-                const uint64_t k0 = st.codes[(kbj + x) * KW], k1 = KW == 2 ? st.codes[(kbj + x) * KW + 1] : 0ull;
-                uint32_t rank = x;
-                for (uint32_t j2 = 0; j2 < R; j2++) {
-                    if (j2 == j) continue;
-                    const UnitOut3 u2 = st.unit_out[u + j2];
-                    const uint64_t kb2 = u2.ibase / st.kdiv;
-                    uint32_t a = 0, b = u2.S;  // keys of run j2 smaller than mine
-                    while (a < b) {
-                        const uint32_t m = (a + b) >> 1;
-                        const uint64_t q0 = st.codes[(kb2 + m) * KW];
-                        bool less = q0 < k0;
-                        if constexpr (KW == 2) less = less || (q0 == k0 && st.codes[(kb2 + m) * KW + 1] < k1);
-                        if (less) a = m + 1;
-                        else b = m;
-                    }
-                    rank += a;
+        const int32_t *src = st.ids + uo.ibase;
+        int32_t *dst = fin.read_ids + Nb;
+        for (uint32_t i0 = 0; i0 < uo.N; i0 += 512) {
+            int32_t v[16];
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const uint32_t i = i0 + q * 32 + lane;
+                if (i < uo.N) v[q] = src[i];
+            }
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const uint32_t i = i0 + q * 32 + lane;
+                if (i < uo.N) dst[i] = v[q];
+            }
+        }
+        return;
+    }
+    if (span_len == SPAN_MEMBER) return;  // merged by the warp of the span's first unit
+    if (span_len == SPAN_MEMBER_LONG || span_len > SPAN_SHORT_MAX) {
+        // long span: hand this unit's k-mers to the global sort
+        const uint64_t lx = ls.excl[u];
+        const uint64_t q0 = (lsd_base >> 32) + (lx >> 32), nq0 = (lsd_base & 0xffffffffull) + (lx & 0xffffffffull);
+        if (q0 + uo.S > ls.cap) {  // cannot happen with the caller's bounds
+            if (lane == 0) atomicExch(&gc->overflow, 6u);
+            return;
+        }
+        const uint64_t kb = uo.ibase / st.kdiv;
+        Rec<KW> *rec = static_cast<Rec<KW> *>(ls.rec);
+        for (uint32_t x = lane; x < uo.S; x += 32) {
+            const uint64_t p = q0 + x;
+            Rec<KW> r;
+            r.k[0] = st.codes[(kb + x) * KW];
+            if (KW == 2) r.k[KW - 1] = st.codes[(kb + x) * KW + 1];
+            r.mmer = st.mmer[kb + x];
+            r.arrival = (uint32_t)p;
+            store_rec<KW>(rec + p, r);
+            const uint32_t lo = st.loff[kb + x];
+            ls.src_off[p] = uo.ibase + lo;
+            ls.cnt[p] = (x + 1 < uo.S ? st.loff[kb + x + 1] : uo.N) - lo;
+            ls.fidx[p] = (uint32_t)(Sb + x);
+            ls.nadj[p] = (uint32_t)(Nb - nq0);
+        }
+        return;
+    }
+    const uint32_t R = span_len;
+    // pass 1: every k-mer's place inside the span; its list length goes to kmer_id_off at that place
+    uint32_t S_tot = 0, mmer = 0;
+    bool have_mm = false;
+    for (uint32_t j = 0; j < R; j++) {
+        const UnitOut3 o = st.unit_out[u + j];
+        S_tot += o.S;
+        if (o.S && !have_mm) {  // every unit of the span has the same m-mer code
+            mmer = st.mmer[o.ibase / st.kdiv];
+            have_mm = true;
+        }
+    }
+    mmer = __shfl_sync(0xffffffffu, mmer, 0);  // (all lanes read the same value; it is taken before pass 1 overwrites the staged m-mers)
+    for (uint32_t j = 0; j < R; j++) {
+        const UnitOut3 uj = st.unit_out[u + j];
+        const uint64_t kbj = uj.ibase / st.kdiv;
+        for (uint32_t x = lane; x < uj.S; x += 32) {
+            const uint64_t k0 = st.codes[(kbj + x) * KW], k1 = KW == 2 ? st.codes[(kbj + x) * KW + 1] : 0ull;
+            uint32_t rank = x;
+            for (uint32_t j2 = 0; j2 < R; j2++) {
+                if (j2 == j) continue;
+                const UnitOut3 u2 = st.unit_out[u + j2];
+                const uint64_t kb2 = u2.ibase / st.kdiv;
+                uint32_t a = 0, b = u2.S;  // keys of run j2 smaller than mine
+                while (a < b) {
+                    const uint32_t m = (a + b) >> 1;
+                    const uint64_t q0 = st.codes[(kb2 + m) * KW];
+                    bool less = q0 < k0;
+                    if constexpr (KW == 2) less = less || (q0 == k0 && st.codes[(kb2 + m) * KW + 1] < k1);
+                    if (less) a = m + 1;
+                    else b = m;
                 }
-                const uint32_t cnt = (x + 1 < uj.S ? st.loff[kbj + x + 1] : uj.N) - st.loff[kbj + x];
-                fin.kmer_codes[(Sb + rank) * KW] = k0;
-                if (KW == 2) fin.kmer_codes[(Sb + rank) * KW + 1] = k1;
-                fin.kmer_mmer[Sb + rank] = mmer;
-                fin.kmer_id_off[Sb + rank] = cnt;
-                st.mmer[kbj + x] = rank;  // remembered for pass 3 (the staged m-mer is not needed any more)
+                rank += a;
             }
+            const uint32_t cnt = (x + 1 < uj.S ? st.loff[kbj + x + 1] : uj.N) - st.loff[kbj + x];
+            fin.kmer_codes[(Sb + rank) * KW] = k0;
+            if (KW == 2) fin.kmer_codes[(Sb + rank) * KW + 1] = k1;
+            fin.kmer_mmer[Sb + rank] = mmer;
+            fin.kmer_id_off[Sb + rank] = cnt;
+            st.mmer[kbj + x] = rank;  // remembered for pass 3 (the staged m-mer is not needed any more)
         }
-        __syncwarp();
-        __threadfence();
-        // pass 2: list lengths -> offsets (in place)
-        uint64_t carry = Nb;
-        for (uint32_t x0 = 0; x0 < S_tot; x0 += 32) {
-            const uint32_t x = x0 + lane;
-            const uint32_t c = x < S_tot ? (uint32_t)fin.kmer_id_off[Sb + x] : 0u;
-            const uint32_t inc = warp_incl_scan_u32(c, lane);
-            if (x < S_tot) fin.kmer_id_off[Sb + x] = carry + inc - c;
-            carry += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        __syncwarp();
-        __threadfence();
-        // pass 3: lists, eight lanes per list
-        for (uint32_t j = 0; j < R; j++) {
-            const UnitOut3 uj = st.unit_out[u + j];
-            const uint64_t kbj = uj.ibase / st.kdiv;
-            for (uint32_t x = lane >> 3; x < uj.S; x += 4) {
-                const uint32_t lo = st.loff[kbj + x];
-                const uint32_t cnt = (x + 1 < uj.S ? st.loff[kbj + x + 1] : uj.N) - lo;
-                const uint32_t rank = st.mmer[kbj + x];
-                const int32_t *src = st.ids + uj.ibase + lo;
-                int32_t *dst = fin.read_ids + fin.kmer_id_off[Sb + rank];
-                for (uint32_t i = lane & 7u; i < cnt; i += 8) dst[i] = src[i];
-            }
+    }
+    __syncwarp();
+    __threadfence();
+    // pass 2: list lengths -> offsets (in place)
+    uint64_t carry = Nb;
+    for (uint32_t x0 = 0; x0 < S_tot; x0 += 32) {
+        const uint32_t x = x0 + lane;
+        const uint32_t c = x < S_tot ? (uint32_t)fin.kmer_id_off[Sb + x] : 0u;
+        const uint32_t inc = warp_incl_scan_u32(c, lane);
+        if (x < S_tot) fin.kmer_id_off[Sb + x] = carry + inc - c;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    __syncwarp();
+    __threadfence();
+    // pass 3: lists, eight lanes per list
+    for (uint32_t j = 0; j < R; j++) {
+        const UnitOut3 uj = st.unit_out[u + j];
+        const uint64_t kbj = uj.ibase / st.kdiv;
+        for (uint32_t x = lane >> 3; x < uj.S; x += 4) {
+            const uint32_t lo = st.loff[kbj + x];
+            const uint32_t cnt = (x + 1 < uj.S ? st.loff[kbj + x + 1] : uj.N) - lo;
+            const uint32_t rank = st.mmer[kbj + x];
+            const int32_t *src = st.ids + uj.ibase + lo;
+            int32_t *dst = fin.read_ids + fin.kmer_id_off[Sb + rank];
+            for (uint32_t i = lane & 7u; i < cnt; i += 8) dst[i] = src[i];
         }
     }
 }
 
-// chunk_bounds[c] = first unit of chunk c, moved back to the first round of a split atom so that no atom straddles two chunks.
+template <int KW>
+__global__ void __launch_bounds__(128)
+    finalize3_kernel(const Unit3 *__restrict__ units, const uint64_t *__restrict__ unit_excl, const unsigned long long *__restrict__ totals,
+                     const unsigned long long *__restrict__ lsd_totals, G3Stage st, G3Final fin, G3Lsd ls, G3Counters *__restrict__ gc,
+                     const uint32_t *__restrict__ chunk_bounds, uint32_t chunk) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t unit_begin = chunk_bounds[chunk], unit_end = chunk_bounds[chunk + 1];
+    const unsigned long long base = chunk ? totals[chunk - 1] : 0ull;
+    const unsigned long long lsd_base = chunk ? lsd_totals[chunk - 1] : 0ull;
+    for (uint32_t u = unit_begin + blockIdx.x * 4 + (threadIdx.x >> 5); u < unit_end; u += gridDim.x * 4)
+        finalize3_unit<KW>(units, unit_excl, base, lsd_base, st, fin, ls, gc, u, lane);
+}
+
+// ---- after the global sort of the long spans' k-mers (Rec<KW> sorted by (m-mer, k-mer); record.arrival = its place before the sort)
+template <int KW>
+struct LsdCnt {
+    const Rec<KW> *rec;
+    const uint32_t *cnt;
+    __device__ __forceinline__ uint64_t operator()(uint64_t q) const { return cnt[rec[q].arrival]; }
+};
+
+template <int KW>
+__global__ void lsd_place_kernel(const Rec<KW> *__restrict__ rec, uint64_t n, const uint64_t *__restrict__ dnew, G3Lsd ls, G3Final fin) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const Rec<KW> r = load_rec<KW>(rec + q);
+    const uint64_t f = ls.fidx[q];
+    fin.kmer_codes[f * KW] = r.k[0];
+    if (KW == 2) fin.kmer_codes[f * KW + 1] = r.k[KW - 1];
+    fin.kmer_mmer[f] = r.mmer;
+    fin.kmer_id_off[f] = dnew[q] + ls.nadj[q];
+}
+
+template <int KW>
+__global__ void __launch_bounds__(256)
+    lsd_lists_kernel(const Rec<KW> *__restrict__ rec, uint64_t n, const uint64_t *__restrict__ dnew, G3Lsd ls, const int32_t *__restrict__ stg_ids, G3Final fin) {
+    const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;  // eight lanes per list
+    if (q >= n) return;
+    const uint32_t p = rec[q].arrival;
+    const uint32_t c = ls.cnt[p];
+    const int32_t *src = stg_ids + ls.src_off[p];
+    int32_t *dst = fin.read_ids + dnew[q] + ls.nadj[q];
+    for (uint32_t i = threadIdx.x & 7u; i < c; i += 8) dst[i] = src[i];
+}
+
+// chunk_bounds[c] = first unit of chunk c, moved back to the first unit of a span so that no span straddles two chunks.
 __global__ void v3_chunk_bounds_kernel(const Unit3 *__restrict__ units, const G3Counters *__restrict__ gc, uint32_t n_chunks, uint32_t *__restrict__ chunk_bounds) {
     const uint32_t nu = gc->n_units;
     for (uint32_t c = 0; c <= n_chunks; c++) {
         uint32_t b = (uint32_t)(((uint64_t)nu * c) / n_chunks);
         if (c == n_chunks) b = nu;
-        else if (b < nu && units[b].rounds != 0) b -= units[b].round;
+        else {
+            while (b > 0 && b < nu && (units[b].span_len == SPAN_MEMBER || units[b].span_len == SPAN_MEMBER_LONG)) b--;  // back to the span's first unit
+        }
         chunk_bounds[c] = b;
     }
 }
@@ -1006,20 +1187,23 @@ struct PtrIn64 {
     __device__ __forceinline__ uint64_t operator()(uint64_t j) const { return p[j]; }
 };
 
-// Units over the n_runs atoms.  nunits64 / base64: [n_runs + 1] u64 scratch each; head_run: [max_units].
-int v3_plan_units(const void *skr, const uint64_t *ent, const KeyLayout &kl, int cap, const uint32_t *inst_prefix, const uint32_t *run_start, uint64_t n_runs, uint64_t *nunits64, uint64_t *base64,
-                  uint32_t *head_run, void *scratch, void *units, uint64_t max_units, void *gc_dev, uint32_t n_chunks, uint32_t *chunk_bounds, cudaStream_t st) {
+// Units over the n_runs atoms.  nunits64 / base64: [n_runs + 1] u64 scratch each; atom3: [3 * n_runs] u32 scratch; spanlen: [n_runs] u32; head_run: [max_units].
+int v3_plan_units(const void *skr, const uint64_t *ent, const KeyLayout &kl, int cap, const uint32_t *inst_prefix, const uint32_t *run_start, uint64_t n_runs,
+                  uint64_t *nunits64, uint64_t *base64, uint32_t *atom3, uint32_t *spanlen, uint32_t *head_run, void *scratch, void *units, uint64_t max_units,
+                  void *gc_dev, uint32_t n_chunks, uint32_t *chunk_bounds, cudaStream_t st) {
     RunView3 rv{run_start, inst_prefix};
     const Plan3 pp = v3_plan_params(kl, cap);
     G3Counters *gc = static_cast<G3Counters *>(gc_dev);
     cudaMemsetAsync(gc, 0, sizeof(G3Counters), st);
     int l = 0;
     if (n_runs) {
-        const uint64_t per_cta = (uint64_t)PLAN_CTA_BLOCKS * PLAN_BLOCK;
-        v3_pack_kernel<<<(unsigned)((n_runs + per_cta - 1) / per_cta), 256, 0, st>>>(rv, n_runs, pp, nunits64);
-        l += 1 + exclusive_scan<uint64_t, PtrIn64>(PtrIn64{nunits64}, base64, n_runs, static_cast<uint64_t *>(scratch), base64 + n_runs, st);
+        uint32_t *atom_c = atom3, *atom_e = atom3 + n_runs, *atom_mm = atom3 + 2 * n_runs;
+        v3_atoms_kernel<<<(unsigned)((n_runs + 255) / 256), 256, 0, st>>>(rv, ent, n_runs, kl.mshift, atom_c, atom_e, atom_mm);
+        const uint64_t walkers = (n_runs + PLAN_BLOCK - 1) / PLAN_BLOCK;
+        v3_pack_kernel<<<(unsigned)((walkers + 127) / 128), 128, 0, st>>>(atom_c, atom_e, atom_mm, n_runs, pp, nunits64, spanlen);
+        l += 2 + exclusive_scan<uint64_t, PtrIn64>(PtrIn64{nunits64}, base64, n_runs, static_cast<uint64_t *>(scratch), base64 + n_runs, st);
         v3_head_runs_kernel<<<(unsigned)((n_runs + 255) / 256), 256, 0, st>>>(nunits64, base64, n_runs, head_run);
-        v3_fill_units_kernel<<<(unsigned)((max_units + 255) / 256), 256, 0, st>>>(rv, base64, base64 + n_runs, n_runs, pp, head_run, static_cast<Unit3 *>(units), gc);
+        v3_fill_units_kernel<<<(unsigned)((max_units + 255) / 256), 256, 0, st>>>(rv, nunits64, spanlen, base64, base64 + n_runs, n_runs, head_run, static_cast<Unit3 *>(units), gc);
         v3_round_cuts_kernel<<<592, 128, 0, st>>>(static_cast<const uint32_t *>(skr), kl.K <= 32 ? 8 : 12, ent, kl, static_cast<Unit3 *>(units), gc, pp.cap);
         l += 3;
     }
@@ -1034,8 +1218,8 @@ size_t v3_group_smem_bytes(int KW, int cap) {
 }
 
 int v3_group_launch(const void *skr, const uint64_t *ent, const void *units, const KeyLayout &kl, int cap, int cutoff, const int32_t *ids_by_arrival, int32_t id_base,
-                    const V3Out &o, uint64_t max_units, uint64_t *unit_excl, void *scan_scratch, void *gc_dev, const V3Chunks &ch, int sm_count, KernelProf *prof,
-                    cudaStream_t st) {
+                    const V3Out &o, uint64_t max_units, uint64_t *unit_excl, uint64_t *lsd_excl, void *scan_scratch, void *gc_dev, const V3Chunks &ch, const V3Lsd &lsd,
+                    bool finalize_only, int sm_count, KernelProf *prof, cudaStream_t st) {
     const int KW = kl.K <= 32 ? 1 : 2;
     constexpr int WARPS = G3_WARPS;
     const size_t smem = v3_group_smem_bytes(KW, cap);
@@ -1043,6 +1227,7 @@ int v3_group_launch(const void *skr, const uint64_t *ent, const void *units, con
     const uint32_t kdiv = cutoff >= 0 ? (uint32_t)cutoff + 1u : 1u;
     G3Stage stg{o.stg_codes, o.stg_mmer, o.stg_loff, o.stg_ids, static_cast<UnitOut3 *>(o.unit_out), o.kmer_cap, o.id_cap, kdiv};
     G3Final fin{o.kmer_codes, o.kmer_mmer, o.kmer_id_off, o.read_ids};
+    G3Lsd ls{lsd_excl, lsd.rec, lsd.src_off, lsd.cnt, lsd.fidx, lsd.nadj, lsd.cap};
     G3Counters *gc = static_cast<G3Counters *>(gc_dev);
     const uint32_t *sk = static_cast<const uint32_t *>(skr);
     const Unit3 *un = static_cast<const Unit3 *>(units);
@@ -1052,27 +1237,100 @@ int v3_group_launch(const void *skr, const uint64_t *ent, const void *units, con
     auto launch = [&](auto kern, auto fin_kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         for (uint32_t c = 0; c < ch.n; c++) {
-            bool on = prof && prof->begin(KK_SKR_GROUP, st);
-            kern<<<sm_count * per_sm, WARPS * 32, smem, st>>>(sk, ent, un, kl, cutoff, ids_by_arrival, id_base, stg, gc, ch.bounds, c, ch.tickets);
-            if (prof) prof->end(on, 1, st);
-            on = prof && prof->begin(KK_V3_SPAN, st);
+            if (!finalize_only) {
+                bool on = prof && prof->begin(KK_SKR_GROUP, st);
+                kern<<<sm_count * per_sm, WARPS * 32, smem, st>>>(sk, ent, un, kl, cutoff, ids_by_arrival, id_base, stg, gc, ch.bounds, c, ch.tickets);
+                if (prof) prof->end(on, 1, st);
+                launches++;
+            }
+            bool on = prof && prof->begin(KK_V3_SPAN, st);
             int l = exclusive_scan<uint64_t, UnitSN>(UnitSN{stg.unit_out, ch.bounds, c}, unit_excl, max_units, static_cast<uint64_t *>(scan_scratch), ch.chunk_sum, st);
-            v3_chunk_total_kernel<<<1, 1, 0, st>>>(ch.chunk_sum, c, ch.totals_dev, gc, ch.n);
-            fin_kern<<<sm_count * 8, 128, 0, st>>>(un, unit_excl, ch.totals_dev, stg, fin, ch.bounds, c, ch.tickets + ch.n);
-            if (prof) prof->end(on, l + 2, st);
+            v3_chunk_total_kernel<<<1, 1, 0, st>>>(ch.chunk_sum, c, ch.totals_dev, gc, ch.n, 0);
+            l += exclusive_scan<uint64_t, UnitSNLong>(UnitSNLong{stg.unit_out, un, ch.bounds, c}, lsd_excl, max_units, static_cast<uint64_t *>(scan_scratch), ch.chunk_sum, st);
+            v3_chunk_total_kernel<<<1, 1, 0, st>>>(ch.chunk_sum, c, ch.lsd_totals_dev, gc, ch.n, 1);
+            fin_kern<<<sm_count * 16, 128, 0, st>>>(un, unit_excl, ch.totals_dev, ch.lsd_totals_dev, stg, fin, ls, gc, ch.bounds, c);
+            if (prof) prof->end(on, l + 3, st);
             launches += l + 3;
-            if (ch.totals_host) cudaMemcpyAsync(ch.totals_host + c, ch.totals_dev + c, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+            if (ch.totals_host) {
+                cudaMemcpyAsync(ch.totals_host + c, ch.totals_dev + c, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+                cudaMemcpyAsync(ch.lsd_totals_host + c, ch.lsd_totals_dev + c, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+            }
             if (ch.done) cudaEventRecord(ch.done[c], st);
         }
     };
-    if (KW == 1) {
-        if (cap == 512) launch(group3_kernel<2, 1, 512, WARPS>, finalize3_kernel<1>);
-        else launch(group3_kernel<2, 1, 1024, WARPS>, finalize3_kernel<1>);
-    } else {
-        if (cap == 512) launch(group3_kernel<4, 2, 512, WARPS>, finalize3_kernel<2>);
-        else launch(group3_kernel<4, 2, 1024, WARPS>, finalize3_kernel<2>);
+    static int uu = 0;  // GBIN_V3_U = 1|2|4: instances per lane in flight (experiments)
+    if (!uu) {
+        const char *e = getenv("GBIN_V3_U");
+        uu = e ? atoi(e) : G3_U;
+        if (uu != 1 && uu != 2 && uu != 4) uu = G3_U;
     }
+#define G3_LAUNCH(PW_, KW_, CAP_) \
+    (uu == 1 ? launch(group3_kernel<PW_, KW_, CAP_, WARPS, 1>, finalize3_kernel<KW_>) \
+             : (uu == 2 ? launch(group3_kernel<PW_, KW_, CAP_, WARPS, 2>, finalize3_kernel<KW_>) : launch(group3_kernel<PW_, KW_, CAP_, WARPS, 4>, finalize3_kernel<KW_>)))
+    if (KW == 1) {
+        if (cap == 512) G3_LAUNCH(2, 1, 512);
+        else G3_LAUNCH(2, 1, 1024);
+    } else {
+        if (cap == 512) G3_LAUNCH(4, 2, 512);
+        else G3_LAUNCH(4, 2, 1024);
+    }
+#undef G3_LAUNCH
     return launches;
+}
+
+// The long spans' k-mers (n records, appended by finalize3_kernel) are sorted by (m-mer, k-mer) — a permutation inside every span —
+// and then written, with their id lists, to the table.  rec_a / rec_b: Rec<KW> [n] each; dnew: [n + 1] u64.
+int v3_lsd_finish(const KeyLayout &kl, uint64_t n, void *rec_a, void *rec_b, void *radix_scratch, uint64_t *dnew, void *scan_scratch, const V3Out &o, const V3Lsd &lsd,
+                  KernelProf *prof, cudaStream_t st) {
+    if (n == 0) return 0;
+    const int KW = kl.K <= 32 ? 1 : 2;
+    bool in_b = false;
+    int passes = 0;
+    int l = radix_sort_records(rec_a, rec_b, n, KW, kl.K, kl.M, radix_scratch, &in_b, &passes, prof, st);
+    const void *sorted = in_b ? rec_b : rec_a;
+    G3Final fin{o.kmer_codes, o.kmer_mmer, o.kmer_id_off, o.read_ids};
+    G3Lsd ls{nullptr, nullptr, lsd.src_off, lsd.cnt, lsd.fidx, lsd.nadj, lsd.cap};
+    bool on = prof && prof->begin(KK_V3_SPAN, st);
+    int l2 = 0;
+    if (KW == 1) {
+        const Rec<1> *r = static_cast<const Rec<1> *>(sorted);
+        l2 += exclusive_scan<uint64_t, LsdCnt<1>>(LsdCnt<1>{r, lsd.cnt}, dnew, n, static_cast<uint64_t *>(scan_scratch), nullptr, st);
+        lsd_place_kernel<1><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r, n, dnew, ls, fin);
+        lsd_lists_kernel<1><<<(unsigned)((n * 8 + 255) / 256), 256, 0, st>>>(r, n, dnew, ls, o.stg_ids, fin);
+    } else {
+        const Rec<2> *r = static_cast<const Rec<2> *>(sorted);
+        l2 += exclusive_scan<uint64_t, LsdCnt<2>>(LsdCnt<2>{r, lsd.cnt}, dnew, n, static_cast<uint64_t *>(scan_scratch), nullptr, st);
+        lsd_place_kernel<2><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r, n, dnew, ls, fin);
+        lsd_lists_kernel<2><<<(unsigned)((n * 8 + 255) / 256), 256, 0, st>>>(r, n, dnew, ls, o.stg_ids, fin);
+    }
+    if (prof) prof->end(on, l2 + 2, st);
+    return l + l2 + 2;
+}
+
+// ---- how many different m-mer codes do the records hold?  (bitmap over the code space; decides the key layout)
+__global__ void mmer_bitmap_kernel(const uint32_t *__restrict__ skr, int skr_words, uint64_t n_rec, uint32_t *__restrict__ bitmap) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rec) return;
+    const uint32_t mm = skr[i * skr_words + 1];
+    const uint32_t bit = 1u << (mm & 31u);
+    if (!(bitmap[mm >> 5] & bit)) atomicOr(&bitmap[mm >> 5], bit);
+}
+__global__ void bitmap_count_kernel(const uint32_t *__restrict__ bitmap, uint64_t words, unsigned long long *__restrict__ count) {
+    uint32_t c = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (uint64_t)gridDim.x * blockDim.x) c += __popc(bitmap[i]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, (unsigned long long)c);
+}
+size_t v3_mmer_bitmap_bytes(int M) { return ((size_t)1 << (2 * M)) / 8 + 64; }
+int v3_count_mmers(const void *skr, int skr_words, uint64_t n_rec, int M, uint32_t *bitmap, unsigned long long *count_dev, cudaStream_t st) {
+    const uint64_t words = ((uint64_t)1 << (2 * M)) / 32;
+    cudaMemsetAsync(bitmap, 0, words * 4, st);
+    cudaMemsetAsync(count_dev, 0, sizeof(unsigned long long), st);
+    if (n_rec == 0) return 0;
+    mmer_bitmap_kernel<<<(unsigned)((n_rec + 255) / 256), 256, 0, st>>>(static_cast<const uint32_t *>(skr), skr_words, n_rec, bitmap);
+    bitmap_count_kernel<<<592, 256, 0, st>>>(bitmap, words, count_dev);
+    return 2;
 }
 
 }  // namespace gbin

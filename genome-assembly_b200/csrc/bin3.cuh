@@ -81,15 +81,16 @@ __host__ __device__ inline void piece_of(uint32_t meta, uint32_t cls, const KeyL
 // One unit of the grouping kernel = one warp's worth of work.
 //   packed unit: whole atoms (runs of equal key) [ent_begin, ent_end) of the sorted entries, n_inst <= capacity;
 //   round unit : round `round` of `rounds` over ONE atom that is larger than the capacity: the atom's instances are cut
-//                by ranges of d (chosen in the kernel from the atom's d-histogram), every round groups one range.  The
-//                k-mers of such an atom come out round by round, not ascending: the finalize pass merges the rounds.
+//                by ranges of d (chosen by the planner from the atom's d-histogram), every round groups one range.
+// A bucket (all atoms of one m-mer code) that does not fit one unit is a *span* of consecutive units that hold nothing else;
+// its k-mers come out unit by unit, each unit ascending: the finalize pass merges them into one ascending run.
 struct __align__(16) Unit3 {
     uint32_t ent_begin, ent_end;
-    uint32_t n_inst;         // packed: instances of the unit; round: instances of the whole atom
+    uint32_t n_inst;         // instances of the unit (round units: of the atom until the planner has cut it, then of the round)
     uint32_t round, rounds;  // rounds == 0: packed unit
-    uint32_t span;           // index of the atom among the split atoms
-    uint32_t ibase;          // instance coordinate of the unit's (round: the atom's) first instance
-    uint32_t pad;
+    uint32_t drange;         // round units: dlo | dhi << 8
+    uint32_t ibase;          // instance coordinate of the unit's first instance
+    uint32_t span_len;       // 0: the unit holds whole buckets; L: first of the L units of a bucket that does not fit one unit; ~0: another unit of such a bucket
 };
 
 }  // namespace gbin

@@ -82,6 +82,7 @@ struct Misc {  // small device-resident scalars
     unsigned long long n_real_entries;
     uint32_t chunk_bounds[SKR_MAX_CHUNKS + 1];
     uint32_t v3_tickets[2 * SKR_MAX_CHUNKS];
+    unsigned long long lsd_totals[SKR_MAX_CHUNKS];
     uint64_t v3_chunk_sum;
 };
 
@@ -124,7 +125,10 @@ struct gbin_ctx {
     // pipeline v2 workspace
     DevBuf skr_a, skr_b, tile_state, inst_prefix, run_excl, skr_run_start, small_prefix, unit_base, units, unit_state, o_kmer_mmer, bucket_excl, big_list, big_k0, big_k1, big_arr, stg_ids, stg_codes, stg_mmer, stg_off, skr_side;
     // pipeline v3 workspace
-    DevBuf ent_a, ent_b, piece_n, v3_base64, v3_head_run, v3_unit_out, v3_unit_excl;
+    DevBuf ent_a, ent_b, piece_n, v3_base64, v3_head_run, v3_unit_out, v3_unit_excl, v3_atoms, v3_lsd_aux, v3_bitmap;
+    bool v3_lsd_seen = false;         // a batch on this context had long spans: keep the arrays of their global sort
+    uint64_t v3_auto_n = 0;           // record count for which the key layout below was chosen (v3_nc == 0: automatic)
+    int v3_auto_h = 0, v3_auto_nc = 1;
     int v3_h, v3_nc, v3_cap;  // key layout and unit capacity of pipeline 3 (gbin_set_tuning; GBIN_V3_H / GBIN_V3_NC / GBIN_V3_CAP)
     int pipeline;        // 3: sort by reference + warp units, falling back to 2, then 1 (default); 2: super-k-mer path with v1 as fallback; 1: v1 only
     int last_pipeline;   // which one produced the last table
@@ -540,17 +544,64 @@ int run_v2_group(gbin_ctx *ctx, void *skr, void *twin, uint64_t n_skr, const int
     return GBIN_OK;
 }
 
-// ---- pipeline v3: entries sorted by reference, one warp per unit, table written once (bin3.cu)
-// The records in `skr` are read, not moved.  *done = false when a unit or a span overflowed (the batch then goes through
-// pipeline 2, which sorts the records themselves).
+// ---- pipeline v3: entries sorted by reference, one warp per unit, staging + finalize (bin3.cu)
+// The records in `skr` are read, not moved.  *done = false when the batch does not fit (a (bucket, d) class larger than a unit);
+// it then goes through pipeline 2, which sorts the records themselves.
+
+// Key layout for this batch: explicit (gbin_set_tuning v3_nc = 1 | 2) or chosen from the mean m-mer bucket size (v3_nc = 0):
+// buckets that fit a unit need nothing but the m-mer code; larger ones are broken up by extending the key (bin3.cuh).
+int v3_choose_layout(gbin_ctx *ctx, const void *skr, uint64_t n_skr, cudaStream_t st, KeyLayout *out, int *launches) {
+    const int K = ctx->cfg.kmer_size, M = ctx->cfg.mmer_size;
+    if (ctx->v3_nc != 0) {
+        *out = make_key_layout(K, M, ctx->v3_h, ctx->v3_nc);
+        return GBIN_OK;
+    }
+    if (2 * M + 2 > 31 || M > 13 || n_skr == 0) {  // no room for a longer key / code space too large for the bitmap: plain m-mer keys
+        *out = make_key_layout(K, M, 0, 1);
+        return GBIN_OK;
+    }
+    // the decision is kept for batches of similar size on this context
+    if (ctx->v3_auto_n && n_skr >= ctx->v3_auto_n / 2 && n_skr <= ctx->v3_auto_n * 2) {
+        *out = make_key_layout(K, M, ctx->v3_auto_h, ctx->v3_auto_nc);
+        return GBIN_OK;
+    }
+    Misc *dm = ctx->misc.as<Misc>();
+    Misc *hm = static_cast<Misc *>(ctx->h_misc.p);
+    CU(ctx->v3_bitmap.ensure(v3_mmer_bitmap_bytes(M)));
+    *launches += v3_count_mmers(skr, K <= 32 ? 8 : 12, n_skr, M, ctx->v3_bitmap.as<uint32_t>(), &dm->n_real_entries, st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&hm->n_real_entries, &dm->n_real_entries, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const double buckets = hm->n_real_entries ? (double)hm->n_real_entries : 1.0;
+    const double mean_inst = (double)n_skr / buckets * ((K - M + 2) / 2.0);  // a record holds about (K-M+2)/2 windows
+    int nc = 1, h = 0;
+    if (mean_inst > ctx->v3_cap / 3.0) {
+        nc = 2;
+        double per = mean_inst / 2.0;
+        while (per > ctx->v3_cap / 8.0 && h < 15) {
+            per /= 4.0;
+            h++;
+        }
+    }
+    *out = make_key_layout(K, M, h, nc);
+    ctx->v3_auto_n = n_skr;
+    ctx->v3_auto_h = out->h;
+    ctx->v3_auto_nc = out->nc;
+    return GBIN_OK;
+}
+
 int run_v3_group(gbin_ctx *ctx, const void *skr, uint64_t n_skr, const int32_t *d_ids, int32_t id_base, cudaStream_t st, gbin_table *out, int *launches,
                  bool *done, uint64_t *n_inst_out, HostSink *sink = nullptr) {
     *done = false;
     const int K = ctx->cfg.kmer_size, M = ctx->cfg.mmer_size, cutoff = ctx->cfg.abundance_cutoff, KW = ctx->KW;
     Misc *dm = ctx->misc.as<Misc>();
     Misc *hm = static_cast<Misc *>(ctx->h_misc.p);
-    const KeyLayout kl = make_key_layout(K, M, ctx->v3_h, ctx->v3_nc);
+    KeyLayout kl;
+    int rc = v3_choose_layout(ctx, skr, n_skr, st, &kl, launches);
+    if (rc) return rc;
     if (n_skr >= (1ull << (32 - kl.cshift))) return GBIN_OK;  // slots are 32-bit
+    ctx->rs.key_nc = (uint32_t)kl.nc;
+    ctx->rs.key_h = (uint32_t)kl.h;
 
     // ---- entries + level 1: stable sort of the entries by key
     const uint64_t n_slots = n_skr << kl.cshift;
@@ -597,20 +648,23 @@ int run_v3_group(gbin_ctx *ctx, const void *skr, uint64_t n_skr, const int32_t *
     const uint64_t max_units = v3_max_units(n, n_runs, ctx->v3_cap);
     CU(ctx->small_prefix.ensure((n_runs + 2) * 8));
     CU(ctx->v3_base64.ensure((n_runs + 2) * 8));
+    CU(ctx->v3_atoms.ensure((4 * n_runs + 8) * 4));
     CU(ctx->v3_head_run.ensure((max_units + 1) * 4));
     CU(ctx->units.ensure(max_units * v3_unit_bytes()));
     CU(ctx->v3_unit_out.ensure(max_units * v3_unit_out_bytes()));
-    CU(ctx->v3_unit_excl.ensure((max_units + 1) * 8));
+    CU(ctx->v3_unit_excl.ensure((2 * max_units + 2) * 8));
     CU(ctx->scan_scratch.ensure(group_scan_scratch_bytes(n_runs + max_units + 1024)));
-    V3Chunks ch{1u, dm->v3_tickets, dm->chunk_bounds, &dm->v3_chunk_sum, dm->chunk_totals, nullptr, nullptr};
+    V3Chunks ch{1u, dm->v3_tickets, dm->chunk_bounds, &dm->v3_chunk_sum, dm->chunk_totals, dm->lsd_totals, nullptr, nullptr, nullptr};
     if (sink && sink->chunks > 1) {
         ch.n = (uint32_t)sink->chunks;
         ch.totals_host = hm->chunk_totals;
+        ch.lsd_totals_host = hm->lsd_totals;
         ch.done = ctx->ev_chunk;
     }
     on = ctx->prof.begin(KK_SKR_PLAN, st);
     lp = v3_plan_units(skr, ent, kl, ctx->v3_cap, ctx->inst_prefix.as<uint32_t>(), ctx->skr_run_start.as<uint32_t>(), n_runs, ctx->small_prefix.as<uint64_t>(),
-                       ctx->v3_base64.as<uint64_t>(), ctx->v3_head_run.as<uint32_t>(), ctx->scan_scratch.p, ctx->units.p, max_units, &dm->gc3, ch.n, dm->chunk_bounds, st);
+                       ctx->v3_base64.as<uint64_t>(), ctx->v3_atoms.as<uint32_t>(), ctx->v3_atoms.as<uint32_t>() + 3 * n_runs, ctx->v3_head_run.as<uint32_t>(),
+                       ctx->scan_scratch.p, ctx->units.p, max_units, &dm->gc3, ch.n, dm->chunk_bounds, st);
     ctx->prof.end(on, lp, st);
     *launches += lp;
     CU(cudaGetLastError());
@@ -627,15 +681,32 @@ int run_v3_group(gbin_ctx *ctx, const void *skr, uint64_t n_skr, const int32_t *
     CU(ctx->stg_off.ensure((kmer_cap + 1) * sizeof(uint32_t)));
     V3Out vo{ctx->o_kmer_codes.as<uint64_t>(), ctx->o_kmer_mmer.as<uint32_t>(), ctx->o_kmer_id_off.as<uint64_t>(), ctx->o_read_ids.as<int32_t>(), kmer_cap, n,
              ctx->stg_codes.as<uint64_t>(), ctx->stg_mmer.as<uint32_t>(), ctx->stg_off.as<uint32_t>(), ctx->stg_ids.as<int32_t>(), ctx->v3_unit_out.p};
-    lp = v3_group_launch(skr, ent, ctx->units.p, kl, ctx->v3_cap, cutoff, d_ids, id_base, vo, max_units, ctx->v3_unit_excl.as<uint64_t>(), ctx->scan_scratch.p,
-                         &dm->gc3, ch, ctx->sm_count, &ctx->prof, st);
+    const size_t rb = sizeof(uint64_t) * KW + 8;
+    auto lsd_arrays = [&](uint64_t cap) -> int {  // arrays of the global sort for long spans, for `cap` k-mers
+        if (cap == 0) return GBIN_OK;
+        CU(ctx->rec_a.ensure((cap + 1) * rb));
+        CU(ctx->rec_b.ensure((cap + 1) * rb));
+        CU(ctx->v3_lsd_aux.ensure((cap + 1) * 16));
+        return GBIN_OK;
+    };
+    uint64_t lsd_cap = (kl.nc == 2 || ctx->v3_lsd_seen) ? kmer_cap : 0;  // buckets large enough for extended keys are large enough for long spans
+    rc = lsd_arrays(lsd_cap);
+    if (rc) return rc;
+    auto lsd_view = [&](uint64_t cap) {
+        uint32_t *aux = ctx->v3_lsd_aux.as<uint32_t>();
+        return cap ? V3Lsd{ctx->rec_a.p, aux, aux + (cap + 1), aux + 2 * (cap + 1), aux + 3 * (cap + 1), cap} : V3Lsd{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+    };
+    uint64_t *unit_excl = ctx->v3_unit_excl.as<uint64_t>(), *lsd_excl = unit_excl + max_units + 1;
+    lp = v3_group_launch(skr, ent, ctx->units.p, kl, ctx->v3_cap, cutoff, d_ids, id_base, vo, max_units, unit_excl, lsd_excl, ctx->scan_scratch.p, &dm->gc3, ch,
+                         lsd_view(lsd_cap), false, ctx->sm_count, &ctx->prof, st);
     *launches += lp;
     CU(cudaGetLastError());
     if (ch.done) {
         // Stream the finished part of the table to the host while later chunks are grouped: the output of the units of a chunk
-        // (and of the split atoms inside it) is final once the chunk's two launches have completed.
+        // is final once the chunk's launches have completed — unless the chunk holds long spans, which wait for the global sort.
         for (uint32_t c = 0; c < ch.n; c++) {
             CU(cudaEventSynchronize(ctx->ev_chunk[c]));
+            if (hm->lsd_totals[c]) break;
             const unsigned long long tot = hm->chunk_totals[c];
             const uint64_t s1 = tot >> 32, n1 = tot & 0xffffffffull;
             if (s1 > sink->kmer_cap || n1 > sink->id_cap || s1 < sink->kmers_done || n1 < sink->ids_done) break;  // arena too small: the rest is copied at the end
@@ -651,13 +722,40 @@ int run_v3_group(gbin_ctx *ctx, const void *skr, uint64_t n_skr, const int32_t *
     }
     CU(cudaMemcpyAsync(&hm->gc3, &dm->gc3, sizeof(V3Counters), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (hm->gc3.overflow == 6u && hm->gc3.lsd_kmers > lsd_cap) {
+        // long spans met no (or too small) sort arrays: allocate them and redo the placement (the staged results are still there)
+        ctx->v3_lsd_seen = true;
+        lsd_cap = kmer_cap;
+        rc = lsd_arrays(lsd_cap);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(&dm->gc3.overflow, 0, sizeof(unsigned int), st));
+        V3Chunks ch1 = ch;
+        ch1.totals_host = ch1.lsd_totals_host = nullptr;
+        ch1.done = nullptr;
+        lp = v3_group_launch(skr, ent, ctx->units.p, kl, ctx->v3_cap, cutoff, d_ids, id_base, vo, max_units, unit_excl, lsd_excl, ctx->scan_scratch.p, &dm->gc3, ch1,
+                             lsd_view(lsd_cap), true, ctx->sm_count, &ctx->prof, st);
+        *launches += lp;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&hm->gc3, &dm->gc3, sizeof(V3Counters), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
     ctx->rs.n_units = hm->gc3.n_units;
-    ctx->rs.reserved = hm->gc3.n_spans;
+    ctx->rs.n_lsd_kmers = hm->gc3.lsd_kmers;
     if (hm->gc3.overflow) {  // not done: the caller falls back
         snprintf(ctx->err, sizeof ctx->err, "pipeline 3 gave the batch up (code %u: a (bucket, d) class larger than a unit)", hm->gc3.overflow);
         return GBIN_OK;
     }
     const uint64_t S = hm->gc3.total_kmers, NS = hm->gc3.total_ids;
+    if (hm->gc3.lsd_kmers) {
+        const uint64_t nl = hm->gc3.lsd_kmers;
+        CU(ctx->radix_scratch.ensure(radix_scratch_bytes(nl)));
+        CU(ctx->run_excl.ensure((nl + 2) * 8));
+        CU(ctx->scan_scratch.ensure(group_scan_scratch_bytes(nl + 1024)));
+        lp = v3_lsd_finish(kl, nl, ctx->rec_a.p, ctx->rec_b.p, ctx->radix_scratch.p, ctx->run_excl.as<uint64_t>(), ctx->scan_scratch.p, vo, lsd_view(lsd_cap), &ctx->prof,
+                           st);
+        *launches += lp;
+        CU(cudaGetLastError());
+    }
 
     // ---- bucket directory
     CU(ctx->bucket_excl.ensure((S + 1) * 4));
@@ -823,8 +921,11 @@ int gbin_create(const gbin_config *cfg, gbin_ctx **out) {
         ctx->pipeline = (v >= 1 && v <= 3) ? v : 3;
     }
     ctx->v3_h = 0;
-    ctx->v3_nc = 1;
-    if (const char *e = getenv("GBIN_V3_NC")) ctx->v3_nc = atoi(e) == 2 ? 2 : 1;
+    ctx->v3_nc = 0;  // automatic
+    if (const char *e = getenv("GBIN_V3_NC")) {
+        const int v = atoi(e);
+        ctx->v3_nc = (v == 1 || v == 2) ? v : 0;
+    }
     if (const char *e = getenv("GBIN_V3_H")) ctx->v3_h = atoi(e);
     ctx->v3_cap = 1024;
     if (const char *e = getenv("GBIN_V3_CAP")) ctx->v3_cap = atoi(e) == 512 ? 512 : 1024;
@@ -868,7 +969,7 @@ void gbin_destroy(gbin_ctx *ctx) {
                       &ctx->o_kmer_codes, &ctx->o_kmer_id_off, &ctx->o_read_ids, &ctx->skr_a, &ctx->skr_b, &ctx->tile_state,
                       &ctx->inst_prefix, &ctx->run_excl, &ctx->skr_run_start, &ctx->small_prefix, &ctx->unit_base, &ctx->units,
                       &ctx->unit_state, &ctx->o_kmer_mmer, &ctx->bucket_excl, &ctx->big_list, &ctx->big_k0, &ctx->big_k1, &ctx->big_arr, &ctx->stg_ids, &ctx->stg_codes, &ctx->stg_mmer, &ctx->stg_off, &ctx->skr_side,
-                      &ctx->ent_a, &ctx->ent_b, &ctx->piece_n, &ctx->v3_base64, &ctx->v3_head_run, &ctx->v3_unit_out, &ctx->v3_unit_excl};
+                      &ctx->ent_a, &ctx->ent_b, &ctx->piece_n, &ctx->v3_base64, &ctx->v3_head_run, &ctx->v3_unit_out, &ctx->v3_unit_excl, &ctx->v3_atoms, &ctx->v3_lsd_aux, &ctx->v3_bitmap};
     for (DevBuf *b : bufs) b->release();
     ctx->h_misc.release();
     ctx->h_result.release();
@@ -955,8 +1056,9 @@ int gbin_set_tuning(gbin_ctx *ctx, const char *name, int value) {
         if (value != 512 && value != 1024) return GBIN_E_INVALID_ARG;
         ctx->v3_cap = value;
     } else if (!strcmp(name, "v3_nc")) {
-        if (value != 1 && value != 2) return GBIN_E_INVALID_ARG;
+        if (value != 0 && value != 1 && value != 2) return GBIN_E_INVALID_ARG;
         ctx->v3_nc = value;
+        ctx->v3_auto_n = 0;
     } else if (!strcmp(name, "v3_h")) {
         if (value < 0 || value > 15) return GBIN_E_INVALID_ARG;
         ctx->v3_h = value;

@@ -155,9 +155,11 @@ size_t v3_counters_bytes();
 struct V3Counters {  // mirror of G3Counters in bin3.cu
     unsigned long long distinct, total_kmers, total_ids;
     unsigned int overflow, n_units, n_spans, pad;
+    unsigned long long lsd_kmers, lsd_ids;
 };
-int v3_plan_units(const void *skr, const uint64_t *ent, const KeyLayout &kl, int cap, const uint32_t *inst_prefix, const uint32_t *run_start, uint64_t n_runs, uint64_t *nunits64, uint64_t *base64,
-                  uint32_t *head_run, void *scratch, void *units, uint64_t max_units, void *gc_dev, uint32_t n_chunks, uint32_t *chunk_bounds, cudaStream_t st);
+int v3_plan_units(const void *skr, const uint64_t *ent, const KeyLayout &kl, int cap, const uint32_t *inst_prefix, const uint32_t *run_start, uint64_t n_runs,
+                  uint64_t *nunits64, uint64_t *base64, uint32_t *atom3, uint32_t *spanlen, uint32_t *head_run, void *scratch, void *units, uint64_t max_units,
+                  void *gc_dev, uint32_t n_chunks, uint32_t *chunk_bounds, cudaStream_t st);
 struct V3Out {
     // the flat table
     uint64_t *kmer_codes;
@@ -172,19 +174,29 @@ struct V3Out {
     int32_t *stg_ids;
     void *unit_out;
 };
+struct V3Lsd {  // arrays of the global sort that puts long spans in order (cap = 0: none allocated)
+    void *rec;
+    uint32_t *src_off, *cnt, *fidx, *nadj;
+    uint64_t cap;
+};
 struct V3Chunks {
     uint32_t n;                       // 1..SKR_MAX_CHUNKS launches over consecutive ranges of the unit list
     uint32_t *tickets;                // device, [2 * n], zeroed by the launcher
     uint32_t *bounds;                 // device, [n + 1], filled by v3_plan_units
     uint64_t *chunk_sum;              // device scalar (scratch)
     unsigned long long *totals_dev;   // device, [n]: {k-mers << 32 | ids} emitted up to the end of every chunk
-    unsigned long long *totals_host;  // pinned, [n] or nullptr
+    unsigned long long *lsd_totals_dev;  // device, [n]: the same for the k-mers handed to the global sort
+    unsigned long long *totals_host, *lsd_totals_host;  // pinned, [n] or nullptr
     cudaEvent_t *done;                // [n] or nullptr
 };
 size_t v3_group_smem_bytes(int KW, int cap);
 int v3_group_launch(const void *skr, const uint64_t *ent, const void *units, const KeyLayout &kl, int cap, int cutoff, const int32_t *ids_by_arrival, int32_t id_base,
-                    const V3Out &o, uint64_t max_units, uint64_t *unit_excl, void *scan_scratch, void *gc_dev, const V3Chunks &ch, int sm_count, KernelProf *prof,
-                    cudaStream_t st);
+                    const V3Out &o, uint64_t max_units, uint64_t *unit_excl, uint64_t *lsd_excl, void *scan_scratch, void *gc_dev, const V3Chunks &ch, const V3Lsd &lsd,
+                    bool finalize_only, int sm_count, KernelProf *prof, cudaStream_t st);
+int v3_lsd_finish(const KeyLayout &kl, uint64_t n, void *rec_a, void *rec_b, void *radix_scratch, uint64_t *dnew, void *scan_scratch, const V3Out &o, const V3Lsd &lsd,
+                  KernelProf *prof, cudaStream_t st);
+size_t v3_mmer_bitmap_bytes(int M);
+int v3_count_mmers(const void *skr, int skr_words, uint64_t n_rec, int M, uint32_t *bitmap, unsigned long long *count_dev, cudaStream_t st);
 
 // ---- split_reads.cu (main's fgets loop on the device)
 uint32_t split_tiles(uint64_t n);

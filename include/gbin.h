@@ -154,13 +154,15 @@ typedef struct gbin_run_stats {
     uint64_t n_super_kmers; /* records emitted by the scan stage */
     uint64_t n_mmer_runs;   /* distinct m-mer codes before the prune (level-1 buckets) */
     uint64_t n_units;       /* shared-memory work units of the grouping kernel */
-    uint64_t reserved;
+    uint64_t n_lsd_kmers;   /* pipeline 3: surviving k-mers of buckets spread over more than 8 units (ordered by a global sort) */
+    uint32_t key_nc, key_h; /* pipeline 3: key layout of the batch (pieces per record, flank bases in the key) */
 } gbin_run_stats;
 int gbin_get_run_stats(const gbin_ctx *ctx, gbin_run_stats *out);
 int gbin_set_pipeline(gbin_ctx *ctx, int pipeline);
 /* Tuning knobs (tests and experiments; every setting produces the same table):
  *   "v3_cap" 512|1024      k-mer instances per work unit of pipeline 3 (default 1024)
- *   "v3_nc"  1|2           pieces per super-k-mer record: 1 = key is the m-mer code; 2 = windows split by the signature's offset
+ *   "v3_nc"  0|1|2         pieces per super-k-mer record: 1 = key is the m-mer code; 2 = windows split by the signature's offset
+ *                          and the key extended by v3_h bases next to the signature; 0 (default) = chosen per batch from the mean bucket size
  *   "v3_h"   0..           with v3_nc = 2: bases next to the signature that extend the level-1 key (clamped to what K, M allow)
  *   "host_chunks" 1..16    pieces in which gbin_bin_reads_host streams reads in / the table out */
 int gbin_set_tuning(gbin_ctx *ctx, const char *name, int value);

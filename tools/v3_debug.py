@@ -24,7 +24,7 @@ def compare(got, want, tag):
     return ok
 
 
-def run_case(tag, buf, n, stride, L, K, M, cutoff, cap=1024, nc=1, h=0, pipeline=3):
+def run_case(tag, buf, n, stride, L, K, M, cutoff, cap=1024, nc=0, h=0, pipeline=3):
     starts = np.arange(n, dtype=np.uint64) * stride
     lens = np.full(n, L, dtype=np.uint32)
     want = O.run(bytes(buf[: n * stride]), starts, lens, K, M, cutoff)
@@ -55,8 +55,14 @@ if __name__ == "__main__":
     rs3 = synth.generate(60000, 100, error_rate=0.01, seed=20, starts="triangular")
     allok &= run_case("medium", rs3.buf, 60000, rs3.stride, 100, 31, 11, 1)
     allok &= run_case("medium512", rs3.buf, 60000, rs3.stride, 100, 31, 11, 1, cap=512)
-    if "--nc2" in sys.argv:
-        allok &= run_case("nc2", rs.buf, 3000, rs.stride, 100, 31, 11, 1, nc=2, h=0)
-        allok &= run_case("nc2h2", rs3.buf, 60000, rs3.stride, 100, 31, 11, 1, nc=2, h=2)
+    allok &= run_case("nc2", rs.buf, 3000, rs.stride, 100, 31, 11, 1, nc=2, h=0)
+    allok &= run_case("nc2h2", rs3.buf, 60000, rs3.stride, 100, 31, 11, 1, nc=2, h=2)
+    allok &= run_case("nc2h4_512", rs3.buf, 60000, rs3.stride, 100, 31, 11, 1, nc=2, h=4, cap=512)
+    allok &= run_case("deep_nc2", rs2.buf, 2500, rs2.stride, 100, 31, 11, 1, nc=2, h=1)
+    allok &= run_case("deep63_nc2", rs2.buf, 2500, rs2.stride, 100, 63, 15, 1, nc=2, h=0)
+    allok &= run_case("m4_nc2", rs.buf, 3000, rs.stride, 100, 31, 4, 1, nc=2, h=3)
+    rs4 = synth.generate(150000, 150, error_rate=0.01, seed=31, starts="uniform")
+    allok &= run_case("m7_auto", rs4.buf, 150000, rs4.stride, 150, 25, 7, 1, nc=0)
+    allok &= run_case("m7_auto512", rs4.buf, 150000, rs4.stride, 150, 25, 7, 1, nc=0, cap=512)
     print("ALL OK" if allok else "FAILURES")
     sys.exit(0 if allok else 1)

@@ -961,8 +961,9 @@ struct UnitSNLong {  // {S << 32 | N} of the units of long spans of one chunk, 0
 template <int KW>
 __device__ __forceinline__ void finalize3_unit(const Unit3 *__restrict__ units, const uint64_t *__restrict__ unit_excl, unsigned long long base,
                                                unsigned long long lsd_base, const G3Stage &st, const G3Final &fin, const G3Lsd &ls, G3Counters *gc, uint32_t u,
-                                               uint32_t lane) {
+                                               uint32_t lane, bool only_long) {
     const uint32_t span_len = units[u].span_len;
+    if (only_long && span_len != SPAN_MEMBER_LONG && (span_len <= SPAN_SHORT_MAX || span_len == SPAN_MEMBER)) return;  // done by the first run
     const uint64_t ex = unit_excl[u];
     const UnitOut3 uo = st.unit_out[u];
     const uint64_t Sb = (base >> 32) + (ex >> 32), Nb = (base & 0xffffffffull) + (ex & 0xffffffffull);
@@ -1111,13 +1112,13 @@ template <int KW>
 __global__ void __launch_bounds__(128)
     finalize3_kernel(const Unit3 *__restrict__ units, const uint64_t *__restrict__ unit_excl, const unsigned long long *__restrict__ totals,
                      const unsigned long long *__restrict__ lsd_totals, G3Stage st, G3Final fin, G3Lsd ls, G3Counters *__restrict__ gc,
-                     const uint32_t *__restrict__ chunk_bounds, uint32_t chunk) {
+                     const uint32_t *__restrict__ chunk_bounds, uint32_t chunk, bool only_long) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t unit_begin = chunk_bounds[chunk], unit_end = chunk_bounds[chunk + 1];
     const unsigned long long base = chunk ? totals[chunk - 1] : 0ull;
     const unsigned long long lsd_base = chunk ? lsd_totals[chunk - 1] : 0ull;
     for (uint32_t u = unit_begin + blockIdx.x * 4 + (threadIdx.x >> 5); u < unit_end; u += gridDim.x * 4)
-        finalize3_unit<KW>(units, unit_excl, base, lsd_base, st, fin, ls, gc, u, lane);
+        finalize3_unit<KW>(units, unit_excl, base, lsd_base, st, fin, ls, gc, u, lane, only_long);
 }
 
 // ---- after the global sort of the long spans' k-mers (Rec<KW> sorted by (m-mer, k-mer); record.arrival = its place before the sort)
@@ -1248,7 +1249,8 @@ int v3_group_launch(const void *skr, const uint64_t *ent, const void *units, con
             v3_chunk_total_kernel<<<1, 1, 0, st>>>(ch.chunk_sum, c, ch.totals_dev, gc, ch.n, 0);
             l += exclusive_scan<uint64_t, UnitSNLong>(UnitSNLong{stg.unit_out, un, ch.bounds, c}, lsd_excl, max_units, static_cast<uint64_t *>(scan_scratch), ch.chunk_sum, st);
             v3_chunk_total_kernel<<<1, 1, 0, st>>>(ch.chunk_sum, c, ch.lsd_totals_dev, gc, ch.n, 1);
-            fin_kern<<<sm_count * 16, 128, 0, st>>>(un, unit_excl, ch.totals_dev, ch.lsd_totals_dev, stg, fin, ls, gc, ch.bounds, c);
+            // a second run (after the arrays of the global sort were allocated) only handles the long spans: the short-span merge is not idempotent
+            fin_kern<<<sm_count * 16, 128, 0, st>>>(un, unit_excl, ch.totals_dev, ch.lsd_totals_dev, stg, fin, ls, gc, ch.bounds, c, finalize_only);
             if (prof) prof->end(on, l + 3, st);
             launches += l + 3;
             if (ch.totals_host) {

@@ -137,7 +137,14 @@ __global__ void __launch_bounds__(RS_THREADS)
         if (valid) {
             items[r] = load_blob<NU64>(in + base + idx);
             const uint32_t d = digit_of<NU64>(items[r], sel);
-            const unsigned peers = __match_any_sync(act, d);
+            // lanes with my digit: eight ballots (one per bit) — a fixed cost, whereas MATCH.ANY iterates over the distinct values in the warp
+            unsigned peers = act;
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                const bool bit = (d >> b) & 1u;
+                const unsigned m = __ballot_sync(act, bit);
+                peers &= bit ? m : ~m;
+            }
             const int leader = __ffs(peers) - 1;
             uint32_t c = 0;
             if ((int)lane == leader) {

@@ -20,6 +20,7 @@ def compare(got, want, tag):
                 i = int(bad[0])
                 print("     got ", a[max(0, i - 2): i + 6])
                 print("     want", b[max(0, i - 2): i + 6])
+                print("     bad idx", bad[:40])
     print(f"  [{tag}] instances {got.n_instances}/{want.n_instances} distinct {got.n_distinct}/{want.n_distinct} kmers {got.n_kmers}/{want.n_kmers} -> {'OK' if ok else 'MISMATCH'}")
     return ok
 
@@ -42,6 +43,12 @@ def run_case(tag, buf, n, stride, L, K, M, cutoff, cap=1024, nc=0, h=0, pipeline
 
 if __name__ == "__main__":
     allok = True
+    if "--k64" in sys.argv:
+        rs = synth.generate(1500, 200, genome_len=2000, error_rate=0.01, seed=6415, starts="uniform")
+        for pl in (3, 2):
+            run_case("k64", rs.buf, 1500, rs.stride, 200, 64, 15, 1, pipeline=pl)
+        run_case("k64_512", rs.buf, 1500, rs.stride, 200, 64, 15, 1, cap=512)
+        sys.exit(0)
     rs = synth.generate(3000, 100, error_rate=0.01, seed=3, starts="uniform")
     allok &= run_case("tiny", rs.buf, 200, rs.stride, 100, 31, 11, 1)
     allok &= run_case("small", rs.buf, 3000, rs.stride, 100, 31, 11, 1)

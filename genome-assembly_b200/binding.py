@@ -64,7 +64,7 @@ EXPORTS = [
     "gbin_strerror", "gbin_last_error", "gbin_version", "gbin_create", "gbin_destroy", "gbin_get_config",
     "gbin_bin_reads_host", "gbin_table_clone", "gbin_table_free", "gbin_pinned_alloc", "gbin_pinned_free",
     "gbin_bin_reads_device", "gbin_table_to_host", "gbin_table_to_pinned", "gbin_get_timings", "gbin_record_bytes",
-    "gbin_set_kernel_profiling", "gbin_get_kernel_profile", "gbin_kernel_kind_name", "gbin_set_pipeline", "gbin_set_tuning", "gbin_get_pipeline_info", "gbin_get_run_stats",
+    "gbin_set_kernel_profiling", "gbin_get_kernel_profile", "gbin_kernel_kind_name", "gbin_table_digest", "gbin_set_pipeline", "gbin_set_tuning", "gbin_get_pipeline_info", "gbin_get_run_stats",
     "gbin_count_instances_device", "gbin_scan_reads_device", "gbin_partition_records_device",
     "gbin_group_records_device", "gbin_owner_of", "gbin_xchg_create", "gbin_xchg_attach", "gbin_xchg_exchange_skr", "gbin_xchg_destroy", "gbin_skr_record_bytes", "gbin_scan_skr_device", "gbin_partition_skr_device", "gbin_group_skr_device",
     "gbin_split_reads_device", "gbin_copy_to_host", "gbin_bin_file_host", "gbin_read_file_fgets", "gbin_table_dump", "gbin_table_dump_reference_format", "gbin_table_dump_expanded_format",
@@ -105,8 +105,9 @@ def load_library() -> C.CDLL:
     L.gbin_pinned_free.argtypes = [vp]
     L.gbin_pinned_free.restype = None
     L.gbin_get_timings.argtypes = [vp, C.POINTER(Timings)]
-    L.gbin_get_run_stats.argtypes = [vp, C.POINTER(u64 * 5)]
+    L.gbin_get_run_stats.argtypes = [vp, C.POINTER(u64 * 6)]
     L.gbin_set_pipeline.argtypes = [vp, C.c_int]
+    L.gbin_table_digest.argtypes = [vp, C.POINTER(CTable), vp, C.POINTER(u64)]
     L.gbin_set_tuning.argtypes = [vp, C.c_char_p, C.c_int]
     L.gbin_get_pipeline_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint32)]
     L.gbin_set_kernel_profiling.argtypes = [vp, C.c_int]
@@ -278,6 +279,12 @@ class Binner:
     def set_pipeline(self, pipeline: int):
         self._check(self.lib.gbin_set_pipeline(self.h, pipeline))
 
+    def table_digest(self, table: CTable, stream=None) -> int:
+        """Order-independent 64-bit digest of a device or host table (gbin_table_digest)."""
+        d = C.c_uint64()
+        self._check(self.lib.gbin_table_digest(self.h, C.byref(table), stream, C.byref(d)))
+        return int(d.value)
+
     def set_tuning(self, name: str, value: int):
         self._check(self.lib.gbin_set_tuning(self.h, name.encode(), int(value)))
 
@@ -287,10 +294,10 @@ class Binner:
         return {"configured": a.value, "last_used": b.value, "fallbacks": c.value}
 
     def run_stats(self) -> dict:
-        a = (C.c_uint64 * 5)()
+        a = (C.c_uint64 * 6)()
         self._check(self.lib.gbin_get_run_stats(self.h, C.byref(a)))
         return {"n_super_kmers": int(a[0]), "n_mmer_runs": int(a[1]), "n_units": int(a[2]), "n_lsd_kmers": int(a[3]),
-                "key_nc": int(a[4]) & 0xffffffff, "key_h": int(a[4]) >> 32}
+                "key_nc": int(a[4]) & 0xffffffff, "key_h": int(a[4]) >> 32, "n_passes": int(a[5]) & 0xffffffff}
 
     def set_kernel_profiling(self, enable: bool):
         self._check(self.lib.gbin_set_kernel_profiling(self.h, int(enable)))

@@ -137,7 +137,7 @@ int v3_plan_runs(const uint64_t *ent, const uint8_t *piece_n, uint64_t n_ent, ui
 // packing is a sequential recurrence; it is made parallel by restarting it at every block of PLAN_BLOCK atoms (one extra
 // partial unit per block, under 2 % of the units).  An atom with more than `cap` instances gets 2 * ceil(c / cap) + 1
 // round units (enough for a greedy cut of its d-histogram whenever no single d holds more than cap instances).
-constexpr int PLAN_BLOCK = 256;   // atoms walked by one thread
+constexpr int PLAN_BLOCK = 64;    // atoms walked by one thread
 constexpr int PLAN_CTA_BLOCKS = 32;
 struct Plan3 {
     uint32_t cap, nb_max, ecap, max_rounds;
@@ -918,11 +918,12 @@ __global__ void v3_chunk_total_kernel(const uint64_t *__restrict__ chunk_sum, ui
     }
 }
 
-struct G3Final {
+struct G3Final {  // this pass's part of the table (pointers at the pass's first k-mer / id)
     uint64_t *kmer_codes;   // [S * KW]
     uint32_t *kmer_mmer;    // [S]
     uint64_t *kmer_id_off;  // [S + 1]
     int32_t *read_ids;      // [N]
+    uint64_t id_off_base;   // ids of the passes before this one (kmer_id_off holds offsets into the whole read_ids array)
 };
 
 // One warp per unit: copy its staged k-mers and ids to their place in the table (place = totals of all units before it).  The
@@ -990,7 +991,7 @@ __device__ __forceinline__ void finalize3_unit(const Unit3 *__restrict__ units, 
                     fin.kmer_codes[(Sb + x) * KW] = c0[q];
                     if (KW == 2) fin.kmer_codes[(Sb + x) * KW + 1] = c1[q];
                     fin.kmer_mmer[Sb + x] = mm[q];
-                    fin.kmer_id_off[Sb + x] = Nb + lo[q];
+                    fin.kmer_id_off[Sb + x] = fin.id_off_base + Nb + lo[q];
                 }
             }
         }
@@ -1083,7 +1084,7 @@ __device__ __forceinline__ void finalize3_unit(const Unit3 *__restrict__ units, 
     __syncwarp();
     __threadfence();
     // pass 2: list lengths -> offsets (in place)
-    uint64_t carry = Nb;
+    uint64_t carry = fin.id_off_base + Nb;
     for (uint32_t x0 = 0; x0 < S_tot; x0 += 32) {
         const uint32_t x = x0 + lane;
         const uint32_t c = x < S_tot ? (uint32_t)fin.kmer_id_off[Sb + x] : 0u;
@@ -1093,17 +1094,32 @@ __device__ __forceinline__ void finalize3_unit(const Unit3 *__restrict__ units, 
     }
     __syncwarp();
     __threadfence();
-    // pass 3: lists, eight lanes per list
+    // pass 3: lists.  Lane = list for the bookkeeping of 32 lists at a time (independent loads), then eight lanes copy each list.
     for (uint32_t j = 0; j < R; j++) {
         const UnitOut3 uj = st.unit_out[u + j];
         const uint64_t kbj = uj.ibase / st.kdiv;
-        for (uint32_t x = lane >> 3; x < uj.S; x += 4) {
-            const uint32_t lo = st.loff[kbj + x];
-            const uint32_t cnt = (x + 1 < uj.S ? st.loff[kbj + x + 1] : uj.N) - lo;
-            const uint32_t rank = st.mmer[kbj + x];
-            const int32_t *src = st.ids + uj.ibase + lo;
-            int32_t *dst = fin.read_ids + fin.kmer_id_off[Sb + rank];
-            for (uint32_t i = lane & 7u; i < cnt; i += 8) dst[i] = src[i];
+        for (uint32_t x0 = 0; x0 < uj.S; x0 += 32) {
+            const uint32_t x = x0 + lane;
+            uint32_t lo = 0, cnt = 0;
+            uint64_t dsto = 0;
+            if (x < uj.S) {
+                lo = st.loff[kbj + x];
+                const uint32_t hi = x + 1 < uj.S ? st.loff[kbj + x + 1] : uj.N;
+                cnt = hi - lo;
+                dsto = fin.kmer_id_off[Sb + st.mmer[kbj + x]] - fin.id_off_base;
+            }
+            const uint32_t nl = min(32u, uj.S - x0);
+            for (uint32_t l0 = 0; l0 < nl; l0 += 4) {  // four lists per step, eight lanes each
+                const uint32_t l = l0 + (lane >> 3);
+                const uint32_t c = __shfl_sync(0xffffffffu, cnt, l & 31);
+                const uint32_t so = __shfl_sync(0xffffffffu, lo, l & 31);
+                const uint64_t d = __shfl_sync(0xffffffffu, dsto, l & 31);
+                if (l < nl) {
+                    const int32_t *src = st.ids + uj.ibase + so;
+                    int32_t *dst = fin.read_ids + d;
+                    for (uint32_t i = lane & 7u; i < c; i += 8) dst[i] = src[i];
+                }
+            }
         }
     }
 }
@@ -1138,7 +1154,7 @@ __global__ void lsd_place_kernel(const Rec<KW> *__restrict__ rec, uint64_t n, co
     fin.kmer_codes[f * KW] = r.k[0];
     if (KW == 2) fin.kmer_codes[f * KW + 1] = r.k[KW - 1];
     fin.kmer_mmer[f] = r.mmer;
-    fin.kmer_id_off[f] = dnew[q] + ls.nadj[q];
+    fin.kmer_id_off[f] = fin.id_off_base + dnew[q] + ls.nadj[q];
 }
 
 template <int KW>
@@ -1227,7 +1243,7 @@ int v3_group_launch(const void *skr, const uint64_t *ent, const void *units, con
     cudaMemsetAsync(ch.tickets, 0, sizeof(uint32_t) * 2 * ch.n, st);
     const uint32_t kdiv = cutoff >= 0 ? (uint32_t)cutoff + 1u : 1u;
     G3Stage stg{o.stg_codes, o.stg_mmer, o.stg_loff, o.stg_ids, static_cast<UnitOut3 *>(o.unit_out), o.kmer_cap, o.id_cap, kdiv};
-    G3Final fin{o.kmer_codes, o.kmer_mmer, o.kmer_id_off, o.read_ids};
+    G3Final fin{o.kmer_codes, o.kmer_mmer, o.kmer_id_off, o.read_ids, o.id_off_base};
     G3Lsd ls{lsd_excl, lsd.rec, lsd.src_off, lsd.cnt, lsd.fidx, lsd.nadj, lsd.cap};
     G3Counters *gc = static_cast<G3Counters *>(gc_dev);
     const uint32_t *sk = static_cast<const uint32_t *>(skr);
@@ -1290,7 +1306,7 @@ int v3_lsd_finish(const KeyLayout &kl, uint64_t n, void *rec_a, void *rec_b, voi
     int passes = 0;
     int l = radix_sort_records(rec_a, rec_b, n, KW, kl.K, kl.M, radix_scratch, &in_b, &passes, prof, st);
     const void *sorted = in_b ? rec_b : rec_a;
-    G3Final fin{o.kmer_codes, o.kmer_mmer, o.kmer_id_off, o.read_ids};
+    G3Final fin{o.kmer_codes, o.kmer_mmer, o.kmer_id_off, o.read_ids, o.id_off_base};
     G3Lsd ls{nullptr, nullptr, lsd.src_off, lsd.cnt, lsd.fidx, lsd.nadj, lsd.cap};
     bool on = prof && prof->begin(KK_V3_SPAN, st);
     int l2 = 0;
@@ -1307,6 +1323,47 @@ int v3_lsd_finish(const KeyLayout &kl, uint64_t n, void *rec_a, void *rec_b, voi
     }
     if (prof) prof->end(on, l2 + 2, st);
     return l + l2 + 2;
+}
+
+// ---- passes: a batch with more k-mer instances than 32-bit coordinates hold is grouped in several passes over consecutive
+// ranges of the sorted entries, cut between m-mer buckets; every pass appends its part of the table.
+constexpr uint32_t PASS_TILE = 1u << 16;
+__global__ void pass_tile_sums_kernel(const uint64_t *__restrict__ ent, const uint8_t *__restrict__ piece_n, uint64_t n_ent, unsigned long long *__restrict__ sums) {
+    const uint64_t base = (uint64_t)blockIdx.x * PASS_TILE;
+    unsigned long long acc = 0;
+    for (uint64_t i = base + threadIdx.x; i < base + PASS_TILE && i < n_ent; i += blockDim.x) acc += piece_n[(uint32_t)ent[i]];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    __shared__ unsigned long long s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s[w];
+        sums[blockIdx.x] = t;
+    }
+}
+// bounds[i] (an entry index) is moved forward to the first entry of the next m-mer bucket; one thread per bound
+__global__ void pass_bounds_kernel(const uint64_t *__restrict__ ent, uint64_t n_ent, int mshift, unsigned long long *__restrict__ bounds, uint32_t n_bounds) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_bounds) return;
+    unsigned long long b = bounds[i];
+    if (b == 0 || b >= n_ent) return;
+    const uint32_t mm = (uint32_t)(ent[b - 1] >> 32) >> mshift;
+    while (b < n_ent && ((uint32_t)(ent[b] >> 32) >> mshift) == mm) b++;
+    bounds[i] = b;
+}
+uint32_t v3_pass_tiles(uint64_t n_ent) { return (uint32_t)((n_ent + PASS_TILE - 1) / PASS_TILE); }
+uint32_t v3_pass_tile_entries() { return PASS_TILE; }
+int v3_pass_tile_sums(const uint64_t *ent, const uint8_t *piece_n, uint64_t n_ent, unsigned long long *sums_dev, cudaStream_t st) {
+    if (n_ent == 0) return 0;
+    pass_tile_sums_kernel<<<v3_pass_tiles(n_ent), 256, 0, st>>>(ent, piece_n, n_ent, sums_dev);
+    return 1;
+}
+int v3_pass_bounds(const uint64_t *ent, uint64_t n_ent, int mshift, unsigned long long *bounds_dev, uint32_t n_bounds, cudaStream_t st) {
+    if (n_bounds == 0) return 0;
+    pass_bounds_kernel<<<(n_bounds + 63) / 64, 64, 0, st>>>(ent, n_ent, mshift, bounds_dev, n_bounds);
+    return 1;
 }
 
 // ---- how many different m-mer codes do the records hold?  (bitmap over the code space; decides the key layout)

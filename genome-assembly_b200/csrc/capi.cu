@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "../../include/gbin.h"
 #include "gbin_internal.h"
@@ -32,6 +33,21 @@ struct DevBuf {
             want = bytes;
         }
         if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    // grows like ensure() but keeps the first `keep` bytes (the parts of a table that earlier passes of a batch have written)
+    cudaError_t ensure_keep(size_t bytes, size_t keep, cudaStream_t st) {
+        if (bytes <= cap) return cudaSuccess;
+        if (!p || keep == 0) return ensure(bytes);
+        void *q = nullptr;
+        const size_t want = bytes + bytes / 16 + 256;
+        cudaError_t e = cudaMalloc(&q, want);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(q, p, keep, cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaFree(p);
+        p = q;
+        cap = want;
         return e;
     }
     void release() {
@@ -127,6 +143,8 @@ struct gbin_ctx {
     // pipeline v3 workspace
     DevBuf ent_a, ent_b, piece_n, v3_base64, v3_head_run, v3_unit_out, v3_unit_excl, v3_atoms, v3_lsd_aux, v3_bitmap;
     bool v3_lsd_seen = false;         // a batch on this context had long spans: keep the arrays of their global sort
+    uint64_t v3_lsd_cap_seen = 0;     // and how many k-mers they were sized for
+    uint64_t v3_pass_max = 2000000000ull;  // k-mer instances per pass of pipeline 3 (gbin_set_tuning "v3_pass_max")
     uint64_t v3_auto_n = 0;           // record count for which the key layout below was chosen (v3_nc == 0: automatic)
     int v3_auto_h = 0, v3_auto_nc = 1;
     int v3_h, v3_nc, v3_cap;  // key layout and unit capacity of pipeline 3 (gbin_set_tuning; GBIN_V3_H / GBIN_V3_NC / GBIN_V3_CAP)
@@ -590,61 +608,31 @@ int v3_choose_layout(gbin_ctx *ctx, const void *skr, uint64_t n_skr, cudaStream_
     return GBIN_OK;
 }
 
-int run_v3_group(gbin_ctx *ctx, const void *skr, uint64_t n_skr, const int32_t *d_ids, int32_t id_base, cudaStream_t st, gbin_table *out, int *launches,
-                 bool *done, uint64_t *n_inst_out, HostSink *sink = nullptr) {
-    *done = false;
-    const int K = ctx->cfg.kmer_size, M = ctx->cfg.mmer_size, cutoff = ctx->cfg.abundance_cutoff, KW = ctx->KW;
+// One pass of pipeline 3 over the sorted entries [ent, ent + n_ent): plan, group, finalize; the pass's k-mers / ids are appended to
+// the table behind the S_off k-mers / N_off ids of the passes before it.  *ok = false: the pass does not fit (see run_v3_group).
+int run_v3_pass(gbin_ctx *ctx, const void *skr, const uint64_t *ent, uint64_t n_ent, const KeyLayout &kl, const int32_t *d_ids, int32_t id_base, cudaStream_t st,
+                uint64_t S_off, uint64_t N_off, bool single_pass, HostSink *sink, int *launches, bool *ok, uint64_t *n_inst, uint64_t *distinct, uint64_t *S_out,
+                uint64_t *N_out) {
+    *ok = false;
+    const int cutoff = ctx->cfg.abundance_cutoff, KW = ctx->KW;
     Misc *dm = ctx->misc.as<Misc>();
     Misc *hm = static_cast<Misc *>(ctx->h_misc.p);
-    KeyLayout kl;
-    int rc = v3_choose_layout(ctx, skr, n_skr, st, &kl, launches);
-    if (rc) return rc;
-    if (n_skr >= (1ull << (32 - kl.cshift))) return GBIN_OK;  // slots are 32-bit
-    ctx->rs.key_nc = (uint32_t)kl.nc;
-    ctx->rs.key_h = (uint32_t)kl.h;
-
-    // ---- entries + level 1: stable sort of the entries by key
-    const uint64_t n_slots = n_skr << kl.cshift;
-    CU(ctx->ent_a.ensure((n_slots + 2) * 8));
-    CU(ctx->ent_b.ensure((n_slots + 2) * 8));
-    CU(ctx->piece_n.ensure(n_slots + 16));
-    bool on = ctx->prof.begin(KK_V3_ENTRIES, st);
-    int lp = v3_make_entries(skr, n_skr, kl, ctx->ent_a.as<uint64_t>(), ctx->piece_n.as<uint8_t>(), &dm->n_real_entries, st);
-    ctx->prof.end(on, lp, st);
-    *launches += lp;
-    CU(cudaGetLastError());
-    CU(ctx->radix_scratch.ensure(radix_scratch_bytes(n_slots)));
-    bool in_b = false;
-    int passes = 0;
-    *launches += radix_sort_entries(ctx->ent_a.p, ctx->ent_b.p, n_slots, kl.key_bits, ctx->radix_scratch.p, &in_b, &passes, &ctx->prof, st);
-    CU(cudaGetLastError());
-    ctx->tm.sort_passes = (uint32_t)passes;
-    const uint64_t *ent = in_b ? ctx->ent_b.as<uint64_t>() : ctx->ent_a.as<uint64_t>();
-    CU(cudaEventRecord(ctx->ev[3], st));
-    uint64_t n_ent = n_slots;
-    if (kl.nc == 2) {  // empty pieces carry the all-ones key and sort behind everything: plan over the real ones only
-        CU(cudaMemcpyAsync(&hm->n_real_entries, &dm->n_real_entries, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        n_ent = hm->n_real_entries;
-    }
-
     // ---- plan: instance prefix, atoms, units
     CU(ctx->inst_prefix.ensure((n_ent + 2) * 4));
     CU(ctx->run_excl.ensure((n_ent + 2) * 8));
     CU(ctx->skr_run_start.ensure((n_ent + 2) * 4));
     CU(ctx->scan_scratch.ensure(group_scan_scratch_bytes(n_ent)));
-    on = ctx->prof.begin(KK_SKR_PLAN, st);
-    lp = v3_plan_runs(ent, ctx->piece_n.as<uint8_t>(), n_ent, ctx->inst_prefix.as<uint32_t>(), ctx->run_excl.as<uint64_t>(), ctx->skr_run_start.as<uint32_t>(),
-                      ctx->scan_scratch.as<uint64_t>(), &dm->n_inst_dev, &dm->n_runs_dev, st);
+    bool on = ctx->prof.begin(KK_SKR_PLAN, st);
+    int lp = v3_plan_runs(ent, ctx->piece_n.as<uint8_t>(), n_ent, ctx->inst_prefix.as<uint32_t>(), ctx->run_excl.as<uint64_t>(), ctx->skr_run_start.as<uint32_t>(),
+                          ctx->scan_scratch.as<uint64_t>(), &dm->n_inst_dev, &dm->n_runs_dev, st);
     ctx->prof.end(on, lp, st);
     *launches += lp;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(&hm->n_inst_dev, &dm->n_inst_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     const uint64_t n_runs = hm->n_runs_dev, n = hm->n_inst_dev;
-    *n_inst_out = n;
-    ctx->rs.n_super_kmers = n_skr;
-    ctx->rs.n_mmer_runs = n_runs;
+    *n_inst = n;
+    ctx->rs.n_mmer_runs += n_runs;
     const uint64_t max_units = v3_max_units(n, n_runs, ctx->v3_cap);
     CU(ctx->small_prefix.ensure((n_runs + 2) * 8));
     CU(ctx->v3_base64.ensure((n_runs + 2) * 8));
@@ -655,7 +643,7 @@ int run_v3_group(gbin_ctx *ctx, const void *skr, uint64_t n_skr, const int32_t *
     CU(ctx->v3_unit_excl.ensure((2 * max_units + 2) * 8));
     CU(ctx->scan_scratch.ensure(group_scan_scratch_bytes(n_runs + max_units + 1024)));
     V3Chunks ch{1u, dm->v3_tickets, dm->chunk_bounds, &dm->v3_chunk_sum, dm->chunk_totals, dm->lsd_totals, nullptr, nullptr, nullptr};
-    if (sink && sink->chunks > 1) {
+    if (single_pass && sink && sink->chunks > 1) {
         ch.n = (uint32_t)sink->chunks;
         ch.totals_host = hm->chunk_totals;
         ch.lsd_totals_host = hm->lsd_totals;
@@ -671,16 +659,17 @@ int run_v3_group(gbin_ctx *ctx, const void *skr, uint64_t n_skr, const int32_t *
 
     // ---- level 2 + prune + emit.  Output bounds: a surviving k-mer has more than `cutoff` instances.
     const uint64_t kmer_cap = cutoff >= 0 ? n / ((uint64_t)cutoff + 1) + 1 : n + 1;
-    CU(ctx->o_kmer_codes.ensure((kmer_cap * KW + 1) * sizeof(uint64_t)));
-    CU(ctx->o_kmer_mmer.ensure((kmer_cap + 1) * sizeof(uint32_t)));
-    CU(ctx->o_kmer_id_off.ensure((kmer_cap + 2) * sizeof(uint64_t)));
-    CU(ctx->o_read_ids.ensure((n + 1) * sizeof(int32_t)));
+    CU(ctx->o_kmer_codes.ensure_keep(((S_off + kmer_cap) * KW + 1) * sizeof(uint64_t), S_off * KW * sizeof(uint64_t), st));
+    CU(ctx->o_kmer_mmer.ensure_keep((S_off + kmer_cap + 1) * sizeof(uint32_t), S_off * sizeof(uint32_t), st));
+    CU(ctx->o_kmer_id_off.ensure_keep((S_off + kmer_cap + 2) * sizeof(uint64_t), S_off * sizeof(uint64_t), st));
+    CU(ctx->o_read_ids.ensure_keep((N_off + n + 1) * sizeof(int32_t), N_off * sizeof(int32_t), st));
     CU(ctx->stg_ids.ensure((n + 1) * sizeof(int32_t)));
     CU(ctx->stg_codes.ensure((kmer_cap * KW + 1) * sizeof(uint64_t)));
     CU(ctx->stg_mmer.ensure((kmer_cap + 1) * sizeof(uint32_t)));
     CU(ctx->stg_off.ensure((kmer_cap + 1) * sizeof(uint32_t)));
-    V3Out vo{ctx->o_kmer_codes.as<uint64_t>(), ctx->o_kmer_mmer.as<uint32_t>(), ctx->o_kmer_id_off.as<uint64_t>(), ctx->o_read_ids.as<int32_t>(), kmer_cap, n,
-             ctx->stg_codes.as<uint64_t>(), ctx->stg_mmer.as<uint32_t>(), ctx->stg_off.as<uint32_t>(), ctx->stg_ids.as<int32_t>(), ctx->v3_unit_out.p};
+    V3Out vo{ctx->o_kmer_codes.as<uint64_t>() + S_off * KW, ctx->o_kmer_mmer.as<uint32_t>() + S_off, ctx->o_kmer_id_off.as<uint64_t>() + S_off,
+             ctx->o_read_ids.as<int32_t>() + N_off, kmer_cap, n, ctx->stg_codes.as<uint64_t>(), ctx->stg_mmer.as<uint32_t>(), ctx->stg_off.as<uint32_t>(),
+             ctx->stg_ids.as<int32_t>(), ctx->v3_unit_out.p, N_off};
     const size_t rb = sizeof(uint64_t) * KW + 8;
     auto lsd_arrays = [&](uint64_t cap) -> int {  // arrays of the global sort for long spans, for `cap` k-mers
         if (cap == 0) return GBIN_OK;
@@ -689,8 +678,10 @@ int run_v3_group(gbin_ctx *ctx, const void *skr, uint64_t n_skr, const int32_t *
         CU(ctx->v3_lsd_aux.ensure((cap + 1) * 16));
         return GBIN_OK;
     };
-    uint64_t lsd_cap = (kl.nc == 2 || ctx->v3_lsd_seen) ? kmer_cap : 0;  // buckets large enough for extended keys are large enough for long spans
-    rc = lsd_arrays(lsd_cap);
+    // long spans appear when buckets are large enough for extended keys; their k-mers are a fraction of the bound (grown on demand)
+    uint64_t lsd_cap = (kl.nc == 2 || ctx->v3_lsd_seen) ? (kmer_cap < (1u << 22) ? kmer_cap : kmer_cap / 4) : 0;
+    if (lsd_cap && lsd_cap < ctx->v3_lsd_cap_seen && ctx->v3_lsd_cap_seen <= kmer_cap) lsd_cap = ctx->v3_lsd_cap_seen;
+    int rc = lsd_arrays(lsd_cap);
     if (rc) return rc;
     auto lsd_view = [&](uint64_t cap) {
         uint32_t *aux = ctx->v3_lsd_aux.as<uint32_t>();
@@ -723,9 +714,11 @@ int run_v3_group(gbin_ctx *ctx, const void *skr, uint64_t n_skr, const int32_t *
     CU(cudaMemcpyAsync(&hm->gc3, &dm->gc3, sizeof(V3Counters), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (hm->gc3.overflow == 6u && hm->gc3.lsd_kmers > lsd_cap) {
-        // long spans met no (or too small) sort arrays: allocate them and redo the placement (the staged results are still there)
+        // long spans met no (or too small) sort arrays: allocate them and redo their placement (the staged results are still there)
         ctx->v3_lsd_seen = true;
-        lsd_cap = kmer_cap;
+        lsd_cap = hm->gc3.lsd_kmers + hm->gc3.lsd_kmers / 16 + 1024;
+        if (lsd_cap > kmer_cap) lsd_cap = kmer_cap;
+        ctx->v3_lsd_cap_seen = lsd_cap;
         rc = lsd_arrays(lsd_cap);
         if (rc) return rc;
         CU(cudaMemsetAsync(&dm->gc3.overflow, 0, sizeof(unsigned int), st));
@@ -739,13 +732,12 @@ int run_v3_group(gbin_ctx *ctx, const void *skr, uint64_t n_skr, const int32_t *
         CU(cudaMemcpyAsync(&hm->gc3, &dm->gc3, sizeof(V3Counters), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
-    ctx->rs.n_units = hm->gc3.n_units;
-    ctx->rs.n_lsd_kmers = hm->gc3.lsd_kmers;
+    ctx->rs.n_units += hm->gc3.n_units;
+    ctx->rs.n_lsd_kmers += hm->gc3.lsd_kmers;
     if (hm->gc3.overflow) {  // not done: the caller falls back
         snprintf(ctx->err, sizeof ctx->err, "pipeline 3 gave the batch up (code %u: a (bucket, d) class larger than a unit)", hm->gc3.overflow);
         return GBIN_OK;
     }
-    const uint64_t S = hm->gc3.total_kmers, NS = hm->gc3.total_ids;
     if (hm->gc3.lsd_kmers) {
         const uint64_t nl = hm->gc3.lsd_kmers;
         CU(ctx->radix_scratch.ensure(radix_scratch_bytes(nl)));
@@ -756,6 +748,101 @@ int run_v3_group(gbin_ctx *ctx, const void *skr, uint64_t n_skr, const int32_t *
         *launches += lp;
         CU(cudaGetLastError());
     }
+    *distinct = hm->gc3.distinct;
+    *S_out = hm->gc3.total_kmers;
+    *N_out = hm->gc3.total_ids;
+    *ok = true;
+    return GBIN_OK;
+}
+
+int run_v3_group(gbin_ctx *ctx, const void *skr, uint64_t n_skr, const int32_t *d_ids, int32_t id_base, cudaStream_t st, gbin_table *out, int *launches,
+                 bool *done, uint64_t *n_inst_out, HostSink *sink = nullptr) {
+    *done = false;
+    const int K = ctx->cfg.kmer_size, M = ctx->cfg.mmer_size, cutoff = ctx->cfg.abundance_cutoff, KW = ctx->KW;
+    Misc *dm = ctx->misc.as<Misc>();
+    Misc *hm = static_cast<Misc *>(ctx->h_misc.p);
+    KeyLayout kl;
+    int rc = v3_choose_layout(ctx, skr, n_skr, st, &kl, launches);
+    if (rc) return rc;
+    if (n_skr >= (1ull << (32 - kl.cshift))) return GBIN_OK;  // slots are 32-bit
+    memset(&ctx->rs, 0, sizeof ctx->rs);
+    ctx->rs.n_super_kmers = n_skr;
+    ctx->rs.key_nc = (uint32_t)kl.nc;
+    ctx->rs.key_h = (uint32_t)kl.h;
+
+    // ---- entries + level 1: stable sort of the entries by key
+    const uint64_t n_slots = n_skr << kl.cshift;
+    CU(ctx->ent_a.ensure((n_slots + 2) * 8));
+    CU(ctx->ent_b.ensure((n_slots + 2) * 8));
+    CU(ctx->piece_n.ensure(n_slots + 16));
+    bool on = ctx->prof.begin(KK_V3_ENTRIES, st);
+    int lp = v3_make_entries(skr, n_skr, kl, ctx->ent_a.as<uint64_t>(), ctx->piece_n.as<uint8_t>(), &dm->n_real_entries, st);
+    ctx->prof.end(on, lp, st);
+    *launches += lp;
+    CU(cudaGetLastError());
+    CU(ctx->radix_scratch.ensure(radix_scratch_bytes(n_slots)));
+    bool in_b = false;
+    int passes = 0;
+    *launches += radix_sort_entries(ctx->ent_a.p, ctx->ent_b.p, n_slots, kl.key_bits, ctx->radix_scratch.p, &in_b, &passes, &ctx->prof, st);
+    CU(cudaGetLastError());
+    ctx->tm.sort_passes = (uint32_t)passes;
+    const uint64_t *ent = in_b ? ctx->ent_b.as<uint64_t>() : ctx->ent_a.as<uint64_t>();
+    CU(cudaEventRecord(ctx->ev[3], st));
+    uint64_t n_ent = n_slots;
+    if (kl.nc == 2) {  // empty pieces carry the all-ones key and sort behind everything: plan over the real ones only
+        CU(cudaMemcpyAsync(&hm->n_real_entries, &dm->n_real_entries, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        n_ent = hm->n_real_entries;
+    }
+
+    // ---- passes: ranges of the sorted entries with at most pass_max k-mer instances each, cut between m-mer buckets
+    std::vector<uint64_t> bounds{0, n_ent};
+    const uint64_t pass_max = ctx->v3_pass_max;
+    if (n_skr * (uint64_t)(K - M + 1) > pass_max) {  // more than one pass is possible: look at the instance counts
+        const uint32_t nt = v3_pass_tiles(n_ent);
+        CU(ctx->scan_scratch.ensure((size_t)nt * 8 + 64));
+        unsigned long long *sums_dev = ctx->scan_scratch.as<unsigned long long>();
+        *launches += v3_pass_tile_sums(ent, ctx->piece_n.as<uint8_t>(), n_ent, sums_dev, st);
+        std::vector<unsigned long long> sums(nt);
+        CU(cudaMemcpyAsync(sums.data(), sums_dev, (size_t)nt * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        std::vector<unsigned long long> cuts;
+        unsigned long long acc = 0;
+        for (uint32_t t = 0; t < nt; t++) {
+            if (acc && acc + sums[t] > pass_max) {
+                cuts.push_back((unsigned long long)t * v3_pass_tile_entries());
+                acc = 0;
+            }
+            acc += sums[t];
+        }
+        if (!cuts.empty()) {
+            CU(cudaMemcpyAsync(sums_dev, cuts.data(), cuts.size() * 8, cudaMemcpyHostToDevice, st));
+            *launches += v3_pass_bounds(ent, n_ent, kl.mshift, sums_dev, (uint32_t)cuts.size(), st);
+            CU(cudaMemcpyAsync(cuts.data(), sums_dev, cuts.size() * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            bounds.assign(1, 0);
+            for (unsigned long long c : cuts)
+                if (c > bounds.back() && c < n_ent) bounds.push_back(c);
+            bounds.push_back(n_ent);
+        }
+    }
+    const bool single = bounds.size() == 2;
+    uint64_t S_off = 0, N_off = 0, n_total = 0, distinct = 0;
+    for (size_t p = 0; p + 1 < bounds.size(); p++) {
+        bool ok = false;
+        uint64_t n_p = 0, d_p = 0, S_p = 0, N_p = 0;
+        rc = run_v3_pass(ctx, skr, ent + bounds[p], bounds[p + 1] - bounds[p], kl, d_ids, id_base, st, S_off, N_off, single, sink, launches, &ok, &n_p, &d_p, &S_p, &N_p);
+        if (rc) return rc;
+        if (!ok) return GBIN_OK;  // not done: the caller falls back
+        S_off += S_p;
+        N_off += N_p;
+        n_total += n_p;
+        distinct += d_p;
+    }
+    *n_inst_out = n_total;
+    ctx->rs.n_passes = (uint32_t)(bounds.size() - 1);
+    const uint64_t S = S_off, NS = N_off;
+    if (S >= (1ull << 32)) return fail(ctx, GBIN_E_TOO_LARGE, "%llu surviving k-mers in one batch (limit 2^32)", (unsigned long long)S);
 
     // ---- bucket directory
     CU(ctx->bucket_excl.ensure((S + 1) * 4));
@@ -779,8 +866,8 @@ int run_v3_group(gbin_ctx *ctx, const void *skr, uint64_t n_skr, const int32_t *
     out->kmer_words = KW;
     out->on_device = 1;
     out->ctx_owned = 1;
-    out->n_instances = n;
-    out->n_distinct = hm->gc3.distinct;
+    out->n_instances = n_total;
+    out->n_distinct = distinct;
     out->n_kmers = S;
     out->n_ids = NS;
     out->n_buckets = hm->n_buckets_dev;
@@ -811,6 +898,9 @@ int run_skr_group(gbin_ctx *ctx, void *skr, uint64_t n_skr, const int32_t *d_ids
             sink->kmers_done = sink->ids_done = 0;
         }
     }
+    if (n_skr * (uint64_t)(ctx->cfg.kmer_size - ctx->cfg.mmer_size + 1) >= (1ull << 31))  // pipeline 2 holds instance coordinates in 31 bits
+        return fail(ctx, GBIN_E_TOO_LARGE, "the batch is too large for pipeline 2 (%llu super-k-mer records) and pipeline 3 %s", (unsigned long long)n_skr,
+                    ctx->pipeline >= 3 ? "gave it up" : "is switched off");
     CU(ctx->skr_b.ensure((n_skr + 1) * NW * 4));
     int rc = run_v2_group(ctx, skr, ctx->skr_b.p, n_skr, d_ids, id_base, st, out, launches, done, n_inst_out, sink);
     if (rc) return rc;
@@ -821,7 +911,7 @@ int run_skr_group(gbin_ctx *ctx, void *skr, uint64_t n_skr, const int32_t *d_ids
 int run_v2(gbin_ctx *ctx, const gbin_reads *rd, uint64_t n, uint32_t max_len, cudaStream_t st, gbin_table *out, int *launches, bool *done,
            const HostFeed *feed, HostSink *sink, int *used) {
     *done = false;
-    if (n == 0 || n >= (1ull << 31)) return GBIN_OK;
+    if (n == 0 || (ctx->pipeline < 3 && n >= (1ull << 31))) return GBIN_OK;
     uint64_t n_skr = 0, n_chk = 0;
     int rc = run_v2_scan(ctx, rd, n, max_len, 0, nullptr, 0, st, &n_skr, launches, feed);
     if (rc) return rc;
@@ -841,8 +931,9 @@ int bin_device_impl(gbin_ctx *ctx, const gbin_reads *rd, cudaStream_t st, gbin_t
     int rc = plan_reads(ctx, rd, st, &n, &max_len, launches);
     if (rc) return rc;
     if (max_len > GBIN_MAX_READ_LEN) return fail(ctx, GBIN_E_TOO_LARGE, "read length %u exceeds GBIN_MAX_READ_LEN", max_len);
-    if (n >= (1ull << 32) - 8192) return fail(ctx, GBIN_E_TOO_LARGE, "%llu k-mer instances in one batch (limit 2^32)", (unsigned long long)n);
-    const bool v2 = ctx->pipeline >= 2 && n != 0 && n < (1ull << 31);
+    if (ctx->pipeline < 3 && n >= (1ull << 32) - 8192)
+        return fail(ctx, GBIN_E_TOO_LARGE, "%llu k-mer instances in one batch (pipelines 1 and 2 hold 2^32; pipeline 3 works in passes)", (unsigned long long)n);
+    const bool v2 = ctx->pipeline >= 2 && n != 0 && (ctx->pipeline >= 3 || n < (1ull << 31));
     if (feed && !v2) {  // nobody downstream streams the reads in: copy them in one piece
         CU(cudaMemcpyAsync(feed->dst, feed->src, feed->bytes, cudaMemcpyHostToDevice, st));
         CU(cudaEventRecord(ctx->ev[1], st));
@@ -863,6 +954,7 @@ int bin_device_impl(gbin_ctx *ctx, const gbin_reads *rd, cudaStream_t st, gbin_t
             sink->kmers_done = sink->ids_done = 0;
         }
     }
+    if (n >= (1ull << 32) - 8192) return fail(ctx, GBIN_E_TOO_LARGE, "%llu k-mer instances: too many for the pipeline-1 fallback", (unsigned long long)n);
     ctx->last_pipeline = 1;
     memset(&ctx->rs, 0, sizeof ctx->rs);
     const size_t rb = sizeof(uint64_t) * ctx->KW + 8;
@@ -1062,6 +1154,9 @@ int gbin_set_tuning(gbin_ctx *ctx, const char *name, int value) {
     } else if (!strcmp(name, "v3_h")) {
         if (value < 0 || value > 15) return GBIN_E_INVALID_ARG;
         ctx->v3_h = value;
+    } else if (!strcmp(name, "v3_pass_max")) {
+        if (value < 1000) return GBIN_E_INVALID_ARG;
+        ctx->v3_pass_max = (uint64_t)value;
     } else if (!strcmp(name, "host_chunks")) {
         if (value < 1 || value > SKR_MAX_CHUNKS) return GBIN_E_INVALID_ARG;
         ctx->host_chunks = value;
@@ -1346,6 +1441,25 @@ int gbin_bin_file_host(gbin_ctx *ctx, const char *path, int read_length_define, 
     CU(cudaEventRecord(ctx->ev[5], st));
     CU(cudaStreamSynchronize(st));
     finish_timings(ctx, launches, true);
+    return GBIN_OK;
+}
+
+int gbin_table_digest(gbin_ctx *ctx, const gbin_table *t, void *stream, uint64_t *digest_out) {
+    if (!t || !digest_out) return GBIN_E_INVALID_ARG;
+    if (!t->on_device) {
+        *digest_out = table_digest_host(t);
+        return GBIN_OK;
+    }
+    if (!ctx) return GBIN_E_INVALID_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    Misc *dm = ctx->misc.as<Misc>();
+    Misc *hm = static_cast<Misc *>(ctx->h_misc.p);
+    table_digest_device(t, &dm->n_real_entries, st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&hm->n_real_entries, &dm->n_real_entries, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *digest_out = hm->n_real_entries;
     return GBIN_OK;
 }
 

@@ -173,6 +173,7 @@ struct V3Out {
     uint32_t *stg_loff;
     int32_t *stg_ids;
     void *unit_out;
+    uint64_t id_off_base;  // ids emitted by earlier passes of the batch
 };
 struct V3Lsd {  // arrays of the global sort that puts long spans in order (cap = 0: none allocated)
     void *rec;
@@ -195,8 +196,19 @@ int v3_group_launch(const void *skr, const uint64_t *ent, const void *units, con
                     bool finalize_only, int sm_count, KernelProf *prof, cudaStream_t st);
 int v3_lsd_finish(const KeyLayout &kl, uint64_t n, void *rec_a, void *rec_b, void *radix_scratch, uint64_t *dnew, void *scan_scratch, const V3Out &o, const V3Lsd &lsd,
                   KernelProf *prof, cudaStream_t st);
+uint32_t v3_pass_tiles(uint64_t n_ent);
+uint32_t v3_pass_tile_entries();
+int v3_pass_tile_sums(const uint64_t *ent, const uint8_t *piece_n, uint64_t n_ent, unsigned long long *sums_dev, cudaStream_t st);
+int v3_pass_bounds(const uint64_t *ent, uint64_t n_ent, int mshift, unsigned long long *bounds_dev, uint32_t n_bounds, cudaStream_t st);
 size_t v3_mmer_bitmap_bytes(int M);
 int v3_count_mmers(const void *skr, int skr_words, uint64_t n_rec, int M, uint32_t *bitmap, unsigned long long *count_dev, cudaStream_t st);
+
+// ---- table_digest.cu
+}  // namespace gbin
+struct gbin_table;
+namespace gbin {
+int table_digest_device(const ::gbin_table *t, unsigned long long *out_dev, cudaStream_t st);
+uint64_t table_digest_host(const ::gbin_table *t);
 
 // ---- split_reads.cu (main's fgets loop on the device)
 uint32_t split_tiles(uint64_t n);

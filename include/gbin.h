@@ -141,6 +141,11 @@ int gbin_table_to_host(gbin_ctx *ctx, const gbin_table *dev, gbin_table *host);
  * produces a host table) — the fast way to bring a table produced by the staged / device entry points to the host. */
 int gbin_table_to_pinned(gbin_ctx *ctx, const gbin_table *dev, void *stream, gbin_table *host);
 
+/* Order-independent 64-bit digest of a table (device or host): the sum over all surviving k-mers of a hash of (m-mer code, k-mer
+ * code, read-id list in list order), modulo 2^64.  Digests of tables over disjoint bucket sets add up to the digest of their
+ * union, so the owners' digests of a multi-GPU run sum to the single-GPU digest.  ctx may be NULL for a host table. */
+int gbin_table_digest(gbin_ctx *ctx, const gbin_table *table, void *stream, uint64_t *digest_out);
+
 int gbin_get_timings(const gbin_ctx *ctx, gbin_timings *out);
 
 /* Two device pipelines produce the same table:
@@ -156,6 +161,8 @@ typedef struct gbin_run_stats {
     uint64_t n_units;       /* shared-memory work units of the grouping kernel */
     uint64_t n_lsd_kmers;   /* pipeline 3: surviving k-mers of buckets spread over more than 8 units (ordered by a global sort) */
     uint32_t key_nc, key_h; /* pipeline 3: key layout of the batch (pieces per record, flank bases in the key) */
+    uint32_t n_passes;      /* pipeline 3: passes over the sorted entries (more than one above 2 * 10^9 k-mer instances) */
+    uint32_t reserved;
 } gbin_run_stats;
 int gbin_get_run_stats(const gbin_ctx *ctx, gbin_run_stats *out);
 int gbin_set_pipeline(gbin_ctx *ctx, int pipeline);
@@ -164,6 +171,7 @@ int gbin_set_pipeline(gbin_ctx *ctx, int pipeline);
  *   "v3_nc"  0|1|2         pieces per super-k-mer record: 1 = key is the m-mer code; 2 = windows split by the signature's offset
  *                          and the key extended by v3_h bases next to the signature; 0 (default) = chosen per batch from the mean bucket size
  *   "v3_h"   0..           with v3_nc = 2: bases next to the signature that extend the level-1 key (clamped to what K, M allow)
+ *   "v3_pass_max" >= 1000  k-mer instances per pass of pipeline 3 (default 2 * 10^9; small values exercise the multi-pass path)
  *   "host_chunks" 1..16    pieces in which gbin_bin_reads_host streams reads in / the table out */
 int gbin_set_tuning(gbin_ctx *ctx, const char *name, int value);
 int gbin_get_pipeline_info(const gbin_ctx *ctx, int *configured, int *last_used, uint32_t *fallbacks);

@@ -215,3 +215,34 @@ def load_pins():
 def load_case_bytes(case) -> bytes:
     with gzip.open(os.path.join(GOLDEN, case["file"]), "rb") as f:
         return f.read()
+
+
+def _mix64(x: int) -> int:
+    m = (1 << 64) - 1
+    x ^= x >> 33
+    x = (x * 0xff51afd7ed558ccd) & m
+    x ^= x >> 33
+    x = (x * 0xc4ceb9fe1a85ec53) & m
+    x ^= x >> 33
+    return x
+
+
+def table_digest(t) -> int:
+    """Python restatement of gbin_table_digest (csrc/table_digest.cu): sum over k-mers of a hash of (m-mer code, k-mer code,
+    read ids in list order), modulo 2^64.  For small tables only (pure-Python loop)."""
+    m = (1 << 64) - 1
+    kw = t.kw
+    kc = np.asarray(t.kmer_codes).reshape(-1, kw)
+    acc = 0
+    for b in range(len(t.mmer_codes)):
+        mm = int(t.mmer_codes[b])
+        for s in range(int(t.mmer_kmer_off[b]), int(t.mmer_kmer_off[b + 1])):
+            a, e = int(t.kmer_id_off[s]), int(t.kmer_id_off[s + 1])
+            lh = 0x9E3779B97F4A7C15
+            for i in t.read_ids[a:e]:
+                lh = _mix64(lh ^ (int(i) & 0xffffffff))
+            h = ((mm * 0x9E3779B97F4A7C15) & m) ^ _mix64(int(kc[s, 0]))
+            if kw == 2:
+                h ^= _mix64((int(kc[s, 1]) + 0x632BE59BD9B4E019) & m)
+            acc = (acc + _mix64(h ^ lh ^ (((e - a) << 40) & m))) & m
+    return acc

@@ -232,3 +232,33 @@ def test_expanded_dump_equals_the_references_own_expand_and_print(name, tmp_path
     want, got = _parse_expanded(ref, case["k"]), _parse_expanded(p.read_bytes(), case["k"])
     assert len(want) == case["surviving_kmers"]
     assert got == want
+
+
+@pytest.mark.parametrize("name", ["cfg2_small", "cfg4_small", "kat_twice"])
+def test_table_digest_host_matches_its_python_restatement(name):
+    """gbin_table_digest on a HOST table needs no GPU: same value as the Python restatement over the oracle's table, invariant
+    under reordering of the buckets, and additive over a split of the buckets (what the multi-GPU owners' digests rely on)."""
+    case = next(c for c in O.load_pins() if c["name"] == name)
+    data = O.load_case_bytes(case)
+    starts, lens = O.fgets_split(data, case["read_length_define"])
+    t = O.run(data, starts, lens, case["k"], case["m"], case["cutoff"])
+    L = B.load_library()
+    ct, keep = c_table_from_oracle(t)
+    d = C.c_uint64()
+    assert L.gbin_table_digest(None, C.byref(ct), None, C.byref(d)) == 0
+    assert d.value == O.table_digest(t)
+    # split the buckets in two tables: the digests add up
+    nb = t.n_buckets
+    if nb >= 2:
+        h = nb // 2
+        s_h, n_h = int(t.mmer_kmer_off[h]), int(t.kmer_id_off[int(t.mmer_kmer_off[h])])
+        kw = t.kw
+        lo = O.Table(t.K, t.M, t.cutoff, 0, 0, t.mmer_codes[:h], t.mmer_kmer_off[:h + 1], t.kmer_codes[:s_h * kw], t.kmer_id_off[:s_h + 1], t.read_ids[:n_h])
+        hi = O.Table(t.K, t.M, t.cutoff, 0, 0, t.mmer_codes[h:], t.mmer_kmer_off[h:] - np.uint64(s_h), t.kmer_codes[s_h * kw:],
+                     t.kmer_id_off[s_h:] - np.uint64(n_h), t.read_ids[n_h:])
+        tot = 0
+        for part in (lo, hi):
+            cp, keep2 = c_table_from_oracle(part)
+            assert L.gbin_table_digest(None, C.byref(cp), None, C.byref(d)) == 0
+            tot = (tot + d.value) & ((1 << 64) - 1)
+        assert tot == O.table_digest(t)

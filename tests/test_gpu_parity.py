@@ -33,6 +33,15 @@ def assert_tables_equal(got: B.HostTable, want: O.Table):
     np.testing.assert_array_equal(got.read_ids, want.read_ids)
 
 
+def c_table_of(t: B.HostTable):
+    keep = dict(mc=np.ascontiguousarray(t.mmer_codes, np.uint32), mo=np.ascontiguousarray(t.mmer_kmer_off, np.uint64),
+                kc=np.ascontiguousarray(t.kmer_codes, np.uint64), ko=np.ascontiguousarray(t.kmer_id_off, np.uint64),
+                ids=np.ascontiguousarray(t.read_ids, np.int32))
+    ct = B.CTable(t.K, t.M, t.cutoff, t.kw, 0, 1, t.n_instances, t.n_distinct, t.n_buckets, t.n_kmers, len(t.read_ids),
+                  keep["mc"].ctypes.data, keep["mo"].ctypes.data, keep["kc"].ctypes.data, keep["ko"].ctypes.data, keep["ids"].ctypes.data)
+    return ct, keep
+
+
 def as_oracle_table(t: B.HostTable) -> O.Table:
     return O.Table(t.K, t.M, t.cutoff, t.n_instances, t.n_distinct, t.mmer_codes, t.mmer_kmer_off, t.kmer_codes, t.kmer_id_off,
                    t.read_ids)
@@ -145,6 +154,11 @@ def test_table_matches_oracle_and_reference_pin(case, pipeline, tmp_path):
     assert_tables_equal(got, want)
     assert got.n_kmers == case["surviving_kmers"] and got.n_buckets == case["surviving_buckets"]
     assert as_oracle_table(got).md5() == case["md5"]
+    if "digest" in case:  # gbin_table_digest of the host table == the pinned digest (anchored on the reference's dump)
+        dg = C.c_uint64()
+        ct, keep = c_table_of(got)
+        assert B.load_library().gbin_table_digest(None, C.byref(ct), None, C.byref(dg)) == 0
+        assert "%016x" % dg.value == case["digest"]
     tm = b.timings()
     assert tm["kernel_launches"] > 0
     info = b.pipeline_info()
@@ -173,6 +187,7 @@ def test_device_path_and_staged_path_agree_with_host_path():
     rd, keep = dev_reads(torch, data, starts, lens)
     dev = b.bin_device_raw(rd, B.stream_handle(torch.cuda.current_stream()))
     assert dev.on_device == 1
+    assert "%016x" % b.table_digest(dev) == case["digest"]  # digest kernel on the device table == pinned digest
     assert_tables_equal(b.table_to_host(dev), want)
     # staged: scan -> group
     n = b.count_instances_device(rd)
@@ -480,6 +495,25 @@ def test_v3_large_buckets_in_rounds(cap):
     got = b.bin_host(rs.buf, rs.n_reads, stride=rs.stride, read_len=rs.read_len)
     assert b.pipeline_info()["last_used"] in (3, 2)
     assert_tables_equal(got, O.run(rs.as_bytes(), starts, lens, 25, 7, 1))
+    b.close()
+
+
+@pytest.mark.parametrize("nc,h", [(0, 0), (2, 2)])
+def test_v3_passes_append_to_one_table(nc, h):
+    """A batch with more k-mer instances than 32-bit coordinates hold is grouped in passes over ranges of the sorted entries, cut
+    between m-mer buckets, every pass appending to the table.  Forced here on 4.2 M instances with a pass limit of 300 000."""
+    torch_cuda()
+    rs = synth.generate(60000, 100, error_rate=0.01, seed=20, starts="triangular")
+    starts = np.arange(rs.n_reads, dtype=np.uint64) * rs.stride
+    lens = np.full(rs.n_reads, rs.read_len, dtype=np.uint32)
+    b = B.Binner(31, 11, 1, pipeline=3)
+    b.set_tuning("v3_pass_max", 300_000)
+    b.set_tuning("v3_nc", nc)
+    b.set_tuning("v3_h", h)
+    got = b.bin_host(rs.buf, rs.n_reads, stride=rs.stride, read_len=rs.read_len)
+    st = b.run_stats()
+    assert b.pipeline_info()["last_used"] == 3 and st["n_passes"] >= 3, st
+    assert_tables_equal(got, O.run(rs.as_bytes(), starts, lens, 31, 11, 1))
     b.close()
 
 

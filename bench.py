@@ -3,9 +3,11 @@
 
 A step = one pass of the hot path (process_read over every read -> two-level grouping -> prune)
 over one batch of synthetic reads.  N=1: BASELINE config 2 (1 M reads x 100 bp, K=31, M=11, 1 %
-substitutions, generate_reads.py's triangular start walk).  N>1: weak scaling — every rank holds a
-config-2-sized shard drawn from one shared genome N times longer; records are exchanged by m-mer
-owner with one NCCL all-to-all.
+substitutions, generate_reads.py's triangular start walk).  N>1: BASELINE config 3 (100 M reads x 150 bp, the configuration
+north_star names for 2/4/8 GPUs), strong scaling: one read set (the same at every N: it is drawn block by block from one
+genome, every block with its own generator) is split evenly over the ranks by contiguous ranges, records are exchanged by
+m-mer owner (peer stores over NVLink), every rank groups the buckets it owns.  The sum of the owners' table digests is
+printed and checked against profiles/expected_digests.json: it must be the same at every N.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl reference]
 
@@ -39,7 +41,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gbin", choices=["gbin", "reference"])
-    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--workload", default="auto", help="cfg2..cfg5; auto = cfg2 on one GPU, cfg3 on several")
+    ap.add_argument("--no-selftest", action="store_true", help="N > 1: skip the sharded run of the golden fixtures before the timed region")
     ap.add_argument("--reads-per-gpu", type=int, default=0, help="override the workload's read count (debug)")
     ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
                     help="weak: every GPU holds the workload's read count (default for cfg2); strong: the workload's reads are split "
@@ -54,10 +57,16 @@ def parse_args():
     return ap.parse_args()
 
 
+READ_BLOCK = 250_000  # reads per generator block of the strong-scaling read sets
+
+
 def workload_params(name, reads_override=0, scaling="auto", world=1):
     """Per-GPU shape of the workload.  weak: n_reads per GPU = the workload's count; strong: the count is split."""
     from genome_assembly_b200 import synth
+    if name == "auto":
+        name = "cfg2" if world == 1 else "cfg3"
     w = dict(synth.WORKLOADS[name])
+    w["name"] = name
     if scaling == "auto":
         scaling = "weak" if name == "cfg2" else "strong"
     w["scaling"] = scaling
@@ -71,12 +80,26 @@ def workload_params(name, reads_override=0, scaling="auto", world=1):
 
 
 def make_reads(w, rank, world):
-    """This rank's shard: config-shaped reads from one shared genome (30x coverage over all ranks' reads)."""
+    """This rank's shard: config-shaped reads from one shared genome (30x coverage over all ranks' reads).  Strong scaling with
+    uniform starts: the whole read set is a sequence of READ_BLOCK-sized blocks, block b drawn with a generator seeded by b,
+    and rank r holds a contiguous range of blocks — the same read set, in the same order, at every N."""
+    import numpy as np
     from genome_assembly_b200 import synth
     n = w["n_reads"]
-    glen = synth.default_genome_len(n * world, w["read_len"])
-    return synth.generate(n, w["read_len"], genome_len=glen, error_rate=w["error_rate"], seed=20, read_seed=20 + rank,
-                          starts=w["starts"])
+    glen = synth.default_genome_len(w["total_reads"], w["read_len"])
+    blocked = w["scaling"] == "strong" and w["starts"] == "uniform" and w["total_reads"] % (READ_BLOCK * world) == 0
+    w["read_set"] = f"blocks of {READ_BLOCK} reads, one generator per block: identical at every GPU count" if blocked else "one generator per rank"
+    if not blocked:
+        return synth.generate(n, w["read_len"], genome_len=glen, error_rate=w["error_rate"], seed=20, read_seed=20 + rank, starts=w["starts"])
+    genome = synth.make_genome(glen, 20)
+    stride = w["read_len"] + 1
+    buf = np.empty(n * stride, dtype=np.uint8)
+    b0 = rank * (n // READ_BLOCK)
+    for k in range(n // READ_BLOCK):
+        synth.reads_from_genome(genome, READ_BLOCK, w["read_len"], error_rate=w["error_rate"], read_seed=b0 + k,
+                                out=buf[k * READ_BLOCK * stride:(k + 1) * READ_BLOCK * stride])
+    return synth.ReadSet(buf=buf, n_reads=n, read_len=w["read_len"], stride=stride, genome_len=glen, seed=20, error_rate=w["error_rate"],
+                         starts_kind="uniform")
 
 
 # ------------------------------------------------------------------------------------------ CPU reference leg
@@ -121,8 +144,10 @@ def run_reference_arm(a):
     if rank != 0:
         return
     w = workload_params(a.workload, a.reads_per_gpu, a.scaling, max(a.gpus, 1))
+    if w["scaling"] == "strong" and w["n_reads"] > READ_BLOCK and w["n_reads"] % READ_BLOCK == 0:
+        w["n_reads"] = READ_BLOCK  # the sample is a prefix of rank 0's shard: its first generator block is enough
     rs = make_reads(w, 0, max(a.gpus, 1))
-    sample_reads = min(w["n_reads"], 40_000)  # ~2.8 M instances, a few seconds per step
+    sample_reads = min(w["n_reads"], 200_000 if w["read_len"] <= 100 else 100_000)  # the cpu_baseline sample: ~14 M instances, ~9 s per step
     for _ in range(a.warmup):
         time_reference(w, rs, sample_reads)
     vals, info = [], None
@@ -148,12 +173,52 @@ def run_reference_arm(a):
 # ------------------------------------------------------------------------------------------ helpers
 
 def config_dict(a, w, world):
-    return {"workload": f"{a.workload}: {w['n_reads']} reads x {w['read_len']} bp per GPU ({w['n_reads'] * world} in total, {w['scaling']} scaling), "
+    return {"workload": f"{w['name']}: {w['n_reads']} reads x {w['read_len']} bp per GPU ({w['total_reads']} in total, {w['scaling']} scaling), "
                         f"K={w['k']}, M={w['m']}, cutoff={w['cutoff']}, {w['error_rate'] * 100:g}% substitutions, {w['starts']} starts, "
-                        f"genome {w['n_reads'] * world * w['read_len'] // 30} bp",
+                        f"genome {w['total_reads'] * w['read_len'] // 30} bp",
+            "read_set": w.get("read_set"),
             "k": w["k"], "m": w["m"], "cutoff": w["cutoff"], "reads_per_gpu": w["n_reads"], "read_len": w["read_len"],
             "parallelism": f"reads split evenly over {world} GPU(s); records exchanged by owner = hash(mmer) -> [0, {world})" if world > 1 else "single GPU",
             "l2": "L2 flushed (256 MiB memset) before every timed step; per-step device times summed"}
+
+
+def sharded_selftest(B, g, dist, torch, dev, rank, world, local, exchange):
+    """Collective.  The golden fixtures go through the multi-GPU path (reads split by contiguous ranges, records exchanged by
+    owner, every rank groups its buckets); the sum of the owners' digests must equal the digest pinned in tests/golden/pins.json
+    (derived from the unmodified reference binary's dump).  Raises on a mismatch."""
+    import gzip
+    import numpy as np
+    from genome_assembly_b200.dist import GpuStages, ShardedBinner
+    pins = json.load(open(os.path.join(ROOT, "tests", "golden", "pins.json")))["cases"]
+    done = []
+    for name in ("cfg2_small", "cfg3_small", "cfg5_small"):
+        case = next(c for c in pins if c["name"] == name)
+        data = gzip.open(os.path.join(ROOT, "tests", "golden", case["file"]), "rb").read()
+        with tempfile.NamedTemporaryFile(suffix=".txt", delete=False) as tf:
+            tf.write(data)
+        try:
+            buf, starts, lens = B.read_file_fgets(tf.name, case["read_length_define"])
+        finally:
+            os.unlink(tf.name)
+        n = len(starts)
+        lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+        b = g.Binner(case["k"], case["m"], case["cutoff"], device=local)
+        d = torch.from_numpy(np.frombuffer(buf, dtype=np.uint8).copy()).to(dev)
+        st_ = torch.from_numpy(starts[lo:hi].astype(np.int64)).to(dev)
+        ln_ = torch.from_numpy(lens[lo:hi].astype(np.int32)).to(dev)
+        rd = B.Binner._reads(d, d.numel(), hi - lo, starts=st_, lens=ln_)
+        sb = ShardedBinner(GpuStages(b), exchange=exchange)
+        t = sb.run(rd, arrival_base=lo)
+        dg = b.table_digest(t, B.stream_handle(torch.cuda.current_stream()))
+        tot = torch.tensor([dg - (1 << 64) if dg >= (1 << 63) else dg], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        got = "%016x" % (int(tot[0]) & ((1 << 64) - 1))
+        if got != case["digest"]:
+            raise SystemExit(f"bench.py selftest: {name} over {world} GPUs gives digest {got}, the reference's table has {case['digest']}")
+        done.append(name)
+        dist.barrier()
+        b.close()
+    return {"cases": done, "world": world, "result": "digests equal the reference-derived pins"}
 
 
 class ClockSampler:
@@ -278,6 +343,11 @@ def main():
     stream = B.stream_handle(torch.cuda.current_stream())
     rd_dev = B.Binner._reads(d_reads, d_reads.numel(), rs.n_reads, stride=rs.stride, read_len=rs.read_len, id_base=rank * rs.n_reads)
     rd_host = B.Binner._reads(h_reads, h_reads.numel(), rs.n_reads, stride=rs.stride, read_len=rs.read_len, id_base=rank * rs.n_reads)
+
+    # ---- N > 1: before anything is timed, the sharded path must reproduce the pinned digests of the golden fixtures
+    selftest = None
+    if world > 1 and not a.no_selftest:
+        selftest = sharded_selftest(B, g, dist, torch, dev, rank, world, local, a.exchange)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     stages = GpuStages(binner)
@@ -349,6 +419,24 @@ def main():
     # ---- table stats of the last step (sanity: work was really done)
     stats = {"instances": int(table.n_instances), "distinct": int(table.n_distinct), "surviving_kmers": int(table.n_kmers),
              "surviving_ids": int(table.n_ids), "buckets": int(table.n_buckets)}
+    # ---- digest of the whole job's table: the sum (mod 2^64) of the owners' digests; the same at every GPU count for a strong-scaling read set
+    dg = binner.table_digest(table, stream)
+    tot = torch.tensor([dg - (1 << 64) if dg >= (1 << 63) else dg, stats["instances"], stats["surviving_kmers"], stats["surviving_ids"]],
+                       dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)  # two's-complement wrap-around = addition modulo 2^64
+    digest = "%016x" % (int(tot[0]) & ((1 << 64) - 1))
+    job = {"instances": int(tot[1]), "surviving_kmers": int(tot[2]), "surviving_ids": int(tot[3])}
+    dkey = f"{w['name']}:{w['total_reads']}x{w['read_len']}:K{K}:M{M}:C{cutoff}:{w.get('read_set', '')[:6]}"
+    expected = None
+    try:
+        expected = json.load(open(os.path.join(ROOT, "profiles", "expected_digests.json"))).get(dkey)
+    except (OSError, ValueError):
+        pass
+    digest_info = {"table_digest": digest, "key": dkey, "expected": expected, "ok": (digest == expected) if expected else None,
+                   "what": "gbin_table_digest: order-independent hash of every (m-mer, k-mer, ordered id list), summed over the owners"}
+    if expected and digest != expected and rank == 0:
+        print(f"bench.py: table digest {digest} differs from profiles/expected_digests.json[{dkey}] = {expected}", file=sys.stderr)
 
     # ---- e2e: public host-buffer call, pinned H2D + pipeline + D2H of the table inside the timed region
     e2e = None
@@ -444,15 +532,29 @@ def main():
     skr_b = binner.skr_record_bytes
     n_rec = stats["instances"]  # k-mer instances this rank grouped in the last step
     # algorithmic (compulsory) HBM bytes of ONE launch of each kernel class, see DESIGN.md section 4
+    n_ent = n_skr * (rstats.get("key_nc", 1) or 1)
+    out_bytes = stats["surviving_kmers"] * (8.0 * KW + 4 + 8) + 4.0 * stats["surviving_ids"]
+    v3 = binner.pipeline_info()["last_used"] == 3
     alg_bytes = {
-        "radix_scatter": (2.0 * skr_b * n_skr) if n_skr else (2.0 * rb * n_rec),
-        "radix_hist": (1.0 * skr_b * n_skr) if n_skr else (1.0 * rb * n_rec),
+        "radix_scatter": (2.0 * 8 * n_ent if v3 else 2.0 * skr_b * n_skr) if n_skr else (2.0 * rb * n_rec),
+        "radix_hist": (1.0 * 8 * n_ent if v3 else 1.0 * skr_b * n_skr) if n_skr else (1.0 * rb * n_rec),
         "scan_reads": float(h_reads.numel()) + rb * n_inst_rank,
         "skr_scan": float(h_reads.numel()) + skr_b * n_skr,
-        "skr_group": (skr_b + 4.0) * n_skr + stats["surviving_kmers"] * (8.0 * KW + 4 + 8) + 4.0 * stats["surviving_ids"],
+        # pipeline 3: entries + records read once, the unit's part of the table written once (to staging); pipeline 2: records + instance prefix in, table out
+        "skr_group": ((8.0 * n_ent + skr_b * n_skr + out_bytes) if v3 else ((skr_b + 4.0) * n_skr + out_bytes)),
+        "v3_entries": 32.0 * n_skr + 9.0 * n_ent,  # a 32-byte sector per record header, 8-byte entry + 1 byte per slot out
+        "v3_span": 2.0 * out_bytes,                # finalize: staging -> final place
         "find_runs": 3.0 * rb * n_rec + 8.0 * n_rec,
     }
-    ncu_traffic = {"skr_group": 868.2e6, "skr_scan": 271.0e6, "radix_scatter": 457.4e6}  # dram read+write per launch, ncu --set full (profiles/r1_final_kernels_raw.csv)
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu export of this build's kernels (profiles/ncu_traffic.json,
+    # written by profiles/tools/ncu_traffic.py from an `ncu --set full` capture); null when there is no entry for the dominant kernel / workload
+    ncu_traffic = {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if tj.get("workload") == w["name"] and world == 1 and not a.reads_per_gpu:
+            ncu_traffic = {k: v["dram_bytes_per_launch"] for k, v in tj.get("kernels", {}).items()}
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = None
     timed = {k: v for k, v in prof.items() if v["launches"] and k in alg_bytes}
     if timed:
@@ -464,11 +566,11 @@ def main():
         pipe_bytes_per_inst = (rs.read_len + 1) / W + 2 * rb + 4
         pipe_ach = pipe_bytes_per_inst * n_inst_rank * a.steps / (float(sum(step_ms)) / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": ncu_traffic.get(dom) if (world == 1 and a.workload == "cfg2" and not a.reads_per_gpu) else None,
+                    "traffic": ncu_traffic.get(dom),
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "launches": sc["launches"], "avg_launch_ms": avg_ms,
                     "share_of_step": sc["ms"] / float(sum(step_ms)),
-                    "note": "HBM is not what bounds this kernel: it groups k-mers in shared memory (hash, ranking, barriers between the phases of a unit); "
-                            "its DRAM traffic is about 1.6x the algorithmic bytes because every unit's output passes through staging arrays, see DESIGN.md 4.1",
+                    "note": "HBM is not what bounds this kernel: it groups k-mers in shared memory (hash insert, ranks, survivor order), one warp per unit; "
+                            "see DESIGN.md 4 and profiles/ for the ncu evidence",
                     "pipeline": {"algorithmic_bytes_per_kmer": pipe_bytes_per_inst, "achieved": pipe_ach, "frac": pipe_ach / peak,
                                  "note": "whole step against SURVEY 8(d)'s compulsory-traffic model (37.4 B per k-mer instance at cfg2)"},
                     "per_kernel_ms_per_step": {k: v["ms"] / a.steps for k, v in prof.items()},
@@ -492,6 +594,13 @@ def main():
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": f"{type(e).__name__}: {e}"}
 
+    exchange_info = None
+    if sharded is not None and stage_ms["exchange"] > 0:
+        gbps = sharded.stats.sent_bytes_offrank / (stage_ms["exchange"] / 1e3) / 1e9
+        exchange_info = {"GBps_per_dir_rank0": gbps, "nvlink_peak_GBps_per_dir": 900.0, "frac_of_nvlink": gbps / 900.0,
+                         "bytes_sent_offrank_rank0": sharded.stats.sent_bytes_offrank, "ms_rank0": stage_ms["exchange"],
+                         "note": "records this rank stored into the other owners' buffers (peer stores over NVLink, or NCCL all-to-all) divided by the "
+                                 "time of the exchange stage on rank 0, which includes waiting for the slowest rank's scan"}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -501,6 +610,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "table": stats, "input_split": input_split,
             "stage_ms_rank0": (dict(stage_ms, exchange_form=getattr(sharded, "exchange_kind", "nccl"),
                                     sent_bytes_offrank=sharded.stats.sent_bytes_offrank) if sharded is not None else None),
+            "exchange": exchange_info, "table_digest": digest_info, "job_table": job, "selftest": selftest,
             "wall_s_timed_region": wall_s, "step_ms": step_ms,
         }
         emit(line)

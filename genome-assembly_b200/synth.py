@@ -97,6 +97,40 @@ def generate(n_reads: int, read_len: int, *, genome_len: int | None = None, erro
                    seed=seed, error_rate=error_rate, starts_kind=starts)
 
 
+def make_genome(genome_len: int, seed: int = 20) -> np.ndarray:
+    """The shared genome of generate(seed=seed, genome_len=genome_len)."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    return _ACGT[rng.integers(0, 4, size=genome_len, dtype=np.uint8)]
+
+
+def reads_from_genome(genome: np.ndarray, n_reads: int, read_len: int, *, error_rate: float, read_seed: int, out: np.ndarray | None = None,
+                      chunk: int = 1 << 18) -> np.ndarray:
+    """n_reads fixed-stride reads (uniform starts, i.i.d. substitutions) drawn from `genome` with a generator that depends on
+    read_seed alone — so a read set cut into blocks with read_seed = block index is the same whatever process draws which block."""
+    rng = np.random.Generator(np.random.Philox(key=read_seed + (1 << 40)))
+    hi = len(genome) - 1 - read_len
+    pos = rng.integers(0, hi + 1, size=n_reads, dtype=np.int64)
+    stride = read_len + 1
+    buf = out if out is not None else np.empty(n_reads * stride, dtype=np.uint8)
+    view = buf.reshape(n_reads, stride)
+    view[:, read_len] = ord("\n")
+    ar = np.arange(read_len, dtype=np.int64)
+    lut = np.zeros(256, dtype=np.uint8)
+    lut[_ACGT] = np.arange(4, dtype=np.uint8)
+    for lo in range(0, n_reads, chunk):
+        hi_i = min(n_reads, lo + chunk)
+        bases = genome[pos[lo:hi_i, None] + ar[None, :]]
+        if error_rate > 0:
+            hit = rng.random(bases.shape, dtype=np.float32) < error_rate
+            nhit = int(hit.sum())
+            if nhit:
+                cur = lut[bases[hit]]
+                rot = rng.integers(1, 4, size=nhit, dtype=np.uint8)
+                bases[hit] = _ACGT[(cur + rot) & 3]
+        view[lo:hi_i, :read_len] = bases
+    return buf
+
+
 # BASELINE.json configs 2-5 (config 1 is the bundled reads.txt)
 WORKLOADS = {
     "cfg2": dict(n_reads=1_000_000, read_len=100, k=31, m=11, cutoff=1, error_rate=0.01, starts="triangular"),

@@ -91,10 +91,25 @@ def make_reads(w, rank, world):
     w["read_set"] = f"blocks of {READ_BLOCK} reads, one generator per block: identical at every GPU count" if blocked else "one generator per rank"
     if not blocked:
         return synth.generate(n, w["read_len"], genome_len=glen, error_rate=w["error_rate"], seed=20, read_seed=20 + rank, starts=w["starts"])
-    genome = synth.make_genome(glen, 20)
     stride = w["read_len"] + 1
-    buf = np.empty(n * stride, dtype=np.uint8)
     b0 = rank * (n // READ_BLOCK)
+    try:
+        import torch
+        cuda = torch.cuda.is_available()
+    except ImportError:
+        cuda = False
+    if cuda:  # drawn on the GPU: seconds instead of minutes for the 100 M-read configurations
+        w["read_set"] += "; drawn on the GPU (torch generators)"
+        d = synth.blocked_reads_torch(glen, n // READ_BLOCK, b0, READ_BLOCK, w["read_len"], error_rate=w["error_rate"], seed=20,
+                                      device=torch.device("cuda", torch.cuda.current_device()))
+        buf = d.cpu().numpy()
+        del d
+        torch.cuda.empty_cache()
+        return synth.ReadSet(buf=buf, n_reads=n, read_len=w["read_len"], stride=stride, genome_len=glen, seed=20, error_rate=w["error_rate"],
+                             starts_kind="uniform")
+    w["read_set"] += "; drawn on the host (numpy generators)"
+    genome = synth.make_genome(glen, 20)
+    buf = np.empty(n * stride, dtype=np.uint8)
     for k in range(n // READ_BLOCK):
         synth.reads_from_genome(genome, READ_BLOCK, w["read_len"], error_rate=w["error_rate"], read_seed=b0 + k,
                                 out=buf[k * READ_BLOCK * stride:(k + 1) * READ_BLOCK * stride])
@@ -427,7 +442,7 @@ def main():
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)  # two's-complement wrap-around = addition modulo 2^64
     digest = "%016x" % (int(tot[0]) & ((1 << 64) - 1))
     job = {"instances": int(tot[1]), "surviving_kmers": int(tot[2]), "surviving_ids": int(tot[3])}
-    dkey = f"{w['name']}:{w['total_reads']}x{w['read_len']}:K{K}:M{M}:C{cutoff}:{w.get('read_set', '')[:6]}"
+    dkey = f"{w['name']}:{w['total_reads']}x{w['read_len']}:K{K}:M{M}:C{cutoff}:{'blocks' if 'blocks' in w.get('read_set', '') else 'ranks'}:{'gpu' if 'GPU' in w.get('read_set', '') else 'host'}"
     expected = None
     try:
         expected = json.load(open(os.path.join(ROOT, "profiles", "expected_digests.json"))).get(dkey)

@@ -1019,6 +1019,10 @@ int gbin_create(const gbin_config *cfg, gbin_ctx **out) {
         ctx->v3_nc = (v == 1 || v == 2) ? v : 0;
     }
     if (const char *e = getenv("GBIN_V3_H")) ctx->v3_h = atoi(e);
+    if (const char *e = getenv("GBIN_V3_PASS_MAX")) {
+        const long long v = atoll(e);
+        if (v >= 1000) ctx->v3_pass_max = (uint64_t)v;
+    }
     ctx->v3_cap = 1024;
     if (const char *e = getenv("GBIN_V3_CAP")) ctx->v3_cap = atoi(e) == 512 ? 512 : 1024;
     ctx->last_pipeline = 0;

@@ -67,7 +67,8 @@ class GpuStages:
     def scan(self, reads: B.CReads, arrival_base: int):
         n = self.b.count_instances_device(reads, self.stream())
         if self.form == "skr":
-            cap = n // 4 + int(reads.n_reads) + 1024  # segments average ~10 windows; the call reports the exact need if this is short
+            # a segment covers about (K-M+2)/2 windows (9-23 at the BASELINE shapes); the call reports the exact need if this is short
+            cap = max(getattr(self, "_skr_cap_seen", 0), n // 6 + int(reads.n_reads) + 1024)
             while True:
                 rec = self.alloc_records(cap)
                 try:
@@ -78,6 +79,7 @@ class GpuStages:
                         raise
                     cap = n
             assert n_inst == n
+            self._skr_cap_seen = max(getattr(self, "_skr_cap_seen", 0), n_skr + n_skr // 16 + 1024)
             self._count()
             return rec, n_skr
         rec = self.alloc_records(n)
@@ -222,7 +224,8 @@ class ShardedBinner:
         if self.exchange_kind != "peer" or getattr(self.stages, "form", "") != "skr":
             return False
         if not self._peer_ready:
-            cap = torch.tensor([max(2 * n + 65536, getattr(self, "_peer_capacity_hint", 0))], dtype=torch.int64, device=self._flag_device())
+            # an owner receives about a world-th of every rank's records: the ranks' record counts and the owners' shares differ by a few per cent
+            cap = torch.tensor([max(n + n // 3 + 65536, getattr(self, "_peer_capacity_hint", 0))], dtype=torch.int64, device=self._flag_device())
             dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=self.group)
             self._peer_ready = self.stages.peer_exchange_setup(self.rank, self.world, int(cap.item()), self.group)
             if not self._peer_ready:
@@ -254,7 +257,11 @@ class ShardedBinner:
                 self.stats.sent_records = sum(counts)
                 self.stats.recv_records = n_in
                 self.stats.sent_bytes_offrank = (sum(counts) - counts[self.rank]) * self.stages.record_bytes
-            self._keep_src = rec  # the peers read nothing from it, but the kernels that stored from it may still be in flight
+            # the exchange call returned after its stream was synchronised: the records have left, and a config-3-sized shard (tens of GB
+            # of records) must make room for the grouping's workspace
+            del rec
+            if n * self.stages.record_bytes > (1 << 30):
+                torch.cuda.empty_cache()
             e3 = self._ev()
         else:
             part, counts = self.stages.partition(rec, n, self.world)

@@ -131,6 +131,34 @@ def reads_from_genome(genome: np.ndarray, n_reads: int, read_len: int, *, error_
     return buf
 
 
+def blocked_reads_torch(genome_len: int, n_blocks: int, first_block: int, block_reads: int, read_len: int, *, error_rate: float, seed: int, device):
+    """The same kind of read set as reads_from_genome, drawn on the GPU with torch generators (one per block, seeded by the block
+    index; the genome with `seed`): a 100 M-read set takes seconds instead of minutes.  Returns a uint8 device tensor
+    [n_blocks * block_reads * (read_len + 1)].  The values differ from the numpy generators' (another RNG) — what matters is that
+    block b holds the same reads whichever process draws it."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    genome = torch.randint(0, 4, (genome_len,), generator=g, device=device, dtype=torch.uint8)  # codes 0..3 = A, C, G, T
+    stride = read_len + 1
+    out = torch.empty(n_blocks * block_reads * stride, dtype=torch.uint8, device=device)
+    ar = torch.arange(read_len, device=device, dtype=torch.int64)
+    hi = genome_len - 1 - read_len
+    for k in range(n_blocks):
+        g.manual_seed((1 << 40) + first_block + k)
+        pos = torch.randint(0, hi + 1, (block_reads,), generator=g, device=device, dtype=torch.int64)
+        codes = genome[pos[:, None] + ar[None, :]]
+        if error_rate > 0:
+            hit = torch.rand(codes.shape, generator=g, device=device) < error_rate
+            rot = torch.randint(1, 4, codes.shape, generator=g, device=device, dtype=torch.uint8)
+            codes = torch.where(hit, (codes + rot) & 3, codes)
+        view = out[k * block_reads * stride:(k + 1) * block_reads * stride].view(block_reads, stride)
+        view[:, :read_len] = acgt[codes.long()]
+        view[:, read_len] = ord("\n")
+    return out
+
+
 # BASELINE.json configs 2-5 (config 1 is the bundled reads.txt)
 WORKLOADS = {
     "cfg2": dict(n_reads=1_000_000, read_len=100, k=31, m=11, cutoff=1, error_rate=0.01, starts="triangular"),

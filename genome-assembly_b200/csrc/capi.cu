@@ -807,7 +807,11 @@ int run_v3_group(gbin_ctx *ctx, const void *skr, uint64_t n_skr, const int32_t *
         CU(cudaMemcpyAsync(sums.data(), sums_dev, (size_t)nt * 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         std::vector<unsigned long long> cuts;
-        unsigned long long acc = 0;
+        unsigned long long acc = 0, all = 0;
+        for (uint32_t t = 0; t < nt; t++) all += sums[t];
+        // a batch of several passes is a batch that crowds the HBM: the workspace of a pass (staging, bounds of the table's growth) scales
+        // with the pass, so such a batch is cut into passes of half the size
+        const uint64_t pass_max = all > 2 * ctx->v3_pass_max ? ctx->v3_pass_max / 2 : ctx->v3_pass_max;
         for (uint32_t t = 0; t < nt; t++) {
             if (acc && acc + sums[t] > pass_max) {
                 cuts.push_back((unsigned long long)t * v3_pass_tile_entries());

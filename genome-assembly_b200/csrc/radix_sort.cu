@@ -128,6 +128,13 @@ __global__ void __launch_bounds__(RS_THREADS)
     uint32_t rank[ITEMS];
     uint32_t *mywc = wc + warp * RS_RADIX;
     const uint32_t lt_mask = (1u << lane) - 1;
+    // all loads of the thread are issued before anything waits for one of them (a load per ranking round would put a round trip to
+    // memory on the critical path of every round)
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+        const uint32_t idx = warp * (32 * ITEMS) + r * 32 + lane;
+        if (idx < count) items[r] = load_blob<NU64>(in + base + idx);
+    }
 #pragma unroll
     for (int r = 0; r < ITEMS; r++) {
         const uint32_t idx = warp * (32 * ITEMS) + r * 32 + lane;
@@ -135,7 +142,6 @@ __global__ void __launch_bounds__(RS_THREADS)
         const unsigned act = __ballot_sync(0xffffffffu, valid);
         rank[r] = 0;
         if (valid) {
-            items[r] = load_blob<NU64>(in + base + idx);
             const uint32_t d = digit_of<NU64>(items[r], sel);
             // lanes with my digit: eight ballots (one per bit) — a fixed cost, whereas MATCH.ANY iterates over the distinct values in the warp
             unsigned peers = act;

@@ -68,7 +68,7 @@ class GpuStages:
         n = self.b.count_instances_device(reads, self.stream())
         if self.form == "skr":
             # a segment covers about (K-M+2)/2 windows (9-23 at the BASELINE shapes); the call reports the exact need if this is short
-            cap = max(getattr(self, "_skr_cap_seen", 0), n // 6 + int(reads.n_reads) + 1024)
+            cap = getattr(self, "_skr_cap_seen", 0) or (n // 6 + int(reads.n_reads) + 1024)  # what the last batch needed (+6 %), else an estimate
             while True:
                 rec = self.alloc_records(cap)
                 try:
@@ -260,7 +260,7 @@ class ShardedBinner:
             # the exchange call returned after its stream was synchronised: the records have left, and a config-3-sized shard (tens of GB
             # of records) must make room for the grouping's workspace
             del rec
-            if n * self.stages.record_bytes > (1 << 30):
+            if n * self.stages.record_bytes > (12 << 30):  # only when it matters: returning the block to the driver costs a cudaMalloc next step
                 torch.cuda.empty_cache()
             e3 = self._ev()
         else:

@@ -264,7 +264,8 @@ int run_scan(gbin_ctx *ctx, const gbin_reads *rd, uint32_t arrival_base, void *d
     const bool on = ctx->prof.begin(KK_SCAN, st);
     const int ls = launch_scan_reads(rv, rd->starts ? ctx->rec_off.as<uint64_t>() : nullptr, ctx->cfg.kmer_size, ctx->cfg.mmer_size, ctx->KW,
                                      arrival_base, max_len ? max_len : 1, d_records, &dm->bad_bases, ctx->sm_count, st);
-    ctx->prof.end(on, ls, st);
+    ctx->prof.end(on, ls < 0 ? 0 : ls, st);
+    if (ls < 0) return fail(ctx, GBIN_E_TOO_LARGE, "a read of %u bases does not fit the scan kernel's shared memory (limit %u bases)", max_len, gbin_max_read_len());
     *launches += ls;
     CU(cudaGetLastError());
     return GBIN_OK;
@@ -399,8 +400,13 @@ int run_v2_scan(gbin_ctx *ctx, const gbin_reads *rd, uint64_t n, uint32_t max_le
                 CU(cudaStreamWaitEvent(st, ctx->ev_feed[c], 0));
                 if (c + 1 == chunks) CU(cudaEventRecord(ctx->ev[1], st));  // every byte of the reads is on the device
             }
-            ls += launch_skr_scan(rv, r0, r1, K, M, arrival_base, max_len, ext ? ext : ctx->skr_a.p, cap, ctx->tile_state.as<unsigned long long>(),
-                                  &dm->skr_ticket, dm->skr_counters, ctx->sm_count, st);
+            const int l1 = launch_skr_scan(rv, r0, r1, K, M, arrival_base, max_len, ext ? ext : ctx->skr_a.p, cap, ctx->tile_state.as<unsigned long long>(),
+                                           &dm->skr_ticket, dm->skr_counters, ctx->sm_count, st);
+            if (l1 < 0) {  // reads too long for the shared memory of this kernel: the caller uses the instance-record scan
+                if (feed && attempt == 0) CU(cudaStreamSynchronize(ctx->st_h2d));
+                return GBIN_E_TOO_LARGE;
+            }
+            ls += l1;
         }
         ctx->prof.end(on, ls, st);
         *launches += ls;
@@ -918,6 +924,10 @@ int run_v2(gbin_ctx *ctx, const gbin_reads *rd, uint64_t n, uint32_t max_len, cu
     if (n == 0 || (ctx->pipeline < 3 && n >= (1ull << 31))) return GBIN_OK;
     uint64_t n_skr = 0, n_chk = 0;
     int rc = run_v2_scan(ctx, rd, n, max_len, 0, nullptr, 0, st, &n_skr, launches, feed);
+    if (rc == GBIN_E_TOO_LARGE) {  // reads longer than the super-k-mer scan holds in shared memory: pipeline 1 takes the batch
+        ctx->fallbacks++;
+        return GBIN_OK;
+    }
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[2], st));
     rc = run_skr_group(ctx, ctx->skr_a.p, n_skr, rd->read_ids, rd->id_base, st, out, launches, done, &n_chk, sink, used);
@@ -934,11 +944,11 @@ int bin_device_impl(gbin_ctx *ctx, const gbin_reads *rd, cudaStream_t st, gbin_t
     uint32_t max_len = 0;
     int rc = plan_reads(ctx, rd, st, &n, &max_len, launches);
     if (rc) return rc;
-    if (max_len > GBIN_MAX_READ_LEN) return fail(ctx, GBIN_E_TOO_LARGE, "read length %u exceeds GBIN_MAX_READ_LEN", max_len);
+    if (max_len > gbin_max_read_len()) return fail(ctx, GBIN_E_TOO_LARGE, "read length %u exceeds the limit of %u bases", max_len, gbin_max_read_len());
     if (ctx->pipeline < 3 && n >= (1ull << 32) - 8192)
         return fail(ctx, GBIN_E_TOO_LARGE, "%llu k-mer instances in one batch (pipelines 1 and 2 hold 2^32; pipeline 3 works in passes)", (unsigned long long)n);
     const bool v2 = ctx->pipeline >= 2 && n != 0 && (ctx->pipeline >= 3 || n < (1ull << 31));
-    if (feed && !v2) {  // nobody downstream streams the reads in: copy them in one piece
+    if (feed && (!v2 || max_len > 1500)) {  // nobody downstream streams the reads in (long reads go to pipeline 1's scan): copy them in one piece
         CU(cudaMemcpyAsync(feed->dst, feed->src, feed->bytes, cudaMemcpyHostToDevice, st));
         CU(cudaEventRecord(ctx->ev[1], st));
         feed = nullptr;
@@ -1103,6 +1113,11 @@ int gbin_get_timings(const gbin_ctx *ctx, gbin_timings *out) {
     if (!ctx || !out) return GBIN_E_INVALID_ARG;
     *out = ctx->tm;
     return GBIN_OK;
+}
+
+uint32_t gbin_max_read_len(void) {
+    const uint32_t hw = scan_reads_max_len();  // what one warp's shared memory holds in the instance-record scan
+    return hw < (uint32_t)GBIN_MAX_READ_LEN ? hw : (uint32_t)GBIN_MAX_READ_LEN;
 }
 
 uint32_t gbin_record_bytes(const gbin_ctx *ctx) { return ctx ? (uint32_t)(8 * ctx->KW + 8) : 0; }
@@ -1382,7 +1397,7 @@ int split_reads_impl(gbin_ctx *ctx, const char *d_data, uint64_t size, int read_
     out->n_reads = n_reads;
     out->starts = ctx->d_starts.as<uint64_t>();
     out->lens = ctx->d_lens.as<uint32_t>();
-    out->max_read_len = cap > 1 ? cap - 1 : 1;  // a read is what one fgets call took, minus its last byte
+    out->max_read_len = 0;  // the reads are at most cap - 1 bases long, usually far shorter: the binning call finds the real maximum on the device
     return GBIN_OK;
 }
 }  // namespace

@@ -59,6 +59,7 @@ struct KernelProf {
 int launch_count_windows(const ReadsView &rv, int K, uint32_t *counts, cudaStream_t st);
 int launch_scan_reads(const ReadsView &rv, const uint64_t *rec_off, int K, int M, int KW, uint32_t arrival_base, uint32_t max_len,
                       void *out, unsigned long long *bad_bases, int sm_count, cudaStream_t st);
+uint32_t scan_reads_max_len();
 int launch_pack_reads(const ReadsView &rv, uint32_t words_per_read, uint32_t *packed, unsigned long long *bad_bases, cudaStream_t st);
 
 // ---- radix_sort.cu

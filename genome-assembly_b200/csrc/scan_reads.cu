@@ -68,10 +68,11 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32)
     uint32_t *winfo = wv + max_len;
     const uint32_t FULL = (1u << (2 * M)) - 1;
     const uint32_t C = K - M + 1;  // m-mer positions per window
-    const uint64_t warps_total = (uint64_t)gridDim.x * SCAN_WARPS;
+    const uint32_t wpb = blockDim.x >> 5;  // warps per block: fewer than SCAN_WARPS when long reads need more shared memory per warp
+    const uint64_t warps_total = (uint64_t)gridDim.x * wpb;
     uint32_t nbad = 0;
 
-    for (uint64_t r = (uint64_t)blockIdx.x * SCAN_WARPS + warp; r < rv.n_reads; r += warps_total) {
+    for (uint64_t r = (uint64_t)blockIdx.x * wpb + warp; r < rv.n_reads; r += warps_total) {
         const uint32_t L = rv.len(r);
         if (L < (uint32_t)K) continue;
         const uint32_t W = L - K + 1;
@@ -143,23 +144,47 @@ int launch_count_windows(const ReadsView &rv, int K, uint32_t *counts, cudaStrea
     return 1;
 }
 
+// Returns the kernels launched, or -1 when a read is too long for the shared memory of even one warp per block
+// (the caller reports GBIN_E_TOO_LARGE with gbin_max_read_len()).
 int launch_scan_reads(const ReadsView &rv, const uint64_t *rec_off, int K, int M, int KW, uint32_t arrival_base, uint32_t max_len,
                       void *out, unsigned long long *bad_bases, int sm_count, cudaStream_t st) {
     if (rv.n_reads == 0) return 0;
-    const size_t smem = (size_t)SCAN_WARPS * scan_warp_smem(max_len);
-    uint64_t blocks = (rv.n_reads + SCAN_WARPS - 1) / SCAN_WARPS;
+    int dev = 0, limit = 48 * 1024;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const size_t per_warp = scan_warp_smem(max_len);
+    int warps = SCAN_WARPS;
+    while (warps > 1 && (size_t)warps * per_warp > (size_t)limit) warps >>= 1;
+    if ((size_t)warps * per_warp > (size_t)limit) return -1;
+    const size_t smem = (size_t)warps * per_warp;
+    uint64_t blocks = (rv.n_reads + warps - 1) / warps;
     const uint64_t cap = (uint64_t)sm_count * 8;
     if (blocks > cap) blocks = cap;
+    cudaError_t e = cudaSuccess;
     if (KW == 1) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(scan_reads_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        scan_reads_kernel<1><<<(unsigned)blocks, SCAN_WARPS * 32, smem, st>>>(rv, rec_off, K, M, arrival_base, max_len,
-                                                                            static_cast<Rec<1> *>(out), bad_bases);
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(scan_reads_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return -1;
+        scan_reads_kernel<1><<<(unsigned)blocks, warps * 32, smem, st>>>(rv, rec_off, K, M, arrival_base, max_len, static_cast<Rec<1> *>(out), bad_bases);
     } else {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(scan_reads_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        scan_reads_kernel<2><<<(unsigned)blocks, SCAN_WARPS * 32, smem, st>>>(rv, rec_off, K, M, arrival_base, max_len,
-                                                                            static_cast<Rec<2> *>(out), bad_bases);
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(scan_reads_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return -1;
+        scan_reads_kernel<2><<<(unsigned)blocks, warps * 32, smem, st>>>(rv, rec_off, K, M, arrival_base, max_len, static_cast<Rec<2> *>(out), bad_bases);
     }
     return 1;
+}
+
+// Longest read the v1 scan kernel holds with one warp per block.
+uint32_t scan_reads_max_len() {
+    int dev = 0, limit = 48 * 1024;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    uint32_t lo = 1, hi = 1u << 20;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (scan_warp_smem(mid) <= (size_t)limit) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
 }
 
 int launch_pack_reads(const ReadsView &rv, uint32_t words_per_read, uint32_t *packed, unsigned long long *bad_bases, cudaStream_t st) {

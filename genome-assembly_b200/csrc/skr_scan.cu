@@ -178,11 +178,19 @@ int launch_skr_scan(const ReadsView &rv_all, uint64_t read_begin, uint64_t read_
     uint32_t rpw, seg_cap;
     skr_tile_shape(K, M, max_len, &rpw, &seg_cap);
     const uint32_t ntiles = (uint32_t)((read_end - read_begin + rpw - 1) / rpw);
-    const size_t smem = (size_t)SKR_WARPS * skr_warp_smem(max_len, seg_cap, NW);
+    // long reads need more shared memory per warp: fewer warps per block then (-1: not even one fits; the caller uses the other scan kernel)
+    int dev = 0, limit = 48 * 1024;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const size_t per_warp = skr_warp_smem(max_len, seg_cap, NW);
+    int warps = SKR_WARPS;
+    while (warps > 1 && (size_t)warps * per_warp > (size_t)limit) warps >>= 1;
+    if ((size_t)warps * per_warp > (size_t)limit) return -1;
+    const size_t smem = (size_t)warps * per_warp;
     cudaMemsetAsync(tile_state, 0, sizeof(unsigned long long) * ntiles, st);
     cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
     uint32_t blocks = (uint32_t)sm_count * 8;
-    if (blocks > (ntiles + SKR_WARPS - 1) / SKR_WARPS) blocks = (ntiles + SKR_WARPS - 1) / SKR_WARPS;
+    if (blocks > (ntiles + warps - 1) / warps) blocks = (ntiles + warps - 1) / warps;
     // one-REDUX hops need score, inverted offset and strand bit in 32 bits (read_pack.cuh)
     const bool packed = 2 * M + 1 + ((K - M + 1) <= 32 ? 5 : 6) <= 32;
     // ns between polls of a predecessor tile that has not published yet: the kernel is bound by instruction issue, so a
@@ -192,9 +200,14 @@ int launch_skr_scan(const ReadsView &rv_all, uint64_t read_begin, uint64_t read_
         const char *e = getenv("GBIN_SCAN_SLEEP");
         lkb_sleep = e ? atoi(e) : 800;
     }
+    bool attr_failed = false;
     auto launch = [&](auto kern) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<blocks, SKR_WARPS * 32, smem, st>>>(rv, read_begin, K, M, arrival_base, max_len, rpw, seg_cap, ntiles, static_cast<uint32_t *>(out),
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            (void)cudaGetLastError();
+            attr_failed = true;
+            return;
+        }
+        kern<<<blocks, warps * 32, smem, st>>>(rv, read_begin, K, M, arrival_base, max_len, rpw, seg_cap, ntiles, static_cast<uint32_t *>(out),
                                                    capacity, tile_state, ticket, counters, (uint32_t)lkb_sleep);
     };
     if (PW == 2) {
@@ -204,7 +217,7 @@ int launch_skr_scan(const ReadsView &rv_all, uint64_t read_begin, uint64_t read_
         if (packed) launch(skr_scan_kernel<4, true>);
         else launch(skr_scan_kernel<4, false>);
     }
-    return 1;
+    return attr_failed ? -1 : 1;
 }
 
 uint32_t skr_scan_tiles(uint64_t n_reads, int K, int M, uint32_t max_len) {

@@ -374,8 +374,9 @@ typedef struct ref_session {
     int pruned;
 } ref_session;
 
-#define MAX_SESSIONS 16
-static ref_session g_sessions[MAX_SESSIONS];
+/* Sessions live in a list that grows on demand; a session ends with prune_data (its slot is free again). */
+static ref_session *g_sessions = NULL;
+static int g_n_sessions = 0;
 static gbin_config g_cfg = {31, 4, 1, 0}; /* binning.c:10-12 defaults */
 static gbin_ctx *g_ctx = NULL;
 static gbin_config g_ctx_cfg;
@@ -394,14 +395,35 @@ int gbin_ref_last_status(void) { return g_status; }
 static ref_session *session_for(struct ZHashTable *table, int create)
 {
     ref_session *free_slot = NULL;
-    for (int i = 0; i < MAX_SESSIONS; i++) {
+    for (int i = 0; i < g_n_sessions; i++) {
         if (g_sessions[i].table == table) return &g_sessions[i];
         if (!g_sessions[i].table && !free_slot) free_slot = &g_sessions[i];
     }
-    if (!create || !free_slot) return NULL;
+    if (!create) return NULL;
+    if (!free_slot) {
+        const int nn = g_n_sessions ? 2 * g_n_sessions : 8;
+        ref_session *ns = realloc(g_sessions, (size_t)nn * sizeof *ns);
+        if (!ns) return NULL;
+        memset(ns + g_n_sessions, 0, (size_t)(nn - g_n_sessions) * sizeof *ns);
+        g_sessions = ns;
+        free_slot = &g_sessions[g_n_sessions];
+        g_n_sessions = nn;
+    }
     memset(free_slot, 0, sizeof *free_slot);
     free_slot->table = table;
     return free_slot;
+}
+
+/* The shims cannot return a status (the reference's functions return the table): say on stderr why a call did nothing, once per
+ * status change, and keep the status for gbin_ref_last_status(). */
+static void shim_fail(int status, const char *what)
+{
+    static int last_reported = 0;
+    g_status = status;
+    if (status != last_reported) {
+        fprintf(stderr, "libgbin: %s: %s (gbin_ref_last_status() = %d)\n", what, gbin_strerror(status), status);
+        last_reported = status;
+    }
 }
 
 static void session_drop(ref_session *s)
@@ -417,15 +439,23 @@ static void session_drop(ref_session *s)
  * caller may reuse `read` immediately: the read is copied into the session's staging buffer. */
 struct ZHashTable *process_read(struct ZHashTable *hash_table, char *read, int read_id)
 {
-    ref_session *s = session_for(hash_table, 1);
-    if (!s) { g_status = GBIN_E_NOMEM; return hash_table; }
-    if (s->pruned) { g_status = GBIN_E_STATE; return hash_table; } /* inserts after prune_data are not supported */
+    ref_session *s = session_for(hash_table, 0);
+    if (!s) {
+        /* A table that already holds entries and has no open session was filled by prune_data: the pointer graph cannot take
+         * further inserts.  (An empty table — fresh from zcreate_hash_table, possibly at a recycled address — starts a session.) */
+        if (hash_table && hash_table->entry_count != 0) {
+            shim_fail(GBIN_E_STATE, "process_read on a table that prune_data has already filled: the read is dropped");
+            return hash_table;
+        }
+        s = session_for(hash_table, 1);
+    }
+    if (!s) { shim_fail(GBIN_E_NOMEM, "process_read: the read is dropped"); return hash_table; }
     const size_t len = strlen(read);
     if (s->data_len + len + 1 > s->data_cap) {
         size_t nc = s->data_cap ? s->data_cap * 2 : (1u << 20);
         while (nc < s->data_len + len + 1) nc *= 2;
         char *d = realloc(s->data, nc);
-        if (!d) { g_status = GBIN_E_NOMEM; return hash_table; }
+        if (!d) { shim_fail(GBIN_E_NOMEM, "process_read: the read is dropped"); return hash_table; }
         s->data = d;
         s->data_cap = nc;
     }
@@ -437,7 +467,7 @@ struct ZHashTable *process_read(struct ZHashTable *hash_table, char *read, int r
         if (ln) s->lens = ln;
         int32_t *id = realloc(s->ids, nc * sizeof *id);
         if (id) s->ids = id;
-        if (!st || !ln || !id) { g_status = GBIN_E_NOMEM; return hash_table; }
+        if (!st || !ln || !id) { shim_fail(GBIN_E_NOMEM, "process_read: the read is dropped"); return hash_table; }
         s->cap = nc;
     }
     memcpy(s->data + s->data_len, read, len);
@@ -454,14 +484,24 @@ struct ZHashTable *process_read(struct ZHashTable *hash_table, char *read, int r
 /* binning.c:1130.  Flush: GPU pipeline over everything staged for this table, then the pointer graph. */
 struct ZHashTable *prune_data(struct ZHashTable *hash_table)
 {
-    ref_session *s = session_for(hash_table, 1);
-    if (!s) { g_status = GBIN_E_NOMEM; return hash_table; }
-    if (s->pruned) { g_status = GBIN_E_STATE; return hash_table; }
+    ref_session *s = session_for(hash_table, 0);
+    if (!s) {
+        if (hash_table && hash_table->entry_count != 0) {
+            shim_fail(GBIN_E_STATE, "prune_data on a table that it has already filled: nothing done");
+            return hash_table;
+        }
+        s = session_for(hash_table, 1); /* no reads were staged: an empty batch */
+    }
+    if (!s) { shim_fail(GBIN_E_NOMEM, "prune_data"); return hash_table; }
     if (!g_ctx || memcmp(&g_ctx_cfg, &g_cfg, sizeof g_cfg) != 0) {
         if (g_ctx) gbin_destroy(g_ctx);
         g_ctx = NULL;
-        g_status = gbin_create(&g_cfg, &g_ctx);
-        if (g_status != GBIN_OK) return hash_table;
+        const int rc = gbin_create(&g_cfg, &g_ctx);
+        if (rc != GBIN_OK) {
+            shim_fail(rc, "prune_data: no GPU context, the table stays empty");
+            session_drop(s);
+            return hash_table;
+        }
         g_ctx_cfg = g_cfg;
     }
     gbin_reads rd;
@@ -473,19 +513,12 @@ struct ZHashTable *prune_data(struct ZHashTable *hash_table)
     rd.lens = s->lens;
     rd.read_ids = s->ids;
     gbin_table tab;
-    g_status = gbin_bin_reads_host(g_ctx, &rd, &tab);
-    if (g_status == GBIN_OK) g_status = gbin_table_to_zhash(&tab, hash_table);
-    /* the staged reads are no longer needed; keep the slot marked so late process_read calls fail loudly */
-    free(s->data);
-    free(s->starts);
-    free(s->lens);
-    free(s->ids);
-    s->data = NULL;
-    s->starts = NULL;
-    s->lens = NULL;
-    s->ids = NULL;
-    s->n = s->cap = s->data_len = s->data_cap = 0;
-    s->pruned = 1;
+    int rc = gbin_bin_reads_host(g_ctx, &rd, &tab);
+    if (rc == GBIN_OK) rc = gbin_table_to_zhash(&tab, hash_table);
+    if (rc != GBIN_OK) shim_fail(rc, "prune_data: the pipeline failed, the table stays empty");
+    else g_status = GBIN_OK;
+    /* the session ends here: its slot is free again, whatever address the next table has */
+    session_drop(s);
     return hash_table;
 }
 

@@ -47,6 +47,9 @@ extern "C" {
 #define GBIN_E_IO (-8)
 
 #define GBIN_MAX_READ_LEN 4096
+/* Longest read a batch may hold on this device: min(GBIN_MAX_READ_LEN, what one warp's shared memory holds).  Reads of more than
+ * about 1800 bases are scanned by pipeline 1's kernel (the super-k-mer scan keeps more per read in shared memory). */
+uint32_t gbin_max_read_len(void);
 
 /* Runtime form of binning.c:10-12. */
 typedef struct gbin_config {

@@ -298,6 +298,38 @@ def test_file_to_table_in_one_call(case, tmp_path):
     b.close()
 
 
+@pytest.mark.parametrize("L", [1700, 2600, 4000])
+def test_long_reads_pick_a_scan_kernel_that_fits(L):
+    """Both scan kernels keep a read in shared memory: above about 1 800 bases the super-k-mer scan runs with fewer warps per block
+    or hands the batch to pipeline 1's scan, which holds reads up to gbin_max_read_len().  Same table as the oracle either way."""
+    torch_cuda()
+    assert B.load_library().gbin_max_read_len() >= 4000
+    rs = synth.generate(300, L, genome_len=3 * L, error_rate=0.01, seed=L, starts="uniform")
+    starts = np.arange(rs.n_reads, dtype=np.uint64) * rs.stride
+    lens = np.full(rs.n_reads, rs.read_len, dtype=np.uint32)
+    for K, M in ((31, 11), (63, 15)):
+        b = B.Binner(K, M, 1)
+        got = b.bin_host(rs.buf, rs.n_reads, stride=rs.stride, read_len=rs.read_len)
+        assert_tables_equal(got, O.run(rs.as_bytes(), starts, lens, K, M, 1))
+        b.close()
+
+
+def test_file_call_with_a_large_read_length_define(tmp_path):
+    """gbin_bin_file_host(path, 4096) on 100-base reads: READ_LENGTH bounds the line length only; the kernels are sized by the
+    real maximum read length, found on the device."""
+    torch_cuda()
+    case = next(c for c in CASES if c["name"] == "cfg2_small")
+    data = O.load_case_bytes(case)
+    path = tmp_path / "reads.txt"
+    path.write_bytes(data)
+    starts, lens = O.fgets_split(data, 4096)
+    b = B.Binner(case["k"], case["m"], case["cutoff"])
+    got = b.bin_file_host(str(path), 4096)
+    assert_tables_equal(got, O.run(data, starts, lens, case["k"], case["m"], case["cutoff"]))
+    assert b.pipeline_info()["last_used"] == 3
+    b.close()
+
+
 def test_empty_and_degenerate_batches():
     torch_cuda()
     b = B.Binner(31, 4, 1)

@@ -37,7 +37,7 @@ __device__ __forceinline__ uint32_t payload_bases(const uint32_t *pl, uint32_t n
 
 template <int PW>
 __global__ void __launch_bounds__(256)
-    make_entries_kernel(const uint32_t *__restrict__ skr, uint64_t n_rec, KeyLayout kl, uint64_t *__restrict__ ent, uint8_t *__restrict__ piece_n,
+    make_entries_kernel(const uint32_t *__restrict__ skr, uint64_t n_rec, KeyLayout kl, uint64_t *__restrict__ ent, uint16_t *__restrict__ piece_info,
                         unsigned long long *__restrict__ n_real) {
     constexpr int NW = SkrLayout<PW>::WORDS;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(256)
         const uint32_t mmer = h.y, meta = h.z;
         if (kl.nc == 1) {
             ent[i] = ((uint64_t)mmer << 32) | (uint32_t)i;
-            piece_n[i] = (uint8_t)(meta & 0xffu);
+            const uint32_t n = meta & 0xffu, so1 = (meta >> 16) & 0xffu;
+            piece_info[i] = (uint16_t)(n | ((so1 - (n - 1)) << 8));  // windows | smallest d of the piece << 8
             real = 1;
         } else {
             const bool rev = (meta >> 8) & 1u;
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(256)
                     real++;
                 }
                 ent[slot] = ((uint64_t)key << 32) | slot;
-                piece_n[slot] = (uint8_t)np;
+                piece_info[slot] = (uint16_t)(np | (np ? (so - (t0 + np - 1)) << 8 : 0u));
             }
         }
     }
@@ -80,13 +81,13 @@ __global__ void __launch_bounds__(256)
     if (threadIdx.x == 0 && s_real) atomicAdd(n_real, (unsigned long long)s_real);
 }
 
-int v3_make_entries(const void *skr, uint64_t n_rec, const KeyLayout &kl, uint64_t *ent, uint8_t *piece_n, unsigned long long *n_real_dev,
+int v3_make_entries(const void *skr, uint64_t n_rec, const KeyLayout &kl, uint64_t *ent, uint16_t *piece_info, unsigned long long *n_real_dev,
                     cudaStream_t st) {
     cudaMemsetAsync(n_real_dev, 0, sizeof(unsigned long long), st);
     if (n_rec == 0) return 0;
     const unsigned grid = (unsigned)((n_rec + 255) / 256);
-    if (kl.K <= 32) make_entries_kernel<2><<<grid, 256, 0, st>>>(static_cast<const uint32_t *>(skr), n_rec, kl, ent, piece_n, n_real_dev);
-    else make_entries_kernel<4><<<grid, 256, 0, st>>>(static_cast<const uint32_t *>(skr), n_rec, kl, ent, piece_n, n_real_dev);
+    if (kl.K <= 32) make_entries_kernel<2><<<grid, 256, 0, st>>>(static_cast<const uint32_t *>(skr), n_rec, kl, ent, piece_info, n_real_dev);
+    else make_entries_kernel<4><<<grid, 256, 0, st>>>(static_cast<const uint32_t *>(skr), n_rec, kl, ent, piece_info, n_real_dev);
     return 1;
 }
 
@@ -94,41 +95,42 @@ int v3_make_entries(const void *skr, uint64_t n_rec, const KeyLayout &kl, uint64
 
 struct EntCountAndHead {  // low half: windows of sorted entry i; high half: 1 if it starts a new atom (run of equal key)
     const uint64_t *ent;
-    const uint8_t *piece_n;
+    const uint16_t *info;  // per sorted entry: windows | smallest d << 8 (gathered by the last sort pass)
     __device__ __forceinline__ uint64_t operator()(uint64_t i) const {
         const uint64_t e = ent[i];
         const uint64_t head = (i == 0 || (e >> 32) != (ent[i - 1] >> 32)) ? 1ull : 0ull;
-        return (uint64_t)piece_n[(uint32_t)e] | (head << 32);
+        return (uint64_t)(info[i] & 0xffu) | (head << 32);
     }
 };
 
-__global__ void v3_run_starts_kernel(const uint64_t *__restrict__ ent, uint64_t n, const uint64_t *__restrict__ both, const uint64_t *__restrict__ total,
-                                     uint32_t *__restrict__ inst_prefix, uint32_t *__restrict__ run_start, uint32_t *__restrict__ n_inst_out,
-                                     uint32_t *__restrict__ n_runs_out) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint64_t b = both[i];
-    inst_prefix[i] = (uint32_t)b;
-    if (i == 0 || (ent[i] >> 32) != (ent[i - 1] >> 32)) run_start[b >> 32] = (uint32_t)i;
-    if (i == n - 1) {
-        const uint64_t t = *total;
-        inst_prefix[n] = (uint32_t)t;
-        run_start[t >> 32] = (uint32_t)n;
-        *n_inst_out = (uint32_t)t;
-        *n_runs_out = (uint32_t)(t >> 32);
+struct EntRunSink {  // consumer of the scan above: instance prefix of every sorted entry, first entry of every atom
+    const uint64_t *ent;
+    uint32_t *inst_prefix, *run_start;
+    __device__ __forceinline__ void operator()(uint64_t i, uint64_t b) const {
+        inst_prefix[i] = (uint32_t)b;
+        if (i == 0 || (ent[i] >> 32) != (ent[i - 1] >> 32)) run_start[b >> 32] = (uint32_t)i;
     }
+};
+
+__global__ void v3_run_totals_kernel(const uint64_t *__restrict__ total, uint64_t n, uint32_t *__restrict__ inst_prefix, uint32_t *__restrict__ run_start,
+                                     uint32_t *__restrict__ n_inst_out, uint32_t *__restrict__ n_runs_out) {
+    const uint64_t t = *total;
+    inst_prefix[n] = (uint32_t)t;
+    run_start[t >> 32] = (uint32_t)n;
+    *n_inst_out = (uint32_t)t;
+    *n_runs_out = (uint32_t)(t >> 32);
 }
 
-int v3_plan_runs(const uint64_t *ent, const uint8_t *piece_n, uint64_t n_ent, uint32_t *inst_prefix, uint64_t *both64, uint32_t *run_start,
+int v3_plan_runs(const uint64_t *ent, const uint16_t *sorted_info, uint64_t n_ent, uint32_t *inst_prefix, uint64_t *both64, uint32_t *run_start,
                  uint64_t *scratch64, uint32_t *n_inst_dev, uint32_t *n_runs_dev, cudaStream_t st) {
     if (n_ent == 0) {
         cudaMemsetAsync(n_inst_dev, 0, 4, st);
         cudaMemsetAsync(n_runs_dev, 0, 4, st);
         return 0;
     }
-    int l = exclusive_scan<uint64_t, EntCountAndHead>(EntCountAndHead{ent, piece_n}, both64, n_ent, scratch64, both64 + n_ent, st);
-    v3_run_starts_kernel<<<(unsigned)((n_ent + 255) / 256), 256, 0, st>>>(ent, n_ent, both64, both64 + n_ent, inst_prefix, run_start, n_inst_dev,
-                                                                         n_runs_dev);
+    int l = exclusive_scan_to<uint64_t, EntCountAndHead, EntRunSink>(EntCountAndHead{ent, sorted_info}, EntRunSink{ent, inst_prefix, run_start}, n_ent, scratch64,
+                                                                     both64, st);
+    v3_run_totals_kernel<<<1, 1, 0, st>>>(both64, n_ent, inst_prefix, run_start, n_inst_dev, n_runs_dev);
     return l + 1;
 }
 
@@ -297,13 +299,11 @@ __global__ void v3_fill_units_kernel(RunView3 rv, const uint64_t *__restrict__ n
 // One warp per split atom: d-histogram of the atom (difference array over its pieces, then prefix), greedy cut into rounds of
 // consecutive d whose instances fit a unit.  Fills the atom's round units: d-range, instance coordinate, instances (0 = unused).
 __global__ void __launch_bounds__(128)
-    v3_round_cuts_kernel(const uint32_t *__restrict__ skr, int skr_words, const uint64_t *__restrict__ ent, KeyLayout kl, Unit3 *__restrict__ units,
-                         G3Counters *__restrict__ gc, uint32_t cap) {
+    v3_round_cuts_kernel(const uint16_t *__restrict__ info, Unit3 *__restrict__ units, G3Counters *__restrict__ gc, uint32_t cap) {
     __shared__ int s_hist[4][68];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int *dhist = s_hist[warp];
     const uint32_t n_units = gc->n_units;
-    const uint32_t cls_mask = (uint32_t)(kl.nc - 1);
     for (uint32_t u = blockIdx.x * 4 + warp; u < n_units; u += gridDim.x * 4) {
         const Unit3 un = units[u];
         if (un.rounds == 0 || un.round != 0) continue;
@@ -313,14 +313,11 @@ __global__ void __launch_bounds__(128)
         __syncwarp();
         const uint32_t n_ent = un.ent_end - un.ent_begin;
         for (uint32_t e = lane; e < n_ent; e += 32) {
-            const uint32_t slot = (uint32_t)ent[un.ent_begin + e];
-            const uint32_t meta = skr[(uint64_t)(slot >> kl.cshift) * skr_words + 2];
-            uint32_t t0, np;
-            piece_of(meta, slot & cls_mask, kl, &t0, &np);
+            const uint32_t pi = info[un.ent_begin + e];
+            const uint32_t np = pi & 0xffu, dlo = pi >> 8;
             if (np) {
-                const int so = (int)((meta >> 16) & 0xffu);
-                atomicAdd(&dhist[so - (int)(t0 + np - 1)], 1);  // smallest d of the piece
-                atomicAdd(&dhist[so - (int)t0 + 1], -1);        // one past its largest d
+                atomicAdd(&dhist[dlo], 1);        // smallest d of the piece
+                atomicAdd(&dhist[dlo + np], -1);  // one past its largest d
             }
         }
         __syncwarp();
@@ -997,15 +994,15 @@ __device__ __forceinline__ void finalize3_unit(const Unit3 *__restrict__ units, 
         }
         const int32_t *src = st.ids + uo.ibase;
         int32_t *dst = fin.read_ids + Nb;
-        for (uint32_t i0 = 0; i0 < uo.N; i0 += 512) {
-            int32_t v[16];
+        for (uint32_t i0 = 0; i0 < uo.N; i0 += 256) {
+            int32_t v[8];
 #pragma unroll
-            for (int q = 0; q < 16; q++) {
+            for (int q = 0; q < 8; q++) {
                 const uint32_t i = i0 + q * 32 + lane;
-                if (i < uo.N) v[q] = src[i];
+                if (i < uo.N) v[q] = __ldcs(src + i);  // staged data is read once
             }
 #pragma unroll
-            for (int q = 0; q < 16; q++) {
+            for (int q = 0; q < 8; q++) {
                 const uint32_t i = i0 + q * 32 + lane;
                 if (i < uo.N) dst[i] = v[q];
             }
@@ -1125,7 +1122,7 @@ __device__ __forceinline__ void finalize3_unit(const Unit3 *__restrict__ units, 
 }
 
 template <int KW>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 12)
     finalize3_kernel(const Unit3 *__restrict__ units, const uint64_t *__restrict__ unit_excl, const unsigned long long *__restrict__ totals,
                      const unsigned long long *__restrict__ lsd_totals, G3Stage st, G3Final fin, G3Lsd ls, G3Counters *__restrict__ gc,
                      const uint32_t *__restrict__ chunk_bounds, uint32_t chunk, bool only_long) {
@@ -1192,8 +1189,8 @@ static Plan3 v3_plan_params(const KeyLayout &kl, int cap_i) {
 
 uint64_t v3_max_units(uint64_t n_inst, uint64_t n_runs, int cap) {
     const uint64_t c = cap == 512 ? 512 : 1024;
-    // packed units: two consecutive ones hold more than cap instances, or cap / 4 entries, or cap / 8 atoms; + one per plan block; rounds: 2c/cap + 3 per atom
-    return 2 * (n_inst / c) + 2 * (n_inst / (c / 4)) / 1 + 2 * (n_runs / (c / 8)) + n_runs / PLAN_BLOCK + 3 * n_runs + 16;
+    // a packed unit holds at least one atom; an atom in rounds holds more than cap instances and gets at most 2 * ceil(instances / cap) + 1 units
+    return n_runs + 5 * (n_inst / c) + 16;
 }
 size_t v3_unit_bytes() { return sizeof(Unit3); }
 size_t v3_unit_out_bytes() { return sizeof(UnitOut3); }
@@ -1205,7 +1202,7 @@ struct PtrIn64 {
 };
 
 // Units over the n_runs atoms.  nunits64 / base64: [n_runs + 1] u64 scratch each; atom3: [3 * n_runs] u32 scratch; spanlen: [n_runs] u32; head_run: [max_units].
-int v3_plan_units(const void *skr, const uint64_t *ent, const KeyLayout &kl, int cap, const uint32_t *inst_prefix, const uint32_t *run_start, uint64_t n_runs,
+int v3_plan_units(const uint16_t *sorted_info, const uint64_t *ent, const KeyLayout &kl, int cap, const uint32_t *inst_prefix, const uint32_t *run_start, uint64_t n_runs,
                   uint64_t *nunits64, uint64_t *base64, uint32_t *atom3, uint32_t *spanlen, uint32_t *head_run, void *scratch, void *units, uint64_t max_units,
                   void *gc_dev, uint32_t n_chunks, uint32_t *chunk_bounds, cudaStream_t st) {
     RunView3 rv{run_start, inst_prefix};
@@ -1221,7 +1218,7 @@ int v3_plan_units(const void *skr, const uint64_t *ent, const KeyLayout &kl, int
         l += 2 + exclusive_scan<uint64_t, PtrIn64>(PtrIn64{nunits64}, base64, n_runs, static_cast<uint64_t *>(scratch), base64 + n_runs, st);
         v3_head_runs_kernel<<<(unsigned)((n_runs + 255) / 256), 256, 0, st>>>(nunits64, base64, n_runs, head_run);
         v3_fill_units_kernel<<<(unsigned)((max_units + 255) / 256), 256, 0, st>>>(rv, nunits64, spanlen, base64, base64 + n_runs, n_runs, head_run, static_cast<Unit3 *>(units), gc);
-        v3_round_cuts_kernel<<<592, 128, 0, st>>>(static_cast<const uint32_t *>(skr), kl.K <= 32 ? 8 : 12, ent, kl, static_cast<Unit3 *>(units), gc, pp.cap);
+        v3_round_cuts_kernel<<<592, 128, 0, st>>>(sorted_info, static_cast<Unit3 *>(units), gc, pp.cap);
         l += 3;
     }
     v3_chunk_bounds_kernel<<<1, 1, 0, st>>>(static_cast<const Unit3 *>(units), gc, n_chunks, chunk_bounds);
@@ -1266,7 +1263,7 @@ int v3_group_launch(const void *skr, const uint64_t *ent, const void *units, con
             l += exclusive_scan<uint64_t, UnitSNLong>(UnitSNLong{stg.unit_out, un, ch.bounds, c}, lsd_excl, max_units, static_cast<uint64_t *>(scan_scratch), ch.chunk_sum, st);
             v3_chunk_total_kernel<<<1, 1, 0, st>>>(ch.chunk_sum, c, ch.lsd_totals_dev, gc, ch.n, 1);
             // a second run (after the arrays of the global sort were allocated) only handles the long spans: the short-span merge is not idempotent
-            fin_kern<<<sm_count * 16, 128, 0, st>>>(un, unit_excl, ch.totals_dev, ch.lsd_totals_dev, stg, fin, ls, gc, ch.bounds, c, finalize_only);
+            fin_kern<<<sm_count * 12, 128, 0, st>>>(un, unit_excl, ch.totals_dev, ch.lsd_totals_dev, stg, fin, ls, gc, ch.bounds, c, finalize_only);
             if (prof) prof->end(on, l + 3, st);
             launches += l + 3;
             if (ch.totals_host) {
@@ -1328,10 +1325,10 @@ int v3_lsd_finish(const KeyLayout &kl, uint64_t n, void *rec_a, void *rec_b, voi
 // ---- passes: a batch with more k-mer instances than 32-bit coordinates hold is grouped in several passes over consecutive
 // ranges of the sorted entries, cut between m-mer buckets; every pass appends its part of the table.
 constexpr uint32_t PASS_TILE = 1u << 16;
-__global__ void pass_tile_sums_kernel(const uint64_t *__restrict__ ent, const uint8_t *__restrict__ piece_n, uint64_t n_ent, unsigned long long *__restrict__ sums) {
+__global__ void pass_tile_sums_kernel(const uint16_t *__restrict__ info, uint64_t n_ent, unsigned long long *__restrict__ sums) {
     const uint64_t base = (uint64_t)blockIdx.x * PASS_TILE;
     unsigned long long acc = 0;
-    for (uint64_t i = base + threadIdx.x; i < base + PASS_TILE && i < n_ent; i += blockDim.x) acc += piece_n[(uint32_t)ent[i]];
+    for (uint64_t i = base + threadIdx.x; i < base + PASS_TILE && i < n_ent; i += blockDim.x) acc += info[i] & 0xffu;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
     __shared__ unsigned long long s[8];
@@ -1355,9 +1352,9 @@ __global__ void pass_bounds_kernel(const uint64_t *__restrict__ ent, uint64_t n_
 }
 uint32_t v3_pass_tiles(uint64_t n_ent) { return (uint32_t)((n_ent + PASS_TILE - 1) / PASS_TILE); }
 uint32_t v3_pass_tile_entries() { return PASS_TILE; }
-int v3_pass_tile_sums(const uint64_t *ent, const uint8_t *piece_n, uint64_t n_ent, unsigned long long *sums_dev, cudaStream_t st) {
+int v3_pass_tile_sums(const uint16_t *sorted_info, uint64_t n_ent, unsigned long long *sums_dev, cudaStream_t st) {
     if (n_ent == 0) return 0;
-    pass_tile_sums_kernel<<<v3_pass_tiles(n_ent), 256, 0, st>>>(ent, piece_n, n_ent, sums_dev);
+    pass_tile_sums_kernel<<<v3_pass_tiles(n_ent), 256, 0, st>>>(sorted_info, n_ent, sums_dev);
     return 1;
 }
 int v3_pass_bounds(const uint64_t *ent, uint64_t n_ent, int mshift, unsigned long long *bounds_dev, uint32_t n_bounds, cudaStream_t st) {

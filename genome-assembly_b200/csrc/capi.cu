@@ -141,7 +141,7 @@ struct gbin_ctx {
     // pipeline v2 workspace
     DevBuf skr_a, skr_b, tile_state, inst_prefix, run_excl, skr_run_start, small_prefix, unit_base, units, unit_state, o_kmer_mmer, bucket_excl, big_list, big_k0, big_k1, big_arr, stg_ids, stg_codes, stg_mmer, stg_off, skr_side;
     // pipeline v3 workspace
-    DevBuf ent_a, ent_b, piece_n, v3_base64, v3_head_run, v3_unit_out, v3_unit_excl, v3_atoms, v3_lsd_aux, v3_bitmap;
+    DevBuf ent_a, ent_b, piece_n, sorted_info, v3_base64, v3_head_run, v3_unit_out, v3_unit_excl, v3_atoms, v3_lsd_aux, v3_bitmap;
     bool v3_lsd_seen = false;         // a batch on this context had long spans: keep the arrays of their global sort
     uint64_t v3_lsd_cap_seen = 0;     // and how many k-mers they were sized for
     uint64_t v3_pass_max = 2000000000ull;  // k-mer instances per pass of pipeline 3 (gbin_set_tuning "v3_pass_max")
@@ -616,7 +616,7 @@ int v3_choose_layout(gbin_ctx *ctx, const void *skr, uint64_t n_skr, cudaStream_
 
 // One pass of pipeline 3 over the sorted entries [ent, ent + n_ent): plan, group, finalize; the pass's k-mers / ids are appended to
 // the table behind the S_off k-mers / N_off ids of the passes before it.  *ok = false: the pass does not fit (see run_v3_group).
-int run_v3_pass(gbin_ctx *ctx, const void *skr, const uint64_t *ent, uint64_t n_ent, const KeyLayout &kl, const int32_t *d_ids, int32_t id_base, cudaStream_t st,
+int run_v3_pass(gbin_ctx *ctx, const void *skr, const uint64_t *ent, const uint16_t *sorted_info, uint64_t n_ent, const KeyLayout &kl, const int32_t *d_ids, int32_t id_base, cudaStream_t st,
                 uint64_t S_off, uint64_t N_off, bool single_pass, HostSink *sink, int *launches, bool *ok, uint64_t *n_inst, uint64_t *distinct, uint64_t *S_out,
                 uint64_t *N_out) {
     *ok = false;
@@ -629,7 +629,7 @@ int run_v3_pass(gbin_ctx *ctx, const void *skr, const uint64_t *ent, uint64_t n_
     CU(ctx->skr_run_start.ensure((n_ent + 2) * 4));
     CU(ctx->scan_scratch.ensure(group_scan_scratch_bytes(n_ent)));
     bool on = ctx->prof.begin(KK_SKR_PLAN, st);
-    int lp = v3_plan_runs(ent, ctx->piece_n.as<uint8_t>(), n_ent, ctx->inst_prefix.as<uint32_t>(), ctx->run_excl.as<uint64_t>(), ctx->skr_run_start.as<uint32_t>(),
+    int lp = v3_plan_runs(ent, sorted_info, n_ent, ctx->inst_prefix.as<uint32_t>(), ctx->run_excl.as<uint64_t>(), ctx->skr_run_start.as<uint32_t>(),
                           ctx->scan_scratch.as<uint64_t>(), &dm->n_inst_dev, &dm->n_runs_dev, st);
     ctx->prof.end(on, lp, st);
     *launches += lp;
@@ -656,7 +656,7 @@ int run_v3_pass(gbin_ctx *ctx, const void *skr, const uint64_t *ent, uint64_t n_
         ch.done = ctx->ev_chunk;
     }
     on = ctx->prof.begin(KK_SKR_PLAN, st);
-    lp = v3_plan_units(skr, ent, kl, ctx->v3_cap, ctx->inst_prefix.as<uint32_t>(), ctx->skr_run_start.as<uint32_t>(), n_runs, ctx->small_prefix.as<uint64_t>(),
+    lp = v3_plan_units(sorted_info, ent, kl, ctx->v3_cap, ctx->inst_prefix.as<uint32_t>(), ctx->skr_run_start.as<uint32_t>(), n_runs, ctx->small_prefix.as<uint64_t>(),
                        ctx->v3_base64.as<uint64_t>(), ctx->v3_atoms.as<uint32_t>(), ctx->v3_atoms.as<uint32_t>() + 3 * n_runs, ctx->v3_head_run.as<uint32_t>(),
                        ctx->scan_scratch.p, ctx->units.p, max_units, &dm->gc3, ch.n, dm->chunk_bounds, st);
     ctx->prof.end(on, lp, st);
@@ -780,16 +780,18 @@ int run_v3_group(gbin_ctx *ctx, const void *skr, uint64_t n_skr, const int32_t *
     const uint64_t n_slots = n_skr << kl.cshift;
     CU(ctx->ent_a.ensure((n_slots + 2) * 8));
     CU(ctx->ent_b.ensure((n_slots + 2) * 8));
-    CU(ctx->piece_n.ensure(n_slots + 16));
+    CU(ctx->piece_n.ensure((n_slots + 16) * 2));
+    CU(ctx->sorted_info.ensure((n_slots + 16) * 2));
     bool on = ctx->prof.begin(KK_V3_ENTRIES, st);
-    int lp = v3_make_entries(skr, n_skr, kl, ctx->ent_a.as<uint64_t>(), ctx->piece_n.as<uint8_t>(), &dm->n_real_entries, st);
+    int lp = v3_make_entries(skr, n_skr, kl, ctx->ent_a.as<uint64_t>(), ctx->piece_n.as<uint16_t>(), &dm->n_real_entries, st);
     ctx->prof.end(on, lp, st);
     *launches += lp;
     CU(cudaGetLastError());
     CU(ctx->radix_scratch.ensure(radix_scratch_bytes(n_slots)));
     bool in_b = false;
     int passes = 0;
-    *launches += radix_sort_entries(ctx->ent_a.p, ctx->ent_b.p, n_slots, kl.key_bits, ctx->radix_scratch.p, &in_b, &passes, &ctx->prof, st);
+    *launches += radix_sort_entries(ctx->ent_a.p, ctx->ent_b.p, n_slots, kl.key_bits, ctx->radix_scratch.p, &in_b, &passes, ctx->piece_n.as<uint16_t>(),
+                                    ctx->sorted_info.as<uint16_t>(), &ctx->prof, st);
     CU(cudaGetLastError());
     ctx->tm.sort_passes = (uint32_t)passes;
     const uint64_t *ent = in_b ? ctx->ent_b.as<uint64_t>() : ctx->ent_a.as<uint64_t>();
@@ -808,7 +810,7 @@ int run_v3_group(gbin_ctx *ctx, const void *skr, uint64_t n_skr, const int32_t *
         const uint32_t nt = v3_pass_tiles(n_ent);
         CU(ctx->scan_scratch.ensure((size_t)nt * 8 + 64));
         unsigned long long *sums_dev = ctx->scan_scratch.as<unsigned long long>();
-        *launches += v3_pass_tile_sums(ent, ctx->piece_n.as<uint8_t>(), n_ent, sums_dev, st);
+        *launches += v3_pass_tile_sums(ctx->sorted_info.as<uint16_t>(), n_ent, sums_dev, st);
         std::vector<unsigned long long> sums(nt);
         CU(cudaMemcpyAsync(sums.data(), sums_dev, (size_t)nt * 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -841,7 +843,7 @@ int run_v3_group(gbin_ctx *ctx, const void *skr, uint64_t n_skr, const int32_t *
     for (size_t p = 0; p + 1 < bounds.size(); p++) {
         bool ok = false;
         uint64_t n_p = 0, d_p = 0, S_p = 0, N_p = 0;
-        rc = run_v3_pass(ctx, skr, ent + bounds[p], bounds[p + 1] - bounds[p], kl, d_ids, id_base, st, S_off, N_off, single, sink, launches, &ok, &n_p, &d_p, &S_p, &N_p);
+        rc = run_v3_pass(ctx, skr, ent + bounds[p], ctx->sorted_info.as<uint16_t>() + bounds[p], bounds[p + 1] - bounds[p], kl, d_ids, id_base, st, S_off, N_off, single, sink, launches, &ok, &n_p, &d_p, &S_p, &N_p);
         if (rc) return rc;
         if (!ok) return GBIN_OK;  // not done: the caller falls back
         S_off += S_p;
@@ -1079,7 +1081,7 @@ void gbin_destroy(gbin_ctx *ctx) {
                       &ctx->o_kmer_codes, &ctx->o_kmer_id_off, &ctx->o_read_ids, &ctx->skr_a, &ctx->skr_b, &ctx->tile_state,
                       &ctx->inst_prefix, &ctx->run_excl, &ctx->skr_run_start, &ctx->small_prefix, &ctx->unit_base, &ctx->units,
                       &ctx->unit_state, &ctx->o_kmer_mmer, &ctx->bucket_excl, &ctx->big_list, &ctx->big_k0, &ctx->big_k1, &ctx->big_arr, &ctx->stg_ids, &ctx->stg_codes, &ctx->stg_mmer, &ctx->stg_off, &ctx->skr_side,
-                      &ctx->ent_a, &ctx->ent_b, &ctx->piece_n, &ctx->v3_base64, &ctx->v3_head_run, &ctx->v3_unit_out, &ctx->v3_unit_excl, &ctx->v3_atoms, &ctx->v3_lsd_aux, &ctx->v3_bitmap};
+                      &ctx->ent_a, &ctx->ent_b, &ctx->piece_n, &ctx->sorted_info, &ctx->v3_base64, &ctx->v3_head_run, &ctx->v3_unit_out, &ctx->v3_unit_excl, &ctx->v3_atoms, &ctx->v3_lsd_aux, &ctx->v3_bitmap};
     for (DevBuf *b : bufs) b->release();
     ctx->h_misc.release();
     ctx->h_result.release();

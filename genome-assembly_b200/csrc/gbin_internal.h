@@ -143,11 +143,12 @@ int skr_emit_buckets(const uint32_t *kmer_mmer, uint64_t n_kmers, uint64_t n_ids
                      uint32_t *mmer_codes, uint64_t *mmer_kmer_off, uint64_t *kmer_id_off, uint32_t *n_buckets_dev, cudaStream_t st);
 
 // ---- bin3.cu (pipeline v3: sort by reference, one warp per unit, table written once at its final place)
-int radix_sort_entries(void *a, void *b, uint64_t n, int key_bits, void *scratch, bool *result_in_b, int *passes_out, KernelProf *prof,
-                       cudaStream_t st);
-int v3_make_entries(const void *skr, uint64_t n_rec, const KeyLayout &kl, uint64_t *ent, uint8_t *piece_n, unsigned long long *n_real_dev,
+// slot_info (per slot) is gathered into sorted_info (per sorted entry) by the last pass
+int radix_sort_entries(void *a, void *b, uint64_t n, int key_bits, void *scratch, bool *result_in_b, int *passes_out, const uint16_t *slot_info,
+                       uint16_t *sorted_info, KernelProf *prof, cudaStream_t st);
+int v3_make_entries(const void *skr, uint64_t n_rec, const KeyLayout &kl, uint64_t *ent, uint16_t *piece_info, unsigned long long *n_real_dev,
                     cudaStream_t st);
-int v3_plan_runs(const uint64_t *ent, const uint8_t *piece_n, uint64_t n_ent, uint32_t *inst_prefix, uint64_t *both64, uint32_t *run_start,
+int v3_plan_runs(const uint64_t *ent, const uint16_t *sorted_info, uint64_t n_ent, uint32_t *inst_prefix, uint64_t *both64, uint32_t *run_start,
                  uint64_t *scratch64, uint32_t *n_inst_dev, uint32_t *n_runs_dev, cudaStream_t st);
 uint64_t v3_max_units(uint64_t n_inst, uint64_t n_runs, int cap);
 size_t v3_unit_bytes();
@@ -158,7 +159,7 @@ struct V3Counters {  // mirror of G3Counters in bin3.cu
     unsigned int overflow, n_units, n_spans, pad;
     unsigned long long lsd_kmers, lsd_ids;
 };
-int v3_plan_units(const void *skr, const uint64_t *ent, const KeyLayout &kl, int cap, const uint32_t *inst_prefix, const uint32_t *run_start, uint64_t n_runs,
+int v3_plan_units(const uint16_t *sorted_info, const uint64_t *ent, const KeyLayout &kl, int cap, const uint32_t *inst_prefix, const uint32_t *run_start, uint64_t n_runs,
                   uint64_t *nunits64, uint64_t *base64, uint32_t *atom3, uint32_t *spanlen, uint32_t *head_run, void *scratch, void *units, uint64_t max_units,
                   void *gc_dev, uint32_t n_chunks, uint32_t *chunk_bounds, cudaStream_t st);
 struct V3Out {
@@ -199,7 +200,7 @@ int v3_lsd_finish(const KeyLayout &kl, uint64_t n, void *rec_a, void *rec_b, voi
                   KernelProf *prof, cudaStream_t st);
 uint32_t v3_pass_tiles(uint64_t n_ent);
 uint32_t v3_pass_tile_entries();
-int v3_pass_tile_sums(const uint64_t *ent, const uint8_t *piece_n, uint64_t n_ent, unsigned long long *sums_dev, cudaStream_t st);
+int v3_pass_tile_sums(const uint16_t *sorted_info, uint64_t n_ent, unsigned long long *sums_dev, cudaStream_t st);
 int v3_pass_bounds(const uint64_t *ent, uint64_t n_ent, int mshift, unsigned long long *bounds_dev, uint32_t n_bounds, cudaStream_t st);
 size_t v3_mmer_bitmap_bytes(int M);
 int v3_count_mmers(const void *skr, int skr_words, uint64_t n_rec, int M, uint32_t *bitmap, unsigned long long *count_dev, cudaStream_t st);

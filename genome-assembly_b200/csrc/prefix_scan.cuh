@@ -106,6 +106,44 @@ __global__ void __launch_bounds__(SCAN_THREADS)
     }
 }
 
+// Same as scan_apply_kernel, but the exclusive prefix of element j is handed to out(j, prefix) instead of being stored in an array
+// (the consumer can write several derived arrays in one go and the prefix array itself never exists).
+template <typename TOut, typename InOp, typename OutOp>
+__global__ void __launch_bounds__(SCAN_THREADS)
+    scan_apply_to_kernel(InOp in, OutOp out, const TOut *__restrict__ block_offsets, uint64_t n, TOut *__restrict__ total_out) {
+    __shared__ TOut ex[SCAN_TILE + SCAN_TILE / 16 + 1];
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        const uint32_t p = (uint32_t)i * SCAN_THREADS + threadIdx.x;
+        const uint64_t j = base + p;
+        ex[scan_pad<TOut>(p)] = j < n ? (TOut)in(j) : TOut(0);
+    }
+    __syncthreads();
+    TOut v[SCAN_ITEMS];
+    TOut s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        v[i] = ex[scan_pad<TOut>(threadIdx.x * SCAN_ITEMS + i)];
+        s += v[i];
+    }
+    TOut total;
+    TOut run = block_exclusive_scan<TOut>(s, &total) + (block_offsets ? block_offsets[blockIdx.x] : TOut(0));
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        ex[scan_pad<TOut>(threadIdx.x * SCAN_ITEMS + i)] = run;
+        run += v[i];
+    }
+    if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) *total_out = run;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        const uint32_t p = (uint32_t)i * SCAN_THREADS + threadIdx.x;
+        const uint64_t j = base + p;
+        if (j < n) out(j, ex[scan_pad<TOut>(p)]);
+    }
+}
+
 template <typename T>
 struct PtrIn {
     const T *p;
@@ -140,6 +178,26 @@ int exclusive_scan(InOp in, TOut *out, uint64_t n, TOut *scratch, TOut *total_ou
     launches++;
     launches += exclusive_scan<TOut, PtrIn<TOut>>(PtrIn<TOut>{scratch}, scratch, blocks, scratch + blocks, nullptr, st);
     scan_apply_kernel<TOut, InOp><<<(unsigned)blocks, SCAN_THREADS, 0, st>>>(in, out, scratch, n, total_out);
+    return launches + 1;
+}
+
+// exclusive_scan whose result goes to out(j, prefix).  scratch as for exclusive_scan.
+template <typename TOut, typename InOp, typename OutOp>
+int exclusive_scan_to(InOp in, OutOp out, uint64_t n, TOut *scratch, TOut *total_out, cudaStream_t st) {
+    if (n == 0) {
+        if (total_out) cudaMemsetAsync(total_out, 0, sizeof(TOut), st);
+        return 0;
+    }
+    const uint64_t blocks = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (blocks == 1) {
+        scan_apply_to_kernel<TOut, InOp, OutOp><<<1, SCAN_THREADS, 0, st>>>(in, out, nullptr, n, total_out);
+        return 1;
+    }
+    int launches = 0;
+    scan_reduce_kernel<TOut, InOp><<<(unsigned)blocks, SCAN_THREADS, 0, st>>>(in, scratch, n);
+    launches++;
+    launches += exclusive_scan<TOut, PtrIn<TOut>>(PtrIn<TOut>{scratch}, scratch, blocks, scratch + blocks, nullptr, st);
+    scan_apply_to_kernel<TOut, InOp, OutOp><<<(unsigned)blocks, SCAN_THREADS, 0, st>>>(in, out, scratch, n, total_out);
     return launches + 1;
 }
 

@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(RS_THREADS)
 template <int NU64>
 __global__ void __launch_bounds__(RS_THREADS)
     radix_scatter_kernel(const Blob<NU64> *__restrict__ in, Blob<NU64> *__restrict__ out, uint64_t n, DigitSel sel,
-                         const uint32_t *__restrict__ tile_off, uint32_t ntiles, char *const *__restrict__ dst_tab, uint64_t *__restrict__ side) {
+                         const uint32_t *__restrict__ tile_off, uint32_t ntiles, char *const *__restrict__ dst_tab, uint64_t *__restrict__ side,
+                         const uint16_t *__restrict__ slot_info = nullptr, uint16_t *__restrict__ sorted_info = nullptr) {
     constexpr int ITEMS = TileShape<NU64>::ITEMS, TILE = TileShape<NU64>::TILE;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     Blob<NU64> *exch = reinterpret_cast<Blob<NU64> *>(smem_raw);
@@ -204,6 +205,9 @@ __global__ void __launch_bounds__(RS_THREADS)
         // whole record for the planning scans that follow
         if constexpr (NU64 >= 2) {
             if (side) side[pos] = (r.w[0] & 0xffffffff00000000ull) | (r.w[1] & 0xffull);
+        } else {
+            // last pass of the entry sort: what the planner needs of every piece (windows, smallest d), in sorted order
+            if (sorted_info) sorted_info[pos] = slot_info[(uint32_t)r.w[0]];
         }
     }
 }
@@ -324,7 +328,7 @@ size_t radix_scratch_bytes(uint64_t n) {
 
 template <int NU64>
 static int one_pass(const void *in_v, void *out_v, uint64_t n, const DigitSel &sel, uint32_t *scratch, KernelProf *prof, cudaStream_t st,
-                    const XchgPlan *xp = nullptr, uint64_t *side = nullptr) {
+                    const XchgPlan *xp = nullptr, uint64_t *side = nullptr, const uint16_t *slot_info = nullptr, uint16_t *sorted_info = nullptr) {
     const Blob<NU64> *in = static_cast<const Blob<NU64> *>(in_v);
     Blob<NU64> *out = static_cast<Blob<NU64> *>(out_v);
     constexpr int TILE = TileShape<NU64>::TILE;
@@ -355,7 +359,7 @@ static int one_pass(const void *in_v, void *out_v, uint64_t n, const DigitSel &s
         xchg_counts_kernel<<<1, 32, 0, st>>>(tile_hist, nt, n, *xp, (uint32_t)sizeof(Blob<NU64>));
         launches++;
     }
-    radix_scatter_kernel<NU64><<<nt, RS_THREADS, smem, st>>>(in, out, n, sel, tile_hist, nt, xp ? xp->dst_tab : nullptr, side);
+    radix_scatter_kernel<NU64><<<nt, RS_THREADS, smem, st>>>(in, out, n, sel, tile_hist, nt, xp ? xp->dst_tab : nullptr, side, slot_info, sorted_info);
     if (prof) prof->end(on, 1, st);
     if (xp) {
         xchg_done_kernel<<<1, 32, 0, st>>>(*xp);
@@ -365,9 +369,10 @@ static int one_pass(const void *in_v, void *out_v, uint64_t n, const DigitSel &s
 }
 
 static int one_pass_any(int nu64, const void *in, void *out, uint64_t n, const DigitSel &sel, uint32_t *scratch, KernelProf *prof,
-                        cudaStream_t st, const XchgPlan *xp = nullptr, uint64_t *side = nullptr) {
+                        cudaStream_t st, const XchgPlan *xp = nullptr, uint64_t *side = nullptr, const uint16_t *slot_info = nullptr,
+                        uint16_t *sorted_info = nullptr) {
     switch (nu64) {
-        case 1: return one_pass<1>(in, out, n, sel, scratch, prof, st, xp, side);
+        case 1: return one_pass<1>(in, out, n, sel, scratch, prof, st, xp, side, slot_info, sorted_info);
         case 2: return one_pass<2>(in, out, n, sel, scratch, prof, st, xp, side);
         case 3: return one_pass<3>(in, out, n, sel, scratch, prof, st, xp, side);
         case 4: return one_pass<4>(in, out, n, sel, scratch, prof, st, xp, side);
@@ -439,15 +444,17 @@ int radix_sort_skr_by_mmer(void *a, void *b, uint64_t n, int skr_words, int M, v
 
 // v3: 8-byte entries {key << 32 | slot} sorted on the low `key_bits` bits of the key (stable, so entries of one key keep
 // their order: slots ascend with arrival).
-int radix_sort_entries(void *a, void *b, uint64_t n, int key_bits, void *scratch, bool *result_in_b, int *passes_out, KernelProf *prof,
-                       cudaStream_t st) {
+int radix_sort_entries(void *a, void *b, uint64_t n, int key_bits, void *scratch, bool *result_in_b, int *passes_out, const uint16_t *slot_info,
+                       uint16_t *sorted_info, KernelProf *prof, cudaStream_t st) {
     *result_in_b = false;
     *passes_out = 0;
     if (n == 0) return 0;
     int launches = 0, passes = 0;
     void *src = a, *dst = b;
     for (int s = 0; s < key_bits; s += 8) {
-        launches += one_pass_any(1, src, dst, n, DigitSel{0, 32 + s, 0}, static_cast<uint32_t *>(scratch), prof, st);
+        const bool last = s + 8 >= key_bits;
+        launches += one_pass_any(1, src, dst, n, DigitSel{0, 32 + s, 0}, static_cast<uint32_t *>(scratch), prof, st, nullptr, nullptr, last ? slot_info : nullptr,
+                                 last ? sorted_info : nullptr);
         void *t = src;
         src = dst;
         dst = t;

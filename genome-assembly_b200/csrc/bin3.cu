@@ -174,7 +174,7 @@ __global__ void v3_atoms_kernel(RunView3 rv, const uint64_t *__restrict__ ent, u
 constexpr uint64_t ATOM_ROUNDS = 1ull << 32;
 constexpr uint32_t SPAN_MEMBER = 0xfffffffeu;       // a further unit of a short span (merged by the warp of its first unit)
 constexpr uint32_t SPAN_MEMBER_LONG = 0xffffffffu;  // a unit of a long span (put in order by the global sort)
-constexpr uint32_t SPAN_SHORT_MAX = 8;              // units of a short span
+constexpr uint32_t SPAN_SHORT_MAX = 17;             // units of a short span (an atom of up to 8 units' worth of instances gets 2 * 8 + 1 round units)
 __global__ void __launch_bounds__(128)
     v3_pack_kernel(const uint32_t *__restrict__ atom_c, const uint32_t *__restrict__ atom_e, const uint32_t *__restrict__ atom_mm, uint64_t n_runs, Plan3 pp,
                    uint64_t *__restrict__ nunits, uint32_t *__restrict__ spanlen) {
@@ -1276,12 +1276,13 @@ int v3_group_launch(const void *skr, const uint64_t *ent, const void *units, con
     static int uu = 0;  // GBIN_V3_U = 1|2|4: instances per lane in flight (experiments)
     if (!uu) {
         const char *e = getenv("GBIN_V3_U");
-        uu = e ? atoi(e) : G3_U;
-        if (uu != 1 && uu != 2 && uu != 4) uu = G3_U;
+        uu = e ? atoi(e) : 0;
+        if (uu != 1 && uu != 2 && uu != 4) uu = -1;
     }
+    const int u_sel = uu > 0 ? uu : (cap == 512 ? 2 : 4);  // more warps per SM at 512: less need for instruction-level parallelism, smaller code
 #define G3_LAUNCH(PW_, KW_, CAP_) \
-    (uu == 1 ? launch(group3_kernel<PW_, KW_, CAP_, WARPS, 1>, finalize3_kernel<KW_>) \
-             : (uu == 2 ? launch(group3_kernel<PW_, KW_, CAP_, WARPS, 2>, finalize3_kernel<KW_>) : launch(group3_kernel<PW_, KW_, CAP_, WARPS, 4>, finalize3_kernel<KW_>)))
+    (u_sel == 1 ? launch(group3_kernel<PW_, KW_, CAP_, WARPS, 1>, finalize3_kernel<KW_>) \
+             : (u_sel == 2 ? launch(group3_kernel<PW_, KW_, CAP_, WARPS, 2>, finalize3_kernel<KW_>) : launch(group3_kernel<PW_, KW_, CAP_, WARPS, 4>, finalize3_kernel<KW_>)))
     if (KW == 1) {
         if (cap == 512) G3_LAUNCH(2, 1, 512);
         else G3_LAUNCH(2, 1, 1024);

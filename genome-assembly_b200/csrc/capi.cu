@@ -599,7 +599,7 @@ int v3_choose_layout(gbin_ctx *ctx, const void *skr, uint64_t n_skr, cudaStream_
     const double buckets = hm->n_real_entries ? (double)hm->n_real_entries : 1.0;
     const double mean_inst = (double)n_skr / buckets * ((K - M + 2) / 2.0);  // a record holds about (K-M+2)/2 windows
     int nc = 1, h = 0;
-    if (mean_inst > ctx->v3_cap / 3.0) {
+    if (mean_inst > ctx->v3_cap / 2.5) {
         nc = 2;
         double per = mean_inst / 2.0;
         while (per > ctx->v3_cap / 8.0 && h < 15) {
@@ -1039,7 +1039,8 @@ int gbin_create(const gbin_config *cfg, gbin_ctx **out) {
         const long long v = atoll(e);
         if (v >= 1000) ctx->v3_pass_max = (uint64_t)v;
     }
-    ctx->v3_cap = 1024;
+    // 128-bit k-mer codes double the shared memory of a unit: units of 512 instances keep the warps per SM up
+    ctx->v3_cap = ctx->KW == 2 ? 512 : 1024;
     if (const char *e = getenv("GBIN_V3_CAP")) ctx->v3_cap = atoi(e) == 512 ? 512 : 1024;
     ctx->last_pipeline = 0;
     ctx->fallbacks = 0;

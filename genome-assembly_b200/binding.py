@@ -64,7 +64,7 @@ EXPORTS = [
     "gbin_strerror", "gbin_last_error", "gbin_version", "gbin_create", "gbin_destroy", "gbin_get_config",
     "gbin_bin_reads_host", "gbin_table_clone", "gbin_table_free", "gbin_pinned_alloc", "gbin_pinned_free",
     "gbin_bin_reads_device", "gbin_table_to_host", "gbin_table_to_pinned", "gbin_get_timings", "gbin_record_bytes",
-    "gbin_set_kernel_profiling", "gbin_get_kernel_profile", "gbin_kernel_kind_name", "gbin_max_read_len", "gbin_table_digest", "gbin_set_pipeline", "gbin_set_tuning", "gbin_get_pipeline_info", "gbin_get_run_stats",
+    "gbin_set_kernel_profiling", "gbin_get_kernel_profile", "gbin_kernel_kind_name", "gbin_max_read_len", "gbin_multi_create", "gbin_multi_destroy", "gbin_multi_devices", "gbin_multi_context", "gbin_multi_last_error", "gbin_multi_bin_reads_host", "gbin_table_digest", "gbin_set_pipeline", "gbin_set_tuning", "gbin_get_pipeline_info", "gbin_get_run_stats",
     "gbin_count_instances_device", "gbin_scan_reads_device", "gbin_partition_records_device",
     "gbin_group_records_device", "gbin_owner_of", "gbin_xchg_create", "gbin_xchg_attach", "gbin_xchg_exchange_skr", "gbin_xchg_destroy", "gbin_skr_record_bytes", "gbin_scan_skr_device", "gbin_partition_skr_device", "gbin_group_skr_device",
     "gbin_split_reads_device", "gbin_copy_to_host", "gbin_bin_file_host", "gbin_read_file_fgets", "gbin_table_dump", "gbin_table_dump_reference_format", "gbin_table_dump_expanded_format",

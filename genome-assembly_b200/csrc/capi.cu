@@ -6,7 +6,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gbin.h"
@@ -1790,6 +1794,255 @@ int gbin_group_records_device(gbin_ctx *ctx, void *d_records, uint64_t n, const 
     CU(cudaEventRecord(ctx->ev[4], st));
     CU(cudaStreamSynchronize(st));
     finish_timings(ctx, launches, false);
+    return GBIN_OK;
+}
+
+
+// ---------------------------------------------------------------- several GPUs behind one C call (one process, one host thread per GPU)
+
+struct gbin_multi {
+    int n = 0;
+    std::vector<gbin_ctx *> ctx;
+    std::vector<int> dev;
+    uint64_t xchg_cap = 0;
+    char err[512] = {0};
+    // a reusable barrier for the worker threads of one call
+    std::mutex mu;
+    std::condition_variable cv;
+    int waiting = 0, generation = 0;
+    void barrier() {
+        std::unique_lock<std::mutex> lk(mu);
+        const int gen = generation;
+        if (++waiting == n) {
+            waiting = 0;
+            generation++;
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&] { return gen != generation; });
+        }
+    }
+};
+
+namespace {
+// Every context's exchange plan gets the peers' buffers by address: one process, peer access enabled, no IPC handles.
+int multi_attach_local(gbin_multi *m, int g) {
+    gbin_ctx *ctx = m->ctx[g];
+    auto &x = ctx->xg;
+    memset(&x.plan, 0, sizeof x.plan);
+    x.plan.rank = x.rank;
+    x.plan.world = x.world;
+    x.plan.dst_tab = x.dst_tab;
+    x.plan.result = x.result;
+    for (int r = 0; r < m->n; r++) {
+        x.plan.cap[r] = m->ctx[r]->xg.cap;
+        x.plan.peer_recv[r] = m->ctx[r]->xg.recv;
+        x.plan.peer_sh[r] = m->ctx[r]->xg.sh;
+    }
+    x.attached = true;
+    return GBIN_OK;
+}
+}  // namespace
+
+int gbin_multi_create(const gbin_config *cfg, const int *devices, int n_devices, gbin_multi **out) {
+    if (!cfg || !out || n_devices < 1 || n_devices > XCHG_MAX_WORLD) return GBIN_E_INVALID_ARG;
+    *out = nullptr;
+    gbin_multi *m = new (std::nothrow) gbin_multi();
+    if (!m) return GBIN_E_NOMEM;
+    m->n = n_devices;
+    for (int g = 0; g < n_devices; g++) {
+        gbin_config c = *cfg;
+        c.device = devices ? devices[g] : g;
+        gbin_ctx *ctx = nullptr;
+        const int rc = gbin_create(&c, &ctx);
+        if (rc) {
+            gbin_multi_destroy(m);
+            return rc;
+        }
+        m->ctx.push_back(ctx);
+        m->dev.push_back(c.device);
+    }
+    for (int a = 0; a < n_devices; a++) {  // peer access both ways between every pair (the exchange stores into the owners' buffers)
+        cudaSetDevice(m->dev[a]);
+        for (int b = 0; b < n_devices; b++) {
+            if (a == b) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, m->dev[a], m->dev[b]);
+            if (!can) {
+                gbin_multi_destroy(m);
+                return GBIN_E_CUDA;
+            }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(m->dev[b], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                (void)cudaGetLastError();
+                gbin_multi_destroy(m);
+                return GBIN_E_CUDA;
+            }
+            (void)cudaGetLastError();
+        }
+    }
+    *out = m;
+    return GBIN_OK;
+}
+
+void gbin_multi_destroy(gbin_multi *m) {
+    if (!m) return;
+    for (gbin_ctx *c : m->ctx) {  // nobody stores into a peer's buffer any more: first let every device finish, then free
+        cudaSetDevice(c->cfg.device);
+        cudaDeviceSynchronize();
+    }
+    for (gbin_ctx *c : m->ctx) gbin_destroy(c);
+    delete m;
+}
+
+const char *gbin_multi_last_error(const gbin_multi *m) { return m ? m->err : ""; }
+int gbin_multi_devices(const gbin_multi *m) { return m ? m->n : 0; }
+gbin_ctx *gbin_multi_context(gbin_multi *m, int i) { return (m && i >= 0 && i < m->n) ? m->ctx[i] : nullptr; }
+
+// reads: HOST memory (pinned for the full PCIe rate).  GPU g takes the contiguous read range [g*n/G, (g+1)*n/G), runs the scan,
+// sends every record to the owner of its m-mer bucket (peer stores over NVLink), groups what it received.  tables_out[g] is GPU
+// g's part of the table (its own m-mer buckets) in that context's pinned arena (ctx-owned, valid until the next call).
+int gbin_multi_bin_reads_host(gbin_multi *m, const gbin_reads *reads, gbin_table *tables_out) {
+    if (!m || !reads || !tables_out) return GBIN_E_INVALID_ARG;
+    const int G = m->n;
+    const uint64_t n = reads->n_reads;
+    if (n && !reads->data) return GBIN_E_INVALID_ARG;
+    if (reads->starts && !reads->lens) return GBIN_E_INVALID_ARG;
+    std::vector<int> rcs(G, GBIN_OK);
+    std::vector<uint64_t> n_skr(G, 0);
+    std::vector<std::string> errs(G);
+    m->err[0] = 0;
+    auto work = [&](int g) {
+        gbin_ctx *ctx = m->ctx[g];
+        int &rc = rcs[g];
+        auto failed = [&](int code, const char *what) {
+            rc = code;
+            errs[g] = std::string(what) + ": " + gbin_last_error(ctx);
+        };
+        cudaSetDevice(ctx->cfg.device);
+        cudaStream_t st = ctx->stream;
+        const uint64_t lo = n * g / G, hi = n * (g + 1) / G, cnt = hi - lo;
+        // ---- this GPU's shard to the device
+        gbin_reads d = *reads;
+        d.n_reads = cnt;
+        d.read_ids = nullptr;
+        cudaError_t e = cudaSuccess;
+        if (cnt) {
+            if (!reads->starts) {
+                const uint64_t b0 = lo * reads->stride, b1 = (hi - 1) * reads->stride + reads->read_len;
+                e = ctx->d_reads.ensure(b1 - b0 + 64);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_reads.p, reads->data + b0, b1 - b0, cudaMemcpyHostToDevice, st);
+                d.data = ctx->d_reads.as<char>();
+                d.data_bytes = b1 - b0;
+            } else {
+                uint64_t b0 = ~0ull, b1 = 0;
+                for (uint64_t i = lo; i < hi; i++) {
+                    if (reads->starts[i] < b0) b0 = reads->starts[i];
+                    if (reads->starts[i] + reads->lens[i] > b1) b1 = reads->starts[i] + reads->lens[i];
+                }
+                if (b1 < b0) b0 = b1 = 0;
+                std::vector<uint64_t> st_rel(cnt);
+                for (uint64_t i = 0; i < cnt; i++) st_rel[i] = reads->starts[lo + i] - b0;
+                e = ctx->d_reads.ensure(b1 - b0 + 64);
+                if (e == cudaSuccess) e = ctx->d_starts.ensure(cnt * sizeof(uint64_t));
+                if (e == cudaSuccess) e = ctx->d_lens.ensure(cnt * sizeof(uint32_t));
+                if (e == cudaSuccess && b1 > b0) e = cudaMemcpyAsync(ctx->d_reads.p, reads->data + b0, b1 - b0, cudaMemcpyHostToDevice, st);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_starts.p, st_rel.data(), cnt * sizeof(uint64_t), cudaMemcpyHostToDevice, st);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_lens.p, reads->lens + lo, cnt * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // st_rel goes out of scope
+                d.data = ctx->d_reads.as<char>();
+                d.data_bytes = b1 - b0;
+                d.starts = ctx->d_starts.as<uint64_t>();
+                d.lens = ctx->d_lens.as<uint32_t>();
+                d.max_read_len = 0;
+            }
+        }
+        const int32_t *d_ids = nullptr;
+        if (e == cudaSuccess && reads->read_ids && n) {  // ids are looked up by global arrival index: every GPU holds the whole array
+            e = ctx->d_ids.ensure(n * sizeof(int32_t));
+            if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_ids.p, reads->read_ids, n * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+            d_ids = ctx->d_ids.as<int32_t>();
+        }
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            failed(e == cudaErrorMemoryAllocation ? GBIN_E_NOMEM : GBIN_E_CUDA, "copying the shard to the device");
+        }
+        // ---- scan into this context's record buffer (sized by an estimate, regrown to the exact need when short)
+        uint64_t ninst = 0, cap = 0;
+        if (!rc && cnt) {
+            uint64_t est = 0;
+            rc = gbin_count_instances_device(ctx, &d, st, &est);
+            cap = est / 6 + cnt + 1024;
+            const size_t rb = gbin_skr_record_bytes(ctx);
+            for (int attempt = 0; !rc && attempt < 2; attempt++) {
+                if (ctx->skr_a.ensure((cap + 1) * rb) != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    failed(GBIN_E_NOMEM, "record buffer");
+                    break;
+                }
+                const int r2 = gbin_scan_skr_device(ctx, &d, (uint32_t)lo, ctx->skr_a.p, cap, st, &n_skr[g], &ninst);
+                if (r2 == GBIN_E_INVALID_ARG && attempt == 0 && cap < est) {
+                    cap = est;  // more segments than estimated
+                    continue;
+                }
+                if (r2) failed(r2, "scan");
+                break;
+            }
+        } else if (!rc) {
+            n_skr[g] = 0;
+        }
+        m->barrier();  // ---- every rank knows every rank's record count (and whether somebody failed)
+        bool any = false;
+        uint64_t mx = 0;
+        for (int r = 0; r < G; r++) {
+            any = any || rcs[r] != GBIN_OK;
+            if (n_skr[r] > mx) mx = n_skr[r];
+        }
+        if (any) return;
+        void *d_recv = nullptr;
+        uint64_t n_recv = 0;
+        const uint64_t want = mx + mx / 3 + 65536;
+        if (G == 1) {  // nothing to exchange
+            d_recv = ctx->skr_a.p;
+            n_recv = n_skr[0];
+        } else {
+        if (!ctx->xg.created || ctx->xg.cap < want || ctx->xg.world != (uint32_t)G) {
+            char blob[GBIN_XCHG_HANDLE_BYTES];
+            const int r2 = gbin_xchg_create(ctx, (uint32_t)g, (uint32_t)G, want + want / 8, blob);
+            if (r2) failed(r2, "exchange buffers");
+        }
+        m->barrier();  // ---- all buffers exist
+        for (int r = 0; r < G; r++) any = any || rcs[r] != GBIN_OK;
+        if (any) return;
+        multi_attach_local(m, g);
+        m->barrier();
+        // ---- owner exchange (collective)
+        const int rx = gbin_xchg_exchange_skr(ctx, ctx->skr_a.p, n_skr[g], st, &d_recv, &n_recv, nullptr);
+        if (rx) {
+            failed(rx, "owner exchange");
+            return;
+        }
+        }
+        // ---- grouping of this GPU's buckets
+        int r2 = GBIN_OK;
+        gbin_table dev;
+        int fell = 0;
+        r2 = gbin_group_skr_device(ctx, d_recv, n_recv, d_ids, reads->id_base, st, &dev, &fell);
+        if (r2) {
+            failed(r2, "grouping");
+            return;
+        }
+        r2 = gbin_table_to_pinned(ctx, &dev, st, &tables_out[g]);
+        if (r2) failed(r2, "table to host");
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < G; g++) th.emplace_back(work, g);
+    work(0);
+    for (auto &t : th) t.join();
+    for (int g = 0; g < G; g++)
+        if (rcs[g]) {
+            snprintf(m->err, sizeof m->err, "GPU %d: %s", m->dev[g], errs[g].c_str());
+            return rcs[g];
+        }
     return GBIN_OK;
 }
 

@@ -245,6 +245,20 @@ int gbin_xchg_exchange_skr(gbin_ctx *ctx, const void *d_skr, uint64_t n, void *s
                            uint64_t *sent_counts);
 void gbin_xchg_destroy(gbin_ctx *ctx);
 
+/* ---- several GPUs of one node behind one C call (one process, one host thread per GPU; no Python, no MPI, no NCCL) ----
+ * gbin_multi_create makes one context per device (devices == NULL: 0 .. n_devices-1) and enables peer access between them.
+ * gbin_multi_bin_reads_host: reads in HOST memory; GPU g takes the contiguous read range [g*n/G, (g+1)*n/G), runs the scan, sends
+ * every record to the owner of its m-mer bucket (gbin_owner_of; peer stores over NVLink, gbin_xchg_* with the peers' buffers passed
+ * by address), groups what it received.  tables_out[g] (host arrays in context g's pinned arena, valid until the next call) is the
+ * part of the table GPU g owns: disjoint m-mer buckets, together the table of a single-GPU run (their digests add up to its digest). */
+typedef struct gbin_multi gbin_multi;
+int gbin_multi_create(const gbin_config *cfg, const int *devices, int n_devices, gbin_multi **out);
+void gbin_multi_destroy(gbin_multi *m);
+int gbin_multi_devices(const gbin_multi *m);
+gbin_ctx *gbin_multi_context(gbin_multi *m, int i);
+const char *gbin_multi_last_error(const gbin_multi *m);
+int gbin_multi_bin_reads_host(gbin_multi *m, const gbin_reads *reads, gbin_table *tables_out);
+
 /* ---- main's read loop on the device (binning.c:1154-1166) ----
  * Splits a file image in DEVICE memory into reads exactly as `while (fgets(read, read_length_define, file)) { read[--len] = 0; ... }`
  * does: at most read_length_define-1 bytes per read, stopping after a newline, last byte dropped, one read (and id) per fgets

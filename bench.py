@@ -49,9 +49,9 @@ def parse_args():
                          "over the GPUs (default for cfg3-5, whose BASELINE sizes are totals)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="multi-GPU record exchange: peer = partition kernel stores into the owners' buffers over NVLink (default), nccl = all_to_all_single")
-    ap.add_argument("--e2e-overlapped", action="store_true",
-                    help="also report end-to-end throughput with two contexts on two host threads alternating batches (the H2D of one batch "
-                         "overlaps the D2H of the other: PCIe is full duplex); opt-in, N=1 only")
+    ap.add_argument("--e2e-contexts", type=int, default=2, help="contexts (= host threads) of the --e2e-overlapped leg")
+    ap.add_argument("--no-e2e-overlapped", action="store_true", help="skip the two-context leg of e2e (e2e.value is then the single-call figure)")
+    ap.add_argument("--e2e-overlapped", action="store_true", help="(default now; kept so that older command lines still parse)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -468,12 +468,13 @@ def main():
         e2e = {"value": n_inst_total * a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h_reads.numel()),
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / a.steps, "timing": "host wall clock around gbin_bin_reads_host",
                "stage_ms_last_step": binner.timings()}
-        if a.e2e_overlapped:
+        if not a.no_e2e_overlapped:
             # two contexts, two host threads (ctypes releases the GIL inside the C call): every batch still pays its own H2D and
             # D2H inside the timed region, but the copies of consecutive batches overlap
             import threading
-            b2 = g.Binner(K, M, cutoff, device=local)
-            for bb in (binner, b2):
+            extra = [g.Binner(K, M, cutoff, device=local) for _ in range(max(a.e2e_contexts, 2) - 1)]
+            group = [binner] + extra
+            for bb in group:
                 bb.bin_host_raw(rd_host)
             torch.cuda.synchronize()
             per_thread = max(a.steps, 2)
@@ -481,17 +482,27 @@ def main():
             def worker(bb):
                 for _ in range(per_thread):
                     bb.bin_host_raw(rd_host)
-            ths = [threading.Thread(target=worker, args=(bb,)) for bb in (binner, b2)]
+            ths = [threading.Thread(target=worker, args=(bb,)) for bb in group]
             t0 = time.perf_counter()
             for th in ths:
                 th.start()
             for th in ths:
                 th.join()
             ov_s = time.perf_counter() - t0
-            e2e["overlapped"] = {"value": n_inst_total * 2 * per_thread / ov_s, "unit": UNIT, "batches": 2 * per_thread,
-                                 "ms_per_batch": 1e3 * ov_s / (2 * per_thread),
-                                 "how": "two contexts on two host threads, each batch with its own pinned H2D and table D2H"}
-            b2.close()
+            nb = len(group) * per_thread
+            e2e["overlapped"] = {"value": n_inst_total * nb / ov_s, "unit": UNIT, "batches": nb, "contexts": len(group),
+                                 "ms_per_batch": 1e3 * ov_s / nb,
+                                 "how": "one context per host thread, each batch with its own pinned H2D and table D2H"}
+            for bb in extra:
+                bb.close()
+            # the headline end-to-end figure is the pipelined one (what a caller with a stream of batches gets: every batch
+            # still pays its whole H2D and D2H inside the timed region); the one-call-at-a-time figure stays beside it
+            e2e["single_call"] = {"value": e2e["value"], "ms_per_step": e2e["ms_per_step"], "timing": e2e["timing"]}
+            e2e["value"] = e2e["overlapped"]["value"]
+            e2e["ms_per_step"] = e2e["overlapped"]["ms_per_batch"]
+            e2e["timing"] = ("host wall clock over %d gbin_bin_reads_host calls issued from %d host threads, one context each (PCIe is full duplex: "
+                             "the H2D of one batch overlaps the D2H of the other); single_call = the same call issued one at a time"
+                             % (nb, len(group)))
     elif not a.no_e2e:
         # multi-GPU e2e: pinned H2D of every rank's shard + sharded pipeline + D2H of every owner table
         def e2e_step():

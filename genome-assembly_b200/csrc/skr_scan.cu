@@ -11,6 +11,7 @@
 // The output is therefore in arrival order (read-major, segment-minor) and deterministic — the
 // later stable sort by m-mer keeps arrival order per bucket.
 #include <cstdlib>
+#include <type_traits>
 
 #include "gbin_device.cuh"
 #include "gbin_internal.h"
@@ -141,6 +142,193 @@ __global__ void __launch_bounds__(SKR_WARPS * 32)
     if (ninst) atomicAdd(&counters[2], ninst);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Scan kernel B (reads of at most 32 * NJ m-mer positions, NJ <= 8): one lane per m-mer position.
+//
+// The hop chain of the kernel above spends one REDUX round trip per segment.  Here the leftmost arg-max A(i) of the
+// m-mer scores over [i, i + C) is computed for ALL windows of a read at once: every lane holds the keys
+// {w(p) << 9 | (255 - p) << 1 | is_rev(p)} of positions p = lane + 32 j in registers, and a sliding maximum of width C is
+// built from widths 1, 2, 4, ... by shuffles (max is idempotent, so the last step may overlap: width C = max of two
+// width-2^b windows C - 2^b apart).  The inverted position below the score makes the maximum the LEFTMOST best position
+// (binning.c:972 replaces the signature only on a strictly larger score).  A(i) goes to shared memory as one byte per
+// window.  The chain i -> A(i) + 1 (binning.c:922: a signature is kept until the window start passes it) is then walked
+// by ONE LANE PER READ for the rpw reads of the tile in parallel, first to count the tile's segments (the count feeds the
+// chained scan over tiles), then to list them.  Records are built one lane per segment (header + payload words from the
+// packed read) and written straight to their final place with 16-byte stores: neighbouring lanes write neighbouring
+// records, so there is no staging copy.
+template <int NJ, typename KeyT>
+__device__ __forceinline__ void s2_shift_max(KeyT (&x)[NJ], uint32_t s, uint32_t lane) {
+    KeyT t[NJ + 1];
+#pragma unroll
+    for (int j = 0; j < NJ; j++) t[j] = __shfl_sync(0xffffffffu, x[j], (lane + s) & 31u);
+    t[NJ] = 0;
+    const bool same = lane + s < 32u;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+        const KeyT y = same ? t[j] : t[j + 1];
+        x[j] = x[j] > y ? x[j] : y;
+    }
+}
+
+__host__ __device__ inline uint32_t s2_pk_words(uint32_t max_len) { return scan_pk_words(max_len) | 1u; }  // odd: reads fall into different banks
+__host__ __device__ inline uint32_t s2_sig_bytes(int nj) { return 32u * (uint32_t)nj + 4u; }                 // odd number of words
+__host__ __device__ inline uint32_t s2_warp_smem(uint32_t max_len, int nj, uint32_t rpw, uint32_t seg_cap) {
+    return (4u * s2_pk_words(max_len) * rpw + s2_sig_bytes(nj) * rpw + 4u * seg_cap + 15u) & ~15u;
+}
+
+template <int PW, int NJ, typename KeyT>
+__global__ void __launch_bounds__(SKR_WARPS * 32)
+    skr_scan2_kernel(ReadsView rv, uint64_t read_begin, int K, int M, uint32_t arrival_base, uint32_t max_len, uint32_t rpw, uint32_t seg_cap,
+                     uint32_t ntiles, uint32_t *__restrict__ out, unsigned long long capacity, unsigned long long *__restrict__ tile_state,
+                     uint32_t *__restrict__ ticket, unsigned long long *__restrict__ counters /* [0] bad bases, [1] records, [2] instances */,
+                     uint32_t lkb_sleep) {
+    constexpr int NW = SkrLayout<PW>::WORDS;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t pkw = s2_pk_words(max_len), sgb = s2_sig_bytes(NJ);
+    uint8_t *wbase = smem + (size_t)warp * s2_warp_smem(max_len, NJ, rpw, seg_cap);
+    uint32_t *pk = reinterpret_cast<uint32_t *>(wbase);
+    uint32_t *segl = pk + pkw * rpw;
+    uint8_t *sig = reinterpret_cast<uint8_t *>(segl + seg_cap);
+    const uint32_t FULL = (1u << (2 * M)) - 1;
+    const uint32_t C = K - M + 1;
+    const uint32_t down = 32u - 2u * (uint32_t)M;
+    uint32_t nbad = 0;
+    unsigned long long ninst = 0;
+    const unsigned long long base0 = counters[1];  // records of earlier launches over the same batch (chunked host feed)
+
+    uint32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(ticket, 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    while (tile < ntiles) {
+        const uint64_t first = read_begin + (uint64_t)tile * rpw;
+        // ---- phase A, the warp over one read at a time: pack, score, sliding arg-max
+        uint32_t myW = 0;  // lane r: windows of read first + r
+        for (uint32_t rr = 0; rr < rpw; rr++) {
+            const uint64_t r = first + rr;
+            if (r >= rv.n_reads) break;
+            const uint32_t L = rv.len(r);
+            if (L < (uint32_t)K) continue;
+            const uint32_t W = L - K + 1;
+            if (lane == rr) myW = W;
+            uint32_t *pkr = pk + rr * pkw;
+            nbad += warp_pack_read(pkr, rv.data + rv.start(r), L, lane);
+            KeyT x[NJ];
+#pragma unroll
+            for (int j = 0; j < NJ; j++) {
+                const uint32_t p = lane + 32u * j;
+                x[j] = 0;
+                if (p + M <= L) {
+                    const uint32_t bit = 2 * p, wi = bit >> 5, sh = bit & 31;
+                    const uint32_t s = __funnelshift_l(pkr[wi + 1], pkr[wi], sh) >> down;
+                    const uint32_t c = FULL - s;
+                    const uint32_t lo = ((255u - p) << 1) | (c > s ? 1u : 0u);
+                    x[j] = ((KeyT)(c > s ? c : s) << 9) | lo;
+                }
+            }
+            uint32_t width = 1;
+            for (; 2 * width <= C; width *= 2) s2_shift_max<NJ, KeyT>(x, width, lane);
+            if (C > width) s2_shift_max<NJ, KeyT>(x, C - width, lane);
+            uint8_t *sg = sig + rr * sgb;
+#pragma unroll
+            for (int j = 0; j < NJ; j++) sg[lane + 32u * j] = (uint8_t)(255u - (((uint32_t)x[j] >> 1) & 255u));
+        }
+        __syncwarp();
+        ninst += myW;
+        // ---- phase B, one lane per read: count the segments of the chain i -> A(i) + 1
+        const uint8_t *sg = sig + lane * sgb;
+        uint32_t cnt = 0;
+        for (uint32_t i = 0; i < myW; cnt++) i = min((uint32_t)sg[i] + 1u, myW);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)lane >= d) incl += up;
+        }
+        const uint32_t off = incl - cnt, nseg = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 0) lkb_publish_aggregate(tile_state, tile, nseg);
+        const unsigned long long base = base0 + lkb_resolve_warp<1>(tile_state, tile, nseg, lane, lkb_sleep);
+        if (tile == ntiles - 1 && lane == 0) counters[1] = base + nseg;
+        if (base + nseg <= capacity) {  // past the capacity only the total is produced (the caller re-runs)
+            // ---- phase C: list the segments (seg_cap at a time), then one lane per segment builds and stores its record
+            for (uint32_t lo = 0; lo < nseg; lo += seg_cap) {
+                uint32_t g = off;
+                for (uint32_t i = 0; i < myW; g++) {
+                    const uint32_t sp = sg[i], nx = min(sp + 1u, myW);
+                    if (g - lo < seg_cap) segl[g - lo] = lane | (i << 8) | (sp << 16) | ((nx - i) << 24);  // g < lo wraps around: not stored
+                    i = nx;
+                }
+                __syncwarp();
+                const uint32_t cw = min(seg_cap, nseg - lo);
+                for (uint32_t e = lane; e < cw; e += 32) {
+                    const uint32_t info = segl[e];
+                    const uint32_t rr = info & 0xffu, st0 = (info >> 8) & 0xffu, sp = (info >> 16) & 0xffu, n = info >> 24;
+                    const uint32_t *pkr = pk + rr * pkw;
+                    uint32_t bit = 2 * sp, wi = bit >> 5, sh = bit & 31;
+                    const uint32_t s = __funnelshift_l(pkr[wi + 1], pkr[wi], sh) >> down;
+                    const uint32_t c = FULL - s;
+                    uint32_t w[NW];
+                    w[0] = arrival_base + (uint32_t)(first + rr);
+                    w[1] = c > s ? c : s;
+                    w[2] = n | ((c > s ? 1u : 0u) << 8) | ((sp - st0) << 16);
+                    w[3] = st0;
+                    bit = 2 * st0, wi = bit >> 5, sh = bit & 31;
+                    uint32_t prev = pkr[wi];
+#pragma unroll
+                    for (int jp = 0; jp < NW - 4; jp++) {
+                        const uint32_t nxw = pkr[wi + jp + 1];
+                        const uint32_t word = __funnelshift_l(nxw, prev, sh);
+                        prev = nxw;
+                        const int keep = 2 * (int)(K + n - 1) - 32 * jp;  // valid payload bits in this word
+                        w[4 + jp] = keep >= 32 ? word : (keep <= 0 ? 0u : (word & (0xffffffffu << (32 - keep))));
+                    }
+                    uint4 *dst = reinterpret_cast<uint4 *>(out + (base + lo + e) * NW);
+#pragma unroll
+                    for (int v = 0; v < NW / 4; v++) dst[v] = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
+                }
+                __syncwarp();
+            }
+        }
+        uint32_t next_tile = 0;
+        if (lane == 0) next_tile = atomicAdd(ticket, 1u);
+        tile = __shfl_sync(0xffffffffu, next_tile, 0);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        nbad += __shfl_xor_sync(0xffffffffu, nbad, d);
+        ninst += __shfl_xor_sync(0xffffffffu, ninst, d);
+    }
+    if (lane == 0 && nbad) atomicAdd(&counters[0], (unsigned long long)nbad);
+    if (lane == 0 && ninst) atomicAdd(&counters[2], ninst);
+}
+
+// Shape of kernel B for a batch, or nj = 0 when the reads are too long for it (more than 256 m-mer positions).
+struct Scan2Shape {
+    int nj;
+    bool wide;  // 64-bit keys: score, position and strand bit do not fit 32 bits (M > 11)
+    uint32_t rpw, seg_cap;
+};
+static Scan2Shape skr_scan2_shape(int K, int M, uint32_t max_len) {
+    Scan2Shape sh{0, false, 0, 0};
+    static int disabled = -1;
+    if (disabled < 0) disabled = getenv("GBIN_SCAN_HOPS") ? 1 : 0;  // experiments: keep the hop-chain kernel
+    if (disabled || max_len < (uint32_t)K) return sh;
+    const uint32_t npos = max_len - M + 1;
+    if (npos > 256u) return sh;
+    sh.nj = npos <= 96u ? 3 : (npos <= 160u ? 5 : 8);
+    sh.wide = 2 * M + 9 > 32;
+    const uint32_t W = max_len - K + 1;
+    uint32_t per_read = (uint32_t)(1.6 * (double)W / ((K - M + 2) / 2.0)) + 2;
+    if (per_read > W) per_read = W;
+    const uint32_t bytes_per_read = 4u * s2_pk_words(max_len) + s2_sig_bytes(sh.nj) + 4u * per_read;
+    uint32_t rpw = 8192u / bytes_per_read;
+    if (rpw > 32u) rpw = 32u;
+    if (rpw < 4u) rpw = 4u;
+    sh.rpw = rpw;
+    sh.seg_cap = (rpw * per_read + 3u) & ~3u;
+    return sh;
+}
+
 // Tile shape: rpw reads per warp and a staging area of seg_cap records, sized for 1.6x the expected number of segments
 // (a segment covers about (K-M+2)/2 windows) within a 6 KB budget per warp; tiles that exceed it are redone in place.
 static void skr_tile_shape(int K, int M, uint32_t max_len, uint32_t *rpw_out, uint32_t *seg_cap_out) {
@@ -175,6 +363,45 @@ int launch_skr_scan(const ReadsView &rv_all, uint64_t read_begin, uint64_t read_
     rv.n_reads = read_end;  // the kernel treats n_reads as the end of its read range
     const int PW = skr_payload_units(K);
     const int NW = 4 + 2 * PW;
+    static int lkb_sleep = -1;
+    if (lkb_sleep < 0) {
+        const char *e = getenv("GBIN_SCAN_SLEEP");
+        lkb_sleep = e ? atoi(e) : 800;
+    }
+    const Scan2Shape s2 = skr_scan2_shape(K, M, max_len);
+    if (s2.nj) {
+        const uint32_t ntiles = (uint32_t)((read_end - read_begin + s2.rpw - 1) / s2.rpw);
+        const size_t smem = (size_t)SKR_WARPS * s2_warp_smem(max_len, s2.nj, s2.rpw, s2.seg_cap);
+        cudaMemsetAsync(tile_state, 0, sizeof(unsigned long long) * ntiles, st);
+        cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
+        uint32_t blocks = (uint32_t)sm_count * 8;
+        if (blocks > (ntiles + SKR_WARPS - 1) / SKR_WARPS) blocks = (ntiles + SKR_WARPS - 1) / SKR_WARPS;
+        bool failed = false;
+        auto launch = [&](auto kern) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+                (void)cudaGetLastError();
+                failed = true;
+                return;
+            }
+            kern<<<blocks, SKR_WARPS * 32, smem, st>>>(rv, read_begin, K, M, arrival_base, max_len, s2.rpw, s2.seg_cap, ntiles, static_cast<uint32_t *>(out),
+                                                       capacity, tile_state, ticket, counters, (uint32_t)lkb_sleep);
+        };
+        auto pick_nj = [&](auto pw, auto key) {
+            constexpr int P = decltype(pw)::value;
+            using KeyT = decltype(key);
+            if (s2.nj == 3) launch(skr_scan2_kernel<P, 3, KeyT>);
+            else if (s2.nj == 5) launch(skr_scan2_kernel<P, 5, KeyT>);
+            else launch(skr_scan2_kernel<P, 8, KeyT>);
+        };
+        if (PW == 2) {
+            if (s2.wide) pick_nj(std::integral_constant<int, 2>{}, (unsigned long long)0);
+            else pick_nj(std::integral_constant<int, 2>{}, (uint32_t)0);
+        } else {
+            if (s2.wide) pick_nj(std::integral_constant<int, 4>{}, (unsigned long long)0);
+            else pick_nj(std::integral_constant<int, 4>{}, (uint32_t)0);
+        }
+        if (!failed) return 1;
+    }
     uint32_t rpw, seg_cap;
     skr_tile_shape(K, M, max_len, &rpw, &seg_cap);
     const uint32_t ntiles = (uint32_t)((read_end - read_begin + rpw - 1) / rpw);
@@ -195,11 +422,6 @@ int launch_skr_scan(const ReadsView &rv_all, uint64_t read_begin, uint64_t read_
     const bool packed = 2 * M + 1 + ((K - M + 1) <= 32 ? 5 : 6) <= 32;
     // ns between polls of a predecessor tile that has not published yet: the kernel is bound by instruction issue, so a
     // spinning warp takes issue slots from the warps that still compute (GBIN_SCAN_SLEEP overrides, for experiments)
-    static int lkb_sleep = -1;
-    if (lkb_sleep < 0) {
-        const char *e = getenv("GBIN_SCAN_SLEEP");
-        lkb_sleep = e ? atoi(e) : 800;
-    }
     bool attr_failed = false;
     auto launch = [&](auto kern) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -223,6 +445,8 @@ int launch_skr_scan(const ReadsView &rv_all, uint64_t read_begin, uint64_t read_
 uint32_t skr_scan_tiles(uint64_t n_reads, int K, int M, uint32_t max_len) {
     uint32_t rpw, seg_cap;
     skr_tile_shape(K, M, max_len, &rpw, &seg_cap);
+    const Scan2Shape s2 = skr_scan2_shape(K, M, max_len);
+    if (s2.nj && s2.rpw < rpw) rpw = s2.rpw;  // enough for either kernel
     return (uint32_t)((n_reads + rpw - 1) / rpw);
 }
 

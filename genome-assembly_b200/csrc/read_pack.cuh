@@ -16,35 +16,53 @@ __host__ __device__ inline uint32_t scan_pk_words(uint32_t max_len) { return (8u
 //   x = (c >> 1) & 3 maps A,C,T,G to 0,1,2,3;  code = 3 ^ x ^ (x >> 1) gives A3 C2 G1 T0 (binning.c:91-111);
 //   a byte is valid iff re-encoding the code gives the byte back (PRMT table lookup), so non-ACGT bytes are
 //   counted exactly.  Returns (per lane) the number of non-ACGT bytes it saw.
-__device__ __forceinline__ uint32_t warp_pack_read(uint32_t *pk, const uint8_t *__restrict__ src, uint32_t L, uint32_t lane) {
+// The loads of one 128-base chunk: lane l gets the aligned word that holds bytes 4l.. of the chunk (w0), lane 31 also the
+// word after its own (w31).  Split from the conversion so that a caller can issue the loads of the NEXT read early.
+__device__ __forceinline__ void warp_pack_load(const uint8_t *__restrict__ src, uint32_t L, uint32_t c0, uint32_t lane, uint32_t &w0, uint32_t &w31) {
     const uintptr_t addr = reinterpret_cast<uintptr_t>(src);
     const uint32_t mis = (uint32_t)(addr & 3u);
     const uint32_t *__restrict__ base = reinterpret_cast<const uint32_t *>(addr - mis);
     const uint32_t nwords_in = (mis + L + 3u) >> 2;  // aligned words that overlap the read
+    const uint32_t idx = (c0 >> 2) + lane;
+    w0 = idx < nwords_in ? base[idx] : 0u;
+    w31 = 0u;
+    if (lane == 31) w31 = (idx + 1 < nwords_in) ? base[idx + 1] : 0u;
+}
+
+// Converts one loaded chunk (bases c0 .. c0+127 of the read) and stores its 8 packed words; returns the lane's count of
+// non-ACGT bytes.
+__device__ __forceinline__ uint32_t warp_pack_chunk(uint32_t *pk, uint32_t w0, uint32_t w31, uint32_t mis, uint32_t L, uint32_t c0, uint32_t lane) {
+    uint32_t w1 = __shfl_down_sync(0xffffffffu, w0, 1);
+    if (lane == 31) w1 = w31;
+    uint32_t chars = __funnelshift_r(w0, w1, mis * 8);  // bytes src[c0+4*lane .. +3], first byte lowest
+    const int rem = (int)L - (int)(c0 + 4 * lane);      // valid bytes in this group of four
+    if (rem <= 0) chars = 0x54545454u;                  // past the end: 'T' = code 0
+    else if (rem < 4) {
+        const uint32_t m = (1u << (8 * rem)) - 1u;
+        chars = (chars & m) | (0x54545454u & ~m);
+    }
+    const uint32_t x = (chars >> 1) & 0x03030303u;
+    const uint32_t y = x ^ ((x >> 1) & 0x01010101u) ^ 0x03030303u;  // per byte: A3 C2 G1 T0
+    const uint32_t sel = (y & 0x3u) | ((y >> 4) & 0x30u) | ((y >> 8) & 0x300u) | ((y >> 12) & 0x3000u);
+    const uint32_t recon = __byte_perm(0x41434754u, 0u, sel);  // bytes T,G,C,A indexed by code
+    const uint32_t diff = recon ^ chars;
+    uint32_t nbad = 0;
+    if (diff) nbad = __popc((((diff & 0x7f7f7f7fu) + 0x7f7f7f7fu) | diff) & 0x80808080u);
+    const uint32_t v8 = (y * 0x40100401u) >> 24;  // four 2-bit codes, first base most significant
+    uint32_t part = v8 << (24 - 8 * (lane & 3));
+    part |= __shfl_xor_sync(0xffffffffu, part, 1);
+    part |= __shfl_xor_sync(0xffffffffu, part, 2);
+    if ((lane & 3) == 0) pk[(c0 >> 4) + (lane >> 2)] = part;
+    return nbad;
+}
+
+__device__ __forceinline__ uint32_t warp_pack_read(uint32_t *pk, const uint8_t *__restrict__ src, uint32_t L, uint32_t lane) {
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
     uint32_t nbad = 0, nchunks = 0;
     for (uint32_t c0 = 0; c0 < L; c0 += 128, nchunks++) {
-        const uint32_t idx = (c0 >> 2) + lane;
-        const uint32_t w0 = idx < nwords_in ? base[idx] : 0u;
-        uint32_t w1 = __shfl_down_sync(0xffffffffu, w0, 1);
-        if (lane == 31) w1 = (idx + 1 < nwords_in) ? base[idx + 1] : 0u;
-        uint32_t chars = __funnelshift_r(w0, w1, mis * 8);  // bytes src[c0+4*lane .. +3], first byte lowest
-        const int rem = (int)L - (int)(c0 + 4 * lane);      // valid bytes in this group of four
-        if (rem <= 0) chars = 0x54545454u;                  // past the end: 'T' = code 0
-        else if (rem < 4) {
-            const uint32_t m = (1u << (8 * rem)) - 1u;
-            chars = (chars & m) | (0x54545454u & ~m);
-        }
-        const uint32_t x = (chars >> 1) & 0x03030303u;
-        const uint32_t y = x ^ ((x >> 1) & 0x01010101u) ^ 0x03030303u;  // per byte: A3 C2 G1 T0
-        const uint32_t sel = (y & 0x3u) | ((y >> 4) & 0x30u) | ((y >> 8) & 0x300u) | ((y >> 12) & 0x3000u);
-        const uint32_t recon = __byte_perm(0x41434754u, 0u, sel);  // bytes T,G,C,A indexed by code
-        const uint32_t diff = recon ^ chars;
-        if (diff) nbad += __popc((((diff & 0x7f7f7f7fu) + 0x7f7f7f7fu) | diff) & 0x80808080u);
-        const uint32_t v8 = (y * 0x40100401u) >> 24;  // four 2-bit codes, first base most significant
-        uint32_t part = v8 << (24 - 8 * (lane & 3));
-        part |= __shfl_xor_sync(0xffffffffu, part, 1);
-        part |= __shfl_xor_sync(0xffffffffu, part, 2);
-        if ((lane & 3) == 0) pk[(c0 >> 4) + (lane >> 2)] = part;
+        uint32_t w0, w31;
+        warp_pack_load(src, L, c0, lane, w0, w31);
+        nbad += warp_pack_chunk(pk, w0, w31, mis, L, c0, lane);
     }
     if (lane < PK_PAD_WORDS) pk[8 * nchunks + lane] = 0u;
     __syncwarp();

@@ -156,17 +156,59 @@ __global__ void __launch_bounds__(SKR_WARPS * 32)
 // chained scan over tiles), then to list them.  Records are built one lane per segment (header + payload words from the
 // packed read) and written straight to their final place with 16-byte stores: neighbouring lanes write neighbouring
 // records, so there is no staging copy.
-template <int NJ, typename KeyT>
-__device__ __forceinline__ void s2_shift_max(KeyT (&x)[NJ], uint32_t s, uint32_t lane) {
-    KeyT t[NJ + 1];
+template <typename KeyT>
+__device__ __forceinline__ KeyT s2_down(KeyT v, uint32_t d, uint32_t lane) {  // value of lane + d, 0 past the last lane
+    const KeyT t = __shfl_down_sync(0xffffffffu, v, d & 31u);
+    return lane + d < 32u ? t : (KeyT)0;
+}
+template <typename KeyT>
+__device__ __forceinline__ KeyT s2_max(KeyT a, KeyT b) { return a > b ? a : b; }
+
+// Sliding maximum of width C over the keys of a read, lane l holding positions PL*l .. PL*l + PL-1 in x[] (C >= PL).
+// In: x[a] = key of position PL*l + a.  Out: x[a] = max over [PL*l + a, PL*l + a + C).  With C - PL = F0*PL + B0 the window
+// of position PL*l + a is: the lane's own suffix from a, then F whole lanes, then the first b positions of lane l + F + 1,
+// where (F, b) = (F0, B0 + a) if B0 + a < PL, else (F0 + 1, B0 + a - PL).  Whole-lane ranges come from a doubling over the
+// per-lane maxima (one register per step instead of PL), prefixes and suffixes are local.  B0 is a template parameter so that
+// every register index is static.
+template <int PL, int B0, typename KeyT>
+__device__ __forceinline__ void s2_window_max(KeyT (&x)[PL], uint32_t F0, uint32_t lane) {
+    KeyT pre[PL], suf[PL];
+    pre[0] = x[0];
 #pragma unroll
-    for (int j = 0; j < NJ; j++) t[j] = __shfl_sync(0xffffffffu, x[j], (lane + s) & 31u);
-    t[NJ] = 0;
-    const bool same = lane + s < 32u;
+    for (int a = 1; a < PL; a++) pre[a] = s2_max(pre[a - 1], x[a]);
+    suf[PL - 1] = x[PL - 1];
 #pragma unroll
-    for (int j = 0; j < NJ; j++) {
-        const KeyT y = same ? t[j] : t[j + 1];
-        x[j] = x[j] > y ? x[j] : y;
+    for (int a = PL - 2; a >= 0; a--) suf[a] = s2_max(suf[a + 1], x[a]);
+    const KeyT m = pre[PL - 1];
+    KeyT mm = m;  // max over lanes [l, l + w)
+    uint32_t w = 1;
+    for (; 2 * w <= F0; w *= 2) mm = s2_max(mm, s2_down(mm, w, lane));
+    KeyT full0 = 0;  // lanes l+1 .. l+F0
+    if (F0) {
+        full0 = s2_down(mm, 1, lane);
+        if (F0 > w) full0 = s2_max(full0, s2_down(mm, 1 + F0 - w, lane));
+    }
+    KeyT full1 = full0;  // lanes l+1 .. l+F0+1
+    if (B0 > 0) full1 = s2_max(full0, s2_down(m, F0 + 1, lane));
+#pragma unroll
+    for (int a = 0; a < PL; a++) {
+        const int t = B0 + a;
+        KeyT r;
+        if (t < PL) {
+            r = s2_max(suf[a], full0);
+            if (t > 0) r = s2_max(r, s2_down(pre[t > 0 ? t - 1 : 0], F0 + 1, lane));
+        } else {
+            r = s2_max(suf[a], full1);
+            if (t - PL > 0) r = s2_max(r, s2_down(pre[t - PL > 0 ? t - PL - 1 : 0], F0 + 2, lane));
+        }
+        x[a] = r;
+    }
+}
+template <int PL, typename KeyT, int B = 0>
+__device__ __forceinline__ void s2_window_max_sel(KeyT (&x)[PL], uint32_t b0, uint32_t F0, uint32_t lane) {
+    if constexpr (B < PL) {
+        if (b0 == (uint32_t)B) s2_window_max<PL, B, KeyT>(x, F0, lane);
+        else s2_window_max_sel<PL, KeyT, B + 1>(x, b0, F0, lane);
     }
 }
 
@@ -176,6 +218,9 @@ __host__ __device__ inline uint32_t s2_warp_smem(uint32_t max_len, int nj, uint3
     return (4u * s2_pk_words(max_len) * rpw + s2_sig_bytes(nj) * rpw + 4u * seg_cap + 15u) & ~15u;
 }
 
+#ifndef S2_LKB_DEPTH
+#define S2_LKB_DEPTH 4
+#endif
 template <int PW, int NJ, typename KeyT>
 __global__ void __launch_bounds__(SKR_WARPS * 32)
     skr_scan2_kernel(ReadsView rv, uint64_t read_begin, int K, int M, uint32_t arrival_base, uint32_t max_len, uint32_t rpw, uint32_t seg_cap,
@@ -193,6 +238,7 @@ __global__ void __launch_bounds__(SKR_WARPS * 32)
     const uint32_t FULL = (1u << (2 * M)) - 1;
     const uint32_t C = K - M + 1;
     const uint32_t down = 32u - 2u * (uint32_t)M;
+    const uint32_t win_f0 = (C - NJ) / NJ, win_b0 = (C - NJ) % NJ;  // C >= NJ (the launcher sees to it)
     uint32_t nbad = 0;
     unsigned long long ninst = 0;
     const unsigned long long base0 = counters[1];  // records of earlier launches over the same batch (chunked host feed)
@@ -203,35 +249,59 @@ __global__ void __launch_bounds__(SKR_WARPS * 32)
     while (tile < ntiles) {
         const uint64_t first = read_begin + (uint64_t)tile * rpw;
         // ---- phase A, the warp over one read at a time: pack, score, sliding arg-max
-        uint32_t myW = 0;  // lane r: windows of read first + r
+        // lane q holds start and length of read first + q (length 0: past the end of the range, or shorter than K)
+        uint64_t my_start = 0;
+        uint32_t myL = 0;
+        if (lane < rpw && first + lane < rv.n_reads) {
+            myL = rv.len(first + lane);
+            my_start = rv.start(first + lane);
+            if (myL < (uint32_t)K) myL = 0;
+        }
+        const uint32_t myW = myL ? myL - K + 1 : 0;
+        // the loads of read rr + 1 are issued before read rr is worked on
+        uint32_t nw0 = 0, nw31 = 0;
+        uint32_t nL = __shfl_sync(0xffffffffu, myL, 0);
+        uint64_t nstart = __shfl_sync(0xffffffffu, my_start, 0);
+        if (nL) warp_pack_load(rv.data + nstart, nL, 0, lane, nw0, nw31);
         for (uint32_t rr = 0; rr < rpw; rr++) {
-            const uint64_t r = first + rr;
-            if (r >= rv.n_reads) break;
-            const uint32_t L = rv.len(r);
-            if (L < (uint32_t)K) continue;
-            const uint32_t W = L - K + 1;
-            if (lane == rr) myW = W;
+            const uint32_t L = nL, w0 = nw0, w31 = nw31;
+            const uint8_t *src = rv.data + nstart;
+            if (rr + 1 < rpw) {
+                nL = __shfl_sync(0xffffffffu, myL, rr + 1);
+                nstart = __shfl_sync(0xffffffffu, my_start, rr + 1);
+                if (nL) warp_pack_load(rv.data + nstart, nL, 0, lane, nw0, nw31);
+            }
+            if (!L) continue;
             uint32_t *pkr = pk + rr * pkw;
-            nbad += warp_pack_read(pkr, rv.data + rv.start(r), L, lane);
-            KeyT x[NJ];
+            {
+                const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+                nbad += warp_pack_chunk(pkr, w0, w31, mis, L, 0, lane);
+                uint32_t nchunks = 1;
+                for (uint32_t c0 = 128; c0 < L; c0 += 128, nchunks++) {
+                    uint32_t v0, v31;
+                    warp_pack_load(src, L, c0, lane, v0, v31);
+                    nbad += warp_pack_chunk(pkr, v0, v31, mis, L, c0, lane);
+                }
+                if (lane < PK_PAD_WORDS) pkr[8 * nchunks + lane] = 0u;
+                __syncwarp();
+            }
+            KeyT x[NJ];  // keys of positions NJ * lane + a
+            {
+                const uint32_t p0 = NJ * lane, bit0 = 2 * p0, wi = bit0 >> 5, sh0 = bit0 & 31;
+                const uint32_t q0 = pkr[wi], q1 = pkr[wi + 1], q2 = pkr[wi + 2];
 #pragma unroll
-            for (int j = 0; j < NJ; j++) {
-                const uint32_t p = lane + 32u * j;
-                x[j] = 0;
-                if (p + M <= L) {
-                    const uint32_t bit = 2 * p, wi = bit >> 5, sh = bit & 31;
-                    const uint32_t s = __funnelshift_l(pkr[wi + 1], pkr[wi], sh) >> down;
+                for (int a = 0; a < NJ; a++) {
+                    const uint32_t p = p0 + a, sh = sh0 + 2 * a;
+                    const uint32_t s = __funnelshift_l(sh < 32 ? q1 : q2, sh < 32 ? q0 : q1, sh) >> down;  // shift taken modulo 32
                     const uint32_t c = FULL - s;
                     const uint32_t lo = ((255u - p) << 1) | (c > s ? 1u : 0u);
-                    x[j] = ((KeyT)(c > s ? c : s) << 9) | lo;
+                    x[a] = p + M <= L ? (((KeyT)(c > s ? c : s) << 9) | lo) : (KeyT)0;
                 }
             }
-            uint32_t width = 1;
-            for (; 2 * width <= C; width *= 2) s2_shift_max<NJ, KeyT>(x, width, lane);
-            if (C > width) s2_shift_max<NJ, KeyT>(x, C - width, lane);
-            uint8_t *sg = sig + rr * sgb;
+            s2_window_max_sel<NJ, KeyT>(x, win_b0, win_f0, lane);
+            uint8_t *sg = sig + rr * sgb + NJ * lane;
 #pragma unroll
-            for (int j = 0; j < NJ; j++) sg[lane + 32u * j] = (uint8_t)(255u - (((uint32_t)x[j] >> 1) & 255u));
+            for (int a = 0; a < NJ; a++) sg[a] = (uint8_t)(255u - (((uint32_t)x[a] >> 1) & 255u));
         }
         __syncwarp();
         ninst += myW;
@@ -247,7 +317,9 @@ __global__ void __launch_bounds__(SKR_WARPS * 32)
         }
         const uint32_t off = incl - cnt, nseg = __shfl_sync(0xffffffffu, incl, 31);
         if (lane == 0) lkb_publish_aggregate(tile_state, tile, nseg);
-        const unsigned long long base = base0 + lkb_resolve_warp<1>(tile_state, tile, nseg, lane, lkb_sleep);
+        // a window of 128 predecessors per step: a step is one round trip to L2, and with thousands of warps finishing tiles
+        // every few ns a 32-wide walk falls behind the tiles that publish meanwhile (measured: ~40 steps per tile)
+        const unsigned long long base = base0 + lkb_resolve_warp<S2_LKB_DEPTH>(tile_state, tile, nseg, lane, lkb_sleep);
         if (tile == ntiles - 1 && lane == 0) counters[1] = base + nseg;
         if (base + nseg <= capacity) {  // past the capacity only the total is produced (the caller re-runs)
             // ---- phase C: list the segments (seg_cap at a time), then one lane per segment builds and stores its record
@@ -316,6 +388,7 @@ static Scan2Shape skr_scan2_shape(int K, int M, uint32_t max_len) {
     const uint32_t npos = max_len - M + 1;
     if (npos > 256u) return sh;
     sh.nj = npos <= 96u ? 3 : (npos <= 160u ? 5 : 8);
+    if (K - M + 1 < sh.nj) return Scan2Shape{0, false, 0, 0};  // the window must span at least one lane's positions
     sh.wide = 2 * M + 9 > 32;
     const uint32_t W = max_len - K + 1;
     uint32_t per_read = (uint32_t)(1.6 * (double)W / ((K - M + 2) / 2.0)) + 2;

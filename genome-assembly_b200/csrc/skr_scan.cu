@@ -156,10 +156,12 @@ __global__ void __launch_bounds__(SKR_WARPS * 32)
 // chained scan over tiles), then to list them.  Records are built one lane per segment (header + payload words from the
 // packed read) and written straight to their final place with 16-byte stores: neighbouring lanes write neighbouring
 // records, so there is no staging copy.
+// Value of lane + d.  Past the last lane the result is garbage (the caller's own value), which is harmless here: a window
+// that starts at a real window start i < W ends at position i + C - 1 <= L - M, inside the 32 lanes, so garbage only ever
+// reaches the outputs of window starts that do not exist.
 template <typename KeyT>
-__device__ __forceinline__ KeyT s2_down(KeyT v, uint32_t d, uint32_t lane) {  // value of lane + d, 0 past the last lane
-    const KeyT t = __shfl_down_sync(0xffffffffu, v, d & 31u);
-    return lane + d < 32u ? t : (KeyT)0;
+__device__ __forceinline__ KeyT s2_down(KeyT v, uint32_t d, uint32_t) {
+    return __shfl_down_sync(0xffffffffu, v, d);
 }
 template <typename KeyT>
 __device__ __forceinline__ KeyT s2_max(KeyT a, KeyT b) { return a > b ? a : b; }
@@ -287,28 +289,32 @@ __global__ void __launch_bounds__(SKR_WARPS * 32)
             }
             KeyT x[NJ];  // keys of positions NJ * lane + a
             {
+                // the 64 packed bits from position p0 on, then one static funnel shift per position.  Positions past L - M get
+                // keys made of the zero padding: they only reach windows that do not exist (see s2_down).
                 const uint32_t p0 = NJ * lane, bit0 = 2 * p0, wi = bit0 >> 5, sh0 = bit0 & 31;
                 const uint32_t q0 = pkr[wi], q1 = pkr[wi + 1], q2 = pkr[wi + 2];
+                const uint32_t v0 = __funnelshift_l(q1, q0, sh0), v1 = __funnelshift_l(q2, q1, sh0);
+                const uint32_t lob = ((255u - p0) << 1) | 1u;
 #pragma unroll
                 for (int a = 0; a < NJ; a++) {
-                    const uint32_t p = p0 + a, sh = sh0 + 2 * a;
-                    const uint32_t s = __funnelshift_l(sh < 32 ? q1 : q2, sh < 32 ? q0 : q1, sh) >> down;  // shift taken modulo 32
-                    const uint32_t c = FULL - s;
-                    const uint32_t lo = ((255u - p) << 1) | (c > s ? 1u : 0u);
-                    x[a] = p + M <= L ? (((KeyT)(c > s ? c : s) << 9) | lo) : (KeyT)0;
+                    const uint32_t s = __funnelshift_l(v1, v0, 2 * a) >> down;
+                    // c = FULL - s = FULL ^ s scores higher iff the top bit of s is clear (binning.c:943,948: strictly higher)
+                    const uint32_t top = s >> (2 * M - 1);              // 1: forward strand kept
+                    const uint32_t mx = s ^ ((top - 1u) & FULL);        // max(s, FULL - s)
+                    x[a] = ((KeyT)mx << 9) | ((lob - 2u * a) ^ top);   // ... | (255 - p) << 1 | is_rev
                 }
             }
             s2_window_max_sel<NJ, KeyT>(x, win_b0, win_f0, lane);
-            uint8_t *sg = sig + rr * sgb + NJ * lane;
+            uint8_t *sg = sig + rr * sgb + NJ * lane;  // stored inverted: 255 - A(i)
 #pragma unroll
-            for (int a = 0; a < NJ; a++) sg[a] = (uint8_t)(255u - (((uint32_t)x[a] >> 1) & 255u));
+            for (int a = 0; a < NJ; a++) sg[a] = (uint8_t)((uint32_t)x[a] >> 1);
         }
         __syncwarp();
         ninst += myW;
         // ---- phase B, one lane per read: count the segments of the chain i -> A(i) + 1
         const uint8_t *sg = sig + lane * sgb;
         uint32_t cnt = 0;
-        for (uint32_t i = 0; i < myW; cnt++) i = min((uint32_t)sg[i] + 1u, myW);
+        for (uint32_t i = 0; i < myW; cnt++) i = min(256u - (uint32_t)sg[i], myW);
         uint32_t incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(SKR_WARPS * 32)
             for (uint32_t lo = 0; lo < nseg; lo += seg_cap) {
                 uint32_t g = off;
                 for (uint32_t i = 0; i < myW; g++) {
-                    const uint32_t sp = sg[i], nx = min(sp + 1u, myW);
+                    const uint32_t sp = 255u - (uint32_t)sg[i], nx = min(sp + 1u, myW);
                     if (g - lo < seg_cap) segl[g - lo] = lane | (i << 8) | (sp << 16) | ((nx - i) << 24);  // g < lo wraps around: not stored
                     i = nx;
                 }

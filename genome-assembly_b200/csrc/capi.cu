@@ -151,7 +151,8 @@ struct gbin_ctx {
     uint64_t v3_pass_max = 2000000000ull;  // k-mer instances per pass of pipeline 3 (gbin_set_tuning "v3_pass_max")
     uint64_t v3_auto_n = 0;           // record count for which the key layout below was chosen (v3_nc == 0: automatic)
     int v3_auto_h = 0, v3_auto_nc = 1;
-    int v3_h, v3_nc, v3_cap;  // key layout and unit capacity of pipeline 3 (gbin_set_tuning; GBIN_V3_H / GBIN_V3_NC / GBIN_V3_CAP)
+    int v3_h, v3_nc, v3_cap;  // key layout and unit capacity of pipeline 3 (gbin_set_tuning; GBIN_V3_H / GBIN_V3_NC / GBIN_V3_CAP); v3_cap 0 = by layout
+    int v3_cap_eff;           // the capacity of the current batch
     int pipeline;        // 3: sort by reference + warp units, falling back to 2, then 1 (default); 2: super-k-mer path with v1 as fallback; 1: v1 only
     int last_pipeline;   // which one produced the last table
     uint32_t fallbacks;  // v2 -> v1 fallbacks since creation
@@ -580,17 +581,24 @@ int run_v2_group(gbin_ctx *ctx, void *skr, void *twin, uint64_t n_skr, const int
 // buckets that fit a unit need nothing but the m-mer code; larger ones are broken up by extending the key (bin3.cuh).
 int v3_choose_layout(gbin_ctx *ctx, const void *skr, uint64_t n_skr, cudaStream_t st, KeyLayout *out, int *launches) {
     const int K = ctx->cfg.kmer_size, M = ctx->cfg.mmer_size;
+    // Unit capacity: 1024 instances when whole m-mer buckets are units (fewer buckets straddle units), 512 when the key is
+    // extended or the k-mers are two words wide (twice the warps per SM: the grouping kernel is latency-bound; measured
+    // 17.1 -> 11.3 ms on a config-3 shaped batch, 13.4 -> 7.9 ms on a config-5 shaped one).
+    auto set_cap = [&](const KeyLayout &kl) { ctx->v3_cap_eff = ctx->v3_cap ? ctx->v3_cap : ((ctx->KW == 2 || kl.nc == 2) ? 512 : 1024); };
     if (ctx->v3_nc != 0) {
         *out = make_key_layout(K, M, ctx->v3_h, ctx->v3_nc);
+        set_cap(*out);
         return GBIN_OK;
     }
     if (2 * M + 2 > 31 || M > 13 || n_skr == 0) {  // no room for a longer key / code space too large for the bitmap: plain m-mer keys
         *out = make_key_layout(K, M, 0, 1);
+        set_cap(*out);
         return GBIN_OK;
     }
     // the decision is kept for batches of similar size on this context
     if (ctx->v3_auto_n && n_skr >= ctx->v3_auto_n / 2 && n_skr <= ctx->v3_auto_n * 2) {
         *out = make_key_layout(K, M, ctx->v3_auto_h, ctx->v3_auto_nc);
+        set_cap(*out);
         return GBIN_OK;
     }
     Misc *dm = ctx->misc.as<Misc>();
@@ -603,15 +611,17 @@ int v3_choose_layout(gbin_ctx *ctx, const void *skr, uint64_t n_skr, cudaStream_
     const double buckets = hm->n_real_entries ? (double)hm->n_real_entries : 1.0;
     const double mean_inst = (double)n_skr / buckets * ((K - M + 2) / 2.0);  // a record holds about (K-M+2)/2 windows
     int nc = 1, h = 0;
-    if (mean_inst > ctx->v3_cap / 2.5) {
+    const int cap1 = ctx->v3_cap ? ctx->v3_cap : 1024, cap2 = ctx->v3_cap ? ctx->v3_cap : 512;
+    if (mean_inst > cap1 / 2.5) {
         nc = 2;
         double per = mean_inst / 2.0;
-        while (per > ctx->v3_cap / 8.0 && h < 15) {
+        while (per > cap2 / 8.0 && h < 15) {
             per /= 4.0;
             h++;
         }
     }
     *out = make_key_layout(K, M, h, nc);
+    set_cap(*out);
     ctx->v3_auto_n = n_skr;
     ctx->v3_auto_h = out->h;
     ctx->v3_auto_nc = out->nc;
@@ -643,7 +653,7 @@ int run_v3_pass(gbin_ctx *ctx, const void *skr, const uint64_t *ent, const uint1
     const uint64_t n_runs = hm->n_runs_dev, n = hm->n_inst_dev;
     *n_inst = n;
     ctx->rs.n_mmer_runs += n_runs;
-    const uint64_t max_units = v3_max_units(n, n_runs, ctx->v3_cap);
+    const uint64_t max_units = v3_max_units(n, n_runs, ctx->v3_cap_eff);
     CU(ctx->small_prefix.ensure((n_runs + 2) * 8));
     CU(ctx->v3_base64.ensure((n_runs + 2) * 8));
     CU(ctx->v3_atoms.ensure((4 * n_runs + 8) * 4));
@@ -660,7 +670,7 @@ int run_v3_pass(gbin_ctx *ctx, const void *skr, const uint64_t *ent, const uint1
         ch.done = ctx->ev_chunk;
     }
     on = ctx->prof.begin(KK_SKR_PLAN, st);
-    lp = v3_plan_units(sorted_info, ent, kl, ctx->v3_cap, ctx->inst_prefix.as<uint32_t>(), ctx->skr_run_start.as<uint32_t>(), n_runs, ctx->small_prefix.as<uint64_t>(),
+    lp = v3_plan_units(sorted_info, ent, kl, ctx->v3_cap_eff, ctx->inst_prefix.as<uint32_t>(), ctx->skr_run_start.as<uint32_t>(), n_runs, ctx->small_prefix.as<uint64_t>(),
                        ctx->v3_base64.as<uint64_t>(), ctx->v3_atoms.as<uint32_t>(), ctx->v3_atoms.as<uint32_t>() + 3 * n_runs, ctx->v3_head_run.as<uint32_t>(),
                        ctx->scan_scratch.p, ctx->units.p, max_units, &dm->gc3, ch.n, dm->chunk_bounds, st);
     ctx->prof.end(on, lp, st);
@@ -698,7 +708,7 @@ int run_v3_pass(gbin_ctx *ctx, const void *skr, const uint64_t *ent, const uint1
         return cap ? V3Lsd{ctx->rec_a.p, aux, aux + (cap + 1), aux + 2 * (cap + 1), aux + 3 * (cap + 1), cap} : V3Lsd{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
     };
     uint64_t *unit_excl = ctx->v3_unit_excl.as<uint64_t>(), *lsd_excl = unit_excl + max_units + 1;
-    lp = v3_group_launch(skr, ent, ctx->units.p, kl, ctx->v3_cap, cutoff, d_ids, id_base, vo, max_units, unit_excl, lsd_excl, ctx->scan_scratch.p, &dm->gc3, ch,
+    lp = v3_group_launch(skr, ent, ctx->units.p, kl, ctx->v3_cap_eff, cutoff, d_ids, id_base, vo, max_units, unit_excl, lsd_excl, ctx->scan_scratch.p, &dm->gc3, ch,
                          lsd_view(lsd_cap), false, ctx->sm_count, &ctx->prof, st);
     *launches += lp;
     CU(cudaGetLastError());
@@ -735,7 +745,7 @@ int run_v3_pass(gbin_ctx *ctx, const void *skr, const uint64_t *ent, const uint1
         V3Chunks ch1 = ch;
         ch1.totals_host = ch1.lsd_totals_host = nullptr;
         ch1.done = nullptr;
-        lp = v3_group_launch(skr, ent, ctx->units.p, kl, ctx->v3_cap, cutoff, d_ids, id_base, vo, max_units, unit_excl, lsd_excl, ctx->scan_scratch.p, &dm->gc3, ch1,
+        lp = v3_group_launch(skr, ent, ctx->units.p, kl, ctx->v3_cap_eff, cutoff, d_ids, id_base, vo, max_units, unit_excl, lsd_excl, ctx->scan_scratch.p, &dm->gc3, ch1,
                              lsd_view(lsd_cap), true, ctx->sm_count, &ctx->prof, st);
         *launches += lp;
         CU(cudaGetLastError());
@@ -795,7 +805,7 @@ int run_v3_group(gbin_ctx *ctx, const void *skr, uint64_t n_skr, const int32_t *
     bool in_b = false;
     int passes = 0;
     *launches += radix_sort_entries(ctx->ent_a.p, ctx->ent_b.p, n_slots, kl.key_bits, ctx->radix_scratch.p, &in_b, &passes, ctx->piece_n.as<uint16_t>(),
-                                    ctx->sorted_info.as<uint16_t>(), &ctx->prof, st);
+                                    ctx->sorted_info.as<uint16_t>(), &ctx->prof, st, kl.nc == 2 ? &dm->n_real_entries : nullptr);
     CU(cudaGetLastError());
     ctx->tm.sort_passes = (uint32_t)passes;
     const uint64_t *ent = in_b ? ctx->ent_b.as<uint64_t>() : ctx->ent_a.as<uint64_t>();
@@ -1044,8 +1054,9 @@ int gbin_create(const gbin_config *cfg, gbin_ctx **out) {
         if (v >= 1000) ctx->v3_pass_max = (uint64_t)v;
     }
     // 128-bit k-mer codes double the shared memory of a unit: units of 512 instances keep the warps per SM up
-    ctx->v3_cap = ctx->KW == 2 ? 512 : 1024;
-    if (const char *e = getenv("GBIN_V3_CAP")) ctx->v3_cap = atoi(e) == 512 ? 512 : 1024;
+    ctx->v3_cap = 0;
+    ctx->v3_cap_eff = ctx->KW == 2 ? 512 : 1024;
+    if (const char *e = getenv("GBIN_V3_CAP")) ctx->v3_cap = atoi(e) == 512 ? 512 : (atoi(e) == 1024 ? 1024 : 0);
     ctx->last_pipeline = 0;
     ctx->fallbacks = 0;
     memset(&ctx->rs, 0, sizeof ctx->rs);
@@ -1175,7 +1186,7 @@ int gbin_set_pipeline(gbin_ctx *ctx, int pipeline) {
 int gbin_set_tuning(gbin_ctx *ctx, const char *name, int value) {
     if (!ctx || !name) return GBIN_E_INVALID_ARG;
     if (!strcmp(name, "v3_cap")) {
-        if (value != 512 && value != 1024) return GBIN_E_INVALID_ARG;
+        if (value != 0 && value != 512 && value != 1024) return GBIN_E_INVALID_ARG;
         ctx->v3_cap = value;
     } else if (!strcmp(name, "v3_nc")) {
         if (value != 0 && value != 1 && value != 2) return GBIN_E_INVALID_ARG;

@@ -82,32 +82,40 @@ __device__ __forceinline__ uint32_t digit_of(const Blob<NU64> &r, const DigitSel
     return s.mod ? owner_of_mmer((uint32_t)x, s.mod) : (uint32_t)x & 0xffu;
 }
 
-template <int NU64>
+// DROP: records whose key (high half of word 0) is all ones are left out (the empty pieces of the entry sort); n_dev: the
+// record count is read from device memory (what is left after the pass that dropped them).
+template <int NU64, bool DROP>
 __global__ void __launch_bounds__(RS_THREADS)
-    radix_hist_kernel(const Blob<NU64> *__restrict__ in, uint64_t n, DigitSel sel, uint32_t *__restrict__ tile_hist, uint32_t ntiles) {
+    radix_hist_kernel(const Blob<NU64> *__restrict__ in, uint64_t n, DigitSel sel, uint32_t *__restrict__ tile_hist, uint32_t ntiles,
+                      const unsigned long long *__restrict__ n_dev) {
+    constexpr bool drop_ones = DROP;
     constexpr int ITEMS = TileShape<NU64>::ITEMS, TILE = TileShape<NU64>::TILE;
     __shared__ uint32_t h[RS_RADIX];
     h[threadIdx.x] = 0;
     __syncthreads();
+    if (n_dev) n = *n_dev;  // the record count is only known on the device (entries left after the pass that dropped the empty ones)
     const uint64_t base = (uint64_t)blockIdx.x * TILE;
 #pragma unroll 4
     for (int i = 0; i < ITEMS; i++) {
         const uint64_t j = base + (uint64_t)i * RS_THREADS + threadIdx.x;
         if (j < n) {
             const Blob<NU64> r = load_blob<NU64>(in + j);
-            atomicAdd(&h[digit_of<NU64>(r, sel)], 1u);
+            if (!(drop_ones && (uint32_t)(r.w[0] >> 32) == 0xffffffffu)) atomicAdd(&h[digit_of<NU64>(r, sel)], 1u);
         }
     }
     __syncthreads();
     tile_hist[(uint64_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
 }
 
-template <int NU64>
+template <int NU64, bool DROP>
 __global__ void __launch_bounds__(RS_THREADS)
     radix_scatter_kernel(const Blob<NU64> *__restrict__ in, Blob<NU64> *__restrict__ out, uint64_t n, DigitSel sel,
                          const uint32_t *__restrict__ tile_off, uint32_t ntiles, char *const *__restrict__ dst_tab, uint64_t *__restrict__ side,
-                         const uint16_t *__restrict__ slot_info = nullptr, uint16_t *__restrict__ sorted_info = nullptr) {
+                         const uint16_t *__restrict__ slot_info, uint16_t *__restrict__ sorted_info, const unsigned long long *__restrict__ n_dev) {
+    constexpr bool drop_ones = DROP;
     constexpr int ITEMS = TileShape<NU64>::ITEMS, TILE = TileShape<NU64>::TILE;
+    if (n_dev) n = *n_dev;
+    if ((uint64_t)blockIdx.x * TILE >= n) return;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     Blob<NU64> *exch = reinterpret_cast<Blob<NU64> *>(smem_raw);
     uint32_t *wc = reinterpret_cast<uint32_t *>(smem_raw + (size_t)TILE * sizeof(Blob<NU64>));  // [RS_WARPS][256]
@@ -120,7 +128,7 @@ __global__ void __launch_bounds__(RS_THREADS)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t base = (uint64_t)blockIdx.x * TILE;
-    const uint32_t count = (uint32_t)min((uint64_t)TILE, n - base);
+    const uint32_t count = (uint32_t)min((uint64_t)TILE, n - base);  // records of the tile; `kept` of them are scattered (drop_ones: entries with the all-ones key are left out)
     for (uint32_t i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) wc[i] = 0;
     __syncthreads();
 
@@ -136,10 +144,12 @@ __global__ void __launch_bounds__(RS_THREADS)
         const uint32_t idx = warp * (32 * ITEMS) + r * 32 + lane;
         if (idx < count) items[r] = load_blob<NU64>(in + base + idx);
     }
+    uint32_t keep_mask = 0;  // bit r: this thread's record of round r takes part
 #pragma unroll
     for (int r = 0; r < ITEMS; r++) {
         const uint32_t idx = warp * (32 * ITEMS) + r * 32 + lane;
-        const bool valid = idx < count;
+        const bool valid = idx < count && !(drop_ones && (uint32_t)(items[r].w[0] >> 32) == 0xffffffffu);
+        keep_mask |= valid ? (1u << r) : 0u;
         const unsigned act = __ballot_sync(0xffffffffu, valid);
         rank[r] = 0;
         if (valid) {
@@ -164,6 +174,7 @@ __global__ void __launch_bounds__(RS_THREADS)
         __syncwarp();
     }
     __syncthreads();
+    uint32_t kept;  // records of the tile that are scattered: all of them unless drop_ones
     {  // thread = digit: exclusive scan over warps, then over digits
         uint32_t run = 0;
 #pragma unroll
@@ -174,21 +185,21 @@ __global__ void __launch_bounds__(RS_THREADS)
         }
         uint32_t tot;
         const uint32_t excl = block_exclusive_scan<uint32_t>(run, &tot);
+        kept = drop_ones ? tot : count;
         dstart[tid] = excl;
         goff[tid] = tile_off[(uint64_t)tid * ntiles + blockIdx.x] - excl;  // mod 2^32, n < 2^32
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < ITEMS; r++) {
-        const uint32_t idx = warp * (32 * ITEMS) + r * 32 + lane;
-        if (idx < count) {
+        if ((keep_mask >> r) & 1u) {
             const uint32_t d = digit_of<NU64>(items[r], sel);
             exch[dstart[d] + mywc[d] + rank[r]] = items[r];
         }
     }
     __syncthreads();
     if (dst_tab) {
-        for (uint32_t i = tid; i < count; i += RS_THREADS) {
+        for (uint32_t i = tid; i < kept; i += RS_THREADS) {
             const Blob<NU64> r = exch[i];
             const uint32_t d = digit_of<NU64>(r, sel);
             char *bp = s_dst[d];
@@ -196,7 +207,7 @@ __global__ void __launch_bounds__(RS_THREADS)
         }
         return;
     }
-    for (uint32_t i = tid; i < count; i += RS_THREADS) {
+    for (uint32_t i = tid; i < kept; i += RS_THREADS) {
         const Blob<NU64> r = exch[i];
         const uint32_t d = digit_of<NU64>(r, sel);
         const uint32_t pos = (uint32_t)(goff[d] + i);
@@ -328,7 +339,8 @@ size_t radix_scratch_bytes(uint64_t n) {
 
 template <int NU64>
 static int one_pass(const void *in_v, void *out_v, uint64_t n, const DigitSel &sel, uint32_t *scratch, KernelProf *prof, cudaStream_t st,
-                    const XchgPlan *xp = nullptr, uint64_t *side = nullptr, const uint16_t *slot_info = nullptr, uint16_t *sorted_info = nullptr) {
+                    const XchgPlan *xp = nullptr, uint64_t *side = nullptr, const uint16_t *slot_info = nullptr, uint16_t *sorted_info = nullptr,
+                    const unsigned long long *n_dev = nullptr, bool drop_ones = false) {
     const Blob<NU64> *in = static_cast<const Blob<NU64> *>(in_v);
     Blob<NU64> *out = static_cast<Blob<NU64> *>(out_v);
     constexpr int TILE = TileShape<NU64>::TILE;
@@ -345,7 +357,8 @@ static int one_pass(const void *in_v, void *out_v, uint64_t n, const DigitSel &s
     uint32_t *scan_tmp = scratch + table;
     int launches = 0;
     bool on = prof && prof->begin(KK_RADIX_HIST, st);
-    radix_hist_kernel<NU64><<<nt, RS_THREADS, 0, st>>>(in, n, sel, tile_hist, nt);
+    if (NU64 == 1 && drop_ones) radix_hist_kernel<NU64, NU64 == 1><<<nt, RS_THREADS, 0, st>>>(in, n, sel, tile_hist, nt, n_dev);
+    else radix_hist_kernel<NU64, false><<<nt, RS_THREADS, 0, st>>>(in, n, sel, tile_hist, nt, n_dev);
     if (prof) prof->end(on, 1, st);
     launches++;
     on = prof && prof->begin(KK_RADIX_TILESCAN, st);
@@ -353,13 +366,17 @@ static int one_pass(const void *in_v, void *out_v, uint64_t n, const DigitSel &s
     if (prof) prof->end(on, ls, st);
     launches += ls;
     const size_t smem = (size_t)TILE * sizeof(Blob<NU64>) + (RS_WARPS * RS_RADIX + 2 * RS_RADIX) * sizeof(uint32_t);
-    cudaFuncSetAttribute(radix_scatter_kernel<NU64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(radix_scatter_kernel<NU64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (NU64 == 1) cudaFuncSetAttribute(radix_scatter_kernel<NU64, NU64 == 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     on = prof && prof->begin(KK_RADIX_SCATTER, st);
     if (xp) {  // counts to every peer, wait for theirs, per-owner destinations
         xchg_counts_kernel<<<1, 32, 0, st>>>(tile_hist, nt, n, *xp, (uint32_t)sizeof(Blob<NU64>));
         launches++;
     }
-    radix_scatter_kernel<NU64><<<nt, RS_THREADS, smem, st>>>(in, out, n, sel, tile_hist, nt, xp ? xp->dst_tab : nullptr, side, slot_info, sorted_info);
+    if (NU64 == 1 && drop_ones)
+        radix_scatter_kernel<NU64, NU64 == 1><<<nt, RS_THREADS, smem, st>>>(in, out, n, sel, tile_hist, nt, xp ? xp->dst_tab : nullptr, side, slot_info, sorted_info, n_dev);
+    else
+        radix_scatter_kernel<NU64, false><<<nt, RS_THREADS, smem, st>>>(in, out, n, sel, tile_hist, nt, xp ? xp->dst_tab : nullptr, side, slot_info, sorted_info, n_dev);
     if (prof) prof->end(on, 1, st);
     if (xp) {
         xchg_done_kernel<<<1, 32, 0, st>>>(*xp);
@@ -370,9 +387,9 @@ static int one_pass(const void *in_v, void *out_v, uint64_t n, const DigitSel &s
 
 static int one_pass_any(int nu64, const void *in, void *out, uint64_t n, const DigitSel &sel, uint32_t *scratch, KernelProf *prof,
                         cudaStream_t st, const XchgPlan *xp = nullptr, uint64_t *side = nullptr, const uint16_t *slot_info = nullptr,
-                        uint16_t *sorted_info = nullptr) {
+                        uint16_t *sorted_info = nullptr, const unsigned long long *n_dev = nullptr, bool drop_ones = false) {
     switch (nu64) {
-        case 1: return one_pass<1>(in, out, n, sel, scratch, prof, st, xp, side, slot_info, sorted_info);
+        case 1: return one_pass<1>(in, out, n, sel, scratch, prof, st, xp, side, slot_info, sorted_info, n_dev, drop_ones);
         case 2: return one_pass<2>(in, out, n, sel, scratch, prof, st, xp, side);
         case 3: return one_pass<3>(in, out, n, sel, scratch, prof, st, xp, side);
         case 4: return one_pass<4>(in, out, n, sel, scratch, prof, st, xp, side);
@@ -444,8 +461,10 @@ int radix_sort_skr_by_mmer(void *a, void *b, uint64_t n, int skr_words, int M, v
 
 // v3: 8-byte entries {key << 32 | slot} sorted on the low `key_bits` bits of the key (stable, so entries of one key keep
 // their order: slots ascend with arrival).
+// n_real_dev != nullptr: entries with the all-ones key (empty pieces) are dropped by the first pass; *n_real_dev (device memory) is
+// the number of the others, which is what the later passes — launched for n, the host's bound — work on.
 int radix_sort_entries(void *a, void *b, uint64_t n, int key_bits, void *scratch, bool *result_in_b, int *passes_out, const uint16_t *slot_info,
-                       uint16_t *sorted_info, KernelProf *prof, cudaStream_t st) {
+                       uint16_t *sorted_info, KernelProf *prof, cudaStream_t st, const unsigned long long *n_real_dev) {
     *result_in_b = false;
     *passes_out = 0;
     if (n == 0) return 0;
@@ -454,7 +473,7 @@ int radix_sort_entries(void *a, void *b, uint64_t n, int key_bits, void *scratch
     for (int s = 0; s < key_bits; s += 8) {
         const bool last = s + 8 >= key_bits;
         launches += one_pass_any(1, src, dst, n, DigitSel{0, 32 + s, 0}, static_cast<uint32_t *>(scratch), prof, st, nullptr, nullptr, last ? slot_info : nullptr,
-                                 last ? sorted_info : nullptr);
+                                 last ? sorted_info : nullptr, (n_real_dev && s > 0) ? n_real_dev : nullptr, n_real_dev && s == 0);
         void *t = src;
         src = dst;
         dst = t;

@@ -170,7 +170,7 @@ typedef struct gbin_run_stats {
 int gbin_get_run_stats(const gbin_ctx *ctx, gbin_run_stats *out);
 int gbin_set_pipeline(gbin_ctx *ctx, int pipeline);
 /* Tuning knobs (tests and experiments; every setting produces the same table):
- *   "v3_cap" 512|1024      k-mer instances per work unit of pipeline 3 (default 1024)
+ *   "v3_cap" 0|512|1024    k-mer instances per work unit of pipeline 3 (default 0: 1024 with plain m-mer keys and one-word k-mers, else 512)
  *   "v3_nc"  0|1|2         pieces per super-k-mer record: 1 = key is the m-mer code; 2 = windows split by the signature's offset
  *                          and the key extended by v3_h bases next to the signature; 0 (default) = chosen per batch from the mean bucket size
  *   "v3_h"   0..           with v3_nc = 2: bases next to the signature that extend the level-1 key (clamped to what K, M allow)

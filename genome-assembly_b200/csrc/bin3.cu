@@ -143,6 +143,9 @@ constexpr int PLAN_BLOCK = 64;    // atoms walked by one thread
 constexpr int PLAN_CTA_BLOCKS = 32;
 struct Plan3 {
     uint32_t cap, nb_max, ecap, max_rounds;
+    // limits for packing several buckets into one unit (<= the limits above).  With cap = 1024 and two grouping kernels these are
+    // the limits of the 512-instance kernel: small buckets share small units, a bucket between the two sizes is a unit of its own.
+    uint32_t cap_s, nb_s, ecap_s;
 };
 struct RunView3 {
     const uint32_t *run_start;    // [NR+1]
@@ -195,7 +198,10 @@ __global__ void __launch_bounds__(128)
             q++;
         } while (q < n_runs && atom_mm[q] == mm);
         if (cb <= pp.cap && eb <= pp.ecap) {  // the whole bucket is one item
-            if (cur_b == 0 || cur_c + cb > pp.cap || cur_e + eb > pp.ecap || cur_b + 1 > pp.nb_max) {
+            if (cb > pp.cap_s || eb > pp.ecap_s) {  // too large to share a unit
+                nunits[r] = 1ull;
+                cur_b = 0;  // the next bucket opens a unit
+            } else if (cur_b == 0 || cur_c + cb > pp.cap_s || cur_e + eb > pp.ecap_s || cur_b + 1 > pp.nb_s) {
                 nunits[r] = 1ull;
                 cur_c = (uint32_t)cb;
                 cur_e = (uint32_t)eb;
@@ -457,13 +463,17 @@ __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, uint32_t lane
 }
 
 constexpr int G3_WARPS = 5;  // warps (= units in flight) per CTA
+constexpr uint32_t G3_SMALL_INST = 512, G3_SMALL_ENT = 128, G3_SMALL_NB = 64;  // what the 512-instance layout holds
 constexpr int G3_U = 4;  // instances per lane that are in flight together in the instance-major phases
 
 template <int PW, int KW, int WCAP, int WARPS, int U>
 __global__ void __launch_bounds__(WARPS * 32)
     group3_kernel(const uint32_t *__restrict__ skr, const uint64_t *__restrict__ ent, const Unit3 *__restrict__ units, KeyLayout kl, int cutoff,
                   const int32_t *__restrict__ ids_by_arrival, int32_t id_base, G3Stage out, G3Counters *__restrict__ gc,
-                  const uint32_t *__restrict__ chunk_bounds, uint32_t chunk, uint32_t *__restrict__ chunk_tickets) {
+                  const uint32_t *__restrict__ chunk_bounds, uint32_t chunk, uint32_t *__restrict__ chunk_tickets, uint32_t size_class) {
+    // size_class: 0 = every unit; 1 = only the small units (no rounds, at most G3_SMALL_INST instances and G3_SMALL_ENT entries);
+    // 2 = only the others.  Two launches (1024-instance layout for the large units, 512-instance layout — twice the warps per SM —
+    // for the small ones) share the unit list.
     constexpr int NW = SkrLayout<PW>::WORDS;
     constexpr int HS = 2 * WCAP;  // hash slots (u16 each)
     constexpr int LOG_HS = WCAP == 512 ? 10 : 11;
@@ -521,6 +531,13 @@ __global__ void __launch_bounds__(WARPS * 32)
         // packed: the unit's entries fit the per-entry tables and every instance remembers its entry; otherwise (a round of a split
         // atom, or one atom of very many entries) the unit is ONE bucket and the id pass walks the entries again
         const bool packed = !is_round && n_ent <= (uint32_t)ECAP;
+        if (size_class) {
+            const bool small = !is_round && un.n_inst <= G3_SMALL_INST && n_ent <= G3_SMALL_ENT;
+            if (small != (size_class == 1u)) {  // the other launch's unit
+                u = __shfl_sync(0xffffffffu, u_next, 0);
+                continue;
+            }
+        }
         if (is_round && un.n_inst == 0) {  // a round the cut did not need
             if (lane == 0) out.unit_out[u_cur] = UnitOut3{un.ibase, 0u, 0u, 0u};
             u = __shfl_sync(0xffffffffu, u_next, 0);
@@ -1182,9 +1199,24 @@ __global__ void v3_chunk_bounds_kernel(const Unit3 *__restrict__ units, const G3
 // ------------------------------------------------------------------ host side
 
 // cap: instances per unit, 512 or 1024 (gbin_set_tuning "v3_cap")
+// Two grouping launches (see group3_kernel's size_class): for one-word k-mers at capacity 1024, unless GBIN_V3_HYBRID=0.
+static bool v3_hybrid(const KeyLayout &kl, int cap_i) {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("GBIN_V3_HYBRID");
+        on = e ? atoi(e) : 1;
+    }
+    return on && cap_i != 512 && kl.K <= 32;
+}
 static Plan3 v3_plan_params(const KeyLayout &kl, int cap_i) {
     const uint32_t cap = cap_i == 512 ? 512u : 1024u;
-    return Plan3{cap, cap / 8, cap / 4, (uint32_t)(kl.K - kl.M + 1)};  // NB_MAX and ECAP of WarpLayout
+    Plan3 pp{cap, cap / 8, cap / 4, (uint32_t)(kl.K - kl.M + 1), cap, cap / 8, cap / 4};  // NB_MAX and ECAP of WarpLayout
+    if (v3_hybrid(kl, cap_i)) {
+        pp.cap_s = G3_SMALL_INST;
+        pp.nb_s = G3_SMALL_NB;
+        pp.ecap_s = G3_SMALL_ENT;
+    }
+    return pp;
 }
 
 uint64_t v3_max_units(uint64_t n_inst, uint64_t n_runs, int cap) {
@@ -1247,15 +1279,22 @@ int v3_group_launch(const void *skr, const uint64_t *ent, const void *units, con
     const Unit3 *un = static_cast<const Unit3 *>(units);
     int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
+    const bool hybrid = v3_hybrid(kl, cap);
+    const size_t smem_s = v3_group_smem_bytes(KW, 512);
+    int per_sm_s = (int)((size_t)(227 * 1024) / (smem_s + 1024));
+    if (per_sm_s < 1) per_sm_s = 1;
     int launches = 0;
-    auto launch = [&](auto kern, auto fin_kern) {
+    auto launch = [&](auto kern, auto kern_small, auto fin_kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (hybrid) cudaFuncSetAttribute(kern_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
         for (uint32_t c = 0; c < ch.n; c++) {
             if (!finalize_only) {
                 bool on = prof && prof->begin(KK_SKR_GROUP, st);
-                kern<<<sm_count * per_sm, WARPS * 32, smem, st>>>(sk, ent, un, kl, cutoff, ids_by_arrival, id_base, stg, gc, ch.bounds, c, ch.tickets);
-                if (prof) prof->end(on, 1, st);
-                launches++;
+                kern<<<sm_count * per_sm, WARPS * 32, smem, st>>>(sk, ent, un, kl, cutoff, ids_by_arrival, id_base, stg, gc, ch.bounds, c, ch.tickets, hybrid ? 2u : 0u);
+                if (hybrid)
+                    kern_small<<<sm_count * per_sm_s, WARPS * 32, smem_s, st>>>(sk, ent, un, kl, cutoff, ids_by_arrival, id_base, stg, gc, ch.bounds, c, ch.tickets + ch.n, 1u);
+                if (prof) prof->end(on, hybrid ? 2 : 1, st);
+                launches += hybrid ? 2 : 1;
             }
             bool on = prof && prof->begin(KK_V3_SPAN, st);
             int l = exclusive_scan<uint64_t, UnitSN>(UnitSN{stg.unit_out, ch.bounds, c}, unit_excl, max_units, static_cast<uint64_t *>(scan_scratch), ch.chunk_sum, st);
@@ -1281,8 +1320,9 @@ int v3_group_launch(const void *skr, const uint64_t *ent, const void *units, con
     }
     const int u_sel = uu > 0 ? uu : (cap == 512 ? 2 : 4);  // more warps per SM at 512: less need for instruction-level parallelism, smaller code
 #define G3_LAUNCH(PW_, KW_, CAP_) \
-    (u_sel == 1 ? launch(group3_kernel<PW_, KW_, CAP_, WARPS, 1>, finalize3_kernel<KW_>) \
-             : (u_sel == 2 ? launch(group3_kernel<PW_, KW_, CAP_, WARPS, 2>, finalize3_kernel<KW_>) : launch(group3_kernel<PW_, KW_, CAP_, WARPS, 4>, finalize3_kernel<KW_>)))
+    (u_sel == 1 ? launch(group3_kernel<PW_, KW_, CAP_, WARPS, 1>, group3_kernel<PW_, KW_, 512, WARPS, 2>, finalize3_kernel<KW_>) \
+             : (u_sel == 2 ? launch(group3_kernel<PW_, KW_, CAP_, WARPS, 2>, group3_kernel<PW_, KW_, 512, WARPS, 2>, finalize3_kernel<KW_>) \
+                           : launch(group3_kernel<PW_, KW_, CAP_, WARPS, 4>, group3_kernel<PW_, KW_, 512, WARPS, 2>, finalize3_kernel<KW_>)))
     if (KW == 1) {
         if (cap == 512) G3_LAUNCH(2, 1, 512);
         else G3_LAUNCH(2, 1, 1024);

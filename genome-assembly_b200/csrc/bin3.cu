@@ -1284,15 +1284,36 @@ int v3_group_launch(const void *skr, const uint64_t *ent, const void *units, con
     int per_sm_s = (int)((size_t)(227 * 1024) / (smem_s + 1024));
     if (per_sm_s < 1) per_sm_s = 1;
     int launches = 0;
+    static int sbs = -1, l_per_sm = 2;  // GBIN_V3_SBS=0: the two launches one after the other; GBIN_V3_LPS: CTAs per SM of the large-unit kernel
+    if (sbs < 0) {
+        const char *e = getenv("GBIN_V3_SBS");
+        sbs = e ? atoi(e) : 1;
+        const char *f = getenv("GBIN_V3_LPS");
+        l_per_sm = f ? atoi(f) : 2;
+        if (l_per_sm < 1 || l_per_sm > 2) l_per_sm = 2;
+    }
+    const bool side_by_side = sbs && ch.aux && ch.ev_fork && ch.ev_join;
     auto launch = [&](auto kern, auto kern_small, auto fin_kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (hybrid) cudaFuncSetAttribute(kern_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
         for (uint32_t c = 0; c < ch.n; c++) {
             if (!finalize_only) {
                 bool on = prof && prof->begin(KK_SKR_GROUP, st);
-                kern<<<sm_count * per_sm, WARPS * 32, smem, st>>>(sk, ent, un, kl, cutoff, ids_by_arrival, id_base, stg, gc, ch.bounds, c, ch.tickets, hybrid ? 2u : 0u);
-                if (hybrid)
+                if (!hybrid) {
+                    kern<<<sm_count * per_sm, WARPS * 32, smem, st>>>(sk, ent, un, kl, cutoff, ids_by_arrival, id_base, stg, gc, ch.bounds, c, ch.tickets, 0u);
+                } else if (!side_by_side) {
+                    kern<<<sm_count * per_sm, WARPS * 32, smem, st>>>(sk, ent, un, kl, cutoff, ids_by_arrival, id_base, stg, gc, ch.bounds, c, ch.tickets, 2u);
                     kern_small<<<sm_count * per_sm_s, WARPS * 32, smem_s, st>>>(sk, ent, un, kl, cutoff, ids_by_arrival, id_base, stg, gc, ch.bounds, c, ch.tickets + ch.n, 1u);
+                } else {
+                    // side by side: the large-unit kernel goes first, the small-unit kernel's CTAs take what is left of
+                    // every SM and, being persistent, the room the other kernel leaves when it runs out of units (its tail is covered)
+                    cudaEventRecord(ch.ev_fork, st);
+                    cudaStreamWaitEvent(ch.aux, ch.ev_fork, 0);
+                    kern<<<sm_count * l_per_sm, WARPS * 32, smem, st>>>(sk, ent, un, kl, cutoff, ids_by_arrival, id_base, stg, gc, ch.bounds, c, ch.tickets, 2u);
+                    kern_small<<<sm_count * per_sm_s, WARPS * 32, smem_s, ch.aux>>>(sk, ent, un, kl, cutoff, ids_by_arrival, id_base, stg, gc, ch.bounds, c, ch.tickets + ch.n, 1u);
+                    cudaEventRecord(ch.ev_join, ch.aux);
+                    cudaStreamWaitEvent(st, ch.ev_join, 0);
+                }
                 if (prof) prof->end(on, hybrid ? 2 : 1, st);
                 launches += hybrid ? 2 : 1;
             }

@@ -132,6 +132,8 @@ struct gbin_ctx {
     cudaStream_t stream;
     cudaStream_t st_h2d, st_d2h;  // copy streams of the host path (H2D of later read chunks / D2H of finished table chunks overlap the kernels)
     cudaEvent_t ev_feed[SKR_MAX_CHUNKS], ev_chunk[SKR_MAX_CHUNKS], ev_copy;
+    cudaStream_t st_aux;          // second compute stream of pipeline 3's grouping stage
+    cudaEvent_t ev_fork, ev_join;
     int host_chunks;              // GBIN_HOST_CHUNKS (default 8; 1 = no overlap)
     char err[512];
     gbin_timings tm;
@@ -663,6 +665,9 @@ int run_v3_pass(gbin_ctx *ctx, const void *skr, const uint64_t *ent, const uint1
     CU(ctx->v3_unit_excl.ensure((2 * max_units + 2) * 8));
     CU(ctx->scan_scratch.ensure(group_scan_scratch_bytes(n_runs + max_units + 1024)));
     V3Chunks ch{1u, dm->v3_tickets, dm->chunk_bounds, &dm->v3_chunk_sum, dm->chunk_totals, dm->lsd_totals, nullptr, nullptr, nullptr};
+    ch.aux = ctx->st_aux;
+    ch.ev_fork = ctx->ev_fork;
+    ch.ev_join = ctx->ev_join;
     if (single_pass && sink && sink->chunks > 1) {
         ch.n = (uint32_t)sink->chunks;
         ch.totals_host = hm->chunk_totals;
@@ -1071,6 +1076,9 @@ int gbin_create(const gbin_config *cfg, gbin_ctx **out) {
     for (int i = 0; i < SKR_MAX_CHUNKS && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_feed[i], cudaEventDisableTiming);
     for (int i = 0; i < SKR_MAX_CHUNKS && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->st_aux, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     ctx->host_chunks = 8;
     if (const char *hc = getenv("GBIN_HOST_CHUNKS")) ctx->host_chunks = atoi(hc);
     if (ctx->host_chunks < 1) ctx->host_chunks = 1;
@@ -1115,6 +1123,9 @@ void gbin_destroy(gbin_ctx *ctx) {
         cudaEventDestroy(ctx->ev_chunk[i]);
     }
     cudaEventDestroy(ctx->ev_copy);
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join);
+    cudaStreamDestroy(ctx->st_aux);
     cudaStreamDestroy(ctx->st_h2d);
     cudaStreamDestroy(ctx->st_d2h);
     cudaStreamDestroy(ctx->stream);

@@ -620,6 +620,30 @@ def main():
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": f"{type(e).__name__}: {e}"}
 
+    # ---- the reference-named entry points (process_read x n + prune_data, as main drives them) on the cpu_baseline's sample: staging
+    # of the reads, the GPU path, and the ZHashTable / ll_node graph the reference's iterators walk
+    shim = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        exe = os.path.join(ROOT, "tools", "shim_bench")
+        try:
+            n = min(200_000, rs.n_reads)
+            with tempfile.NamedTemporaryFile(suffix=".txt", delete=False) as tf:
+                tf.write(rs.buf[: n * rs.stride].tobytes())
+                path = tf.name
+            try:
+                p = subprocess.run([exe, path, str(K), str(M), str(cutoff), str(rs.read_len + 2)], capture_output=True, text=True, check=True, timeout=300)
+                st = json.loads(p.stdout.strip().splitlines()[-1])
+            finally:
+                os.unlink(path)
+            secs = st["process_read_s"] + st["prune_data_s"]
+            shim = {"value": st["instances"] / secs, "unit": UNIT, "sample": f"first {n} reads, main's loop: process_read per read, then prune_data",
+                    "process_read_s": st["process_read_s"], "prune_data_s": st["prune_data_s"], "walk_s": st["walk_s"], "kmers": st["kmers"],
+                    "id_nodes": st["id_nodes"],
+                    "note": "prune_data = H2D + GPU path + D2H + building the reference's pointer graph on one host core (one ZHashEntry per k-mer, "
+                            "one ll_node per id); the graph build is what bounds this path"}
+        except Exception as e:  # noqa: BLE001
+            shim = {"value": None, "unavailable": f"{type(e).__name__}: {e}"}
+
     exchange_info = None
     if sharded is not None and stage_ms["exchange"] > 0:
         gbps = sharded.stats.sent_bytes_offrank / (stage_ms["exchange"] / 1e3) / 1e9
@@ -633,7 +657,7 @@ def main():
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
             "dtype": "u64" if K <= 32 else "u128", "data": "synthetic",
             "config": config_dict(a, w, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cpu, "table": stats, "input_split": input_split,
+            "roofline": roofline, "cpu_baseline": cpu, "shim_path": shim, "table": stats, "input_split": input_split,
             "stage_ms_rank0": (dict(stage_ms, exchange_form=getattr(sharded, "exchange_kind", "nccl"),
                                     sent_bytes_offrank=sharded.stats.sent_bytes_offrank) if sharded is not None else None),
             "exchange": exchange_info, "table_digest": digest_info, "job_table": job, "selftest": selftest,

@@ -41,6 +41,12 @@ class CTable(C.Structure):
                 ("kmer_id_off", C.c_void_p), ("read_ids", C.c_void_p)]
 
 
+class CExpanded(C.Structure):
+    """gbin_expanded: the list of lists expand_read_id_list builds (binning.c:857-888), in CSR form."""
+    _fields_ = [("kmer_size", C.c_int32), ("on_device", C.c_int32), ("n_lists", C.c_uint64), ("n_ids", C.c_uint64),
+                ("list_off", C.c_void_p), ("ids", C.c_void_p)]
+
+
 class CReads(C.Structure):
     _fields_ = [("data", C.c_void_p), ("data_bytes", C.c_uint64), ("n_reads", C.c_uint64), ("stride", C.c_uint64),
                 ("read_len", C.c_uint32), ("id_base", C.c_int32), ("starts", C.c_void_p), ("lens", C.c_void_p),
@@ -68,6 +74,7 @@ EXPORTS = [
     "gbin_count_instances_device", "gbin_scan_reads_device", "gbin_partition_records_device",
     "gbin_group_records_device", "gbin_owner_of", "gbin_xchg_create", "gbin_xchg_attach", "gbin_xchg_exchange_skr", "gbin_xchg_destroy", "gbin_skr_record_bytes", "gbin_scan_skr_device", "gbin_partition_skr_device", "gbin_group_skr_device",
     "gbin_split_reads_device", "gbin_copy_to_host", "gbin_bin_file_host", "gbin_read_file_fgets", "gbin_table_dump", "gbin_table_dump_reference_format", "gbin_table_dump_expanded_format",
+    "gbin_expand_read_ids_device", "gbin_expanded_to_host", "gbin_expanded_free", "gbin_table_dump_expanded_lists",
     "getval", "getbp", "getscore", "process_read", "prune_data", "gbin_ref_configure", "gbin_ref_last_status",
     "gbin_ref_reset", "gbin_table_to_zhash", "gbin_zhash_release",
 ]
@@ -142,6 +149,11 @@ def load_library() -> C.CDLL:
     L.gbin_table_dump.argtypes = [C.POINTER(CTable), C.c_char_p]
     L.gbin_table_dump_reference_format.argtypes = [C.POINTER(CTable), C.c_char_p]
     L.gbin_table_dump_expanded_format.argtypes = [C.POINTER(CTable), C.c_char_p]
+    L.gbin_expand_read_ids_device.argtypes = [C.c_void_p, C.POINTER(CTable), C.c_void_p, C.POINTER(CExpanded)]
+    L.gbin_expanded_to_host.argtypes = [C.c_void_p, C.POINTER(CExpanded), C.POINTER(CExpanded)]
+    L.gbin_expanded_free.argtypes = [C.POINTER(CExpanded)]
+    L.gbin_expanded_free.restype = None
+    L.gbin_table_dump_expanded_lists.argtypes = [C.POINTER(CTable), C.POINTER(CExpanded), C.c_char_p]
     L.getval.argtypes = [C.c_char]
     L.getval.restype = C.c_int
     L.getbp.argtypes = [C.c_int]
@@ -286,6 +298,17 @@ class Binner:
         d = C.c_uint64()
         self._check(self.lib.gbin_table_digest(self.h, C.byref(table), stream, C.byref(d)))
         return int(d.value)
+
+    def expand_read_ids_device(self, dev_table: CTable, stream=None) -> CExpanded:
+        """expand_read_id_list on the device: K copies of every surviving k-mer's id list (device memory of the context)."""
+        x = CExpanded()
+        self._check(self.lib.gbin_expand_read_ids_device(self.h, C.byref(dev_table), stream, C.byref(x)))
+        return x
+
+    def expanded_to_host(self, dev: CExpanded) -> CExpanded:
+        h = CExpanded()
+        self._check(self.lib.gbin_expanded_to_host(self.h, C.byref(dev), C.byref(h)))
+        return h
 
     def set_tuning(self, name: str, value: int):
         self._check(self.lib.gbin_set_tuning(self.h, name.encode(), int(value)))

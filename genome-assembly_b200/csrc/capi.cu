@@ -148,6 +148,7 @@ struct gbin_ctx {
     DevBuf skr_a, skr_b, tile_state, inst_prefix, run_excl, skr_run_start, small_prefix, unit_base, units, unit_state, o_kmer_mmer, bucket_excl, big_list, big_k0, big_k1, big_arr, stg_ids, stg_codes, stg_mmer, stg_off, skr_side;
     // pipeline v3 workspace
     DevBuf ent_a, ent_b, piece_n, sorted_info, v3_base64, v3_head_run, v3_unit_out, v3_unit_excl, v3_atoms, v3_lsd_aux, v3_bitmap;
+    DevBuf x_list_off, x_ids;         // gbin_expand_read_ids_device's result
     bool v3_lsd_seen = false;         // a batch on this context had long spans: keep the arrays of their global sort
     uint64_t v3_lsd_cap_seen = 0;     // and how many k-mers they were sized for
     uint64_t v3_pass_max = 2000000000ull;  // k-mer instances per pass of pipeline 3 (gbin_set_tuning "v3_pass_max")
@@ -1105,7 +1106,7 @@ void gbin_destroy(gbin_ctx *ctx) {
                       &ctx->o_kmer_codes, &ctx->o_kmer_id_off, &ctx->o_read_ids, &ctx->skr_a, &ctx->skr_b, &ctx->tile_state,
                       &ctx->inst_prefix, &ctx->run_excl, &ctx->skr_run_start, &ctx->small_prefix, &ctx->unit_base, &ctx->units,
                       &ctx->unit_state, &ctx->o_kmer_mmer, &ctx->bucket_excl, &ctx->big_list, &ctx->big_k0, &ctx->big_k1, &ctx->big_arr, &ctx->stg_ids, &ctx->stg_codes, &ctx->stg_mmer, &ctx->stg_off, &ctx->skr_side,
-                      &ctx->ent_a, &ctx->ent_b, &ctx->piece_n, &ctx->sorted_info, &ctx->v3_base64, &ctx->v3_head_run, &ctx->v3_unit_out, &ctx->v3_unit_excl, &ctx->v3_atoms, &ctx->v3_lsd_aux, &ctx->v3_bitmap};
+                      &ctx->ent_a, &ctx->ent_b, &ctx->piece_n, &ctx->sorted_info, &ctx->v3_base64, &ctx->v3_head_run, &ctx->v3_unit_out, &ctx->v3_unit_excl, &ctx->v3_atoms, &ctx->v3_lsd_aux, &ctx->v3_bitmap, &ctx->x_list_off, &ctx->x_ids};
     for (DevBuf *b : bufs) b->release();
     ctx->h_misc.release();
     ctx->h_result.release();
@@ -1512,6 +1513,50 @@ int gbin_table_digest(gbin_ctx *ctx, const gbin_table *t, void *stream, uint64_t
     CU(cudaMemcpyAsync(&hm->n_real_entries, &dm->n_real_entries, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     *digest_out = hm->n_real_entries;
+    return GBIN_OK;
+}
+
+int gbin_expand_read_ids_device(gbin_ctx *ctx, const gbin_table *t, void *stream, gbin_expanded *out) {
+    if (!ctx || !t || !out || !t->on_device) return GBIN_E_INVALID_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    const uint64_t K = (uint64_t)t->kmer_size, S = t->n_kmers, N = t->n_ids;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t need = (S * K + 1) * sizeof(uint64_t) + (K * N + 1) * sizeof(int32_t);
+    if (need > (uint64_t)free_b + ctx->x_list_off.cap + ctx->x_ids.cap)
+        return fail(ctx, GBIN_E_TOO_LARGE, "expanded id lists need %llu bytes (K = %llu copies of %llu ids), %llu are free", (unsigned long long)need,
+                    (unsigned long long)K, (unsigned long long)N, (unsigned long long)free_b);
+    CU(ctx->x_list_off.ensure((S * K + 1) * sizeof(uint64_t)));
+    CU(ctx->x_ids.ensure((K * N + 1) * sizeof(int32_t)));
+    expand_ids_device(t->kmer_id_off, t->read_ids, S, (uint32_t)K, ctx->x_list_off.as<uint64_t>(), ctx->x_ids.as<int32_t>(), ctx->sm_count, st);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    out->kmer_size = t->kmer_size;
+    out->on_device = 1;
+    out->n_lists = S * K;
+    out->n_ids = K * N;
+    out->list_off = ctx->x_list_off.as<uint64_t>();
+    out->ids = ctx->x_ids.as<int32_t>();
+    return GBIN_OK;
+}
+
+int gbin_expanded_to_host(gbin_ctx *ctx, const gbin_expanded *dev, gbin_expanded *host) {
+    if (!ctx || !dev || !host || !dev->on_device) return GBIN_E_INVALID_ARG;
+    CU(cudaSetDevice(ctx->cfg.device));
+    *host = *dev;
+    host->on_device = 0;
+    host->list_off = static_cast<uint64_t *>(malloc((dev->n_lists + 1) * sizeof(uint64_t)));
+    host->ids = static_cast<int32_t *>(malloc((dev->n_ids + 1) * sizeof(int32_t)));
+    if (!host->list_off || !host->ids) {
+        free(host->list_off);
+        free(host->ids);
+        host->list_off = nullptr;
+        host->ids = nullptr;
+        return GBIN_E_NOMEM;
+    }
+    CU(cudaMemcpy(host->list_off, dev->list_off, (dev->n_lists + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (dev->n_ids) CU(cudaMemcpy(host->ids, dev->ids, dev->n_ids * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return GBIN_OK;
 }
 

@@ -238,6 +238,42 @@ int gbin_table_dump_expanded_format(const gbin_table *t, const char *path)
     return GBIN_OK;
 }
 
+/* The same text from the expanded lists (gbin_expand_read_ids_device + gbin_expanded_to_host): one line per list of lists entry. */
+int gbin_table_dump_expanded_lists(const gbin_table *t, const gbin_expanded *x, const char *path)
+{
+    if (!t || !x || t->on_device || x->on_device) return GBIN_E_INVALID_ARG;
+    if (x->kmer_size != t->kmer_size || x->n_lists != t->n_kmers * (uint64_t)t->kmer_size) return GBIN_E_INVALID_ARG;
+    FILE *f = open_out(path);
+    if (!f) return GBIN_E_IO;
+    char mm[40], km[80];
+    for (uint64_t b = 0; b < t->n_buckets; b++) {
+        decode_code(0, t->mmer_codes[b], t->mmer_size, mm);
+        fprintf(f, "%s\n", mm);
+        for (uint64_t s = t->mmer_kmer_off[b]; s < t->mmer_kmer_off[b + 1]; s++) {
+            kmer_string(t, s, km);
+            fprintf(f, "%s\n", km);
+            for (uint64_t l = s * (uint64_t)t->kmer_size; l < (s + 1) * (uint64_t)t->kmer_size; l++) {
+                for (uint64_t q = x->list_off[l]; q < x->list_off[l + 1]; q++) fprintf(f, "%d ", x->ids[q]);
+                fputc('\n', f);
+            }
+        }
+        fputc('\n', f);
+    }
+    if (f != stdout) fclose(f);
+    else fflush(f);
+    return GBIN_OK;
+}
+
+void gbin_expanded_free(gbin_expanded *x)
+{
+    if (!x || x->on_device) return;
+    free(x->list_off);
+    free(x->ids);
+    x->list_off = NULL;
+    x->ids = NULL;
+    x->n_lists = x->n_ids = 0;
+}
+
 /* ------------------------------------------------------------------ ZHashTable / ll_node adapter */
 
 /* zhash.c:171-182: h = (17*h + ch) % size over the key bytes — needed so that the reference's own

@@ -286,6 +286,25 @@ int gbin_table_dump_reference_format(const gbin_table *host, const char *path);
  * so print_kmer_read_ids prints K lines of ids per k-mer — the layout generate_reads.py:14-62 parses. */
 int gbin_table_dump_expanded_format(const gbin_table *host, const char *path);
 
+/* ---- expand_read_id_list (binning.c:857-888): every base of every surviving k-mer gets its own copy of the k-mer's id list ----
+ * CSR again: list (j, b) of k-mer j (table order) and base b is ids[list_off[j*K + b] .. list_off[j*K + b + 1]); the K lists of a
+ * k-mer are stored back to back.  n_lists = n_kmers * K, n_ids = K * (the table's n_ids): K times the memory of the table's ids. */
+typedef struct gbin_expanded {
+    int32_t kmer_size;
+    int32_t on_device;   /* 1: device pointers owned by the context (valid until its next gbin_expand_read_ids_device call) */
+    uint64_t n_lists, n_ids;
+    uint64_t *list_off;  /* [n_lists + 1] */
+    int32_t *ids;        /* [n_ids] */
+} gbin_expanded;
+/* Device table in, expanded lists out (device memory of the context).  GBIN_E_TOO_LARGE when K * n_ids ids do not fit the device. */
+int gbin_expand_read_ids_device(gbin_ctx *ctx, const gbin_table *dev_table, void *stream, gbin_expanded *out);
+/* Copies a device result into malloc'ed host arrays (release with gbin_expanded_free). */
+int gbin_expanded_to_host(gbin_ctx *ctx, const gbin_expanded *dev, gbin_expanded *host);
+void gbin_expanded_free(gbin_expanded *host);
+/* gbin_table_dump_expanded_format's text, written from the expanded lists themselves (what print_kmer_read_ids, binning.c:792-823,
+ * prints when it walks the list of lists).  `table` and `lists` are HOST objects of the same batch. */
+int gbin_table_dump_expanded_lists(const gbin_table *table, const gbin_expanded *lists, const char *path);
+
 /* ---- the reference's own entry points (binning.c) ---- */
 struct ZHashTable;
 int getval(char c);            /* binning.c:91 */

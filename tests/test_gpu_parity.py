@@ -591,3 +591,54 @@ def test_full_size_cfg2_properties_and_prefix_parity():
     got = b.bin_host(rs.buf[: n * rs.stride], n, stride=rs.stride, read_len=rs.read_len)
     assert_tables_equal(got, O.run(rs.buf[: n * rs.stride].tobytes(), starts, lens, 31, 11, 1))
     b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cfg1_reads", "cfg2_small", "cfg4_small", "kat_twice"])
+def test_expand_read_id_list_on_the_device(name, tmp_path):
+    """expand_read_id_list (binning.c:857-888) as a device CSR replicate.  The expanded lists, copied back and
+    printed in print_kmer_read_ids's layout, give byte for byte the text of gbin_table_dump_expanded_format (which the CPU suite
+    pins against the unmodified reference's own expand + print), and — where the reference harness is built — the same
+    {(m-mer, k-mer): K id lines} as the reference's --expanded output."""
+    import os
+    import subprocess
+    torch = torch_cuda()
+    case = next(c for c in CASES if c["name"] == name)
+    data = O.load_case_bytes(case)
+    starts, lens = O.fgets_split(data, case["read_length_define"])
+    K = case["k"]
+    b = B.Binner(K, case["m"], case["cutoff"])
+    rd, keep = dev_reads(torch, data, starts, lens)
+    dev = b.bin_device_raw(rd)
+    xd = b.expand_read_ids_device(dev)
+    assert (xd.n_lists, xd.n_ids, xd.on_device) == (dev.n_kmers * K, dev.n_ids * K, 1)
+    xh = b.expanded_to_host(xd)
+    ht = B.CTable()
+    b._check(b.lib.gbin_table_to_host(b.h, C.byref(dev), C.byref(ht)))
+    try:
+        off = np.ctypeslib.as_array(C.cast(xh.list_off, C.POINTER(C.c_uint64)), shape=(xh.n_lists + 1,))
+        ids = np.ctypeslib.as_array(C.cast(xh.ids, C.POINTER(C.c_int32)), shape=(max(xh.n_ids, 1),))[: xh.n_ids]
+        t_off = np.ctypeslib.as_array(C.cast(ht.kmer_id_off, C.POINTER(C.c_uint64)), shape=(ht.n_kmers + 1,))
+        t_ids = np.ctypeslib.as_array(C.cast(ht.read_ids, C.POINTER(C.c_int32)), shape=(max(ht.n_ids, 1),))[: ht.n_ids]
+        # CSR replicate: list (j, b) is a copy of list j, the K lists of a k-mer back to back
+        cnt = np.diff(t_off)
+        np.testing.assert_array_equal(np.diff(off), np.repeat(cnt, K))
+        assert off[0] == 0 and off[-1] == K * ht.n_ids
+        want = np.concatenate([np.tile(t_ids[t_off[j]:t_off[j + 1]], K) for j in range(int(ht.n_kmers))]) if ht.n_kmers else np.zeros(0, np.int32)
+        np.testing.assert_array_equal(ids, want)
+        p1, p2 = tmp_path / "lists.txt", tmp_path / "format.txt"
+        assert b.lib.gbin_table_dump_expanded_lists(C.byref(ht), C.byref(xh), str(p1).encode()) == 0
+        assert b.lib.gbin_table_dump_expanded_format(C.byref(ht), str(p2).encode()) == 0
+        assert p1.read_bytes() == p2.read_bytes()
+        exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref",
+                           f"ref_K{K}_M{case['m']}_C{case['cutoff']}_R{case['read_length_define']}")
+        if os.path.exists(exe) and name in ("cfg1_reads", "cfg2_small"):
+            src = tmp_path / "reads.txt"
+            src.write_bytes(data)
+            ref = subprocess.run([exe, str(src), "--expanded"], capture_output=True, check=True).stdout
+            from test_capi_cpu import _parse_expanded
+            assert _parse_expanded(p1.read_bytes(), K) == _parse_expanded(ref, K)
+    finally:
+        b.lib.gbin_expanded_free(C.byref(xh))
+        b.lib.gbin_table_free(C.byref(ht))
+    b.close()

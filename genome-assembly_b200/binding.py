@@ -72,7 +72,7 @@ EXPORTS = [
     "gbin_bin_reads_device", "gbin_table_to_host", "gbin_table_to_pinned", "gbin_get_timings", "gbin_record_bytes",
     "gbin_set_kernel_profiling", "gbin_get_kernel_profile", "gbin_kernel_kind_name", "gbin_max_read_len", "gbin_multi_create", "gbin_multi_destroy", "gbin_multi_devices", "gbin_multi_context", "gbin_multi_last_error", "gbin_multi_bin_reads_host", "gbin_table_digest", "gbin_set_pipeline", "gbin_set_tuning", "gbin_get_pipeline_info", "gbin_get_run_stats",
     "gbin_count_instances_device", "gbin_scan_reads_device", "gbin_partition_records_device",
-    "gbin_group_records_device", "gbin_owner_of", "gbin_xchg_create", "gbin_xchg_attach", "gbin_xchg_exchange_skr", "gbin_xchg_destroy", "gbin_skr_record_bytes", "gbin_scan_skr_device", "gbin_partition_skr_device", "gbin_group_skr_device",
+    "gbin_group_records_device", "gbin_owner_of", "gbin_xchg_create", "gbin_xchg_attach", "gbin_xchg_exchange_skr", "gbin_xchg_detach", "gbin_xchg_destroy", "gbin_skr_record_bytes", "gbin_scan_skr_device", "gbin_partition_skr_device", "gbin_group_skr_device",
     "gbin_split_reads_device", "gbin_copy_to_host", "gbin_bin_file_host", "gbin_read_file_fgets", "gbin_table_dump", "gbin_table_dump_reference_format", "gbin_table_dump_expanded_format",
     "gbin_expand_read_ids_device", "gbin_expanded_to_host", "gbin_expanded_free", "gbin_table_dump_expanded_lists",
     "getval", "getbp", "getscore", "process_read", "prune_data", "gbin_ref_configure", "gbin_ref_last_status",
@@ -141,6 +141,8 @@ def load_library() -> C.CDLL:
     L.gbin_xchg_exchange_skr.argtypes = [vp, vp, u64, vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
     L.gbin_xchg_destroy.argtypes = [vp]
     L.gbin_xchg_destroy.restype = None
+    L.gbin_xchg_detach.argtypes = [vp]
+    L.gbin_xchg_detach.restype = None
     L.gbin_split_reads_device.argtypes = [vp, vp, u64, C.c_int, vp, C.POINTER(CReads)]
     L.gbin_copy_to_host.argtypes = [vp, vp, vp, u64]
     L.gbin_bin_file_host.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(CTable)]
@@ -460,6 +462,9 @@ class Binner:
         sent = (C.c_uint64 * 16)()
         self._check(self.lib.gbin_xchg_exchange_skr(self.h, _ptr(d_skr), n, stream, C.byref(recv), C.byref(n_in), sent))
         return int(recv.value or 0), int(n_in.value), [int(sent[i]) for i in range(world)]
+
+    def xchg_detach(self):
+        self.lib.gbin_xchg_detach(self.h)
 
     def xchg_destroy(self):
         self.lib.gbin_xchg_destroy(self.h)

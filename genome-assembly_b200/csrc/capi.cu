@@ -156,6 +156,7 @@ struct gbin_ctx {
     int v3_auto_h = 0, v3_auto_nc = 1;
     int v3_h, v3_nc, v3_cap;  // key layout and unit capacity of pipeline 3 (gbin_set_tuning; GBIN_V3_H / GBIN_V3_NC / GBIN_V3_CAP); v3_cap 0 = by layout
     int v3_cap_eff;           // the capacity of the current batch
+    int xchg_timeout_ms = 120000;  // gbin_set_tuning "xchg_timeout_ms" / GBIN_XCHG_TIMEOUT_MS
     int pipeline;        // 3: sort by reference + warp units, falling back to 2, then 1 (default); 2: super-k-mer path with v1 as fallback; 1: v1 only
     int last_pipeline;   // which one produced the last table
     uint32_t fallbacks;  // v2 -> v1 fallbacks since creation
@@ -1062,6 +1063,8 @@ int gbin_create(const gbin_config *cfg, gbin_ctx **out) {
     // 128-bit k-mer codes double the shared memory of a unit: units of 512 instances keep the warps per SM up
     ctx->v3_cap = 0;
     ctx->v3_cap_eff = ctx->KW == 2 ? 512 : 1024;
+    if (const char *e = getenv("GBIN_XCHG_TIMEOUT_MS"))
+        if (atoi(e) >= 100) ctx->xchg_timeout_ms = atoi(e);
     if (const char *e = getenv("GBIN_V3_CAP")) ctx->v3_cap = atoi(e) == 512 ? 512 : (atoi(e) == 1024 ? 1024 : 0);
     ctx->last_pipeline = 0;
     ctx->fallbacks = 0;
@@ -1210,6 +1213,10 @@ int gbin_set_tuning(gbin_ctx *ctx, const char *name, int value) {
     } else if (!strcmp(name, "v3_pass_max")) {
         if (value < 1000) return GBIN_E_INVALID_ARG;
         ctx->v3_pass_max = (uint64_t)value;
+    } else if (!strcmp(name, "xchg_timeout_ms")) {  // how long the exchange kernels wait for a peer's flag before they give up (status 2)
+        if (value < 100) return GBIN_E_INVALID_ARG;
+        ctx->xchg_timeout_ms = value;
+        ctx->xg.plan.timeout_cycles = (long long)value * 2000000ll;
     } else if (!strcmp(name, "host_chunks")) {
         if (value < 1 || value > SKR_MAX_CHUNKS) return GBIN_E_INVALID_ARG;
         ctx->host_chunks = value;
@@ -1689,7 +1696,9 @@ int gbin_xchg_attach(gbin_ctx *ctx, const void *all_handles) {
     if (!ctx || !all_handles || !ctx->xg.created) return GBIN_E_INVALID_ARG;
     CU(cudaSetDevice(ctx->cfg.device));
     auto &x = ctx->xg;
+    if (x.n_opened) gbin_xchg_detach(ctx);  // a second attach replaces the first one's mappings
     memset(&x.plan, 0, sizeof x.plan);
+    x.plan.timeout_cycles = (long long)ctx->xchg_timeout_ms * 2000000ll;  // about 2 GHz
     x.plan.rank = x.rank;
     x.plan.world = x.world;
     x.plan.dst_tab = x.dst_tab;
@@ -1717,13 +1726,23 @@ int gbin_xchg_attach(gbin_ctx *ctx, const void *all_handles) {
     return GBIN_OK;
 }
 
-void gbin_xchg_destroy(gbin_ctx *ctx) {
+// Phase 1 of a collective teardown: close the mappings of the peers' buffers.  Every rank detaches, the caller barriers, and only then
+// does an owner free what it exported (gbin_xchg_destroy): freeing exported memory while an importer still has it open is undefined.
+void gbin_xchg_detach(gbin_ctx *ctx) {
     if (!ctx || !ctx->xg.created) return;
     auto &x = ctx->xg;
     cudaSetDevice(ctx->cfg.device);
     cudaDeviceSynchronize();
     for (int i = 0; i < x.n_opened; i++) cudaIpcCloseMemHandle(x.opened[i]);
     x.n_opened = 0;
+    x.attached = false;
+    (void)cudaGetLastError();
+}
+
+void gbin_xchg_destroy(gbin_ctx *ctx) {
+    if (!ctx || !ctx->xg.created) return;
+    auto &x = ctx->xg;
+    gbin_xchg_detach(ctx);
     cudaFree(x.recv);
     cudaFree(x.sh);
     cudaFree(x.dst_tab);
@@ -1895,7 +1914,9 @@ namespace {
 int multi_attach_local(gbin_multi *m, int g) {
     gbin_ctx *ctx = m->ctx[g];
     auto &x = ctx->xg;
+    if (x.n_opened) gbin_xchg_detach(ctx);  // a second attach replaces the first one's mappings
     memset(&x.plan, 0, sizeof x.plan);
+    x.plan.timeout_cycles = (long long)ctx->xchg_timeout_ms * 2000000ll;  // about 2 GHz
     x.plan.rank = x.rank;
     x.plan.world = x.world;
     x.plan.dst_tab = x.dst_tab;

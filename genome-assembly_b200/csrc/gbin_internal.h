@@ -92,6 +92,7 @@ struct XchgPlan {  // passed to the kernels by value
     unsigned long long cap[XCHG_MAX_WORLD];  // their capacities in records
     char **dst_tab;                        // device, [XCHG_MAX_WORLD]: per-owner destinations of this exchange
     XchgResult *result;                    // device
+    long long timeout_cycles;              // how long a kernel waits for a peer's flag (0: the default below)
 };
 int radix_exchange_skr_by_owner(const void *in, uint64_t n, int skr_words, void *scratch, const XchgPlan &xp, cudaStream_t st);
 

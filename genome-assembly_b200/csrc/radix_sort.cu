@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(RS_THREADS)
 //   4. xchg_done_kernel: "my stores are done" to every peer, then waits for all peers' flags: the receive buffer is
 //      complete.  A rank publishes the counts of its NEXT exchange only after it has consumed its receive buffer (stream
 //      order), so waiting for all rows in step 2 also means every receive buffer is free again.
-// Waits are bounded (XCHG_TIMEOUT_CYCLES) so a missing peer yields an error code, not a hung GPU.
+// Waits are bounded (XchgPlan::timeout_cycles, two minutes unless set) so a missing peer yields an error code, not a hung GPU.
 
 __device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -250,12 +250,13 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-constexpr long long XCHG_TIMEOUT_CYCLES = 6000000000ll;  // about 3 s
+constexpr long long XCHG_TIMEOUT_CYCLES = 240000000000ll;  // about 2 minutes (gbin_set_tuning "xchg_timeout_ms" sets XchgPlan::timeout_cycles)
 
-__device__ __forceinline__ bool xchg_wait_flag(const unsigned int *p, unsigned int epoch) {
+__device__ __forceinline__ bool xchg_wait_flag(const unsigned int *p, unsigned int epoch, long long timeout_cycles) {
     const long long t0 = clock64();
+    const long long limit = timeout_cycles > 0 ? timeout_cycles : XCHG_TIMEOUT_CYCLES;
     while (ld_acquire_sys(p) != epoch) {
-        if (clock64() - t0 > XCHG_TIMEOUT_CYCLES) return false;
+        if (clock64() - t0 > limit) return false;
         __nanosleep(200);
     }
     return true;
@@ -275,7 +276,7 @@ __global__ void xchg_counts_kernel(const uint32_t *__restrict__ tile_off, uint32
     bool ok = true;
     if (lane < G) {
         st_release_sys(&xp.peer_sh[lane]->count_flag[me], xp.epoch);
-        ok = xchg_wait_flag(&xp.peer_sh[me]->count_flag[lane], xp.epoch);
+        ok = xchg_wait_flag(&xp.peer_sh[me]->count_flag[lane], xp.epoch, xp.timeout_cycles);
     }
     const bool all_here = __all_sync(0xffffffffu, ok);
     unsigned long long off = 0, tot = 0;
@@ -306,7 +307,7 @@ __global__ void xchg_done_kernel(XchgPlan xp) {
     bool ok = true;
     if (lane < G) {
         st_release_sys(&xp.peer_sh[lane]->done_flag[me], xp.epoch);
-        ok = xchg_wait_flag(&xp.peer_sh[me]->done_flag[lane], xp.epoch);
+        ok = xchg_wait_flag(&xp.peer_sh[me]->done_flag[lane], xp.epoch, xp.timeout_cycles);
     }
     if (!__all_sync(0xffffffffu, ok) && lane == 0) xp.result->status = 2u;
 }

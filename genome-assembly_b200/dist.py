@@ -103,6 +103,9 @@ class GpuStages:
         group).  False when the form has no peer path (instance records use the NCCL all-to-all)."""
         if self.form != "skr":
             return False
+        if getattr(self, "peer_world", 0):  # regrow: all ranks close their mappings before any owner frees what it exported
+            self.b.xchg_detach()
+            dist.barrier(group=group)
         mine = self.b.xchg_create(rank, world, capacity_records)
         blobs = [None] * world
         dist.all_gather_object(blobs, mine, group=group)

@@ -175,6 +175,7 @@ int gbin_set_pipeline(gbin_ctx *ctx, int pipeline);
  *                          and the key extended by v3_h bases next to the signature; 0 (default) = chosen per batch from the mean bucket size
  *   "v3_h"   0..           with v3_nc = 2: bases next to the signature that extend the level-1 key (clamped to what K, M allow)
  *   "v3_pass_max" >= 1000  k-mer instances per pass of pipeline 3 (default 2 * 10^9; small values exercise the multi-pass path)
+ *   "xchg_timeout_ms" >= 100  how long the multi-GPU exchange kernels wait for a peer before they give up (default 120000)
  *   "host_chunks" 1..16    pieces in which gbin_bin_reads_host streams reads in / the table out */
 int gbin_set_tuning(gbin_ctx *ctx, const char *name, int value);
 int gbin_get_pipeline_info(const gbin_ctx *ctx, int *configured, int *last_used, uint32_t *fallbacks);
@@ -243,6 +244,10 @@ int gbin_xchg_create(gbin_ctx *ctx, uint32_t rank, uint32_t world, uint64_t capa
 int gbin_xchg_attach(gbin_ctx *ctx, const void *all_handles);
 int gbin_xchg_exchange_skr(gbin_ctx *ctx, const void *d_skr, uint64_t n, void *stream, void **d_recv_out, uint64_t *n_recv_out,
                            uint64_t *sent_counts);
+/* Teardown is collective and has two phases: every rank calls gbin_xchg_detach (closes its mappings of the peers' buffers), the
+ * caller barriers, then every rank calls gbin_xchg_destroy (frees what it exported).  gbin_xchg_destroy alone detaches first, which
+ * is only safe when the peers have already detached (or are gone). */
+void gbin_xchg_detach(gbin_ctx *ctx);
 void gbin_xchg_destroy(gbin_ctx *ctx);
 
 /* ---- several GPUs of one node behind one C call (one process, one host thread per GPU; no Python, no MPI, no NCCL) ----

@@ -1355,15 +1355,327 @@ int v3_group_launch(const void *skr, const uint64_t *ent, const void *units, con
     return launches;
 }
 
+// ---- long spans, the common case: every span sorted on its own in shared memory.
+// The records of a long span are contiguous, all carry the span's m-mer code, and consist of the ascending runs its units wrote
+// (a unit's survivors are in k-mer order).  One CTA loads a span, finds the natural runs (a run ends where the k-mer decreases),
+// and merges neighbouring runs pairwise, log2(runs) rounds between two buffers in shared memory: a k-mer's place in the merged
+// run = its index in its own run + the number of smaller k-mers in the sibling run (binary search; k-mers of a span are
+// distinct).  One read and one write of the records instead of the 11 radix passes of the global sort, which is kept for
+// spans that do not fit shared memory (more than SS_CAP_BIG k-mers).
+template <int KW>
+struct RecHead {
+    const Rec<KW> *rec;
+    __device__ __forceinline__ uint32_t operator()(uint64_t p) const { return (p == 0 || rec[p].mmer != rec[p - 1].mmer) ? 1u : 0u; }
+};
+template <int KW>
+__global__ void span_starts_kernel(const Rec<KW> *__restrict__ rec, uint64_t n, const uint32_t *__restrict__ idx, uint32_t *__restrict__ starts,
+                                   uint32_t *__restrict__ n_spans, uint32_t *__restrict__ flag) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const bool head = p == 0 || rec[p].mmer != rec[p - 1].mmer;
+    if (head) starts[idx[p]] = (uint32_t)p;
+    if (p == n - 1) {
+        const uint32_t total = idx[p] + (head ? 1u : 0u);  // idx = heads before p
+        starts[total] = (uint32_t)n;
+        *n_spans = total;
+        *flag = 0u;
+    }
+}
+
+constexpr int SS_RMAX = 1024;  // runs of a span (more: left to the global sort)
+template <int KW, int CAP, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+    span_sort_kernel(Rec<KW> *__restrict__ rec, const uint32_t *__restrict__ starts, const uint32_t *__restrict__ n_spans_ptr, uint32_t m_min, uint32_t m_max,
+                     uint32_t *__restrict__ too_big) {
+    extern __shared__ __align__(16) uint8_t ss_smem[];
+    uint64_t *ka = reinterpret_cast<uint64_t *>(ss_smem);        // [KW][CAP] keys, buffer a
+    uint64_t *kb = ka + KW * CAP;                                // buffer b
+    uint16_t *sa = reinterpret_cast<uint16_t *>(kb + KW * CAP);  // [CAP] place of the record before the sort (relative to the span), buffer a
+    uint16_t *sb = sa + CAP;
+    uint16_t *ra = sb + CAP;  // [SS_RMAX + 2] run starts, buffer a
+    uint16_t *rb = ra + SS_RMAX + 2;
+    __shared__ uint32_t s_nruns;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t n_spans = *n_spans_ptr;
+    for (uint32_t s = blockIdx.x; s < n_spans; s += gridDim.x) {
+        const uint32_t b = starts[s], m = starts[s + 1] - b;
+        if (m < m_min) continue;
+        if (m > m_max) continue;  // another launch's span
+        const uint32_t mmer = rec[b].mmer;
+        for (uint32_t i = tid; i < m; i += THREADS) {
+            const Rec<KW> r = load_rec<KW>(rec + b + i);
+            ka[i] = r.k[0];
+            if (KW == 2) ka[CAP + i] = r.k[KW - 1];
+            sa[i] = (uint16_t)i;
+        }
+        __syncthreads();
+        if (tid < 32) {  // natural runs
+            uint32_t nr = 0;
+            for (uint32_t i0 = 0; i0 < m; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                bool head = false;
+                if (i < m) {
+                    head = i == 0 || ka[i] < ka[i - 1];
+                    if (KW == 2 && i && ka[i] == ka[i - 1]) head = ka[CAP + i] < ka[CAP + i - 1];
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, head);
+                if (head) {
+                    const uint32_t pos = nr + __popc(bal & ((1u << lane) - 1u));
+                    if (pos < (uint32_t)SS_RMAX) ra[pos] = (uint16_t)i;
+                }
+                nr += __popc(bal);
+            }
+            if (lane == 0) {
+                s_nruns = nr;
+                if (nr <= (uint32_t)SS_RMAX) ra[nr] = (uint16_t)m;
+            }
+        }
+        __syncthreads();
+        uint32_t nr = s_nruns;
+        if (nr > (uint32_t)SS_RMAX) {
+            if (tid == 0) atomicExch(too_big, 1u);
+            __syncthreads();
+            continue;
+        }
+        uint64_t *src_k = ka, *dst_k = kb;
+        uint16_t *src_s = sa, *dst_s = sb, *src_r = ra, *dst_r = rb;
+        while (nr > 1) {
+            for (uint32_t i = tid; i < m; i += THREADS) {
+                // my run: the last a with src_r[a] <= i
+                uint32_t lo = 0, hi = nr;
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (src_r[mid] <= i) lo = mid;
+                    else hi = mid;
+                }
+                const uint32_t a = lo, sib = a ^ 1u;
+                const uint32_t pair0 = src_r[a & ~1u];
+                uint32_t place;
+                if (sib >= nr) {
+                    place = i;  // the odd run out keeps its place
+                } else {
+                    const uint64_t k0 = src_k[i], k1 = KW == 2 ? src_k[CAP + i] : 0ull;
+                    uint32_t l = src_r[sib], h = src_r[sib + 1];
+                    const uint32_t sib0 = l;
+                    while (l < h) {  // k-mers of the sibling run smaller than mine
+                        const uint32_t mid = (l + h) >> 1;
+                        const uint64_t q0 = src_k[mid];
+                        bool less = q0 < k0;
+                        if (KW == 2) less = less || (q0 == k0 && src_k[CAP + mid] < k1);
+                        if (less) l = mid + 1;
+                        else h = mid;
+                    }
+                    place = pair0 + (i - src_r[a]) + (l - sib0);
+                }
+                dst_k[place] = src_k[i];
+                if (KW == 2) dst_k[CAP + place] = src_k[CAP + i];
+                dst_s[place] = src_s[i];
+            }
+            const uint32_t nr2 = (nr + 1) >> 1;
+            for (uint32_t a = tid; a <= nr2; a += THREADS) dst_r[a] = a < nr2 ? src_r[2 * a] : (uint16_t)m;
+            __syncthreads();
+            uint64_t *tk = src_k;
+            src_k = dst_k;
+            dst_k = tk;
+            uint16_t *ts = src_s;
+            src_s = dst_s;
+            dst_s = ts;
+            uint16_t *tr = src_r;
+            src_r = dst_r;
+            dst_r = tr;
+            nr = nr2;
+        }
+        if (s_nruns > 1) {  // (one run: the span was in order already)
+            for (uint32_t i = tid; i < m; i += THREADS) {
+                Rec<KW> r;
+                r.k[0] = src_k[i];
+                if (KW == 2) r.k[KW - 1] = src_k[CAP + i];
+                r.mmer = mmer;
+                r.arrival = b + src_s[i];
+                store_rec<KW>(rec + b + i, r);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// The same merge for a span that does not fit shared memory: the two buffers are the span's ranges of rec and rec2 in global
+// memory (L2-resident: such a span is a few hundred KB), only the run starts live in shared memory.  One CTA per span.
+constexpr int SS_RMAX_G = 8192;
+template <int KW>
+__device__ __forceinline__ bool rec_less(const Rec<KW> *a, uint64_t k0, uint64_t k1) {  // *a < (k0, k1), loads that bypass L1
+    const uint64_t q0 = __ldcg(reinterpret_cast<const unsigned long long *>(&a->k[0]));
+    if (KW == 1) return q0 < k0;
+    if (q0 != k0) return q0 < k0;
+    return __ldcg(reinterpret_cast<const unsigned long long *>(&a->k[KW - 1])) < k1;
+}
+template <int KW>
+__global__ void __launch_bounds__(1024)
+    span_sort_global_kernel(Rec<KW> *__restrict__ rec, Rec<KW> *__restrict__ rec2, const uint32_t *__restrict__ starts, const uint32_t *__restrict__ n_spans_ptr,
+                            uint32_t m_min, uint32_t *__restrict__ too_big) {
+    extern __shared__ __align__(16) uint8_t ssg_smem[];
+    uint32_t *ra = reinterpret_cast<uint32_t *>(ssg_smem);  // [SS_RMAX_G + 2]
+    uint32_t *rb = ra + SS_RMAX_G + 2;
+    __shared__ uint32_t s_cnt[33];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_spans = *n_spans_ptr;
+    for (uint32_t s = blockIdx.x; s < n_spans; s += gridDim.x) {
+        const uint32_t b = starts[s], m = starts[s + 1] - b;
+        if (m < m_min) continue;
+        // natural runs: warp w takes the w-th 32nd of the span (count, prefix over the warps, list)
+        const uint32_t per = (m + 31) / 32, c0 = warp * per, c1 = min(m, c0 + per);
+        auto is_head = [&](uint32_t i) {
+            if (i == 0) return true;
+            const Rec<KW> *pr = rec + b + i - 1;
+            const uint64_t k0 = __ldcg(reinterpret_cast<const unsigned long long *>(&rec[b + i].k[0]));
+            const uint64_t k1 = KW == 2 ? __ldcg(reinterpret_cast<const unsigned long long *>(&rec[b + i].k[KW - 1])) : 0ull;
+            return !rec_less<KW>(pr, k0, k1);  // the k-mer did not increase (k-mers of a span are distinct: it decreased)
+        };
+        uint32_t cnt = 0;
+        for (uint32_t i0 = c0; i0 < c1; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            cnt += __popc(__ballot_sync(0xffffffffu, i < c1 && is_head(i)));
+        }
+        if (lane == 0) s_cnt[warp] = cnt;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t acc = 0;
+            for (int w = 0; w < 32; w++) {
+                const uint32_t c = s_cnt[w];
+                s_cnt[w] = acc;
+                acc += c;
+            }
+            s_cnt[32] = acc;
+        }
+        __syncthreads();
+        uint32_t nr = s_cnt[32];
+        if (nr > (uint32_t)SS_RMAX_G) {
+            if (tid == 0) atomicExch(too_big, 1u);
+            __syncthreads();
+            continue;
+        }
+        {
+            uint32_t at = s_cnt[warp];
+            for (uint32_t i0 = c0; i0 < c1; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const bool head = i < c1 && is_head(i);
+                const unsigned bal = __ballot_sync(0xffffffffu, head);
+                if (head) ra[at + __popc(bal & ((1u << lane) - 1u))] = i;
+                at += __popc(bal);
+            }
+            if (tid == 0) ra[nr] = m;
+        }
+        __syncthreads();
+        Rec<KW> *src = rec + b, *dst = rec2 + b;
+        uint32_t *src_r = ra, *dst_r = rb;
+        const uint32_t nr0 = nr;
+        while (nr > 1) {
+            for (uint32_t i = tid; i < m; i += 1024) {
+                uint32_t lo = 0, hi = nr;
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (src_r[mid] <= i) lo = mid;
+                    else hi = mid;
+                }
+                const uint32_t a = lo, sib = a ^ 1u;
+                Rec<KW> r;
+                r.k[0] = __ldcg(reinterpret_cast<const unsigned long long *>(&src[i].k[0]));
+                if (KW == 2) r.k[KW - 1] = __ldcg(reinterpret_cast<const unsigned long long *>(&src[i].k[KW - 1]));
+                r.mmer = __ldcg(&src[i].mmer);
+                r.arrival = __ldcg(&src[i].arrival);
+                uint32_t place = i;
+                if (sib < nr) {
+                    uint32_t l = src_r[sib], h = src_r[sib + 1];
+                    const uint32_t sib0 = l;
+                    while (l < h) {
+                        const uint32_t mid = (l + h) >> 1;
+                        if (rec_less<KW>(src + mid, r.k[0], KW == 2 ? r.k[KW - 1] : 0ull)) l = mid + 1;
+                        else h = mid;
+                    }
+                    place = src_r[a & ~1u] + (i - src_r[a]) + (l - sib0);
+                }
+                dst[place] = r;
+            }
+            const uint32_t nr2 = (nr + 1) >> 1;
+            for (uint32_t a = tid; a <= nr2; a += 1024) dst_r[a] = a < nr2 ? src_r[2 * a] : m;
+            __threadfence();
+            __syncthreads();
+            Rec<KW> *t = src;
+            src = dst;
+            dst = t;
+            uint32_t *tr = src_r;
+            src_r = dst_r;
+            dst_r = tr;
+            nr = nr2;
+        }
+        if (nr0 > 1 && src != rec + b) {  // an odd number of rounds: the result is in rec2
+            for (uint32_t i = tid; i < m; i += 1024) {
+                Rec<KW> r;
+                r.k[0] = __ldcg(reinterpret_cast<const unsigned long long *>(&src[i].k[0]));
+                if (KW == 2) r.k[KW - 1] = __ldcg(reinterpret_cast<const unsigned long long *>(&src[i].k[KW - 1]));
+                r.mmer = __ldcg(&src[i].mmer);
+                r.arrival = __ldcg(&src[i].arrival);
+                rec[b + i] = r;
+            }
+        }
+        __threadfence();
+        __syncthreads();
+    }
+}
+
+constexpr int SS_CAP_SMALL = 2048, SS_CAP_BIG = 8192;
+template <int KW, int CAP>
+constexpr size_t ss_smem_bytes() {
+    return (size_t)2 * KW * CAP * 8 + (size_t)2 * CAP * 2 + (size_t)2 * (SS_RMAX + 2) * 2;
+}
+
+// Sorts every span of rec[0, n) (spans = runs of equal m-mer code) in shared memory.  work32: [2 n + 4] u32.  *too_big (device,
+// = work32 + 2 n + 3) ends up non-zero when some span was left as it was.
+template <int KW>
+static int v3_span_sort(void *rec_v, void *rec2_v, uint64_t n, uint32_t *work32, void *scan_scratch, int sm_count, cudaStream_t st) {
+    Rec<KW> *rec = static_cast<Rec<KW> *>(rec_v);
+    uint32_t *idx = work32, *starts = work32 + n, *n_spans = work32 + 2 * n + 2, *flag = work32 + 2 * n + 3;
+    int l = exclusive_scan<uint32_t, RecHead<KW>>(RecHead<KW>{rec}, idx, n, static_cast<uint32_t *>(scan_scratch), nullptr, st);
+    span_starts_kernel<KW><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rec, n, idx, starts, n_spans, flag);
+    constexpr int CS = SS_CAP_SMALL / KW, CB = SS_CAP_BIG / KW;
+    constexpr size_t smem_s = ss_smem_bytes<KW, CS>(), smem_b = ss_smem_bytes<KW, CB>();
+    cudaFuncSetAttribute(span_sort_kernel<KW, CS, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
+    cudaFuncSetAttribute(span_sort_kernel<KW, CB, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+    const int per_sm = (int)((size_t)(227 * 1024) / (smem_s + 1024));
+    span_sort_kernel<KW, CS, 256><<<sm_count * (per_sm < 1 ? 1 : per_sm), 256, smem_s, st>>>(rec, starts, n_spans, 2u, (uint32_t)CS, flag);
+    span_sort_kernel<KW, CB, 1024><<<sm_count, 1024, smem_b, st>>>(rec, starts, n_spans, (uint32_t)CS + 1u, (uint32_t)CB, flag);
+    constexpr size_t smem_g = (size_t)2 * (SS_RMAX_G + 2) * 4;
+    cudaFuncSetAttribute(span_sort_global_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g);
+    span_sort_global_kernel<KW><<<sm_count * 2, 1024, smem_g, st>>>(rec, static_cast<Rec<KW> *>(rec2_v), starts, n_spans, (uint32_t)CB + 1u, flag);
+    return l + 4;
+}
+
 // The long spans' k-mers (n records, appended by finalize3_kernel) are sorted by (m-mer, k-mer) — a permutation inside every span —
 // and then written, with their id lists, to the table.  rec_a / rec_b: Rec<KW> [n] each; dnew: [n + 1] u64.
 int v3_lsd_finish(const KeyLayout &kl, uint64_t n, void *rec_a, void *rec_b, void *radix_scratch, uint64_t *dnew, void *scan_scratch, const V3Out &o, const V3Lsd &lsd,
-                  KernelProf *prof, cudaStream_t st) {
+                  int sm_count, KernelProf *prof, cudaStream_t st) {
     if (n == 0) return 0;
     const int KW = kl.K <= 32 ? 1 : 2;
     bool in_b = false;
     int passes = 0;
-    int l = radix_sort_records(rec_a, rec_b, n, KW, kl.K, kl.M, radix_scratch, &in_b, &passes, prof, st);
+    int l = 0;
+    static int span_sort_on = -1;  // GBIN_V3_SPAN_SORT=0: always the global sort (experiments)
+    if (span_sort_on < 0) {
+        const char *e = getenv("GBIN_V3_SPAN_SORT");
+        span_sort_on = e ? atoi(e) : 1;
+    }
+    bool need_global = true;
+    if (span_sort_on && n < (1ull << 31)) {
+        uint32_t *work32 = reinterpret_cast<uint32_t *>(dnew);  // [n + 2] u64 = [2 n + 4] u32; free until the list-length scan below
+        bool on = prof && prof->begin(KK_V3_SPAN, st);
+        const int ls_ = KW == 1 ? v3_span_sort<1>(rec_a, rec_b, n, work32, scan_scratch, sm_count, st) : v3_span_sort<2>(rec_a, rec_b, n, work32, scan_scratch, sm_count, st);
+        if (prof) prof->end(on, ls_, st);
+        l += ls_;
+        uint32_t flag = 1;
+        cudaMemcpyAsync(&flag, work32 + 2 * n + 3, sizeof flag, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) == cudaSuccess) need_global = flag != 0;
+    }
+    if (need_global) l += radix_sort_records(rec_a, rec_b, n, KW, kl.K, kl.M, radix_scratch, &in_b, &passes, prof, st);
     const void *sorted = in_b ? rec_b : rec_a;
     G3Final fin{o.kmer_codes, o.kmer_mmer, o.kmer_id_off, o.read_ids, o.id_off_base};
     G3Lsd ls{nullptr, nullptr, lsd.src_off, lsd.cnt, lsd.fidx, lsd.nadj, lsd.cap};

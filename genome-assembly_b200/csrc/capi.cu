@@ -770,7 +770,7 @@ int run_v3_pass(gbin_ctx *ctx, const void *skr, const uint64_t *ent, const uint1
         CU(ctx->radix_scratch.ensure(radix_scratch_bytes(nl)));
         CU(ctx->run_excl.ensure((nl + 2) * 8));
         CU(ctx->scan_scratch.ensure(group_scan_scratch_bytes(nl + 1024)));
-        lp = v3_lsd_finish(kl, nl, ctx->rec_a.p, ctx->rec_b.p, ctx->radix_scratch.p, ctx->run_excl.as<uint64_t>(), ctx->scan_scratch.p, vo, lsd_view(lsd_cap), &ctx->prof,
+        lp = v3_lsd_finish(kl, nl, ctx->rec_a.p, ctx->rec_b.p, ctx->radix_scratch.p, ctx->run_excl.as<uint64_t>(), ctx->scan_scratch.p, vo, lsd_view(lsd_cap), ctx->sm_count, &ctx->prof,
                            st);
         *launches += lp;
         CU(cudaGetLastError());

@@ -202,7 +202,7 @@ int v3_group_launch(const void *skr, const uint64_t *ent, const void *units, con
                     const V3Out &o, uint64_t max_units, uint64_t *unit_excl, uint64_t *lsd_excl, void *scan_scratch, void *gc_dev, const V3Chunks &ch, const V3Lsd &lsd,
                     bool finalize_only, int sm_count, KernelProf *prof, cudaStream_t st);
 int v3_lsd_finish(const KeyLayout &kl, uint64_t n, void *rec_a, void *rec_b, void *radix_scratch, uint64_t *dnew, void *scan_scratch, const V3Out &o, const V3Lsd &lsd,
-                  KernelProf *prof, cudaStream_t st);
+                  int sm_count, KernelProf *prof, cudaStream_t st);
 uint32_t v3_pass_tiles(uint64_t n_ent);
 uint32_t v3_pass_tile_entries();
 int v3_pass_tile_sums(const uint16_t *sorted_info, uint64_t n_ent, unsigned long long *sums_dev, cudaStream_t st);

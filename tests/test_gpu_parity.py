@@ -642,3 +642,25 @@ def test_expand_read_id_list_on_the_device(name, tmp_path):
         b.lib.gbin_expanded_free(C.byref(xh))
         b.lib.gbin_table_free(C.byref(ht))
     b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M", [4, 5, 7])
+def test_v3_long_spans_are_sorted_span_by_span(M):
+    """Few, huge m-mer buckets (M = 4: at most 136 of them for 4.2 M instances): every bucket is a long span whose surviving k-mers
+    are put in k-mer order by the per-span merge sort in shared memory (2 048- and 8 192-k-mer launches) or, for spans above that,
+    by the global radix sort.  The table must be the oracle's whichever path a span took."""
+    torch_cuda()
+    rs = synth.generate(60000, 100, error_rate=0.01, seed=20, starts="triangular")
+    starts = np.arange(rs.n_reads, dtype=np.uint64) * rs.stride
+    lens = np.full(rs.n_reads, rs.read_len, dtype=np.uint32)
+    b = B.Binner(25, M, 1, pipeline=3)
+    got = b.bin_host(rs.buf, rs.n_reads, stride=rs.stride, read_len=rs.read_len)
+    want = O.run(rs.as_bytes(), starts, lens, 25, M, 1)
+    assert_tables_equal(got, want)
+    info, st = b.pipeline_info(), b.run_stats()
+    if info["last_used"] == 3:
+        assert st["n_lsd_kmers"] > 0, st
+        sizes = np.diff(want.mmer_kmer_off.astype(np.int64))
+        print("M", M, "buckets", len(sizes), "largest", int(sizes.max()), "lsd k-mers", st["n_lsd_kmers"])
+    b.close()

@@ -1461,7 +1461,7 @@ __global__ void __launch_bounds__(THREADS)
                         const uint32_t mid = (l + h) >> 1;
                         const uint64_t q0 = src_k[mid];
                         bool less = q0 < k0;
-                        if (KW == 2) less = less || (q0 == k0 && src_k[CAP + mid] < k1);
+                        if constexpr (KW == 2) less = less || (q0 == k0 && src_k[CAP + mid] < k1);
                         if (less) l = mid + 1;
                         else h = mid;
                     }

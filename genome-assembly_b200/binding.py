@@ -70,7 +70,7 @@ EXPORTS = [
     "gbin_strerror", "gbin_last_error", "gbin_version", "gbin_create", "gbin_destroy", "gbin_get_config",
     "gbin_bin_reads_host", "gbin_table_clone", "gbin_table_free", "gbin_pinned_alloc", "gbin_pinned_free",
     "gbin_bin_reads_device", "gbin_table_to_host", "gbin_table_to_pinned", "gbin_get_timings", "gbin_record_bytes",
-    "gbin_set_kernel_profiling", "gbin_get_kernel_profile", "gbin_kernel_kind_name", "gbin_max_read_len", "gbin_multi_create", "gbin_multi_destroy", "gbin_multi_devices", "gbin_multi_context", "gbin_multi_last_error", "gbin_multi_bin_reads_host", "gbin_table_digest", "gbin_set_pipeline", "gbin_set_tuning", "gbin_get_pipeline_info", "gbin_get_run_stats",
+    "gbin_set_kernel_profiling", "gbin_get_kernel_profile", "gbin_kernel_kind_name", "gbin_max_read_len", "gbin_multi_create", "gbin_multi_destroy", "gbin_multi_devices", "gbin_multi_context", "gbin_multi_last_error", "gbin_multi_bin_reads_host", "gbin_table_digest", "gbin_set_pipeline", "gbin_set_tuning", "gbin_donate_scratch", "gbin_get_pipeline_info", "gbin_get_run_stats",
     "gbin_count_instances_device", "gbin_scan_reads_device", "gbin_partition_records_device",
     "gbin_group_records_device", "gbin_owner_of", "gbin_xchg_create", "gbin_xchg_attach", "gbin_xchg_exchange_skr", "gbin_xchg_detach", "gbin_xchg_destroy", "gbin_skr_record_bytes", "gbin_scan_skr_device", "gbin_partition_skr_device", "gbin_group_skr_device",
     "gbin_split_reads_device", "gbin_copy_to_host", "gbin_bin_file_host", "gbin_read_file_fgets", "gbin_table_dump", "gbin_table_dump_reference_format", "gbin_table_dump_expanded_format",
@@ -116,6 +116,7 @@ def load_library() -> C.CDLL:
     L.gbin_set_pipeline.argtypes = [vp, C.c_int]
     L.gbin_table_digest.argtypes = [vp, C.POINTER(CTable), vp, C.POINTER(u64)]
     L.gbin_set_tuning.argtypes = [vp, C.c_char_p, C.c_int]
+    L.gbin_donate_scratch.argtypes = [vp, vp, C.c_uint64]
     L.gbin_get_pipeline_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint32)]
     L.gbin_set_kernel_profiling.argtypes = [vp, C.c_int]
     L.gbin_get_kernel_profile.argtypes = [vp, C.POINTER(KernelProfile)]
@@ -311,6 +312,10 @@ class Binner:
         h = CExpanded()
         self._check(self.lib.gbin_expanded_to_host(self.h, C.byref(dev), C.byref(h)))
         return h
+
+    def donate_scratch(self, d_buf, nbytes: int):
+        """Lends device memory to the next grouping call (gbin_donate_scratch); keep `d_buf` alive until that call has returned."""
+        self._check(self.lib.gbin_donate_scratch(self.h, _ptr(d_buf), int(nbytes)))
 
     def set_tuning(self, name: str, value: int):
         self._check(self.lib.gbin_set_tuning(self.h, name.encode(), int(value)))

@@ -149,6 +149,8 @@ struct gbin_ctx {
     // pipeline v3 workspace
     DevBuf ent_a, ent_b, piece_n, sorted_info, v3_base64, v3_head_run, v3_unit_out, v3_unit_excl, v3_atoms, v3_lsd_aux, v3_bitmap;
     DevBuf x_list_off, x_ids;         // gbin_expand_read_ids_device's result
+    void *donated = nullptr;          // gbin_donate_scratch: caller-owned device memory the next grouping call may use for its sort buffers
+    uint64_t donated_bytes = 0;
     bool v3_lsd_seen = false;         // a batch on this context had long spans: keep the arrays of their global sort
     uint64_t v3_lsd_cap_seen = 0;     // and how many k-mers they were sized for
     uint64_t v3_pass_max = 2000000000ull;  // k-mer instances per pass of pipeline 3 (gbin_set_tuning "v3_pass_max")
@@ -799,23 +801,40 @@ int run_v3_group(gbin_ctx *ctx, const void *skr, uint64_t n_skr, const int32_t *
 
     // ---- entries + level 1: stable sort of the entries by key
     const uint64_t n_slots = n_skr << kl.cshift;
-    CU(ctx->ent_a.ensure((n_slots + 2) * 8));
-    CU(ctx->ent_b.ensure((n_slots + 2) * 8));
+    // the two entry buffers of the sort: in donated memory when the caller gave enough of it (the multi-GPU path hands over the
+    // scan's record buffer, dead after the exchange — one allocation of that size less per step), else the context's own
+    const uint64_t ent_bytes = ((n_slots + 2) * 8 + 255) & ~255ull;
+    uint64_t *ent_a_p, *ent_b_p;
+    if (ctx->donated && ctx->donated_bytes >= 2 * ent_bytes && (reinterpret_cast<uintptr_t>(ctx->donated) & 15u) == 0) {
+        ent_a_p = static_cast<uint64_t *>(ctx->donated);
+        ent_b_p = ent_a_p + ent_bytes / 8;
+        if (ctx->ent_a.cap + ctx->ent_b.cap > (1ull << 30)) {  // a large batch on donated memory: the own buffers of an earlier one would only crowd the HBM
+            ctx->ent_a.release();
+            ctx->ent_b.release();
+        }
+    } else {
+        CU(ctx->ent_a.ensure(ent_bytes));
+        CU(ctx->ent_b.ensure(ent_bytes));
+        ent_a_p = ctx->ent_a.as<uint64_t>();
+        ent_b_p = ctx->ent_b.as<uint64_t>();
+    }
+    ctx->donated = nullptr;  // one call only
+    ctx->donated_bytes = 0;
     CU(ctx->piece_n.ensure((n_slots + 16) * 2));
     CU(ctx->sorted_info.ensure((n_slots + 16) * 2));
     bool on = ctx->prof.begin(KK_V3_ENTRIES, st);
-    int lp = v3_make_entries(skr, n_skr, kl, ctx->ent_a.as<uint64_t>(), ctx->piece_n.as<uint16_t>(), &dm->n_real_entries, st);
+    int lp = v3_make_entries(skr, n_skr, kl, ent_a_p, ctx->piece_n.as<uint16_t>(), &dm->n_real_entries, st);
     ctx->prof.end(on, lp, st);
     *launches += lp;
     CU(cudaGetLastError());
     CU(ctx->radix_scratch.ensure(radix_scratch_bytes(n_slots)));
     bool in_b = false;
     int passes = 0;
-    *launches += radix_sort_entries(ctx->ent_a.p, ctx->ent_b.p, n_slots, kl.key_bits, ctx->radix_scratch.p, &in_b, &passes, ctx->piece_n.as<uint16_t>(),
+    *launches += radix_sort_entries(ent_a_p, ent_b_p, n_slots, kl.key_bits, ctx->radix_scratch.p, &in_b, &passes, ctx->piece_n.as<uint16_t>(),
                                     ctx->sorted_info.as<uint16_t>(), &ctx->prof, st, kl.nc == 2 ? &dm->n_real_entries : nullptr);
     CU(cudaGetLastError());
     ctx->tm.sort_passes = (uint32_t)passes;
-    const uint64_t *ent = in_b ? ctx->ent_b.as<uint64_t>() : ctx->ent_a.as<uint64_t>();
+    const uint64_t *ent = in_b ? ent_b_p : ent_a_p;
     CU(cudaEventRecord(ctx->ev[3], st));
     uint64_t n_ent = n_slots;
     if (kl.nc == 2) {  // empty pieces carry the all-ones key and sort behind everything: plan over the real ones only
@@ -1195,6 +1214,13 @@ int gbin_get_run_stats(const gbin_ctx *ctx, gbin_run_stats *out) {
 int gbin_set_pipeline(gbin_ctx *ctx, int pipeline) {
     if (!ctx || pipeline < 1 || pipeline > 3) return GBIN_E_INVALID_ARG;
     ctx->pipeline = pipeline;
+    return GBIN_OK;
+}
+
+int gbin_donate_scratch(gbin_ctx *ctx, void *d_ptr, uint64_t bytes) {
+    if (!ctx) return GBIN_E_INVALID_ARG;
+    ctx->donated = bytes ? d_ptr : nullptr;
+    ctx->donated_bytes = d_ptr ? bytes : 0;
     return GBIN_OK;
 }
 

@@ -127,6 +127,11 @@ class GpuStages:
         self._count()
         return out
 
+    def lend_scratch(self, buf: torch.Tensor):
+        """The next group() call may use `buf` (device memory, dead data) for its sort buffers."""
+        if self.form == "skr":
+            self.b.donate_scratch(buf, buf.numel() * buf.element_size())
+
     def group(self, rec, n: int, id_base: int):
         """Returns the device table, or None when a shared-memory unit overflowed (form "skr" only)."""
         if self.form == "skr":
@@ -260,10 +265,14 @@ class ShardedBinner:
                 self.stats.sent_records = sum(counts)
                 self.stats.recv_records = n_in
                 self.stats.sent_bytes_offrank = (sum(counts) - counts[self.rank]) * self.stages.record_bytes
-            # the exchange call returned after its stream was synchronised: the records have left, and a config-3-sized shard (tens of GB
-            # of records) must make room for the grouping's workspace
+            # the exchange call returned after its stream was synchronised: the records have left.  Their buffer (tens of GB for a
+            # config-3-sized shard) is lent to the grouping call for its sort buffers and goes back to the allocator's cache afterwards,
+            # where the next step's scan finds it: no cudaFree / cudaMalloc of that size inside the step.
+            lent = rec if (got is not None and hasattr(self.stages, "lend_scratch")) else None
             del rec
-            if n * self.stages.record_bytes > (12 << 30):  # only when it matters: returning the block to the driver costs a cudaMalloc next step
+            if lent is not None:
+                self.stages.lend_scratch(lent)
+            elif n * self.stages.record_bytes > (12 << 30):  # nothing to lend it to: a block of that size must not idle in the cache
                 torch.cuda.empty_cache()
             e3 = self._ev()
         else:
@@ -274,6 +283,7 @@ class ShardedBinner:
             del part
             e3 = self._ev()
         table = self.stages.group(inbuf, n_in, id_base)
+        lent = None  # (the group call has returned: its stream was synchronised)
         e4 = self._ev()
         if self.time_stages:
             torch.cuda.synchronize()

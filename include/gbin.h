@@ -178,6 +178,11 @@ int gbin_set_pipeline(gbin_ctx *ctx, int pipeline);
  *   "xchg_timeout_ms" >= 100  how long the multi-GPU exchange kernels wait for a peer before they give up (default 120000)
  *   "host_chunks" 1..16    pieces in which gbin_bin_reads_host streams reads in / the table out */
 int gbin_set_tuning(gbin_ctx *ctx, const char *name, int value);
+/* Lends `bytes` of device memory (16-byte aligned, caller-owned) to the NEXT grouping call on the context (gbin_group_skr_device,
+ * gbin_bin_reads_device): pipeline 3 puts the two buffers of its entry sort there when they fit, instead of allocating them.  The
+ * memory must stay valid and unused by the caller until that call returns; the loan ends with it.  The multi-GPU path lends the scan's
+ * record buffer, which is dead once the exchange has sent the records away. */
+int gbin_donate_scratch(gbin_ctx *ctx, void *d_ptr, uint64_t bytes);
 int gbin_get_pipeline_info(const gbin_ctx *ctx, int *configured, int *last_used, uint32_t *fallbacks);
 
 /* Optional per-kernel-class device timing (CUDA events around each launch on the call's stream),

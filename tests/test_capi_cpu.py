@@ -262,3 +262,30 @@ def test_table_digest_host_matches_its_python_restatement(name):
             assert L.gbin_table_digest(None, C.byref(cp), None, C.byref(d)) == 0
             tot = (tot + d.value) & ((1 << 64) - 1)
         assert tot == O.table_digest(t)
+
+
+@pytest.mark.parametrize("name", ["cfg1_reads", "kat_twice"])
+def test_dump_from_expanded_lists_equals_the_expanded_dump(name, tmp_path):
+    """Host half of row f3 (no GPU needed): gbin_table_dump_expanded_lists prints a list-of-lists object (what
+    gbin_expand_read_ids_device + gbin_expanded_to_host deliver; built here with numpy as the CSR replicate of the oracle's table)
+    byte for byte like gbin_table_dump_expanded_format, which the test above pins against the reference's own expand + print.
+    A list-of-lists object of another batch (wrong list count) is refused."""
+    case = next(c for c in CASES if c["name"] == name)
+    data = O.load_case_bytes(case)
+    starts, lens = O.fgets_split(data, case["read_length_define"])
+    t = O.run(data, starts, lens, case["k"], case["m"], case["cutoff"])
+    ct, keep = c_table_from_oracle(t)
+    K = case["k"]
+    off = np.asarray(t.kmer_id_off, np.int64)
+    cnt = np.diff(off)
+    ids = np.asarray(t.read_ids, np.int32)
+    x_ids = np.concatenate([np.tile(ids[off[j]:off[j + 1]], K) for j in range(t.n_kmers)]).astype(np.int32) if t.n_kmers else np.zeros(1, np.int32)
+    x_off = np.concatenate([[0], np.cumsum(np.repeat(cnt, K))]).astype(np.uint64)
+    x = B.CExpanded(K, 0, t.n_kmers * K, int(x_off[-1]), x_off.ctypes.data, x_ids.ctypes.data)
+    L = B.load_library()
+    p1, p2 = tmp_path / "lists.txt", tmp_path / "format.txt"
+    assert L.gbin_table_dump_expanded_lists(C.byref(ct), C.byref(x), str(p1).encode()) == 0
+    assert L.gbin_table_dump_expanded_format(C.byref(ct), str(p2).encode()) == 0
+    assert p1.read_bytes() == p2.read_bytes() and p1.stat().st_size > 0
+    bad = B.CExpanded(K, 0, t.n_kmers * K + 1, int(x_off[-1]), x_off.ctypes.data, x_ids.ctypes.data)
+    assert L.gbin_table_dump_expanded_lists(C.byref(ct), C.byref(bad), str(p1).encode()) == B.GBIN_E_INVALID_ARG

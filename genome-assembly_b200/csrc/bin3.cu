@@ -140,7 +140,6 @@ int v3_plan_runs(const uint64_t *ent, const uint16_t *sorted_info, uint64_t n_en
 // partial unit per block, under 2 % of the units).  An atom with more than `cap` instances gets 2 * ceil(c / cap) + 1
 // round units (enough for a greedy cut of its d-histogram whenever no single d holds more than cap instances).
 constexpr int PLAN_BLOCK = 64;    // atoms walked by one thread
-constexpr int PLAN_CTA_BLOCKS = 32;
 struct Plan3 {
     uint32_t cap, nb_max, ecap, max_rounds;
     // limits for packing several buckets into one unit (<= the limits above).  With cap = 1024 and two grouping kernels these are
@@ -464,7 +463,6 @@ __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, uint32_t lane
 
 constexpr int G3_WARPS = 5;  // warps (= units in flight) per CTA
 constexpr uint32_t G3_SMALL_INST = 512, G3_SMALL_ENT = 128, G3_SMALL_NB = 64;  // what the 512-instance layout holds
-constexpr int G3_U = 4;  // instances per lane that are in flight together in the instance-major phases
 
 template <int PW, int KW, int WCAP, int WARPS, int U>
 __global__ void __launch_bounds__(WARPS * 32)

@@ -1856,7 +1856,6 @@ int gbin_group_skr_device(gbin_ctx *ctx, void *d_skr, uint64_t n_skr, const int3
     if (n_skr >= (1ull << 31)) return fail(ctx, GBIN_E_TOO_LARGE, "too many super-k-mer records in one call");
     CU(cudaSetDevice(ctx->cfg.device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
-    const int NW = ctx->cfg.kmer_size <= 32 ? 8 : 12;
     int launches = 0;
     if (used_fallback) *used_fallback = 0;
     CU(cudaEventRecord(ctx->ev[0], st));

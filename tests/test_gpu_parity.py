@@ -664,3 +664,28 @@ def test_v3_long_spans_are_sorted_span_by_span(M):
         sizes = np.diff(want.mmer_kmer_off.astype(np.int64))
         print("M", M, "buckets", len(sizes), "largest", int(sizes.max()), "lsd k-mers", st["n_lsd_kmers"])
     b.close()
+
+
+_SWEEP = (
+    # (read length, K, M): every (positions per lane, (K-M+1 - positions per lane) mod positions per lane) pair of the
+    # lane-per-position scan kernel, 32- and 64-bit keys, windows narrower than a lane's positions + 1 and wider than a warp
+    [(100, K, 11) for K in (31, 32, 33)] + [(100, 4, 2), (100, 5, 2), (100, 6, 2), (100, 9, 4), (100, 31, 13), (100, 40, 15), (100, 63, 15),
+                                             (100, 63, 11), (100, 64, 12), (60, 31, 11), (96, 24, 12)]
+    + [(150, K, 11) for K in (30, 31, 32, 33, 34)] + [(150, 31, 14), (150, 63, 15), (150, 10, 5), (160, 64, 11)]
+    + [(250, K, 11) for K in (31, 32, 33, 34, 35, 36, 37, 38)] + [(250, 63, 15), (250, 64, 13), (250, 16, 8), (266, 22, 11), (267, 31, 11)]
+)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L,K,M", _SWEEP)
+def test_scan_kernel_window_shapes(L, K, M):
+    """The sliding arg-max of the scan stage is composed from per-lane prefix / suffix maxima and a doubling over lane maxima whose
+    shape depends on (read length, K - M + 1); every shape must give the oracle's table (267-base reads go to the hop-chain kernel)."""
+    torch_cuda()
+    rs = synth.generate(400, L, genome_len=6000, error_rate=0.01, seed=1000 * L + 10 * K + M, starts="uniform")
+    starts = np.arange(rs.n_reads, dtype=np.uint64) * rs.stride
+    lens = np.full(rs.n_reads, rs.read_len, dtype=np.uint32)
+    b = B.Binner(K, M, 1)
+    got = b.bin_host(rs.buf, rs.n_reads, stride=rs.stride, read_len=rs.read_len)
+    assert_tables_equal(got, O.run(rs.as_bytes(), starts, lens, K, M, 1))
+    b.close()

@@ -1024,8 +1024,7 @@ __device__ __forceinline__ void finalize3_unit(const Unit3 *__restrict__ units, 
         }
         return;
     }
-    if (span_len == SPAN_MEMBER) return;  // merged by the warp of the span's first unit
-    if (span_len == SPAN_MEMBER_LONG || span_len > SPAN_SHORT_MAX) {
+    if (span_len == SPAN_MEMBER_LONG || (span_len > SPAN_SHORT_MAX && span_len != SPAN_MEMBER)) {
         // long span: hand this unit's k-mers to the global sort
         const uint64_t lx = ls.excl[u];
         const uint64_t q0 = (lsd_base >> 32) + (lx >> 32), nq0 = (lsd_base & 0xffffffffull) + (lx & 0xffffffffull);
@@ -1051,28 +1050,33 @@ __device__ __forceinline__ void finalize3_unit(const Unit3 *__restrict__ units, 
         }
         return;
     }
-    const uint32_t R = span_len;
-    // pass 1: every k-mer's place inside the span; its list length goes to kmer_id_off at that place
-    uint32_t S_tot = 0, mmer = 0;
-    bool have_mm = false;
-    for (uint32_t j = 0; j < R; j++) {
-        const UnitOut3 o = st.unit_out[u + j];
-        S_tot += o.S;
-        if (o.S && !have_mm) {  // every unit of the span has the same m-mer code
-            mmer = st.mmer[o.ibase / st.kdiv];
-            have_mm = true;
-        }
-    }
-    mmer = __shfl_sync(0xffffffffu, mmer, 0);  // (all lanes read the same value; it is taken before pass 1 overwrites the staged m-mers)
-    for (uint32_t j = 0; j < R; j++) {
-        const UnitOut3 uj = st.unit_out[u + j];
-        const uint64_t kbj = uj.ibase / st.kdiv;
-        for (uint32_t x = lane; x < uj.S; x += 32) {
+    // Short span (head or member): every unit's warp places its own run.  The runs of the span's units are ascending and hold
+    // distinct k-mers, so a k-mer's place inside the span = its index in its own run + the number of smaller k-mers in every other
+    // run, and its list starts after the lists of all those k-mers: own list offset + per other run the list offset of the first
+    // k-mer that is not smaller (the staged list offsets of a unit ARE the prefix sums of its list lengths).  No unit waits for
+    // another one and nothing staged is overwritten.
+    uint32_t h = u;
+    while (units[h].span_len == SPAN_MEMBER) h--;  // the span's first unit (at most SPAN_SHORT_MAX - 1 steps back)
+    const uint32_t R = units[h].span_len;
+    const uint64_t exh = unit_excl[h];
+    const uint64_t Sh = (base >> 32) + (exh >> 32), Nh = (base & 0xffffffffull) + (exh & 0xffffffffull);
+    if (uo.S == 0) return;
+    const uint32_t j = u - h;
+    const uint64_t kbj = uo.ibase / st.kdiv;
+    const uint32_t mmer = st.mmer[kbj];  // every k-mer of the span has the same m-mer code
+    for (uint32_t x0 = 0; x0 < uo.S; x0 += 32) {
+        const uint32_t x = x0 + lane;
+        uint32_t lo = 0, cnt = 0;
+        uint64_t idoff = 0;
+        if (x < uo.S) {
             const uint64_t k0 = st.codes[(kbj + x) * KW], k1 = KW == 2 ? st.codes[(kbj + x) * KW + 1] : 0ull;
+            lo = st.loff[kbj + x];
+            cnt = (x + 1 < uo.S ? st.loff[kbj + x + 1] : uo.N) - lo;
             uint32_t rank = x;
+            idoff = lo;
             for (uint32_t j2 = 0; j2 < R; j2++) {
                 if (j2 == j) continue;
-                const UnitOut3 u2 = st.unit_out[u + j2];
+                const UnitOut3 u2 = st.unit_out[h + j2];
                 const uint64_t kb2 = u2.ibase / st.kdiv;
                 uint32_t a = 0, b = u2.S;  // keys of run j2 smaller than mine
                 while (a < b) {
@@ -1084,53 +1088,23 @@ __device__ __forceinline__ void finalize3_unit(const Unit3 *__restrict__ units, 
                     else b = m;
                 }
                 rank += a;
+                idoff += a < u2.S ? st.loff[kb2 + a] : u2.N;
             }
-            const uint32_t cnt = (x + 1 < uj.S ? st.loff[kbj + x + 1] : uj.N) - st.loff[kbj + x];
-            fin.kmer_codes[(Sb + rank) * KW] = k0;
-            if (KW == 2) fin.kmer_codes[(Sb + rank) * KW + 1] = k1;
-            fin.kmer_mmer[Sb + rank] = mmer;
-            fin.kmer_id_off[Sb + rank] = cnt;
-            st.mmer[kbj + x] = rank;  // remembered for pass 3 (the staged m-mer is not needed any more)
+            fin.kmer_codes[(Sh + rank) * KW] = k0;
+            if (KW == 2) fin.kmer_codes[(Sh + rank) * KW + 1] = k1;
+            fin.kmer_mmer[Sh + rank] = mmer;
+            fin.kmer_id_off[Sh + rank] = fin.id_off_base + Nh + idoff;
         }
-    }
-    __syncwarp();
-    __threadfence();
-    // pass 2: list lengths -> offsets (in place)
-    uint64_t carry = fin.id_off_base + Nb;
-    for (uint32_t x0 = 0; x0 < S_tot; x0 += 32) {
-        const uint32_t x = x0 + lane;
-        const uint32_t c = x < S_tot ? (uint32_t)fin.kmer_id_off[Sb + x] : 0u;
-        const uint32_t inc = warp_incl_scan_u32(c, lane);
-        if (x < S_tot) fin.kmer_id_off[Sb + x] = carry + inc - c;
-        carry += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    __syncwarp();
-    __threadfence();
-    // pass 3: lists.  Lane = list for the bookkeeping of 32 lists at a time (independent loads), then eight lanes copy each list.
-    for (uint32_t j = 0; j < R; j++) {
-        const UnitOut3 uj = st.unit_out[u + j];
-        const uint64_t kbj = uj.ibase / st.kdiv;
-        for (uint32_t x0 = 0; x0 < uj.S; x0 += 32) {
-            const uint32_t x = x0 + lane;
-            uint32_t lo = 0, cnt = 0;
-            uint64_t dsto = 0;
-            if (x < uj.S) {
-                lo = st.loff[kbj + x];
-                const uint32_t hi = x + 1 < uj.S ? st.loff[kbj + x + 1] : uj.N;
-                cnt = hi - lo;
-                dsto = fin.kmer_id_off[Sb + st.mmer[kbj + x]] - fin.id_off_base;
-            }
-            const uint32_t nl = min(32u, uj.S - x0);
-            for (uint32_t l0 = 0; l0 < nl; l0 += 4) {  // four lists per step, eight lanes each
-                const uint32_t l = l0 + (lane >> 3);
-                const uint32_t c = __shfl_sync(0xffffffffu, cnt, l & 31);
-                const uint32_t so = __shfl_sync(0xffffffffu, lo, l & 31);
-                const uint64_t d = __shfl_sync(0xffffffffu, dsto, l & 31);
-                if (l < nl) {
-                    const int32_t *src = st.ids + uj.ibase + so;
-                    int32_t *dst = fin.read_ids + d;
-                    for (uint32_t i = lane & 7u; i < c; i += 8) dst[i] = src[i];
-                }
+        const uint32_t nl = min(32u, uo.S - x0);
+        for (uint32_t l0 = 0; l0 < nl; l0 += 4) {  // four lists per step, eight lanes each
+            const uint32_t l = l0 + (lane >> 3);
+            const uint32_t c = __shfl_sync(0xffffffffu, cnt, l & 31);
+            const uint32_t so = __shfl_sync(0xffffffffu, lo, l & 31);
+            const uint64_t d = __shfl_sync(0xffffffffu, idoff, l & 31);
+            if (l < nl) {
+                const int32_t *src = st.ids + uo.ibase + so;
+                int32_t *dst = fin.read_ids + Nh + d;
+                for (uint32_t i = lane & 7u; i < c; i += 8) dst[i] = src[i];
             }
         }
     }
